@@ -1,0 +1,148 @@
+"""ctypes front-end of the CPU oracle (oracle/cpu_sim.c, oracle/cpu_legacy.c).  TEST INFRASTRUCTURE:
+imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
+
+`prepare_trace` restates JobTraceReader.prepare_jobs (/root/reference/core/jobs/job_generator.py:181-196)
+and the Job constructor's derived fields (/root/reference/core/jobs/jobs_manager.py:233-238);
+`format_job_csv` / `format_cluster_csv` restate LogManager.jcts / step_cluster
+(/root/reference/log_manager.py:118-155) with the csv module, as the reference does.
+"""
+import csv
+import ctypes as C
+import io
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Cluster(C.Structure):
+    _fields_ = [('num_switch', C.c_int32), ('num_node_p_switch', C.c_int32), ('num_gpu_p_node', C.c_int32),
+                ('num_cpu_p_node', C.c_int32), ('mem_p_node', C.c_int32), ('gpu_memory_capacity_mib', C.c_int32)]
+
+
+ROW_DTYPE = np.dtype([('idle_nodes', 'i4'), ('busy_nodes', 'i4'), ('busy_gpus', 'i4'), ('idle_gpus', 'i4'),
+                      ('running', 'i4'), ('queued', 'i4'), ('finished', 'i4'), ('max_is_int_zero', 'i4'),
+                      ('avg_gpu_memory_allocated', 'f8'), ('avg_pending', 'f8'), ('median_pending', 'f8'),
+                      ('max_pending', 'f8'), ('util_mu_sum', 'f8')])
+
+
+def build(force=False):
+    so = os.path.join(HERE, 'liboracle.so')
+    srcs = [os.path.join(HERE, f) for f in ('cpu_sim.c', 'cpu_legacy.c') if os.path.exists(os.path.join(HERE, f))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(['make', '-C', HERE, '-s', '-B', 'liboracle.so'])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def make_cluster(num_switch=1, num_node_p_switch=32, num_gpu_p_node=8, num_cpu_p_node=128, mem_p_node=512,
+                 gpu_memory_capacity=32, cluster_spec=None, **_):
+    """Defaults = /root/reference/run_sim.py:50-82; cluster_spec = infra/infrastructure.py:78-105."""
+    if cluster_spec and os.path.exists(cluster_spec):
+        with open(cluster_spec) as f:
+            rd = csv.DictReader(f)
+            need = ['num_switch', 'num_node_p_switch', 'num_gpu_p_node', 'num_cpu_p_node', 'mem_p_node']
+            if all(k in rd.fieldnames for k in need):
+                for row in rd:
+                    num_switch, num_node_p_switch, num_gpu_p_node, num_cpu_p_node, mem_p_node = (int(row[k]) for k in need)
+    return Cluster(num_switch, num_node_p_switch, num_gpu_p_node, num_cpu_p_node, mem_p_node, gpu_memory_capacity * 1024)
+
+
+def prepare_trace(trace, scale_factor=0.5):
+    """trace: CSV path or DataFrame -> dict of per-job arrays in queue-arrival order."""
+    import pandas as pd
+    df = pd.read_csv(trace) if isinstance(trace, (str, os.PathLike)) else trace.copy()
+    df = df[df['type'] == 'noninteractive']
+    df = df.sort_values(by='normalized_time')
+    df = df.dropna()
+    nt = df['normalized_time'] - df['normalized_time'].min()
+    nt = nt / 10000
+    return dict(label=df.index.to_numpy().astype(np.int64),
+                nt=np.ascontiguousarray(nt.to_numpy(dtype=np.float64)),
+                duration=np.ascontiguousarray(df['minutes'].to_numpy(dtype=np.float64) * scale_factor),
+                used_gpus=np.ascontiguousarray(df['used_gpus'].to_numpy(dtype=np.float64)),
+                gpc=np.ascontiguousarray(df['gpu_per_container'].to_numpy(dtype=np.int32)),
+                mem_mib=np.ascontiguousarray(df['memory_max'].to_numpy(dtype=np.float64) / 1024 / 1024),
+                util_avg=np.ascontiguousarray(df['gpu_utilization_avg'].to_numpy(dtype=np.float64)),
+                util_max=np.ascontiguousarray(df['gpu_utilization_max'].to_numpy(dtype=np.float64)))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def run_fifo_yarn(cluster, tr, rows_cap=None):
+    """Returns dict(finish_order, start, end, rows (ROW_DTYPE), n_ticks, counters)."""
+    L = lib()
+    n = len(tr['nt'])
+    fin = np.empty(max(n, 1), np.int32); st = np.empty(max(n, 1), np.int32); en = np.empty(max(n, 1), np.int32)
+    nfin = C.c_int32(0); nticks = C.c_int64(0); counters = np.zeros(4, np.int64)
+    cap = rows_cap or max(4096, 4 * n)
+    while True:
+        rows = np.zeros(cap, ROW_DTYPE)
+        rc = L.oracle_fifo_yarn(C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
+                                _p(tr['used_gpus'], C.c_double), _p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double),
+                                _p(tr['util_avg'], C.c_double), _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32),
+                                C.byref(nfin), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks),
+                                _p(counters, C.c_int64))
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc != 0:
+            raise RuntimeError('oracle_fifo_yarn rc=%d (the reference would raise on this input)' % rc)
+        break
+    k = nfin.value
+    return dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
+                counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]),
+                              starts=int(counters[3])))
+
+
+def format_job_csv(tr, res):
+    """job.csv as LogManager.jcts writes it (/root/reference/log_manager.py:45-54,137-155)."""
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    w.writerow(['job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'original_duration',
+                'actual_duration', 'jct', 'preempt'])
+    dur = res.get('actual_duration', tr['duration'])
+    pre = res.get('preempt')
+    for k, i in enumerate(res['finish_order']):
+        i = int(i)
+        w.writerow([str(int(tr['label'][i])), float(tr['used_gpus'][i]), int(tr['nt'][i]), int(res['start'][i]),
+                    int(res['end'][i]), float(tr['duration'][i]),
+                    float(dur[i]) if dur[i] > 0 else 0,   # Job.get_duration: max(0, d) keeps the int 0 (job.py:206-210)
+                    int(res['jct'][i]) if 'jct' in res else int(res['end'][i] - res['start'][i]),
+                    int(pre[i]) if pre is not None else 1])
+    return buf.getvalue()
+
+
+def format_cluster_csv(res, with_util=False):
+    """cluster.csv as LogManager.step_cluster writes it (log_manager.py:37-44,118-135); by default
+    WITHOUT the avg_gpu_utilization column (unseeded RNG in the reference)."""
+    hdr = ['delta', 'num_idle_nodes', 'num_busy_nodes', 'num_busy_gpus', 'num_idle_gpus', 'avg_gpu_utilization',
+           'avg_gpu_memory_allocated', 'avg_pending_time', 'median_pending_time', 'max_pending_time',
+           'num_running_jobs', 'num_queuing_jobs', 'num_finish_jobs']
+    if not with_util:
+        hdr.remove('avg_gpu_utilization')
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    w.writerow(hdr)
+    rows = res['rows']
+    for d in range(len(rows)):
+        r = rows[d]
+        row = [d + 1, int(r['idle_nodes']), int(r['busy_nodes']), int(r['busy_gpus']), int(r['idle_gpus'])]
+        if with_util:
+            row.append(0.0)
+        row += [float(r['avg_gpu_memory_allocated']), float(r['avg_pending']), float(r['median_pending']),
+                0 if r['max_is_int_zero'] else float(r['max_pending']),
+                int(r['running']), int(r['queued']), int(r['finished'])]
+        w.writerow(row)
+    return buf.getvalue()

@@ -1,0 +1,134 @@
+"""Registry of parity cases shared by oracle/make_golden.py (which runs the real reference in
+this container) and tests/ (which replay the same traces through oracle/cpu_sim.c and the CUDA
+path).  Test infrastructure only.
+
+Each case: name -> dict(frame=callable returning the trace DataFrame, flags=dict of run_sim.py
+cluster flags, big=bool (fixture stored gzip'ed / hashed instead of plain text)).
+Edge cases follow the quirk list in SURVEY.md Appendix A (q1..q13).
+"""
+import numpy as np
+
+import tracegen as tg
+
+C148 = dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8)
+C4328 = dict(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
+
+
+def _kat6(drop_last=False):
+    rows = [dict(normalized_time=0, minutes=20, used_gpus=8.0, gpu_per_container=8),
+            dict(normalized_time=10000, minutes=4, used_gpus=8.0, gpu_per_container=8),
+            dict(normalized_time=20000, minutes=4, used_gpus=8.0, gpu_per_container=8),
+            dict(normalized_time=30000, minutes=4, used_gpus=4.0, gpu_per_container=4),
+            dict(normalized_time=30000, minutes=4, used_gpus=4.0, gpu_per_container=4),
+            dict(normalized_time=600000, minutes=2, used_gpus=1.0, gpu_per_container=1)]
+    if drop_last:
+        rows = rows[:-1]
+    return tg.frame_rows(rows)
+
+
+def _multi_node():
+    # 2 switches x 2 nodes x 4 GPUs: cross-node yarn (gpus > 4), the `<=` off-by-one (q11),
+    # least_num_full_nodes, and a job that can never be placed (9 GPUs in one 8-GPU task).
+    rows = [dict(normalized_time=0, minutes=30, used_gpus=8.0, gpu_per_container=4),
+            dict(normalized_time=11000, minutes=12, used_gpus=6.0, gpu_per_container=2),
+            dict(normalized_time=23000, minutes=8, used_gpus=5.0, gpu_per_container=1),
+            dict(normalized_time=31000, minutes=9, used_gpus=2.0, gpu_per_container=1),
+            dict(normalized_time=45000, minutes=20, used_gpus=16.0, gpu_per_container=2),
+            dict(normalized_time=52000, minutes=5, used_gpus=3.0, gpu_per_container=3),
+            dict(normalized_time=90000, minutes=7, used_gpus=12.0, gpu_per_container=4),
+            dict(normalized_time=150000, minutes=3, used_gpus=4.0, gpu_per_container=4),
+            dict(normalized_time=400000, minutes=6, used_gpus=1.0, gpu_per_container=1),
+            dict(normalized_time=410000, minutes=6, used_gpus=9.0, gpu_per_container=8),
+            dict(normalized_time=900000, minutes=2, used_gpus=1.0, gpu_per_container=1)]
+    return tg.frame_rows(rows)
+
+
+def _resource_bound(seed):
+    rng = np.random.default_rng(seed)
+    n = 60
+    g = rng.choice([1, 2, 4, 8, 16], n, p=[.4, .2, .2, .15, .05])
+    gpc = np.minimum(g, rng.choice([1, 2, 4], n))
+    gpc = np.where(g % gpc == 0, gpc, 1)
+    rows = [dict(normalized_time=float(t), minutes=float(m), used_gpus=float(a), gpu_per_container=int(b))
+            for t, m, a, b in zip(np.sort(rng.uniform(0, 3e6, n)), rng.uniform(2, 80, n), g, gpc)]
+    return tg.frame_rows(rows)
+
+
+def _big_mem():
+    # memory_max above cap-500 MiB: no device accepts the task and the reference leaks
+    # cpu_used/mem_used on every visited node every tick (q8).  Newer arrivals jump the queue (q1).
+    rows = [dict(normalized_time=0, minutes=10, used_gpus=2.0, gpu_per_container=1),
+            dict(normalized_time=20000, minutes=6, used_gpus=2.0, gpu_per_container=1, memory_max=40000000000),
+            dict(normalized_time=50000, minutes=6, used_gpus=1.0, gpu_per_container=1),
+            dict(normalized_time=90000, minutes=4, used_gpus=12.0, gpu_per_container=4, memory_max=36000000000),
+            dict(normalized_time=120000, minutes=8, used_gpus=4.0, gpu_per_container=2),
+            dict(normalized_time=300000, minutes=3, used_gpus=8.0, gpu_per_container=8),
+            dict(normalized_time=700000, minutes=2, used_gpus=1.0, gpu_per_container=1)]
+    return tg.frame_rows(rows)
+
+
+def _nondivisible():
+    rows = [dict(normalized_time=0, minutes=9, used_gpus=3.0, gpu_per_container=2),
+            dict(normalized_time=10000, minutes=7, used_gpus=6.0, gpu_per_container=4),
+            dict(normalized_time=12000, minutes=11, used_gpus=12.0, gpu_per_container=5),
+            dict(normalized_time=30000, minutes=5, used_gpus=7.0, gpu_per_container=2),
+            dict(normalized_time=35000, minutes=3, used_gpus=8.0, gpu_per_container=3),
+            dict(normalized_time=250000, minutes=2, used_gpus=1.0, gpu_per_container=1)]
+    return tg.frame_rows(rows)
+
+
+def _filter_nan():
+    # q13: interactive rows and rows with NaN are dropped; input unsorted; first arrival != 0.
+    rows = [dict(normalized_time=530000, minutes=6, used_gpus=2.0, gpu_per_container=2),
+            dict(normalized_time=500000, minutes=3, used_gpus=1.0, gpu_per_container=1, type='interactive'),
+            dict(normalized_time=512345, minutes=14.5, used_gpus=8.0, gpu_per_container=4),
+            dict(normalized_time=505000, minutes=np.nan, used_gpus=1.0, gpu_per_container=1),
+            dict(normalized_time=641000, minutes=2.2, used_gpus=4.0, gpu_per_container=1),
+            dict(normalized_time=511111, minutes=1.0, used_gpus=1.0, gpu_per_container=1),
+            dict(normalized_time=700000, minutes=5, used_gpus=1.0, gpu_per_container=1, memory_avg=np.nan),
+            dict(normalized_time=909090, minutes=0.9, used_gpus=1.0, gpu_per_container=1)]
+    return tg.frame_rows(rows)
+
+
+def _short():
+    # cf5: runtime = max(1, ceil(minutes*0.5)); includes duration 0, 0.25, exactly 1.0 and 2.0
+    mins = [0.0, 0.5, 2.0, 4.0, 4.0000001, 1.999999, 3.0, 0.01, 6.0, 2.0]
+    rows = [dict(normalized_time=7000.0 * i, minutes=m, used_gpus=2.0, gpu_per_container=2)
+            for i, m in enumerate(mins)]
+    return tg.frame_rows(rows)
+
+
+def _ties():
+    # batches of simultaneous arrivals (front insertion keeps batch order, q1) under load
+    rng = np.random.default_rng(11)
+    rows = []
+    for b in range(12):
+        t = float(b * 40000 + 5000)
+        for _ in range(int(rng.integers(1, 6))):
+            g = int(rng.choice([1, 2, 4, 8]))
+            rows.append(dict(normalized_time=t, minutes=float(rng.uniform(3, 40)), used_gpus=float(g),
+                             gpu_per_container=int(rng.choice([1, g]))))
+    rows.append(dict(normalized_time=2.5e6, minutes=2, used_gpus=1.0, gpu_per_container=1))
+    return tg.frame_rows(rows)
+
+
+CASES = {
+    'kat6': dict(frame=_kat6, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8)),
+    'kat5_early': dict(frame=lambda: _kat6(True), flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8)),
+    'probe100': dict(frame=tg.frame_probe100, flags=C148),
+    'multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4)),
+    'cpu_bound': dict(frame=lambda: _resource_bound(21), flags=dict(num_switch=1, num_node_p_switch=6, num_gpu_p_node=8, num_cpu_p_node=30)),
+    'mem_bound': dict(frame=lambda: _resource_bound(22), flags=dict(num_switch=2, num_node_p_switch=3, num_gpu_p_node=8, mem_p_node=130)),
+    'big_mem_leak': dict(frame=_big_mem, flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4, num_cpu_p_node=64, mem_p_node=256)),
+    'gpu_cap16': dict(frame=lambda: tg.frame_gen(120, 7, 150), flags=dict(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8, gpu_memory_capacity=12)),
+    'nondivisible': dict(frame=_nondivisible, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8)),
+    'filter_nan': dict(frame=_filter_nan, flags=C148),
+    'short_durations': dict(frame=_short, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=4)),
+    'ties': dict(frame=_ties, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8)),
+    'cluster_spec': dict(frame=lambda: tg.frame_gen(150, 9, 400), flags=dict(cluster_spec='@cluster_spec.csv')),
+    'dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)),
+    'probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, big=True),
+    'probe10k': dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, big=True),
+    'loaded10k': dict(frame=lambda: tg.frame_gen(10000, 4, 2500), flags=C4328, big=True),
+    'probe60k': dict(frame=lambda: tg.frame_gen(60000, 3, 60000), flags=C4328, big=True, huge=True),
+}
