@@ -1,0 +1,173 @@
+/*
+ * rlgs.h — C ABI of the B200-native cluster-simulator hot path (librlgs.so).
+ *
+ * This is the drop-in boundary for the reference's per-tick / per-event advance.  Every entry
+ * point names the reference interface it replaces (paths are relative to the reference repo,
+ * matthewygf/RLGPUSchedule); INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only; every function returns an int32 status (RLGS_OK or a negative RLGS_ERR_*);
+ *    rlgs_last_error() gives a thread-local message; no exception crosses the boundary.
+ *  - the opaque rlgs_sim handle owns all device memory and its pinned host staging; host buffers
+ *    passed in are caller-owned and never retained after the call returns.
+ *  - a handle is not thread-safe; distinct handles may be used from distinct host threads.
+ *  - a "replica" is one independent simulation (one trace on one simulated cluster); replicas never
+ *    communicate.  On the device one warp advances one replica.
+ *  - the library needs a CUDA device: there is no CPU fallback (rlgs_create fails with RLGS_ERR_CUDA).
+ */
+#ifndef RLGS_H
+#define RLGS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLGS_VERSION 100 /* 0.1.0 */
+
+enum {
+    RLGS_OK = 0,
+    RLGS_ERR_BAD_ARG = -1,
+    RLGS_ERR_CUDA = -2,
+    RLGS_ERR_OOM = -3,
+    RLGS_ERR_UNSUPPORTED = -4, /* policy / option the device path does not implement */
+    RLGS_ERR_CAPACITY = -5,    /* a fixed-size device table overflowed and could not be grown */
+    RLGS_ERR_STATE = -6        /* call order (e.g. run before load_trace) */
+};
+
+/* --schedule (run_sim.py:38-49); live fifo = core/scheduling/algorithm.py:189-202,
+ * sjf = run_sim.py:162-287 (dead code, restated), dlas-gpu = run_sim.py:664-947 (dead code, restated) */
+enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2 };
+/* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
+ * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
+enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1 };
+enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1 };
+
+/* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
+ * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
+typedef struct {
+    int32_t num_switch;
+    int32_t num_node_p_switch;
+    int32_t num_gpu_p_node; /* 1..32 */
+    int32_t num_cpu_p_node;
+    int32_t mem_p_node;
+    int32_t reserved;
+} rlgs_cluster_spec;
+
+#define RLGS_MAX_QUEUES 8
+
+typedef struct {
+    int32_t device;        /* CUDA ordinal */
+    int32_t n_replicas;    /* >= 1 */
+    int32_t schedule;      /* RLGS_SCHED_* */
+    int32_t placement;     /* RLGS_PLACE_* */
+    int32_t rows_mode;     /* RLGS_ROWS_*: keep one cluster.csv row per tick / event */
+    int32_t slot_cap;      /* running-job slots per replica held on chip; 0 = auto (grown on overflow) */
+    int32_t chunk_ticks;   /* ticks advanced per kernel launch; 0 = auto */
+    int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES */
+    int32_t queue_limit[RLGS_MAX_QUEUES]; /* dlas-gpu demotion thresholds in GPU-ticks */
+    int32_t enable_network_costs;         /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
+    int32_t reserved0;
+    double bandwidth;          /* --bandwidth MB/s (run_sim.py:59) */
+    double internode_latency;  /* --internode_latency s (run_sim.py:65) */
+    int64_t max_ticks;         /* safety stop; 0 = none */
+} rlgs_opts;
+
+/*
+ * One job of a trace, already in queue-arrival order (the row order of JobTraceReader.prepare_jobs,
+ * core/jobs/job_generator.py:181-196).  32-byte records, the unit the device streams from HBM.
+ * Derived on the host exactly as the reference's Job constructor derives them (core/jobs/job.py:75-110,
+ * jobs_manager.py:233-238) — see rlgpuschedule_b200/ingest.py.
+ */
+typedef struct {
+    int32_t arrival_tick;  /* first integer tick d with normalized_time <= d (job_generator.py:203) */
+    int32_t dur_ticks;     /* max(1, ceil(duration)): ticks from start to finish (jobs_manager.py:243-250) */
+    uint16_t gpus;         /* ceil(used_gpus): the value `free_devices >= job.gpus` compares against */
+    uint16_t tasks;        /* int(used_gpus // gpu_per_container) (job.py:96-99) */
+    uint16_t gpus_per_task;/* gpu_per_container */
+    uint16_t least_nodes_fits; /* bit15 = an empty device accepts the task (infra/device.py:67-77);
+                                  bits0-14 = ceil(used_gpus / num_gpu_p_node) (algorithm.py:310) */
+    int64_t mem_term;      /* min(cap, memory_max MiB) per occupied device in units of 2^-mem_shift MiB */
+    uint16_t util_mu_q;    /* gpu_utilization_avg * 512 (statistics of the unseeded RNG column only) */
+    uint16_t util_sd_q;    /* (gpu_utilization_max - gpu_utilization_avg)/2 * 512 */
+    int32_t index;         /* position of this job in the trace (0..n-1) */
+} rlgs_job;
+
+/* Optional per-job inputs of the network-cost model (core/network/network_service.py:34-37). */
+typedef struct {
+    const double *duration;   /* minutes * scale_factor, float64 */
+    const double *model_mb;   /* model size in MB (model/model_factory.py:19-55), 0 if unknown */
+    const double *iterations; /* training iterations, 0 if unknown */
+} rlgs_netcost_inputs;
+
+/* One cluster.csv row as integer sufficient statistics (core/scheduling/schedule.py:95-133,
+ * log_manager.py:118-135).  The float columns are finished on the host (rlgpuschedule_b200/log_manager.py). */
+typedef struct {
+    int32_t idle_nodes;   /* num_idle_nodes; num_busy_nodes = N - idle_nodes */
+    int32_t busy_gpus;    /* num_busy_gpus; num_idle_gpus = D - busy_gpus */
+    int32_t running, queued, finished;
+    int32_t median_lo, median_hi; /* pending time of the two middle queued jobs (np.median = their mean) */
+    int32_t max_pending;
+    int64_t sum_pending;  /* avg_pending_time = sum_pending / (queued + 1e-9) */
+    int64_t mem_sum;      /* sum over busy devices of mem_term: avg_gpu_memory_allocated numerator */
+    int64_t util_mu_sum;  /* sum over busy devices of util_mu_q */
+    int64_t util_var_sum; /* sum over busy devices of util_sd_q^2 */
+} rlgs_row;
+
+typedef struct {
+    int64_t n_ticks;       /* rows produced (fifo: ticks; sjf/dlas: events) */
+    int64_t makespan;      /* last simulated time */
+    int64_t sum_jct;       /* sum over finished jobs of end - submit-arrival tick */
+    int64_t sum_queued;    /* sum over ticks of queued jobs  (job-updates accounting) */
+    int64_t sum_running;   /* sum over ticks of running jobs */
+    int64_t events;        /* arrivals + starts + finishes + preemptions + queue jumps */
+    int32_t n_jobs, n_arrived, n_started, n_finished;
+    int32_t max_queued, max_running;
+    int32_t status;        /* RLGS_OK or RLGS_ERR_* raised on the device for this replica */
+    int32_t done;
+} rlgs_summary;
+
+typedef struct rlgs_sim rlgs_sim;
+
+int32_t rlgs_version(void);
+const char *rlgs_last_error(void);
+
+/* Replaces Infrastructure(FLAGS) + JobQueueManager/JobsManager/Scheduler construction (run_sim.py:1716-1735). */
+int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *opts, rlgs_sim **out);
+void rlgs_destroy(rlgs_sim *sim);
+
+/* Replaces JobTraceReader ingestion into JobsManager (jobs_manager.py:16-18,228-241): copies `n` job
+ * records to the device once and attaches them to replicas [first_replica, first_replica+n_replicas).
+ * mem_shift/mem_cap_term describe the fixed-point unit of rlgs_job.mem_term.  `net` may be NULL. */
+int32_t rlgs_load_trace(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas, const rlgs_job *jobs, int32_t n,
+                        const rlgs_netcost_inputs *net);
+
+/* Replaces Scheduler.start() (core/scheduling/schedule.py:178-216): runs every replica to completion.
+ * Blocking.  Resets replica state first, so it can be called repeatedly (bench steps). */
+int32_t rlgs_run(rlgs_sim *sim);
+/* Device time of the kernels of the last rlgs_run, from CUDA events on the launch stream. */
+int32_t rlgs_last_run_ms(rlgs_sim *sim, float *kernel_ms, int32_t *n_launches);
+/* Launch on a caller-provided cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); NULL = own stream. */
+int32_t rlgs_set_stream(rlgs_sim *sim, void *cuda_stream);
+
+int32_t rlgs_get_summary(rlgs_sim *sim, int32_t replica, rlgs_summary *out);
+/* Replaces LogManager.jcts' walk over finished_jobs (log_manager.py:137-155): per job (trace order)
+ * start/end tick (-1 = never) and preempt count; finish_order[k] = trace index of the k-th finished job.
+ * Any pointer may be NULL.  Arrays must hold n_jobs entries. */
+int32_t rlgs_read_jobs(rlgs_sim *sim, int32_t replica, int32_t *finish_order, int32_t *start_tick, int32_t *end_tick,
+                       int32_t *preempt, int32_t *first_node);
+/* Replaces the per-tick LogManager.step_cluster rows (log_manager.py:118-135): copies rows
+ * [first, first+count) of `replica` (rows_mode FULL). */
+int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row *out);
+/* Zero-copy variant: pointer into the handle's pinned host store, valid until the next rlgs_run / destroy. */
+int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, const rlgs_row **rows, int64_t *count);
+/* Episode return per replica: -(sum of job completion times), the reward of the vectorised Environment. */
+int32_t rlgs_returns(rlgs_sim *sim, int64_t *out_n_replicas);
+/* Device pointer to the same int64[n_replicas] buffer (the NCCL all-gather send buffer). */
+int32_t rlgs_returns_device_ptr(rlgs_sim *sim, void **dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLGS_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of librlgs.so (include/rlgs.h).  Fails loudly: there is no CPU fallback.
+
+The library is built in-tree by rlgpuschedule_b200/build.py (nvcc, sm_100a) and loaded from the
+package directory so the driver can see which .so a test / bench process used.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, 'librlgs.so')
+
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2}
+PLACE = {'yarn': 0, 'count': 1}
+ROWS_NONE, ROWS_FULL = 0, 1
+MAX_QUEUES = 8
+
+
+class ClusterSpec(C.Structure):
+    _fields_ = [('num_switch', C.c_int32), ('num_node_p_switch', C.c_int32), ('num_gpu_p_node', C.c_int32),
+                ('num_cpu_p_node', C.c_int32), ('mem_p_node', C.c_int32), ('reserved', C.c_int32)]
+
+
+class Opts(C.Structure):
+    _fields_ = [('device', C.c_int32), ('n_replicas', C.c_int32), ('schedule', C.c_int32), ('placement', C.c_int32),
+                ('rows_mode', C.c_int32), ('slot_cap', C.c_int32), ('chunk_ticks', C.c_int32), ('num_queue', C.c_int32),
+                ('queue_limit', C.c_int32 * MAX_QUEUES), ('enable_network_costs', C.c_int32), ('reserved0', C.c_int32),
+                ('bandwidth', C.c_double), ('internode_latency', C.c_double), ('max_ticks', C.c_int64)]
+
+
+class NetcostInputs(C.Structure):
+    _fields_ = [('duration', C.POINTER(C.c_double)), ('model_mb', C.POINTER(C.c_double)),
+                ('iterations', C.POINTER(C.c_double))]
+
+
+class Summary(C.Structure):
+    _fields_ = [('n_ticks', C.c_int64), ('makespan', C.c_int64), ('sum_jct', C.c_int64), ('sum_queued', C.c_int64),
+                ('sum_running', C.c_int64), ('events', C.c_int64), ('n_jobs', C.c_int32), ('n_arrived', C.c_int32),
+                ('n_started', C.c_int32), ('n_finished', C.c_int32), ('max_queued', C.c_int32), ('max_running', C.c_int32),
+                ('status', C.c_int32), ('done', C.c_int32)]
+
+
+# numpy views of the plain structs of rlgs.h
+JOB_DTYPE = np.dtype([('arrival_tick', '<i4'), ('dur_ticks', '<i4'), ('gpus', '<u2'), ('tasks', '<u2'),
+                      ('gpus_per_task', '<u2'), ('least_nodes_fits', '<u2'), ('mem_term', '<i8'),
+                      ('util_mu_q', '<u2'), ('util_sd_q', '<u2'), ('index', '<i4')])
+ROW_DTYPE = np.dtype([('idle_nodes', '<i4'), ('busy_gpus', '<i4'), ('running', '<i4'), ('queued', '<i4'),
+                      ('finished', '<i4'), ('median_lo', '<i4'), ('median_hi', '<i4'), ('max_pending', '<i4'),
+                      ('sum_pending', '<i8'), ('mem_sum', '<i8'), ('util_mu_sum', '<i8'), ('util_var_sum', '<i8')])
+assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64
+
+EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_run',
+           'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
+           'rlgs_rows_view', 'rlgs_returns', 'rlgs_returns_device_ptr']
+
+_lib = None
+
+
+class RlgsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('librlgs error %d: %s' % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Loads librlgs.so; raises if it has not been built (python -m rlgpuschedule_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError('%s is missing: build it with `python -m rlgpuschedule_b200.build` '
+                           '(nvcc, sm_100a). There is no CPU fallback.' % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.rlgs_version.restype = i32
+    L.rlgs_last_error.restype = C.c_char_p
+    L.rlgs_create.argtypes = [C.POINTER(ClusterSpec), C.POINTER(Opts), C.POINTER(vp)]
+    L.rlgs_destroy.argtypes = [vp]
+    L.rlgs_destroy.restype = None
+    L.rlgs_load_trace.argtypes = [vp, i32, i32, vp, i32, C.POINTER(NetcostInputs)]
+    L.rlgs_run.argtypes = [vp]
+    L.rlgs_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.rlgs_set_stream.argtypes = [vp, vp]
+    L.rlgs_get_summary.argtypes = [vp, i32, C.POINTER(Summary)]
+    L.rlgs_read_jobs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.rlgs_read_rows.argtypes = [vp, i32, i64, i64, vp]
+    L.rlgs_rows_view.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.rlgs_returns.argtypes = [vp, vp]
+    L.rlgs_returns_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    for name in EXPORTS:
+        if name not in ('rlgs_last_error', 'rlgs_destroy'):
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise RlgsError(rc, lib().rlgs_last_error().decode(errors='replace'))

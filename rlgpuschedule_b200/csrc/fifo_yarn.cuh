@@ -1,0 +1,344 @@
+// fifo_yarn.cuh — the live tick loop of the reference (fifo schedule + yarn placement) as a
+// persistent one-warp-per-replica kernel.
+//
+// Restates Scheduler.start() (core/scheduling/schedule.py:178-216) and what it drives each tick:
+//   arrivals + front insertion   jobs_manager.py:228-241,115-140; job_queue_manager.py:147-154   (q1)
+//   one scheduling attempt       schedule.py:40-60; algorithm.py:189-202                          (q5)
+//   step (pending / processed)   jobs_manager.py:143-148,65-70; job.py:154-158,183-188
+//   finish scan + release        jobs_manager.py:243-250; schedule.py:141-162; node.py:71-91
+//   stats row                    schedule.py:95-133; jobs_manager.py:72-87
+//
+// Data movement per replica: job records (32 B) stream in from HBM in arrival order through a
+// register ring (one coalesced 1 KB read per 32 jobs); the queue is a stack of the same records in
+// global memory whose two front entries live in registers; node counters / busy masks and the
+// running-job slots live in shared memory for the whole launch; one 64 B row per tick and
+// start/end ticks per job stream out.  pending_time and time_processed are not stored: a queued
+// job's pending time is d - arrival and a running job's processed time is d - start, so the
+// per-tick "+= 1" sweeps of the reference reduce to the finish scan over the running slots.
+#pragma once
+#include "yarn_place.cuh"
+
+struct SlotView {
+    int32_t *end;      // finish tick, RLGS_NEVER = free slot
+    int32_t *job;
+    uint32_t *place;   // node | tasks<<16, or 0xffff | nnodes<<16 for a multi-node job
+    uint32_t *mask;    // device mask, or first placement-log entry for a multi-node job
+    int32_t *seq;      // start sequence number
+    uint32_t *util;    // util_mu_q | util_sd_q<<16
+    int64_t *memterm;
+};
+
+struct FifoSmem {
+    NodeView nv;
+    SlotView sv;
+};
+
+__host__ __device__ inline size_t fifo_smem_bytes(int N, int slot_cap) {
+    size_t node_words = 3 * (size_t)N + (size_t)((N + 31) / 32);
+    node_words = (node_words + 1) & ~(size_t)1;  // keep the int64 array 8-byte aligned
+    return node_words * 4 + (size_t)slot_cap * (6 * 4 + 8);
+}
+
+__device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int slot_cap) {
+    FifoSmem s;
+    int32_t *w = reinterpret_cast<int32_t *>(smem);
+    s.nv.cpu = w; w += N;
+    s.nv.mem = w; w += N;
+    s.nv.busy = reinterpret_cast<uint32_t *>(w); w += N;
+    s.nv.ever = reinterpret_cast<uint32_t *>(w); w += (N + 31) / 32;
+    if ((w - reinterpret_cast<int32_t *>(smem)) & 1) w += 1;
+    s.sv.memterm = reinterpret_cast<int64_t *>(w); w += 2 * slot_cap;
+    s.sv.end = w; w += slot_cap;
+    s.sv.job = w; w += slot_cap;
+    s.sv.place = reinterpret_cast<uint32_t *>(w); w += slot_cap;
+    s.sv.mask = reinterpret_cast<uint32_t *>(w); w += slot_cap;
+    s.sv.seq = w; w += slot_cap;
+    s.sv.util = reinterpret_cast<uint32_t *>(w); w += slot_cap;
+    return s;
+}
+
+__device__ __forceinline__ JobRec load_rec(const rlgs_job *p) {
+    JobRec r;
+    const int4 *q = reinterpret_cast<const int4 *>(p);
+    r.a = q[0]; r.b = q[1];
+    return r;
+}
+__device__ __forceinline__ void store_rec(rlgs_job *p, const JobRec &r) {
+    int4 *q = reinterpret_cast<int4 *>(p);
+    q[0] = r.a; q[1] = r.b;
+}
+__device__ __forceinline__ JobRec shfl_rec(const JobRec &r, int src) {
+    JobRec o; o.a = shfl_int4(r.a, src); o.b = shfl_int4(r.b, src);
+    return o;
+}
+
+// Saves / restores the shared-memory state of a replica (chunked runs and env steps).
+__device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, int N, int slot_cap, int hw, int lane, bool save) {
+    int nw = 3 * N + (N + 31) / 32;
+    int32_t *sm = s.nv.cpu;  // cpu, mem, busy, ever are contiguous
+    for (int i = lane; i < nw; i += 32) {
+        if (save) D.node_save[i] = sm[i]; else sm[i] = D.node_save[i];
+    }
+    for (int i = lane; i < slot_cap; i += 32) {
+        if (save) {
+            if (i < hw) {
+                D.slot_save[2 * i] = make_int4(s.sv.end[i], s.sv.job[i], (int)s.sv.place[i], (int)s.sv.mask[i]);
+                int64_t m = s.sv.memterm[i];
+                D.slot_save[2 * i + 1] = make_int4(s.sv.seq[i], (int)s.sv.util[i], (int)(uint32_t)m, (int)(m >> 32));
+            }
+        } else {
+            if (i < hw) {
+                int4 a = D.slot_save[2 * i], b = D.slot_save[2 * i + 1];
+                s.sv.end[i] = a.x; s.sv.job[i] = a.y; s.sv.place[i] = (uint32_t)a.z; s.sv.mask[i] = (uint32_t)a.w;
+                s.sv.seq[i] = b.x; s.sv.util[i] = (uint32_t)b.y;
+                s.sv.memterm[i] = (int64_t)(((uint64_t)(uint32_t)b.w << 32) | (uint32_t)b.z);
+            } else {
+                s.sv.end[i] = RLGS_NEVER;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Releases the resources of the job in slot `sl` at tick d and records its completion.
+__device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, const ClusterConst &c, RepState &st, int sl, int lane) {
+    int job = s.sv.job[sl];
+    uint32_t place = s.sv.place[sl], mask = s.sv.mask[sl];
+    uint32_t util = s.sv.util[sl];
+    int64_t mterm = s.sv.memterm[sl];
+    int ndev;
+    if ((place & 0xffff) != 0xffff) {
+        release_entry(s.nv, c, lane == 0, make_int2((int)place, (int)mask), st.n_free_nodes);
+        ndev = __popc(mask);
+    } else {
+        int nn = (int)(place >> 16), off = (int)mask;
+        ndev = 0;
+        for (int b = 0; b < nn; b += 32) {
+            bool act = b + lane < nn;
+            int2 e = act ? D.place_log[off + b + lane] : make_int2(0, 0);
+            release_entry(s.nv, c, act, e, st.n_free_nodes);
+            int cnt = act ? __popc((uint32_t)e.y) : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(RLGS_FULL, cnt, o);
+            ndev += cnt;
+        }
+    }
+    __syncwarp();
+    st.busy_gpus -= ndev;
+    st.mem_sum -= mterm * ndev;
+    int64_t mu = util & 0xffff, sd = util >> 16;
+    st.util_mu_sum -= mu * ndev;
+    st.util_var_sum -= sd * sd * ndev;
+    if (lane == 0) {
+        s.sv.end[sl] = RLGS_NEVER;
+        D.end_tick[job] = st.d;
+        D.finish_order[st.F] = job;
+    }
+    st.F += 1; st.R -= 1;
+    if (st.free_hint < 0 || sl < st.free_hint) st.free_hint = sl;
+    st.head_blocked = 0;  // resources were freed: the queue head may fit now
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
+                                                       ClusterConst c, int slot_cap, int tick_budget,
+                                                       rlgs_row *__restrict__ rows_base, int rows_stride,
+                                                       int64_t *__restrict__ returns, int64_t max_ticks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = lane_id();
+    const RepDesc D = descs[blockIdx.x];
+    RepState st = states[blockIdx.x];
+    if (st.done || st.status != RLGS_OK) return;
+    FifoSmem s = fifo_carve(smem_raw, c.N, slot_cap);
+    const bool rows_mode = rows_base != nullptr;
+    rlgs_row *const rows = rows_base + (size_t)blockIdx.x * rows_stride;
+    if (st.d == 0) {  // first launch of a run: empty cluster, no running jobs
+        int nw = 3 * c.N + (c.N + 31) / 32;
+        for (int i = lane; i < nw; i += 32) s.nv.cpu[i] = 0;
+        for (int i = lane; i < slot_cap; i += 32) s.sv.end[i] = RLGS_NEVER;
+        __syncwarp();
+    } else {
+        fifo_state_io(D, s, c.N, slot_cap, st.hw, lane, false);
+    }
+    const int J = D.J;
+
+    // register ring over the trace: lane l holds job ring_base + l
+    int ring_base = st.cursor & ~31;
+    JobRec ring;
+    {
+        int idx = ring_base + lane;
+        if (idx < J) ring = load_rec(D.trace + idx); else { ring.a = make_int4(RLGS_NEVER, 0, 0, 0); ring.b = make_int4(0, 0, 0, 0); }
+    }
+    // the two front entries of the queue live in registers
+    JobRec h0, h1;
+    h0.a = h0.b = h1.a = h1.b = make_int4(0, 0, 0, 0);
+    if (st.Q > 0) h0 = load_rec(D.stack + st.head);
+    if (st.Q > 1) h1 = load_rec(D.stack + st.head + 1);
+
+    const int d_stop = st.d + tick_budget;
+    while (true) {
+        if ((J - st.cursor) + st.R == 0) { st.done = 1; break; }   // schedule.py:185 (queue not consulted, q2)
+        if (st.d == d_stop) break;
+        if (max_ticks > 0 && st.d >= max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
+        const int d = st.d;
+
+        // ---------------- arrivals: every job with arrival_tick <= d, pushed to the FRONT in order (q1)
+        if (st.cursor < J) {
+            int idx = ring_base + lane;
+            bool arr = idx >= st.cursor && idx < J && ring.arrival() <= d;
+            unsigned ab = __ballot_sync(RLGS_FULL, arr);
+            if (ab) {
+                int k = __popc(ab);
+                bool ring_covers_batch = (st.cursor + k < ring_base + 32) || (ring_base + 32 >= J);
+                if (ring_covers_batch) {
+                    int first = st.cursor - ring_base;
+                    if (arr) store_rec(D.stack + (st.head - k) + (idx - st.cursor), ring);
+                    JobRec n0 = shfl_rec(ring, first);
+                    JobRec n1 = shfl_rec(ring, (first + 1) & 31);
+                    h1 = (k >= 2) ? n1 : h0;
+                    h0 = n0;
+                } else {
+                    // batch runs past the ring: count it from global memory, then copy records
+                    int pos = ring_base + 32;
+                    while (pos < J) {
+                        int i2 = pos + lane;
+                        bool a2 = i2 < J && D.trace[i2].arrival_tick <= d;
+                        int c2 = __popc(__ballot_sync(RLGS_FULL, a2));
+                        k += c2;
+                        if (c2 < 32) break;
+                        pos += 32;
+                    }
+                    for (int b = 0; b < k; b += 32) {
+                        int i2 = b + lane;
+                        if (i2 < k) store_rec(D.stack + (st.head - k) + i2, load_rec(D.trace + st.cursor + i2));
+                    }
+                    __syncwarp();
+                    JobRec old0 = h0;
+                    h0 = load_rec(D.stack + st.head - k);
+                    h1 = (k >= 2) ? load_rec(D.stack + st.head - k + 1) : old0;
+                }
+                if (st.Q == 0) st.bottom_arr = d;
+                st.head -= k; st.Q += k; st.cursor += k;
+                st.sum_arr += (int64_t)k * d;
+                st.events += k;
+                st.head_blocked = 0;
+                if (st.Q > st.max_q) st.max_q = st.Q;
+                if (st.cursor >= ring_base + 32) {
+                    ring_base = st.cursor & ~31;
+                    int i3 = ring_base + lane;
+                    if (i3 < J) ring = load_rec(D.trace + i3); else { ring.a = make_int4(RLGS_NEVER, 0, 0, 0); }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---------------- one scheduling attempt on the queue head (schedule.py:188-190)
+        if (st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked) {
+            PlaceResult pr = yarn_place(s.nv, c, h0, lane, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
+            if (pr.ok) {
+                int job = h0.index();
+                int ndev = h0.tasks() * h0.gpc();
+                int sl = st.free_hint;
+                if (sl < 0) { sl = st.hw; }
+                if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
+                if (sl == st.hw) st.hw += 1;
+                st.free_hint = -1;
+                if (lane == 0) {
+                    s.sv.end[sl] = d + h0.dur();
+                    s.sv.job[sl] = job;
+                    s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (h0.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
+                    s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
+                    s.sv.seq[sl] = st.start_seq;
+                    s.sv.util[sl] = h0.util();
+                    s.sv.memterm[sl] = h0.mem_term();
+                    D.start_tick[job] = d;
+                    D.place_off[job] = st.log_len;
+                }
+                st.log_len += pr.nnodes;
+                st.start_seq += 1;
+                st.busy_gpus += ndev;
+                st.mem_sum += h0.mem_term() * ndev;
+                int64_t mu = h0.util() & 0xffff, sd = h0.util() >> 16;
+                st.util_mu_sum += mu * ndev;
+                st.util_var_sum += sd * sd * ndev;
+                st.sum_arr -= h0.arrival();
+                st.sum_jct += (int64_t)(d + h0.dur() - h0.arrival());  // end is fixed at start (no preemption)
+                st.R += 1; st.Q -= 1; st.head += 1;
+                st.events += 1;
+                if (st.R > st.max_r) st.max_r = st.R;
+                h0 = h1;
+                if (st.Q > 1) h1 = load_rec(D.stack + st.head + 1);
+                __syncwarp();
+            } else if (h0.fits()) {
+                st.head_blocked = 1;  // a failed attempt has no side effect: skip retries until a release
+            }
+        }
+
+        // median loads are issued early; they are consumed when the row is written
+        int med_lo_arr = 0, med_hi_arr = 0;
+        if (rows_mode && st.Q > 0) {
+            med_lo_arr = D.stack[st.head + (st.Q - 1) / 2].arrival_tick;
+            med_hi_arr = D.stack[st.head + st.Q / 2].arrival_tick;
+        }
+
+        // ---------------- delta_time += 1; step; release finished jobs in start order
+        st.d = d + 1;
+        {
+            int nfin = 0, first_slot = -1, hole = -1;
+            for (int b = 0; b < st.hw; b += 32) {
+                int i = b + lane;
+                int e = i < st.hw ? s.sv.end[i] : 0;
+                unsigned fb = __ballot_sync(RLGS_FULL, e == st.d);
+                unsigned hb = __ballot_sync(RLGS_FULL, e == RLGS_NEVER);
+                if (fb) { if (first_slot < 0) first_slot = b + __ffs(fb) - 1; nfin += __popc(fb); }
+                if (hb && hole < 0) hole = b + __ffs(hb) - 1;
+            }
+            st.free_hint = hole;  // lowest free slot below hw (at most one start per tick consumes it)
+            if (nfin == 1) {
+                fifo_finish_slot(D, s, c, st, first_slot, lane);
+                st.events += 1;
+            } else if (nfin > 1) {
+                // several jobs finish this tick: running_jobs dict order = start order (schedule.py:144)
+                for (int n = 0; n < nfin; ++n) {
+                    int best_seq = RLGS_NEVER, best_slot = -1;
+                    for (int b = 0; b < st.hw; b += 32) {
+                        int i = b + lane;
+                        if (i < st.hw && s.sv.end[i] == st.d && s.sv.seq[i] < best_seq) { best_seq = s.sv.seq[i]; best_slot = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        int os = __shfl_xor_sync(RLGS_FULL, best_seq, o), ol = __shfl_xor_sync(RLGS_FULL, best_slot, o);
+                        if (os < best_seq) { best_seq = os; best_slot = ol; }
+                    }
+                    fifo_finish_slot(D, s, c, st, best_slot, lane);
+                }
+                st.events += nfin;
+            }
+            if (nfin) {
+                while (st.hw > 0 && s.sv.end[st.hw - 1] == RLGS_NEVER) st.hw -= 1;
+                if (st.free_hint >= st.hw) st.free_hint = -1;
+            }
+        }
+
+        // ---------------- stats row (schedule.py:204-205)
+        st.sumQ += st.Q; st.sumR += st.R;
+        if (rows_mode && lane == 0) {
+            rlgs_row *row = rows + (st.d - 1 - (d_stop - tick_budget));
+            int4 w0 = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
+            int4 w1 = make_int4(st.F, st.Q > 0 ? st.d - med_lo_arr : 0, st.Q > 0 ? st.d - med_hi_arr : 0,
+                                st.Q > 0 ? st.d - st.bottom_arr : 0);
+            int64_t sp = (int64_t)st.Q * st.d - st.sum_arr;
+            int4 *o = reinterpret_cast<int4 *>(row);
+            o[0] = w0; o[1] = w1;
+            o[2] = make_int4((int)(uint32_t)sp, (int)(sp >> 32), (int)(uint32_t)st.mem_sum, (int)(st.mem_sum >> 32));
+            o[3] = make_int4((int)(uint32_t)st.util_mu_sum, (int)(st.util_mu_sum >> 32), (int)(uint32_t)st.util_var_sum,
+                             (int)(st.util_var_sum >> 32));
+        }
+    }
+
+    fifo_state_io(D, s, c.N, slot_cap, st.hw, lane, true);
+    if (lane == 0) {
+        states[blockIdx.x] = st;
+        if (st.done) returns[blockIdx.x] = -st.sum_jct;  // episode return, read by the all-gather
+    }
+}

@@ -1,0 +1,116 @@
+// rlgs_device.cuh — device-side data layout and warp-level building blocks shared by the simulation
+// kernels (sm_100a).  One warp advances one replica; cluster/node state is staged in shared memory,
+// the per-job structure-of-records streams from / to HBM.
+//
+// Reference semantics restated here (paths relative to the reference repo):
+//   node occupancy predicates   infra/node.py:51-60,99-127,146-171,200-221
+//   device accept rule          infra/device.py:19-43,67-77   (yarn never shares a device)
+//   yarn single / cross fit     core/scheduling/algorithm.py:28-32,301-417
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rlgs.h"
+
+#define RLGS_FULL 0xffffffffu
+#define RLGS_CPUS_PER_TASK 12  // core/jobs/job.py:105
+#define RLGS_MEM_PER_TASK 60   // core/jobs/job.py:106
+#define RLGS_NEVER 0x7fffffff
+
+// Per-replica scalars that survive between kernel launches (chunked runs, env steps).
+struct RepState {
+    int32_t d;            // current tick (delta_time of schedule.py:180)
+    int32_t cursor;       // jobs of the trace already arrived (JobTraceReader "generated" column)
+    int32_t head;         // index of the queue front inside the stack array
+    int32_t Q, R, F;      // queued / running / finished job counts
+    int32_t hw;           // slot high-water mark
+    int32_t idle_nodes, busy_gpus, n_free_nodes;
+    int32_t start_seq;    // starts so far (orders same-tick finishes like the running_jobs dict)
+    int32_t bottom_arr;   // arrival tick of the oldest queued job (max_pending_time)
+    int32_t free_hint;    // a free slot index or -1
+    int32_t head_blocked; // last fit attempt of the current head failed and nothing was released since
+    int32_t done, status;
+    int32_t max_q, max_r, log_len, pad0;
+    int64_t mem_sum, util_mu_sum, util_var_sum;
+    int64_t sum_arr;      // sum of arrival ticks of queued jobs: sum_pending = Q*d - sum_arr
+    int64_t sumQ, sumR, sum_jct, events;
+};
+
+// Per-replica pointers (all device memory; computed on the host once).
+struct RepDesc {
+    const rlgs_job *trace;  // [J] 32-byte records in arrival order (may be shared between replicas)
+    rlgs_job *stack;        // [J] fifo queue as a stack growing towards index 0 (front insertion, q1)
+    int32_t *start_tick;    // [J]
+    int32_t *end_tick;      // [J]
+    int32_t *finish_order;  // [J]
+    int32_t *place_off;     // [J] first entry of the job's placement in place_log (-1 = never placed)
+    int2 *place_log;        // [log_cap] (node | ntasks<<16, device mask) per (job, node), in node order
+    int32_t *node_save;     // [3N + ceil(N/32)] cpu_used, mem_used, busy mask, ever-used bitmap
+    int4 *slot_save;        // [2*slot_cap]
+    int32_t J;
+    int32_t log_cap;
+};
+
+struct ClusterConst {
+    int32_t N, G;          // nodes, GPUs per node
+    int32_t cpu_cap, mem_cap;
+    uint32_t gmask;        // G low bits set
+    int32_t D;             // N*G
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// mask of the k lowest set bits of `freemask` (devices are taken in device-id order, node.py:209-219)
+__device__ __forceinline__ uint32_t lowest_bits(uint32_t freemask, int k) {
+    uint32_t rem = freemask;
+    for (int i = 0; i < k; ++i) rem &= rem - 1;
+    return freemask ^ rem;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(RLGS_FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int4 ld_int4(const void *p) { return *reinterpret_cast<const int4 *>(p); }
+__device__ __forceinline__ void st_int4(void *p, int4 v) { *reinterpret_cast<int4 *>(p) = v; }
+
+__device__ __forceinline__ int4 shfl_int4(int4 v, int src) {
+    int4 r;
+    r.x = __shfl_sync(RLGS_FULL, v.x, src);
+    r.y = __shfl_sync(RLGS_FULL, v.y, src);
+    r.z = __shfl_sync(RLGS_FULL, v.z, src);
+    r.w = __shfl_sync(RLGS_FULL, v.w, src);
+    return r;
+}
+
+// Decoded view of a 32-byte job record held as two int4 (see rlgs_job in include/rlgs.h).
+struct JobRec {
+    int4 a, b;
+    __device__ __forceinline__ int arrival() const { return a.x; }
+    __device__ __forceinline__ int dur() const { return a.y; }
+    __device__ __forceinline__ int gpus() const { return a.z & 0xffff; }
+    __device__ __forceinline__ int tasks() const { return (a.z >> 16) & 0xffff; }
+    __device__ __forceinline__ int gpc() const { return a.w & 0xffff; }
+    __device__ __forceinline__ int least() const { return (a.w >> 16) & 0x7fff; }
+    __device__ __forceinline__ bool fits() const { return (a.w >> 31) & 1; }
+    __device__ __forceinline__ int64_t mem_term() const { return (int64_t)(((uint64_t)(uint32_t)b.y << 32) | (uint32_t)b.x); }
+    __device__ __forceinline__ uint32_t util() const { return (uint32_t)b.z; }
+    __device__ __forceinline__ int index() const { return b.w; }
+};
+
+// Shared-memory view of the simulated cluster of one replica.
+struct NodeView {
+    int32_t *cpu;     // cpu_used per node
+    int32_t *mem;     // mem_used per node
+    uint32_t *busy;   // busy-device bitmask per node
+    uint32_t *ever;   // bitmap: node ever held a placed job (Node.placed_jobs is never cleared, q3)
+};
+
+__device__ __forceinline__ bool node_is_free(int cpu_used, int mem_used, const ClusterConst &c) {
+    return (c.cpu_cap - cpu_used > 0) || (c.mem_cap - mem_used > 0);  // infra/node.py:59-60
+}

@@ -1,0 +1,177 @@
+"""CSV outputs in the reference's exact format, produced from the device's integer statistics.
+
+Host mirror of /log_manager.py of the reference (LogInfo :5-30, LogManager.init :56-116,
+step_cluster :118-135, jcts :137-155): same six files, same headers, same column order, same
+`str(value)` rendering through the csv module ('\\r\\n' line ends).  The float columns are
+finished here in float64 with the reference's own expressions:
+  avg_gpu_memory_allocated = sum(min(cap, mem_max)) / sum(cap)          schedule.py:109-121
+  avg_pending_time         = sum(pending) / (count + 1e-9)              jobs_manager.py:87
+  median_pending_time      = float(np.median(pending))  (nan when empty) jobs_manager.py:87
+  max_pending_time         = max(pending, 0)  (the int 0 when empty)     jobs_manager.py:80-82
+avg_gpu_utilization is an unseeded normal draw per busy device in the reference
+(infra/device.py:48-54); here it is one draw per row from the summed distribution (util_mode
+'sample', seedable) or its mean ('mean').
+"""
+import csv
+import io
+import os
+
+import numpy as np
+
+CLUSTER_HEADER = ['delta', 'num_idle_nodes', 'num_busy_nodes', 'num_busy_gpus', 'num_idle_gpus',
+                  'avg_gpu_utilization', 'avg_gpu_memory_allocated', 'avg_pending_time', 'median_pending_time',
+                  'max_pending_time', 'num_running_jobs', 'num_queuing_jobs', 'num_finish_jobs']
+JOB_HEADER = ['job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'original_duration',
+              'actual_duration', 'jct', 'preempt']
+
+
+class LogInfo(object):
+    """Same fields as the reference's LogInfo (log_manager.py:5-30)."""
+
+    def __init__(self, num_idle_nodes, num_busy_nodes, num_busy_gpus, num_idle_gpus, avg_gpu_utilization,
+                 avg_gpu_memory_allocated, avg_pending_time, median_pending_time, max_pending_time,
+                 num_running_jobs, num_queuing_jobs, num_finish_jobs):
+        self.idle_ns = num_idle_nodes
+        self.busy_ns = num_busy_nodes
+        self.busy_gs = num_busy_gpus
+        self.idle_gs = num_idle_gpus
+        self.avg_g_utils = avg_gpu_utilization
+        self.avg_g_mem = avg_gpu_memory_allocated
+        self.avg_pending = avg_pending_time
+        self.median_pending = median_pending_time
+        self.max_pending = max_pending_time
+        self.num_running_jobs = num_running_jobs
+        self.num_queuing_jobs = num_queuing_jobs
+        self.num_finish_jobs = num_finish_jobs
+
+
+def finish_rows(rows, cluster, mem_shift, util_mode='sample', seed=None):
+    """rows: _ffi.ROW_DTYPE array -> dict of python-ready columns (lists)."""
+    n = len(rows)
+    N, Dv = cluster.num_nodes, cluster.num_gpus
+    q = rows['queued'].astype(np.float64)
+    mem = (rows['mem_sum'].astype(np.float64) / float(2 ** mem_shift)) / float(Dv * cluster.cap_mib)
+    with np.errstate(invalid='ignore'):
+        avg_p = rows['sum_pending'].astype(np.float64) / (q + 1e-9)
+    med = (rows['median_lo'].astype(np.float64) + rows['median_hi'].astype(np.float64)) / 2.0
+    med = np.where(rows['queued'] > 0, med, np.nan)
+    busy = rows['busy_gpus']
+    mu = rows['util_mu_sum'].astype(np.float64) / 512.0
+    if util_mode == 'sample':
+        sd = np.sqrt(rows['util_var_sum'].astype(np.float64)) / 512.0
+        draw = np.random.default_rng(seed).normal(mu, sd)
+        util = np.clip(draw, 0.0, 100.0 * busy) / Dv
+    else:
+        util = mu / Dv
+    maxp = rows['max_pending']
+    qi = rows['queued']
+    return dict(n=n, idle_nodes=rows['idle_nodes'].tolist(), busy_nodes=(N - rows['idle_nodes']).tolist(),
+                busy_gpus=busy.tolist(), idle_gpus=(Dv - busy).tolist(),
+                util=['[%s]' % np.format_float_positional(u, precision=8, unique=True, fractional=True, trim='-')
+                      if b > 0 else '0.0' for u, b in zip(util.tolist(), busy.tolist())],
+                mem=mem.tolist(), avg_pending=avg_p.tolist(), median=med.tolist(),
+                max_pending=[float(m) if k > 0 else 0 for m, k in zip(maxp.tolist(), qi.tolist())],
+                running=rows['running'].tolist(), queued=qi.tolist(), finished=rows['finished'].tolist())
+
+
+def format_cluster_csv(rows, cluster, mem_shift, with_header=True, with_util=True, util_mode='sample', seed=None,
+                       first_delta=1):
+    """cluster.csv text for rows (one per tick, delta = first_delta + i)."""
+    c = finish_rows(rows, cluster, mem_shift, util_mode, seed)
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    hdr = list(CLUSTER_HEADER)
+    if not with_util:
+        hdr.remove('avg_gpu_utilization')
+    if with_header:
+        w.writerow(hdr)
+    cols = [range(first_delta, first_delta + c['n']), c['idle_nodes'], c['busy_nodes'], c['busy_gpus'], c['idle_gpus']]
+    if with_util:
+        cols.append(c['util'])
+    cols += [c['mem'], c['avg_pending'], c['median'], c['max_pending'], c['running'], c['queued'], c['finished']]
+    w.writerows(zip(*cols))
+    return buf.getvalue()
+
+
+def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duration=None, jct=None, with_header=True):
+    """job.csv text: one row per finished job in finish order (finished_jobs dict order, log_manager.py:141-153)."""
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    if with_header:
+        w.writerow(JOB_HEADER)
+    fo = np.asarray(finish_order, dtype=np.int64)
+    dur = trace.duration[fo]
+    act = dur if actual_duration is None else np.asarray(actual_duration)[fo]
+    st, en = np.asarray(start)[fo], np.asarray(end)[fo]
+    jc = (en - st) if jct is None else np.asarray(jct)[fo]
+    pre = np.ones(len(fo), dtype=np.int64) if preempt is None else np.asarray(preempt)[fo]
+    w.writerows(zip([str(x) for x in trace.label[fo].tolist()], trace.used_gpus[fo].tolist(),
+                    trace.nt[fo].astype(np.int64).tolist(), st.tolist(), en.tolist(), dur.tolist(),
+                    [a if a > 0 else 0 for a in act.tolist()],  # Job.get_duration(): max(0, d) keeps the int 0
+                    jc.tolist(), pre.tolist()))
+    return buf.getvalue()
+
+
+class LogManager(object):
+    """Drop-in for the reference's LogManager: same constructor, init(), step_cluster(), jcts();
+    plus bulk writers used by the device backend."""
+
+    def __init__(self, log_path, flags):
+        self.log_path = log_path
+        self.flags = flags
+        self.is_count = getattr(flags, 'scheme', 'yarn') == 'count'
+        self.cluster_stats_header = list(CLUSTER_HEADER)
+        self.job_stats_header = list(JOB_HEADER)
+
+    def init(self, infrastructure):
+        self.log_cluster = os.path.join(self.log_path, 'cluster.csv')
+        self.log_job = os.path.join(self.log_path, 'job.csv')
+        n_nodes = infrastructure.num_nodes
+        n_gpus = infrastructure.num_gpus
+        with open(self.log_cluster, 'w+', newline='') as f:
+            csv.writer(f).writerow(self.cluster_stats_header)
+        if not self.is_count:
+            self.log_cpu = os.path.join(self.log_path, 'cpu.csv')
+            self.log_gpu = os.path.join(self.log_path, 'gpu.csv')
+            self.log_network = os.path.join(self.log_path, 'network.csv')
+            self.log_mem = os.path.join(self.log_path, 'memory.csv')
+            with open(self.log_cpu, 'w+', newline='') as f:
+                csv.writer(f).writerow(['time'] + ['cpu%d' % i for i in range(n_nodes)])
+            with open(self.log_gpu, 'w+', newline='') as f:
+                csv.writer(f).writerow(['time'] + ['gpu%d' % i for i in range(n_gpus)])
+            with open(self.log_mem, 'w+', newline='') as f:
+                csv.writer(f).writerow(['time', 'max', '99th', '95th', 'med'])
+            with open(self.log_network, 'w+', newline='') as f:
+                titles = ['time']
+                for i in range(n_nodes):
+                    titles += ['in%d' % i, 'out%d' % i]
+                csv.writer(f).writerow(titles)
+        with open(self.log_job, 'w+', newline='') as f:
+            csv.writer(f).writerow(self.job_stats_header)
+
+    def step_cluster(self, loginfo, delta):
+        with open(self.log_cluster, 'a+', newline='') as f:
+            csv.writer(f).writerow([delta, loginfo.idle_ns, loginfo.busy_ns, loginfo.busy_gs, loginfo.idle_gs,
+                                    loginfo.avg_g_utils, loginfo.avg_g_mem, loginfo.avg_pending,
+                                    loginfo.median_pending, loginfo.max_pending, loginfo.num_running_jobs,
+                                    loginfo.num_queuing_jobs, loginfo.num_finish_jobs])
+
+    def write_cluster_rows(self, rows, cluster, mem_shift, util_mode='sample', seed=None):
+        with open(self.log_cluster, 'a+', newline='') as f:
+            f.write(format_cluster_csv(rows, cluster, mem_shift, with_header=False, util_mode=util_mode, seed=seed))
+
+    def jcts(self, finished_jobs):
+        """finished_jobs: dict job_id -> object with the reference Job's attributes, or a tuple
+        (trace, finish_order, start, end[, preempt]) from the device backend."""
+        if isinstance(finished_jobs, tuple):
+            text = format_job_csv(*finished_jobs, with_header=False)
+            assert len(finished_jobs[1]) > 0, ValueError("No finished jobs")
+            with open(self.log_job, 'a+', newline='') as f:
+                f.write(text)
+            return
+        assert len(finished_jobs) > 0, ValueError("No finished jobs")
+        with open(self.log_job, 'a+', newline='') as f:
+            w = csv.writer(f)
+            for _, j in finished_jobs.items():
+                w.writerow([j.job_id, j.gpus, j.submit_time, j.start_time, j.end_time, j.duration,
+                            j.get_duration(), j.time_processed(), j.migration_count])

@@ -1,0 +1,134 @@
+"""High-level handle over the C ABI: one object = one batch of replicas on one GPU."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .ingest import Cluster, Trace
+
+
+class Simulator(object):
+    """Replaces the object graph the reference builds in run_sim.py:1716-1735 (Infrastructure,
+    JobQueueManager, JobsManager, Scheduler) by a device-resident state; `run()` replaces
+    Scheduler.start() (core/scheduling/schedule.py:178-216)."""
+
+    def __init__(self, cluster, schedule='fifo', scheme='yarn', n_replicas=1, rows=True, device=0, slot_cap=0,
+                 chunk_ticks=0, num_queue=1, queue_limit=(), max_ticks=0, enable_network_costs=False,
+                 bandwidth=1250, internode_latency=0.015):
+        if schedule not in _ffi.SCHED:
+            raise NotImplementedError('schedule %r has no device implementation' % (schedule,))
+        if scheme not in _ffi.PLACE:
+            raise NotImplementedError('placement scheme %r has no device implementation' % (scheme,))
+        self.cluster = cluster
+        self.n_replicas = n_replicas
+        self.rows = rows
+        self._kw = dict(schedule=schedule, scheme=scheme, rows=rows, device=device, chunk_ticks=chunk_ticks,
+                        num_queue=num_queue, queue_limit=tuple(queue_limit), max_ticks=max_ticks,
+                        enable_network_costs=enable_network_costs, bandwidth=bandwidth,
+                        internode_latency=internode_latency)
+        self._slot_cap = slot_cap
+        self._traces = []   # (first, count, Trace)
+        self._h = None
+        self._create()
+
+    def _create(self):
+        L = _ffi.lib()
+        k = self._kw
+        o = _ffi.Opts()
+        o.device = k['device']; o.n_replicas = self.n_replicas
+        o.schedule = _ffi.SCHED[k['schedule']]; o.placement = _ffi.PLACE[k['scheme']]
+        o.rows_mode = _ffi.ROWS_FULL if k['rows'] else _ffi.ROWS_NONE
+        o.slot_cap = self._slot_cap; o.chunk_ticks = k['chunk_ticks']; o.num_queue = k['num_queue']
+        for i, v in enumerate(k['queue_limit'][:_ffi.MAX_QUEUES]):
+            o.queue_limit[i] = int(v)
+        o.enable_network_costs = int(bool(k['enable_network_costs']))
+        o.bandwidth = float(k['bandwidth']); o.internode_latency = float(k['internode_latency'])
+        o.max_ticks = int(k['max_ticks'])
+        spec = self.cluster.to_ffi()
+        h = C.c_void_p()
+        _ffi.check(L.rlgs_create(C.byref(spec), C.byref(o), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None:
+            _ffi.lib().rlgs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_trace(self, trace, first_replica=0, n_replicas=None):
+        n_replicas = self.n_replicas - first_replica if n_replicas is None else n_replicas
+        rec = np.ascontiguousarray(trace.records)
+        _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec), None))
+        self._traces.append((first_replica, n_replicas, trace))
+
+    def trace_of(self, replica):
+        for f, c, t in self._traces[::-1]:
+            if f <= replica < f + c:
+                return t
+        raise KeyError(replica)
+
+    def run(self):
+        L = _ffi.lib()
+        while True:
+            rc = L.rlgs_run(self._h)
+            if rc == _ffi.ERR_CAPACITY and b'slot table overflow' in L.rlgs_last_error():
+                # more jobs ran concurrently than on-chip slots: rebuild with a larger table
+                cap = max(64, 2 * (self._slot_cap or 256))
+                if cap > 2 * max(self.cluster.num_gpus, 32):
+                    _ffi.check(rc)
+                traces = self._traces
+                self.close()
+                self._slot_cap = cap
+                self._traces = []
+                self._create()
+                for f, c, t in traces:
+                    self.load_trace(t, f, c)
+                continue
+            _ffi.check(rc)
+            return self
+
+    def kernel_ms(self):
+        ms, n = C.c_float(0), C.c_int32(0)
+        _ffi.check(_ffi.lib().rlgs_last_run_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def summary(self, replica=0):
+        s = _ffi.Summary()
+        _ffi.check(_ffi.lib().rlgs_get_summary(self._h, replica, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def jobs(self, replica=0, with_nodes=False):
+        n = len(self.trace_of(replica))
+        fo, st, en, pre = (np.empty(n, np.int32) for _ in range(4))
+        fn = np.empty(n, np.int32) if with_nodes else None
+        _ffi.check(_ffi.lib().rlgs_read_jobs(self._h, replica, fo.ctypes.data, st.ctypes.data, en.ctypes.data,
+                                             pre.ctypes.data, fn.ctypes.data if with_nodes else None))
+        k = self.summary(replica)['n_finished']
+        out = dict(finish_order=fo[:k], start=st, end=en, preempt=pre)
+        if with_nodes:
+            out['first_node'] = fn
+        return out
+
+    def rows_view(self, replica=0):
+        """Zero-copy numpy view of the replica's rows in the handle's pinned host store."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        _ffi.check(_ffi.lib().rlgs_rows_view(self._h, replica, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, _ffi.ROW_DTYPE)
+        buf = (C.c_char * (n.value * _ffi.ROW_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=_ffi.ROW_DTYPE, count=n.value)
+
+    def returns(self):
+        out = np.empty(self.n_replicas, np.int64)
+        _ffi.check(_ffi.lib().rlgs_returns(self._h, out.ctypes.data))
+        return out
+
+    def returns_device_ptr(self):
+        p = C.c_void_p()
+        _ffi.check(_ffi.lib().rlgs_returns_device_ptr(self._h, C.byref(p)))
+        return p.value

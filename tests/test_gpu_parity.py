@@ -1,0 +1,101 @@
+"""CUDA path (through the C ABI, librlgs.so) vs the reference's golden outputs and vs the CPU oracle.
+Bit-exact bar: job.csv and cluster.csv (minus the unseeded-RNG column) must match byte for byte."""
+import numpy as np
+import pytest
+
+import cpu_sim
+import goldutil
+import rlgpuschedule_b200 as rl
+from rlgpuschedule_b200 import log_manager as lm
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(trace_input, flags, n_replicas=1, **kw):
+    cluster = rl.cluster_from_flags(flags)
+    tr = rl.prepare_trace(trace_input, cluster)
+    sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=n_replicas, rows=True, **kw)
+    sim.load_trace(tr)
+    sim.run()
+    return cluster, tr, sim
+
+
+def csv_of(cluster, tr, sim, replica=0):
+    j = sim.jobs(replica)
+    job = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'])
+    clu = lm.format_cluster_csv(sim.rows_view(replica), cluster, tr.mem_shift, with_util=False)
+    return job, clu
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('small'))
+def test_cuda_matches_reference_small(name):
+    g = goldutil.load(name)
+    cluster, tr, sim = run_cuda(goldutil.trace_input(g), g['flags'])
+    job, clu = csv_of(cluster, tr, sim)
+    assert job == g['job']
+    assert clu == g['cluster']
+    assert sim.summary()['n_ticks'] == g['meta']['n_ticks']
+    sim.close()
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('small'))
+def test_cuda_matches_oracle_placement_and_counters(name):
+    g = goldutil.load(name)
+    ti = goldutil.trace_input(g)
+    cluster, tr, sim = run_cuda(ti, g['flags'], chunk_ticks=7)   # odd chunking exercises state save/restore
+    otr = cpu_sim.prepare_trace(ti)
+    ores = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**g['flags']), otr)
+    j = sim.jobs(0)
+    assert np.array_equal(j['finish_order'], ores['finish_order'])
+    assert np.array_equal(j['start'], ores['start'])
+    assert np.array_equal(j['end'], ores['end'])
+    s = sim.summary()
+    assert s['sum_queued'] == ores['counters']['sum_queued']
+    assert s['sum_running'] == ores['counters']['sum_running']
+    assert s['n_started'] == ores['counters']['starts']
+    job, clu = csv_of(cluster, tr, sim)
+    assert job == g['job'] and clu == g['cluster']
+    sim.close()
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('big') + goldutil.case_names('huge'))
+def test_cuda_matches_reference_big(name):
+    g = goldutil.load(name)
+    cluster, tr, sim = run_cuda(goldutil.trace_input(g), g['flags'])
+    job, clu = csv_of(cluster, tr, sim)
+    assert goldutil.sha(job) == g['meta']['job_sha256']
+    assert goldutil.sha(clu) == g['meta']['cluster_noutil_sha256']
+    sim.close()
+
+
+def test_replicas_are_independent_and_identical():
+    g = goldutil.load('dense')
+    cluster, tr, sim = run_cuda(goldutil.trace_input(g), g['flags'], n_replicas=37)
+    ref = csv_of(cluster, tr, sim, 0)
+    assert ref[0] == g['job'] and ref[1] == g['cluster']
+    for r in (1, 17, 36):
+        assert csv_of(cluster, tr, sim, r) == ref
+    ret = sim.returns()
+    assert len(set(ret.tolist())) == 1 and ret[0] < 0
+    sim.close()
+
+
+def test_mixed_traces_per_replica():
+    names = ['kat6', 'ties', 'short_durations']
+    g0 = goldutil.load('ties')
+    cluster = rl.cluster_from_flags(g0['flags'])
+    sim = rl.Simulator(cluster, n_replicas=3, rows=True)
+    traces = []
+    for r, n in enumerate(names):
+        t = rl.prepare_trace(goldutil.trace_input(goldutil.load(n)), cluster)
+        traces.append(t)
+        sim.load_trace(t, r, 1)
+    sim.run()
+    for r, t in enumerate(traces):
+        otr = cpu_sim.prepare_trace(goldutil.trace_input(goldutil.load(names[r])))
+        ores = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**g0['flags']), otr)
+        j = sim.jobs(r)
+        assert np.array_equal(j['finish_order'], ores['finish_order'])
+        assert np.array_equal(j['end'], ores['end'])
+        assert lm.format_cluster_csv(sim.rows_view(r), cluster, t.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(ores)
+    sim.close()
