@@ -42,7 +42,10 @@ enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2 };
 /* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
  * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
 enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1 };
-enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1 };
+/* rows_mode: NONE = no per-tick rows; FULL = one row per tick kept in a device-resident store and
+ * copied to the handle's pinned host store inside rlgs_run (overlapped with compute, one stream per
+ * replica group); DEVICE = rows stay in HBM until rlgs_read_rows / rlgs_rows_view asks for them. */
+enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1, RLGS_ROWS_DEVICE = 2 };
 
 /* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
  * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
@@ -63,15 +66,19 @@ typedef struct {
     int32_t schedule;      /* RLGS_SCHED_* */
     int32_t placement;     /* RLGS_PLACE_* */
     int32_t rows_mode;     /* RLGS_ROWS_*: keep one cluster.csv row per tick / event */
-    int32_t slot_cap;      /* running-job slots per replica held on chip; 0 = auto (grown on overflow) */
-    int32_t chunk_ticks;   /* ticks advanced per kernel launch; 0 = auto */
+    int32_t slot_cap;      /* running-job slots per replica held on chip; 0 = auto */
+    int32_t n_streams;     /* replica groups, each on its own CUDA stream (kernel + result copies); 0 = auto */
+    int32_t ticks_per_launch; /* 0 = run to completion in one launch; >0 = bounded launches (state is saved
+                                 to / restored from HBM between launches) */
     int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES */
-    int32_t queue_limit[RLGS_MAX_QUEUES]; /* dlas-gpu demotion thresholds in GPU-ticks */
-    int32_t enable_network_costs;         /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
+    int32_t enable_network_costs; /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
+    int32_t fetch_jobs;    /* 1 = copy the per-job tables to the host inside rlgs_run as well */
     int32_t reserved0;
+    int32_t queue_limit[RLGS_MAX_QUEUES]; /* dlas-gpu demotion thresholds in GPU-ticks */
     double bandwidth;          /* --bandwidth MB/s (run_sim.py:59) */
     double internode_latency;  /* --internode_latency s (run_sim.py:65) */
     int64_t max_ticks;         /* safety stop; 0 = none */
+    int64_t rows_cap;          /* initial capacity (ticks) of the row store; 0 = auto; grown when a replica fills it */
 } rlgs_opts;
 
 /*

@@ -14,7 +14,7 @@ SO_PATH = os.path.join(HERE, 'librlgs.so')
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2}
 PLACE = {'yarn': 0, 'count': 1}
-ROWS_NONE, ROWS_FULL = 0, 1
+ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
 MAX_QUEUES = 8
 
 
@@ -25,9 +25,11 @@ class ClusterSpec(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_replicas', C.c_int32), ('schedule', C.c_int32), ('placement', C.c_int32),
-                ('rows_mode', C.c_int32), ('slot_cap', C.c_int32), ('chunk_ticks', C.c_int32), ('num_queue', C.c_int32),
-                ('queue_limit', C.c_int32 * MAX_QUEUES), ('enable_network_costs', C.c_int32), ('reserved0', C.c_int32),
-                ('bandwidth', C.c_double), ('internode_latency', C.c_double), ('max_ticks', C.c_int64)]
+                ('rows_mode', C.c_int32), ('slot_cap', C.c_int32), ('n_streams', C.c_int32),
+                ('ticks_per_launch', C.c_int32), ('num_queue', C.c_int32), ('enable_network_costs', C.c_int32),
+                ('fetch_jobs', C.c_int32), ('reserved0', C.c_int32), ('queue_limit', C.c_int32 * MAX_QUEUES),
+                ('bandwidth', C.c_double), ('internode_latency', C.c_double), ('max_ticks', C.c_int64),
+                ('rows_cap', C.c_int64)]
 
 
 class NetcostInputs(C.Structure):

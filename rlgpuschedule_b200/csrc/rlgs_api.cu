@@ -42,42 +42,48 @@ struct TraceBuf {
     int32_t max_arrival = 0;
 };
 
+struct Group {            // a contiguous range of replicas driven through one CUDA stream
+    int first = 0, count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t k_begin = nullptr, k_end = nullptr;
+};
+
 struct rlgs_sim {
     rlgs_cluster_spec spec;
     rlgs_opts opts;
     ClusterConst cc;
     int R = 0;
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    bool own_stream = true;
+    cudaStream_t stream = nullptr;  // main stream: state upload, fork / join point
     void *user_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<Group> groups;
     std::vector<TraceBuf> traces;
     std::vector<int> rep_trace;  // trace id per replica, -1 = none
     std::vector<RepDesc> h_desc;
     RepDesc *d_desc = nullptr;
     RepState *d_state = nullptr;
-    std::vector<RepState> h_state;
+    RepState *h_state = nullptr; // pinned [R]
+    RepState *h_init = nullptr;  // pinned [R] initial states
     std::vector<void *> slabs;   // per load_trace call
-    int *d_done = nullptr;       // unused counter slot (kept for env)
     int slot_cap = 0;
-    int chunk_ticks = 0;
-    // rows
-    rlgs_row *d_rows[2] = {nullptr, nullptr};
-    rlgs_row *h_rows = nullptr;  // pinned [R][h_cap]
+    // rows: device-resident store [R][rows_cap] + pinned host mirror [R][h_cap]
+    rlgs_row *d_rows = nullptr;
+    int64_t rows_cap = 0;
+    rlgs_row *h_rows = nullptr;
     int64_t h_cap = 0;
-    std::vector<int64_t> n_rows;
-    // job-table mirror
-    int32_t *h_jobs = nullptr;   // pinned mirror of the per-replica output arrays
-    size_t h_jobs_bytes = 0;
+    bool rows_fetched = false;
+    // job tables: device [4][R][Jmax] (start, end, finish_order, place_off) + pinned host mirror
+    int32_t *d_jobs = nullptr;
+    int32_t *h_jobs = nullptr;
+    size_t jobs_bytes = 0;
     bool jobs_fetched = false;
     int32_t Jmax = 0;
-    int32_t *d_jobs = nullptr;   // [4][R][Jmax]: start, end, finish_order, place_off
     int64_t *d_returns = nullptr;
     int64_t *h_returns = nullptr;
     bool ran = false;
     float last_ms = 0.f;
     int last_launches = 0;
-    std::vector<cudaEvent_t> ev;
 };
 
 extern "C" int32_t rlgs_version(void) { return RLGS_VERSION; }
@@ -108,22 +114,32 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
     s->cc.D = s->cc.N * s->cc.G;
-    s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(256, std::max(32, s->cc.D));
+    s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
     s->slot_cap = (s->slot_cap + 31) & ~31;
-    s->chunk_ticks = opts->chunk_ticks > 0 ? opts->chunk_ticks : 2048;
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
-    s->h_state.assign(s->R, RepState{});
-    s->n_rows.assign(s->R, 0);
-    cudaError_t ce;
-    if ((ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (ce = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (ce = cudaMalloc(&s->d_desc, sizeof(RepDesc) * s->R)) != cudaSuccess ||
-        (ce = cudaMalloc(&s->d_state, sizeof(RepState) * s->R)) != cudaSuccess ||
-        (ce = cudaMalloc(&s->d_returns, sizeof(int64_t) * s->R)) != cudaSuccess ||
-        (ce = cudaMallocHost(&s->h_returns, sizeof(int64_t) * s->R)) != cudaSuccess) {
+    int ng = opts->n_streams > 0 ? opts->n_streams : (s->R >= 8 * 148 ? 4 : (s->R >= 2 * 148 ? 2 : 1));
+    ng = std::max(1, std::min(ng, s->R));
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; return e == cudaSuccess; };
+    ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&s->ev_fork)); ok(cudaEventCreate(&s->ev_join));
+    for (int g = 0; g < ng; ++g) {
+        Group G;
+        G.first = (int)((int64_t)s->R * g / ng); G.count = (int)((int64_t)s->R * (g + 1) / ng) - G.first;
+        ok(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+        ok(cudaEventCreate(&G.k_begin)); ok(cudaEventCreate(&G.k_end));
+        s->groups.push_back(G);
+    }
+    ok(cudaMalloc(&s->d_desc, sizeof(RepDesc) * s->R));
+    ok(cudaMalloc(&s->d_state, sizeof(RepState) * s->R));
+    ok(cudaMalloc(&s->d_returns, sizeof(int64_t) * s->R));
+    ok(cudaMallocHost(&s->h_returns, sizeof(int64_t) * s->R));
+    ok(cudaMallocHost(&s->h_state, sizeof(RepState) * s->R));
+    ok(cudaMallocHost(&s->h_init, sizeof(RepState) * s->R));
+    if (ce != cudaSuccess) {
         rlgs_destroy(s);
-        return fail(RLGS_ERR_CUDA, "rlgs_create: %s", cudaGetErrorString(ce));
+        return fail(ce == cudaErrorMemoryAllocation ? RLGS_ERR_OOM : RLGS_ERR_CUDA, "rlgs_create: %s", cudaGetErrorString(ce));
     }
     *out = s;
     return RLGS_OK;
@@ -135,14 +151,20 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     cudaDeviceSynchronize();
     for (auto &t : s->traces) cudaFree(t.dev);
     for (void *p : s->slabs) cudaFree(p);
-    cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_rows[0]); cudaFree(s->d_rows[1]);
-    cudaFree(s->d_jobs); cudaFree(s->d_returns);
+    cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_rows); cudaFree(s->d_jobs); cudaFree(s->d_returns);
     if (s->h_rows) cudaFreeHost(s->h_rows);
     if (s->h_jobs) cudaFreeHost(s->h_jobs);
     if (s->h_returns) cudaFreeHost(s->h_returns);
-    for (auto ev : s->ev) cudaEventDestroy(ev);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    if (s->h_init) cudaFreeHost(s->h_init);
+    for (auto &G : s->groups) {
+        if (G.k_begin) cudaEventDestroy(G.k_begin);
+        if (G.k_end) cudaEventDestroy(G.k_end);
+        if (G.stream) cudaStreamDestroy(G.stream);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream) cudaStreamDestroy(s->stream);
-    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
 }
 
@@ -214,8 +236,8 @@ static int32_t setup_job_arrays(rlgs_sim *s) {
         cudaFree(s->d_jobs); s->d_jobs = nullptr;
         if (s->h_jobs) { cudaFreeHost(s->h_jobs); s->h_jobs = nullptr; }
         s->Jmax = Jmax;
-        s->h_jobs_bytes = sizeof(int32_t) * 4 * (size_t)s->R * (size_t)Jmax;
-        CU(cudaMalloc(&s->d_jobs, s->h_jobs_bytes));
+        s->jobs_bytes = sizeof(int32_t) * 4 * (size_t)s->R * (size_t)Jmax;
+        CU(cudaMalloc(&s->d_jobs, s->jobs_bytes));
     }
     size_t plane = (size_t)s->R * (size_t)Jmax;
     for (int r = 0; r < s->R; ++r) {
@@ -228,19 +250,39 @@ static int32_t setup_job_arrays(rlgs_sim *s) {
     return RLGS_OK;
 }
 
-static int32_t ensure_host_rows(rlgs_sim *s, int64_t need_ticks) {
-    if (need_ticks <= s->h_cap) return RLGS_OK;
-    int64_t cap = std::max<int64_t>(need_ticks, s->h_cap * 2);
-    cap = (cap + s->chunk_ticks - 1) / s->chunk_ticks * s->chunk_ticks;
+// grows the device row store to `cap` ticks per replica, keeping the first `keep` rows of each replica
+static int32_t grow_device_rows(rlgs_sim *s, int64_t cap, int64_t keep) {
     rlgs_row *nw = nullptr;
-    CU(cudaStreamSynchronize(s->copy_stream));
-    CU(cudaMallocHost(&nw, sizeof(rlgs_row) * (size_t)cap * (size_t)s->R));
-    if (s->h_rows) {
-        for (int r = 0; r < s->R; ++r)
-            memcpy(nw + (size_t)r * cap, s->h_rows + (size_t)r * s->h_cap, sizeof(rlgs_row) * (size_t)s->h_cap);
-        cudaFreeHost(s->h_rows);
+    CU(cudaMalloc(&nw, sizeof(rlgs_row) * (size_t)cap * (size_t)s->R));
+    if (s->d_rows && keep > 0)
+        CU(cudaMemcpy2D(nw, sizeof(rlgs_row) * (size_t)cap, s->d_rows, sizeof(rlgs_row) * (size_t)s->rows_cap,
+                        sizeof(rlgs_row) * (size_t)keep, (size_t)s->R, cudaMemcpyDeviceToDevice));
+    cudaFree(s->d_rows);
+    s->d_rows = nw; s->rows_cap = cap;
+    return RLGS_OK;
+}
+
+static int32_t ensure_host_rows(rlgs_sim *s, int64_t cap) {
+    if (cap <= s->h_cap) return RLGS_OK;
+    if (s->h_rows) cudaFreeHost(s->h_rows);
+    s->h_rows = nullptr; s->h_cap = 0;
+    CU(cudaMallocHost(&s->h_rows, sizeof(rlgs_row) * (size_t)cap * (size_t)s->R));
+    s->h_cap = cap;
+    return RLGS_OK;
+}
+
+// enqueue the device->host copies of one group's results on its stream
+static int32_t enqueue_fetch(rlgs_sim *s, const Group &G, bool rows, bool jobs, int64_t width) {
+    if (rows && width > 0)
+        CU(cudaMemcpy2DAsync(s->h_rows + (size_t)G.first * s->h_cap, sizeof(rlgs_row) * (size_t)s->h_cap,
+                             s->d_rows + (size_t)G.first * s->rows_cap, sizeof(rlgs_row) * (size_t)s->rows_cap,
+                             sizeof(rlgs_row) * (size_t)width, (size_t)G.count, cudaMemcpyDeviceToHost, G.stream));
+    if (jobs) {
+        size_t plane = (size_t)s->R * (size_t)s->Jmax;
+        for (int k = 0; k < 4; ++k)
+            CU(cudaMemcpyAsync(s->h_jobs + k * plane + (size_t)G.first * s->Jmax, s->d_jobs + k * plane + (size_t)G.first * s->Jmax,
+                               sizeof(int32_t) * (size_t)G.count * (size_t)s->Jmax, cudaMemcpyDeviceToHost, G.stream));
     }
-    s->h_rows = nw; s->h_cap = cap;
     return RLGS_OK;
 }
 
@@ -249,101 +291,97 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     CU(cudaSetDevice(s->device));
     int32_t rc = setup_job_arrays(s);
     if (rc) return rc;
-    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
-    const bool rows = s->opts.rows_mode == RLGS_ROWS_FULL;
+    cudaStream_t main_st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    const int mode = s->opts.rows_mode;
+    const bool rows = mode != RLGS_ROWS_NONE, eager_rows = mode == RLGS_ROWS_FULL, eager_jobs = s->opts.fetch_jobs != 0;
     const int R = s->R;
+    size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
+    if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
+    CU(cudaFuncSetAttribute(fifo_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
-    for (int attempt = 0;; ++attempt) {
-        size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
-        if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // reset state
-        int32_t max_arrival = 0;
-        for (int r = 0; r < R; ++r) {
-            RepState z; memset(&z, 0, sizeof z);
-            z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
-            z.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
-            z.free_hint = -1;
-            s->h_state[r] = z;
-            max_arrival = std::max(max_arrival, s->traces[s->rep_trace[r]].max_arrival);
+    int32_t max_arrival = 0;
+    for (int r = 0; r < R; ++r) {
+        RepState z; memset(&z, 0, sizeof z);
+        z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
+        z.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
+        z.free_hint = -1;
+        s->h_init[r] = z;
+        max_arrival = std::max(max_arrival, s->traces[s->rep_trace[r]].max_arrival);
+    }
+    if (rows && !s->d_rows) {
+        int64_t cap = s->opts.rows_cap > 0 ? s->opts.rows_cap : (int64_t)max_arrival + 4096;
+        rc = grow_device_rows(s, cap, 0);
+        if (rc) return rc;
+    }
+    if (eager_rows) { rc = ensure_host_rows(s, s->rows_cap); if (rc) return rc; }
+    if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
+    s->jobs_fetched = false; s->rows_fetched = false; s->ran = false;
+
+    CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
+    CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, main_st));
+    CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, main_st));
+
+    const int budget = s->opts.ticks_per_launch > 0 ? s->opts.ticks_per_launch : (1 << 30);
+    float total_ms = 0.f;
+    int launches = 0;
+    bool all_done = false, clean_single_pass = true;
+    while (!all_done) {
+        CU(cudaEventRecord(s->ev_fork, main_st));
+        for (auto &G : s->groups) {
+            CU(cudaStreamWaitEvent(G.stream, s->ev_fork, 0));
+            CU(cudaEventRecord(G.k_begin, G.stream));
+            fifo_yarn_kernel<<<G.count, 32, smem, G.stream>>>(s->d_desc + G.first, s->d_state + G.first, s->cc, s->slot_cap, budget,
+                                                             rows ? s->d_rows + (size_t)G.first * s->rows_cap : nullptr,
+                                                             s->rows_cap, s->d_returns + G.first, s->opts.max_ticks);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(G.k_end, G.stream));
+            CU(cudaMemcpyAsync(s->h_state + G.first, s->d_state + G.first, sizeof(RepState) * G.count, cudaMemcpyDeviceToHost, G.stream));
+            if (launches == 0 && s->opts.ticks_per_launch == 0) {
+                // optimistic: results of this group go to the host as soon as its kernel ends, while the
+                // other groups still compute; redone below if a replica had to be continued
+                rc = enqueue_fetch(s, G, eager_rows, eager_jobs, std::min(s->rows_cap, s->h_cap));
+                if (rc) return rc;
+            }
         }
-        CU(cudaMemcpyAsync(s->d_state, s->h_state.data(), sizeof(RepState) * R, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(s->d_jobs, 0xff, s->h_jobs_bytes, st));
-        s->jobs_fetched = false;
-        int chunk = rows ? s->chunk_ticks : (1 << 30);
-        if (rows) {
-            for (int b = 0; b < 2; ++b)
-                if (!s->d_rows[b]) CU(cudaMalloc(&s->d_rows[b], sizeof(rlgs_row) * (size_t)chunk * (size_t)R));
-            rc = ensure_host_rows(s, (int64_t)max_arrival + 2 * chunk);
+        launches++;
+        for (auto &G : s->groups) CU(cudaStreamSynchronize(G.stream));
+        float wave_ms = 0.f;
+        for (auto &G : s->groups) {
+            float t0 = 0.f, t1 = 0.f;
+            CU(cudaEventElapsedTime(&t0, s->ev_fork, G.k_begin));
+            CU(cudaEventElapsedTime(&t1, s->ev_fork, G.k_end));
+            wave_ms = std::max(wave_ms, t1);
+            (void)t0;
+        }
+        total_ms += wave_ms;
+        all_done = true;
+        bool overflow = false, rows_full = false;
+        for (int r = 0; r < R; ++r) {
+            const RepState &z = s->h_state[r];
+            if (z.status == RLGS_ERR_CAPACITY && !(s->opts.max_ticks > 0 && z.d >= s->opts.max_ticks)) overflow = true;
+            if (!z.done) { all_done = false; if (rows && z.d >= s->rows_cap) rows_full = true; }
+        }
+        if (overflow) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap);
+        if (!all_done) clean_single_pass = false;
+        if (rows_full) {
+            rc = grow_device_rows(s, s->rows_cap * 2, s->rows_cap);
             if (rc) return rc;
         }
-        // events for device timing
-        size_t ev_used = 0;
-        auto next_event = [&](cudaEvent_t *out) -> cudaError_t {
-            if (ev_used == s->ev.size()) { cudaEvent_t e; cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) return ce; s->ev.push_back(e); }
-            *out = s->ev[ev_used++];
-            return cudaSuccess;
-        };
-        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
-        bool all_done = false, overflow = false;
-        int64_t base_tick = 0;
-        int launches = 0;
-        cudaEvent_t copy_done[2] = {nullptr, nullptr};
-        while (!all_done) {
-            int b = launches & 1;
-            if (rows) {
-                // the copy that read d_rows[b] two launches ago must be finished before we overwrite it
-                if (copy_done[b]) CU(cudaStreamWaitEvent(st, copy_done[b], 0));
-            }
-            cudaEvent_t e0, e1;
-            CU(next_event(&e0)); CU(next_event(&e1));
-            CU(cudaEventRecord(e0, st));
-            fifo_yarn_kernel<<<R, 32, smem, st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, chunk, rows ? s->d_rows[b] : nullptr,
-                                                  chunk, s->d_returns, s->opts.max_ticks);
-            CU(cudaGetLastError());
-            CU(cudaEventRecord(e1, st));
-            spans.push_back({e0, e1});
-            launches++;
-            CU(cudaMemcpyAsync(s->h_state.data(), s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            all_done = true;
-            int64_t max_d = 0;
-            for (int r = 0; r < R; ++r) {
-                const RepState &z = s->h_state[r];
-                if (!z.done) all_done = false;
-                if (z.status == RLGS_ERR_CAPACITY && !(s->opts.max_ticks > 0 && z.d >= s->opts.max_ticks)) overflow = true;
-                max_d = std::max<int64_t>(max_d, z.d);
-            }
-            if (overflow) break;
-            if (rows) {
-                int64_t width = std::min<int64_t>(chunk, max_d - base_tick);
-                if (width > 0) {
-                    rc = ensure_host_rows(s, base_tick + chunk);
-                    if (rc) return rc;
-                    if (!copy_done[b]) CU(next_event(&copy_done[b]));
-                    CU(cudaMemcpy2DAsync(s->h_rows + base_tick, sizeof(rlgs_row) * (size_t)s->h_cap, s->d_rows[b],
-                                         sizeof(rlgs_row) * (size_t)chunk, sizeof(rlgs_row) * (size_t)width, (size_t)R,
-                                         cudaMemcpyDeviceToHost, s->copy_stream));
-                    CU(cudaEventRecord(copy_done[b], s->copy_stream));
-                }
-                base_tick += chunk;
-            }
-        }
-        if (overflow) {
-            // a replica ran out of running-job slots: double the on-chip table and start over
-            if (s->slot_cap >= s->cc.D || attempt > 8) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d", s->slot_cap);
-            CU(cudaStreamSynchronize(s->copy_stream));
-            int new_cap = std::min((s->cc.D + 31) & ~31, s->slot_cap * 2);
-            return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with opts.slot_cap>=%d", s->slot_cap, new_cap);
-        }
-        CU(cudaStreamSynchronize(s->copy_stream));
-        float ms = 0.f;
-        for (auto &sp : spans) { float t = 0.f; CU(cudaEventElapsedTime(&t, sp.first, sp.second)); ms += t; }
-        s->last_ms = ms; s->last_launches = launches;
-        for (int r = 0; r < R; ++r) { s->n_rows[r] = s->h_state[r].d; s->h_returns[r] = -s->h_state[r].sum_jct; }
-        break;
     }
+    if (!clean_single_pass || s->opts.ticks_per_launch != 0) {
+        // continued run: fetch everything now
+        if (eager_rows) { rc = ensure_host_rows(s, s->rows_cap); if (rc) return rc; }
+        for (auto &G : s->groups) {
+            int64_t w = 0;
+            for (int r = G.first; r < G.first + G.count; ++r) w = std::max<int64_t>(w, s->h_state[r].d);
+            rc = enqueue_fetch(s, G, eager_rows, eager_jobs, w);
+            if (rc) return rc;
+        }
+        for (auto &G : s->groups) CU(cudaStreamSynchronize(G.stream));
+    }
+    s->rows_fetched = eager_rows; s->jobs_fetched = eager_jobs;
+    s->last_ms = total_ms; s->last_launches = launches * (int)s->groups.size();
+    for (int r = 0; r < R; ++r) s->h_returns[r] = -s->h_state[r].sum_jct;
     s->ran = true;
     for (int r = 0; r < R; ++r)
         if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
@@ -371,9 +409,22 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
 
 static int32_t fetch_jobs(rlgs_sim *s) {
     if (s->jobs_fetched) return RLGS_OK;
-    if (!s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->h_jobs_bytes));
-    CU(cudaMemcpy(s->h_jobs, s->d_jobs, s->h_jobs_bytes, cudaMemcpyDeviceToHost));
+    if (!s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
+    CU(cudaMemcpy(s->h_jobs, s->d_jobs, s->jobs_bytes, cudaMemcpyDeviceToHost));
     s->jobs_fetched = true;
+    return RLGS_OK;
+}
+
+static int32_t fetch_rows(rlgs_sim *s) {
+    if (s->rows_fetched) return RLGS_OK;
+    int32_t rc = ensure_host_rows(s, s->rows_cap);
+    if (rc) return rc;
+    int64_t w = 0;
+    for (int r = 0; r < s->R; ++r) w = std::max<int64_t>(w, s->h_state[r].d);
+    if (w > 0)
+        CU(cudaMemcpy2D(s->h_rows, sizeof(rlgs_row) * (size_t)s->h_cap, s->d_rows, sizeof(rlgs_row) * (size_t)s->rows_cap,
+                        sizeof(rlgs_row) * (size_t)w, (size_t)s->R, cudaMemcpyDeviceToHost));
+    s->rows_fetched = true;
     return RLGS_OK;
 }
 
@@ -406,9 +457,12 @@ extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, const rlgs_row **rows,
     if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
-    if (s->opts.rows_mode != RLGS_ROWS_FULL) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
+    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
+    CU(cudaSetDevice(s->device));
+    int32_t rc = fetch_rows(s);
+    if (rc) return rc;
     *rows = s->h_rows + (size_t)r * s->h_cap;
-    *count = s->n_rows[r];
+    *count = s->h_state[r].d;
     return RLGS_OK;
 }
 

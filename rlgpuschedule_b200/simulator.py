@@ -13,8 +13,10 @@ class Simulator(object):
     Scheduler.start() (core/scheduling/schedule.py:178-216)."""
 
     def __init__(self, cluster, schedule='fifo', scheme='yarn', n_replicas=1, rows=True, device=0, slot_cap=0,
-                 chunk_ticks=0, num_queue=1, queue_limit=(), max_ticks=0, enable_network_costs=False,
-                 bandwidth=1250, internode_latency=0.015):
+                 n_streams=0, ticks_per_launch=0, rows_cap=0, fetch_jobs=False, num_queue=1, queue_limit=(),
+                 max_ticks=0, enable_network_costs=False, bandwidth=1250, internode_latency=0.015):
+        """rows: True / 'host' = rows copied to the pinned host store inside run(); 'device' = rows stay in
+        HBM until asked for; False = no rows."""
         if schedule not in _ffi.SCHED:
             raise NotImplementedError('schedule %r has no device implementation' % (schedule,))
         if scheme not in _ffi.PLACE:
@@ -22,7 +24,8 @@ class Simulator(object):
         self.cluster = cluster
         self.n_replicas = n_replicas
         self.rows = rows
-        self._kw = dict(schedule=schedule, scheme=scheme, rows=rows, device=device, chunk_ticks=chunk_ticks,
+        self._kw = dict(schedule=schedule, scheme=scheme, rows=rows, device=device, n_streams=n_streams,
+                        ticks_per_launch=ticks_per_launch, rows_cap=rows_cap, fetch_jobs=fetch_jobs,
                         num_queue=num_queue, queue_limit=tuple(queue_limit), max_ticks=max_ticks,
                         enable_network_costs=enable_network_costs, bandwidth=bandwidth,
                         internode_latency=internode_latency)
@@ -37,8 +40,9 @@ class Simulator(object):
         o = _ffi.Opts()
         o.device = k['device']; o.n_replicas = self.n_replicas
         o.schedule = _ffi.SCHED[k['schedule']]; o.placement = _ffi.PLACE[k['scheme']]
-        o.rows_mode = _ffi.ROWS_FULL if k['rows'] else _ffi.ROWS_NONE
-        o.slot_cap = self._slot_cap; o.chunk_ticks = k['chunk_ticks']; o.num_queue = k['num_queue']
+        o.rows_mode = (_ffi.ROWS_DEVICE if k['rows'] == 'device' else _ffi.ROWS_FULL) if k['rows'] else _ffi.ROWS_NONE
+        o.slot_cap = self._slot_cap; o.n_streams = k['n_streams']; o.ticks_per_launch = k['ticks_per_launch']
+        o.rows_cap = k['rows_cap']; o.fetch_jobs = int(bool(k['fetch_jobs'])); o.num_queue = k['num_queue']
         for i, v in enumerate(k['queue_limit'][:_ffi.MAX_QUEUES]):
             o.queue_limit[i] = int(v)
         o.enable_network_costs = int(bool(k['enable_network_costs']))
@@ -78,7 +82,7 @@ class Simulator(object):
             rc = L.rlgs_run(self._h)
             if rc == _ffi.ERR_CAPACITY and b'slot table overflow' in L.rlgs_last_error():
                 # more jobs ran concurrently than on-chip slots: rebuild with a larger table
-                cap = max(64, 2 * (self._slot_cap or 256))
+                cap = max(64, 2 * (self._slot_cap or 128))
                 if cap > 2 * max(self.cluster.num_gpus, 32):
                     _ffi.check(rc)
                 traces = self._traces

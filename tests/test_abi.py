@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     assert _ffi.ROW_DTYPE.itemsize == 64
     assert C.sizeof(_ffi.ClusterSpec) == 24
     assert C.sizeof(_ffi.Summary) == 6 * 8 + 8 * 4
-    assert C.sizeof(_ffi.Opts) == 8 * 4 + 8 * 4 + 2 * 4 + 2 * 8 + 8
+    assert C.sizeof(_ffi.Opts) == 12 * 4 + 8 * 4 + 2 * 8 + 2 * 8
 
 
 def test_fails_loudly_without_gpu():

@@ -42,7 +42,7 @@ def test_cuda_matches_reference_small(name):
 def test_cuda_matches_oracle_placement_and_counters(name):
     g = goldutil.load(name)
     ti = goldutil.trace_input(g)
-    cluster, tr, sim = run_cuda(ti, g['flags'], chunk_ticks=7)   # odd chunking exercises state save/restore
+    cluster, tr, sim = run_cuda(ti, g['flags'], ticks_per_launch=7, rows_cap=16, n_streams=1)   # bounded launches + a growing row store exercise state save/restore
     otr = cpu_sim.prepare_trace(ti)
     ores = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**g['flags']), otr)
     j = sim.jobs(0)
