@@ -68,6 +68,7 @@ class Simulator(object):
         n_replicas = self.n_replicas - first_replica if n_replicas is None else n_replicas
         rec = np.ascontiguousarray(trace.records)
         _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec), None))
+        self._traces = [x for x in self._traces if (x[0], x[1]) != (first_replica, n_replicas)]
         self._traces.append((first_replica, n_replicas, trace))
 
     def trace_of(self, replica):
