@@ -89,21 +89,17 @@ def run_reference(args, rank, world):
     """CPU arm: the oracle port on all host cores, a bounded sample of the same workload per step."""
     if rank != 0:
         return
-    import concurrent.futures as cf
     import cpu_sim
     cores = os.cpu_count() or 1
     cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
     traces = [cpu_sim.prepare_trace(f) for f in frames(0)[:min(N_TRACES, 4)]]
     cpu_sim.lib()
-    per_step = cores  # replica-runs per step: one per core (~0.25 s each)
-
-    def one(i):
-        r = cpu_sim.run_fifo_yarn(cl, traces[i % len(traces)], rows_cap=70000)
-        return 3 * len(r['finish_order'])
+    per_step = 2 * cores  # replica-runs per step: two per hardware thread (~0.25 s each)
+    k = [0]
 
     def step():
-        with cf.ThreadPoolExecutor(max_workers=cores) as ex:
-            return sum(ex.map(one, range(per_step)))
+        k[0] += 1
+        return cpu_sim.run_fifo_yarn_batch(cl, traces[k[0] % len(traces)], per_step, cores, rows_cap=70000)
 
     for _ in range(args.warmup):
         step()
@@ -113,7 +109,7 @@ def run_reference(args, rank, world):
         ev += step()
     dt = time.perf_counter() - t0
     val = ev / dt
-    sample = '%d replica-runs of the 60k-job trace per step on %d host threads (oracle/cpu_sim.c, -O2)' % (per_step, cores)
+    sample = '%d replica-runs of the 60k-job trace per step on %d pthreads (oracle/cpu_sim.c, gcc -O2)' % (per_step, cores)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -126,27 +122,21 @@ def run_reference(args, rank, world):
 
 def cpu_baseline_sample():
     """Bounded cpu_baseline for the cuda arm's JSON line: a few seconds of the oracle on all cores."""
-    import concurrent.futures as cf
     import cpu_sim
     cores = os.cpu_count() or 1
     cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
     tr = cpu_sim.prepare_trace(frames(0)[0])
     cpu_sim.lib()
+    cpu_sim.run_fifo_yarn_batch(cl, tr, cores, cores, rows_cap=70000)
     n_runs = 4 * cores
-
-    def one(_):
-        return 3 * len(cpu_sim.run_fifo_yarn(cl, tr, rows_cap=70000)['finish_order'])
-
-    one(0)
     t0 = time.perf_counter()
-    with cf.ThreadPoolExecutor(max_workers=cores) as ex:
-        ev = sum(ex.map(one, range(n_runs)))
+    ev = cpu_sim.run_fifo_yarn_batch(cl, tr, n_runs, cores, rows_cap=70000)
     dt = time.perf_counter() - t0
     t1 = time.perf_counter()
-    ev1 = one(0)
+    ev1 = cpu_sim.run_fifo_yarn_batch(cl, tr, 1, 1, rows_cap=70000)
     dt1 = time.perf_counter() - t1
     return {'value': ev / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d replica-runs of the 60k-job trace on %d threads, %.1f s (oracle/cpu_sim.c)' % (n_runs, cores, dt),
+            'sample': '%d replica-runs of the 60k-job trace on %d pthreads, %.1f s (oracle/cpu_sim.c, gcc -O2)' % (n_runs, cores, dt),
             'single_core_value': ev1 / dt1}
 
 

@@ -146,3 +146,17 @@ def format_cluster_csv(res, with_util=False):
                 int(r['running']), int(r['queued']), int(r['finished'])]
         w.writerow(row)
     return buf.getvalue()
+
+
+def run_fifo_yarn_batch(cluster, tr, n_runs, n_threads, rows_cap=None):
+    """n_runs replica-runs of one trace on n_threads pthreads (CPU baseline). Returns total events."""
+    L = lib()
+    L.oracle_fifo_yarn_batch.restype = C.c_int64
+    n = len(tr['nt'])
+    cap = rows_cap or max(4096, 4 * n)
+    ev = L.oracle_fifo_yarn_batch(C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
+                                  _p(tr['used_gpus'], C.c_double), _p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double),
+                                  _p(tr['util_avg'], C.c_double), C.c_int64(cap), C.c_int(n_runs), C.c_int(n_threads))
+    if ev < 0:
+        raise RuntimeError('oracle_fifo_yarn_batch rc=%d' % ev)
+    return int(ev)

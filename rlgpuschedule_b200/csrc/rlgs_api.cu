@@ -58,6 +58,8 @@ struct rlgs_sim {
     cudaStream_t stream = nullptr;  // main stream: state upload, fork / join point
     void *user_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-bound copies of the pipelined (rows FULL) path
+    std::vector<cudaEvent_t> ev_pool;
     std::vector<Group> groups;
     std::vector<TraceBuf> traces;
     std::vector<int> rep_trace;  // trace id per replica, -1 = none
@@ -79,6 +81,7 @@ struct rlgs_sim {
     int32_t *h_jobs = nullptr;
     size_t jobs_bytes = 0;
     bool jobs_fetched = false;
+    bool jobs_partial = false;   // start/end/finish_order planes are on the host, place_off is not
     int32_t Jmax = 0;
     int64_t *d_returns = nullptr;
     int64_t *h_returns = nullptr;
@@ -125,6 +128,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     auto ok = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; return e == cudaSuccess; };
     ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     ok(cudaEventCreate(&s->ev_fork)); ok(cudaEventCreate(&s->ev_join));
+    ok(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     for (int g = 0; g < ng; ++g) {
         Group G;
         G.first = (int)((int64_t)s->R * g / ng); G.count = (int)((int64_t)s->R * (g + 1) / ng) - G.first;
@@ -163,6 +167,8 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
         if (G.k_end) cudaEventDestroy(G.k_end);
         if (G.stream) cudaStreamDestroy(G.stream);
     }
+    for (auto e : s->ev_pool) cudaEventDestroy(e);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -329,12 +335,81 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     }
     if (eager_rows) { rc = ensure_host_rows(s, s->rows_cap); if (rc) return rc; }
     if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
-    s->jobs_fetched = false; s->rows_fetched = false; s->ran = false;
+    s->jobs_fetched = false; s->jobs_partial = false; s->rows_fetched = false; s->ran = false;
 
     CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
     CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, main_st));
     CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, main_st));
 
+    if (eager_rows && s->opts.ticks_per_launch == 0) {
+        // ---- pipelined path: launches bounded to PIPE_TICKS ticks; the rows of chunk k travel to the
+        // pinned host store on the copy stream while chunk k+1 is being simulated.  Nothing here waits
+        // on the host until every chunk is enqueued.
+        const int PIPE_TICKS = 8192;
+        size_t plane = (size_t)s->R * (size_t)s->Jmax;
+        int64_t next_tick = 0;
+        int launches = 0;
+        float total_ms = 0.f;
+        auto get_event = [&](size_t i, cudaEvent_t *out) -> cudaError_t {
+            while (s->ev_pool.size() <= i) { cudaEvent_t e; cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) return ce; s->ev_pool.push_back(e); }
+            *out = s->ev_pool[i];
+            return cudaSuccess;
+        };
+        for (;;) {
+            size_t ev_i = 0;
+            cudaEvent_t e_begin, e_last = nullptr;
+            CU(get_event(ev_i++, &e_begin));
+            CU(cudaEventRecord(e_begin, main_st));
+            for (; next_tick < s->rows_cap; next_tick += PIPE_TICKS) {
+                fifo_yarn_kernel<<<R, 32, smem, main_st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, PIPE_TICKS, s->d_rows, s->rows_cap,
+                                                          s->d_returns, s->opts.max_ticks);
+                CU(cudaGetLastError());
+                launches++;
+                CU(get_event(ev_i++, &e_last));
+                CU(cudaEventRecord(e_last, main_st));
+                CU(cudaStreamWaitEvent(s->copy_stream, e_last, 0));
+                int64_t w = std::min<int64_t>(PIPE_TICKS, s->rows_cap - next_tick);
+                CU(cudaMemcpy2DAsync(s->h_rows + next_tick, sizeof(rlgs_row) * (size_t)s->h_cap, s->d_rows + next_tick,
+                                     sizeof(rlgs_row) * (size_t)s->rows_cap, sizeof(rlgs_row) * (size_t)w, (size_t)R,
+                                     cudaMemcpyDeviceToHost, s->copy_stream));
+            }
+            CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, main_st));
+            CU(cudaStreamSynchronize(main_st));
+            float ms = 0.f;
+            if (e_last) CU(cudaEventElapsedTime(&ms, e_begin, e_last));
+            total_ms += ms;
+            bool all_done = true, overflow = false;
+            for (int r = 0; r < R; ++r) {
+                const RepState &z = s->h_state[r];
+                if (z.status == RLGS_ERR_CAPACITY && !(s->opts.max_ticks > 0 && z.d >= s->opts.max_ticks)) overflow = true;
+                if (!z.done) all_done = false;
+            }
+            if (overflow) { cudaStreamSynchronize(s->copy_stream); return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap); }
+            if (all_done) break;
+            // some replica filled the row store: double it (device and host) and keep going
+            CU(cudaStreamSynchronize(s->copy_stream));
+            int64_t old_cap = s->rows_cap;
+            rc = grow_device_rows(s, old_cap * 2, old_cap);
+            if (rc) return rc;
+            rlgs_row *old_h = s->h_rows; int64_t old_hcap = s->h_cap;
+            s->h_rows = nullptr; s->h_cap = 0;
+            rc = ensure_host_rows(s, s->rows_cap);
+            if (rc) { cudaFreeHost(old_h); return rc; }
+            for (int r = 0; r < R; ++r) memcpy(s->h_rows + (size_t)r * s->h_cap, old_h + (size_t)r * old_hcap, sizeof(rlgs_row) * (size_t)old_cap);
+            cudaFreeHost(old_h);
+        }
+        if (eager_jobs)
+            for (int k = 0; k < 3; ++k)   // start, end, finish_order (place_off stays on the device)
+                CU(cudaMemcpyAsync(s->h_jobs + k * plane, s->d_jobs + k * plane, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s->copy_stream));
+        CU(cudaStreamSynchronize(s->copy_stream));
+        s->rows_fetched = true; s->jobs_fetched = false; s->jobs_partial = eager_jobs;
+        s->last_ms = total_ms; s->last_launches = launches;
+        for (int r = 0; r < R; ++r) s->h_returns[r] = -s->h_state[r].sum_jct;
+        s->ran = true;
+        for (int r = 0; r < R; ++r)
+            if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
+        return RLGS_OK;
+    }
     const int budget = s->opts.ticks_per_launch > 0 ? s->opts.ticks_per_launch : (1 << 30);
     float total_ms = 0.f;
     int launches = 0;
@@ -448,8 +523,10 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     CU(cudaSetDevice(s->device));
-    int32_t rc = fetch_jobs(s);
-    if (rc) return rc;
+    if (!(s->jobs_partial && !first_node)) {
+        int32_t rc = fetch_jobs(s);
+        if (rc) return rc;
+    }
     size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
     int J = s->h_desc[r].J;
     const int32_t *st = s->h_jobs + off, *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off, *po = s->h_jobs + 3 * plane + off;
