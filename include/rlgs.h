@@ -109,7 +109,11 @@ typedef struct {
 } rlgs_netcost_inputs;
 
 /* One cluster.csv row as integer sufficient statistics (core/scheduling/schedule.py:95-133,
- * log_manager.py:118-135).  The float columns are finished on the host (rlgpuschedule_b200/log_manager.py). */
+ * log_manager.py:118-135).  The float columns are finished on the host (rlgpuschedule_b200/log_manager.py).
+ * fifo: one row per tick, row i has delta = i + 1.
+ * sjf / dlas-gpu: one row per event with the legacy cluster.csv columns (log.py:137-258):
+ *   idle_nodes = idle_node, busy_gpus = busy_gpu, running / queued / finished = running_job / pending_job /
+ *   completed_job, median_lo = event time, median_hi = full_node; the remaining fields are 0. */
 typedef struct {
     int32_t idle_nodes;   /* num_idle_nodes; num_busy_nodes = N - idle_nodes */
     int32_t busy_gpus;    /* num_busy_gpus; num_idle_gpus = D - busy_gpus */
@@ -167,8 +171,17 @@ int32_t rlgs_read_jobs(rlgs_sim *sim, int32_t replica, int32_t *finish_order, in
 /* Replaces the per-tick LogManager.step_cluster rows (log_manager.py:118-135): copies rows
  * [first, first+count) of `replica` (rows_mode FULL). */
 int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row *out);
-/* Zero-copy variant: pointer into the handle's pinned host store, valid until the next rlgs_run / destroy. */
-int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, const rlgs_row **rows, int64_t *count);
+/* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
+ * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
+ * valid until the next rlgs_run / destroy. */
+#define RLGS_ROWS_PER_CHUNK 8192
+int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);
+/* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
+ * (log.py:316-330). */
+enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,
+       RLGS_PLANE_AUX = 3,      /* fifo: first placement-log entry; sjf/dlas-gpu: pending_time */
+       RLGS_PLANE_PREEMPT = 4, RLGS_PLANE_RESUME = 5 };
+int32_t rlgs_read_job_plane(rlgs_sim *sim, int32_t replica, int32_t plane, int32_t *out);
 /* Episode return per replica: -(sum of job completion times), the reward of the vectorised Environment. */
 int32_t rlgs_returns(rlgs_sim *sim, int64_t *out_n_replicas);
 /* Device pointer to the same int64[n_replicas] buffer (the NCCL all-gather send buffer). */

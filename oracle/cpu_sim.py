@@ -160,3 +160,60 @@ def run_fifo_yarn_batch(cluster, tr, n_runs, n_threads, rows_cap=None):
     if ev < 0:
         raise RuntimeError('oracle_fifo_yarn_batch rc=%d' % ev)
     return int(ev)
+
+
+LEGACY_ROW_DTYPE = np.dtype([('time', 'i4'), ('idle_nodes', 'i4'), ('full_nodes', 'i4'), ('busy_gpus', 'i4'),
+                             ('pending', 'i4'), ('running', 'i4'), ('completed', 'i4'), ('pad', 'i4')])
+
+
+def _run_legacy(fn_name, cluster, tr, extra_args, rows_cap=None):
+    L = lib()
+    n = len(tr['nt'])
+    outs = [np.full(max(n, 1), -1, np.int32) for _ in range(6)]   # finish_order, start, end, pending, preempt, resume
+    nfin = C.c_int32(0); nev = C.c_int64(0); counters = np.zeros(4, np.int64)
+    cap = rows_cap or max(4096, 8 * n)
+    while True:
+        rows = np.zeros(cap, LEGACY_ROW_DTYPE)
+        args = [C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
+                _p(tr['used_gpus'], C.c_double)] + extra_args + [_p(o, C.c_int32) for o in outs] + [
+                C.byref(nfin), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nev), _p(counters, C.c_int64)]
+        rc = getattr(L, fn_name)(*args)
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc != 0:
+            raise RuntimeError('%s rc=%d' % (fn_name, rc))
+        break
+    k = nfin.value
+    return dict(finish_order=outs[0][:k].copy(), start=outs[1][:n], end=outs[2][:n], pending=outs[3][:n], preempt=outs[4][:n],
+                resume=outs[5][:n], rows=rows[:nev.value], n_events=nev.value,
+                counters=dict(sweep_jobs=int(counters[0]), events=int(counters[1]), demotions=int(counters[2])))
+
+
+def run_sjf_yarn(cluster, tr, rows_cap=None):
+    """Restated smallest_first_sim_jobs (run_sim.py:162-287) with the live yarn fit.  PARITY UNPINNED."""
+    return _run_legacy('oracle_sjf_yarn', cluster, tr, [_p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double)], rows_cap)
+
+
+def run_dlas_gpu(cluster, tr, queue_limit=(30, 60, 150), rows_cap=None):
+    """Restated dlas_sim_jobs(gputime=True) (run_sim.py:664-947), count-based admission.  PARITY UNPINNED."""
+    ql = np.asarray(queue_limit, np.int32)
+    return _run_legacy('oracle_dlas_gpu', cluster, tr, [C.c_int32(len(ql) + 1), _p(ql, C.c_int32)], rows_cap)
+
+
+def format_legacy_job_csv(tr, res, count_scheme):
+    """job.csv in the legacy layout (/root/reference/log.py:86-88,316-330)."""
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    hdr = ['time', 'job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'executed_time', 'JCT', 'duration',
+           'pending_time', 'preempt'] + (['resume'] if count_scheme else []) + ['promote']
+    w.writerow(hdr)
+    sub = np.ceil(tr['nt']).astype(np.int64)
+    dur = np.maximum(1, np.ceil(tr['duration'])).astype(np.int64)
+    for i in res['finish_order']:
+        i = int(i)
+        row = [int(res['end'][i]), str(int(tr['label'][i])), int(np.ceil(tr['used_gpus'][i])), int(sub[i]), int(res['start'][i]),
+               int(res['end'][i]), int(res['end'][i] - res['start'][i]), int(res['end'][i] - sub[i]), int(dur[i]),
+               int(res['pending'][i]), int(res['preempt'][i])] + ([int(res['resume'][i])] if count_scheme else []) + [0]
+        w.writerow(row)
+    return buf.getvalue()

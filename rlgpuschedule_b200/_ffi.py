@@ -16,6 +16,8 @@ SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2}
 PLACE = {'yarn': 0, 'count': 1}
 ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
 MAX_QUEUES = 8
+ROWS_PER_CHUNK = 8192
+PLANE_START, PLANE_END, PLANE_FINISH_ORDER, PLANE_AUX, PLANE_PREEMPT, PLANE_RESUME = range(6)
 
 
 class ClusterSpec(C.Structure):
@@ -55,7 +57,7 @@ assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64
 
 EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_run',
            'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
-           'rlgs_rows_view', 'rlgs_returns', 'rlgs_returns_device_ptr']
+           'rlgs_rows_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr']
 
 _lib = None
 
@@ -88,7 +90,8 @@ def lib():
     L.rlgs_get_summary.argtypes = [vp, i32, C.POINTER(Summary)]
     L.rlgs_read_jobs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.rlgs_read_rows.argtypes = [vp, i32, i64, i64, vp]
-    L.rlgs_rows_view.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.rlgs_rows_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.rlgs_read_job_plane.argtypes = [vp, i32, i32, vp]
     L.rlgs_returns.argtypes = [vp, vp]
     L.rlgs_returns_device_ptr.argtypes = [vp, C.POINTER(vp)]
     for name in EXPORTS:

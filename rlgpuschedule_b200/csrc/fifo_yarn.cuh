@@ -141,8 +141,7 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
 }
 
 __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
-                                                       ClusterConst c, int slot_cap, int tick_budget,
-                                                       rlgs_row *__restrict__ rows_base, int64_t rows_stride,
+                                                       ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
                                                        int64_t *__restrict__ returns, int64_t max_ticks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
@@ -150,10 +149,10 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
     RepState st = states[blockIdx.x];
     if (st.done || st.status != RLGS_OK) return;
     FifoSmem s = fifo_carve(smem_raw, c.N, slot_cap);
-    const bool rows_mode = rows_base != nullptr;
-    // device-resident row store: rows[d-1] of this replica; a launch stops when the store is full
-    rlgs_row *const rows = rows_base + (size_t)blockIdx.x * rows_stride;
-    if (rows_mode && (int64_t)st.d + tick_budget > rows_stride) tick_budget = (int)max((int64_t)0, rows_stride - st.d);
+    const bool rows_mode = rs.chunks != nullptr;
+    // device-resident chunk-major row store: a launch stops when the allocated chunks are full
+    if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
+        tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
     if (st.d == 0) {  // first launch of a run: empty cluster, no running jobs
         int nw = 3 * c.N + (c.N + 31) / 32;
         for (int i = lane; i < nw; i += 32) s.nv.cpu[i] = 0;
@@ -325,7 +324,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
         // ---------------- stats row (schedule.py:204-205)
         st.sumQ += st.Q; st.sumR += st.R;
         if (rows_mode && lane == 0) {
-            rlgs_row *row = rows + (st.d - 1);
+            rlgs_row *row = row_ptr(rs, blockIdx.x, st.d - 1);
             int4 w0 = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
             int4 w1 = make_int4(st.F, st.Q > 0 ? st.d - med_lo_arr : 0, st.Q > 0 ? st.d - med_hi_arr : 0,
                                 st.Q > 0 ? st.d - st.bottom_arr : 0);

@@ -1,9 +1,10 @@
 // rlgs_api.cu — host side of the C ABI declared in include/rlgs.h (librlgs.so).
 //
-// Owns device memory, launches the simulation kernels chunk by chunk, streams the per-tick rows
-// to a pinned host store while the next chunk computes, and hands results back through plain
-// pointers.  No torch types, no CPU fallback: every entry point fails with RLGS_ERR_CUDA when no
-// device is usable.
+// Owns device memory, launches the simulation kernels, keeps the per-tick / per-event rows in a
+// chunk-major device store (chunk k = rows [k*8192, (k+1)*8192) of every replica, contiguous) and,
+// in rows_mode FULL, streams chunk k to a pinned host mirror on a copy stream while chunk k+1 is
+// being simulated.  No torch types, no CPU fallback: every entry point fails with RLGS_ERR_CUDA
+// when no device is usable.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -16,6 +17,7 @@
 
 #include "../../include/rlgs.h"
 #include "fifo_yarn.cuh"
+#include "legacy_sched.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -35,6 +37,9 @@ static int32_t fail(int32_t code, const char *fmt, ...) {
                         cudaGetErrorString(e_));                                                  \
     } while (0)
 
+static const int N_PLANES = 6;   // start, end, finish_order, {place_off | pending_time}, preempt, resume
+static const int MAX_CHUNKS = 1 << 16;
+
 struct TraceBuf {
     rlgs_job *dev = nullptr;
     int32_t n = 0, cap_n = 0;
@@ -46,45 +51,49 @@ struct TraceBuf {
 struct Group {            // a contiguous range of replicas driven through one CUDA stream
     int first = 0, count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t k_begin = nullptr, k_end = nullptr;
+    cudaEvent_t k_end = nullptr;
+};
+
+// Host copy of the per-replica progress, schedule independent
+struct Progress {
+    int64_t rows = 0;
+    int done = 0, status = 0;
 };
 
 struct rlgs_sim {
     rlgs_cluster_spec spec;
     rlgs_opts opts;
     ClusterConst cc;
-    int R = 0;
-    int device = 0;
-    cudaStream_t stream = nullptr;  // main stream: state upload, fork / join point
+    LegParams lp;
+    int R = 0, device = 0;
+    bool legacy = false;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     void *user_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaStream_t copy_stream = nullptr;   // host-bound copies of the pipelined (rows FULL) path
+    cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<Group> groups;
     std::vector<TraceBuf> traces;
-    std::vector<int> rep_trace;  // trace id per replica, -1 = none
+    std::vector<int> rep_trace;
+    // fifo
     std::vector<RepDesc> h_desc;
     RepDesc *d_desc = nullptr;
-    RepState *d_state = nullptr;
-    RepState *h_state = nullptr; // pinned [R]
-    RepState *h_init = nullptr;  // pinned [R] initial states
-    std::vector<void *> slabs;   // per load_trace call
+    RepState *d_state = nullptr, *h_state = nullptr, *h_init = nullptr;
+    // legacy
+    std::vector<LegDesc> h_ldesc;
+    LegDesc *d_ldesc = nullptr;
+    LegState *d_lstate = nullptr, *h_lstate = nullptr, *h_linit = nullptr;
+    std::vector<void *> slabs;
     int slot_cap = 0;
-    // rows: device-resident store [R][rows_cap] + pinned host mirror [R][h_cap]
-    rlgs_row *d_rows = nullptr;
-    int64_t rows_cap = 0;
-    rlgs_row *h_rows = nullptr;
-    int64_t h_cap = 0;
-    bool rows_fetched = false;
-    // job tables: device [4][R][Jmax] (start, end, finish_order, place_off) + pinned host mirror
-    int32_t *d_jobs = nullptr;
-    int32_t *h_jobs = nullptr;
+    // chunk-major row store
+    std::vector<rlgs_row *> d_chunks, h_chunks;
+    std::vector<char> h_chunk_valid;
+    rlgs_row **d_chunk_ptrs = nullptr;
+    // job planes [N_PLANES][R][Jmax]
+    int32_t *d_jobs = nullptr, *h_jobs = nullptr;
     size_t jobs_bytes = 0;
-    bool jobs_fetched = false;
-    bool jobs_partial = false;   // start/end/finish_order planes are on the host, place_off is not
+    int planes_on_host = 0;
     int32_t Jmax = 0;
-    int64_t *d_returns = nullptr;
-    int64_t *h_returns = nullptr;
+    int64_t *d_returns = nullptr, *h_returns = nullptr;
     bool ran = false;
     float last_ms = 0.f;
     int last_launches = 0;
@@ -92,6 +101,9 @@ struct rlgs_sim {
 
 extern "C" int32_t rlgs_version(void) { return RLGS_VERSION; }
 extern "C" const char *rlgs_last_error(void) { return g_err; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t chunk_bytes(const rlgs_sim *s) { return sizeof(rlgs_row) * (size_t)RLGS_ROW_CHUNK * (size_t)s->R; }
 
 extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *opts, rlgs_sim **out) {
     if (!spec || !opts || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
@@ -102,10 +114,17 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (spec->num_gpu_p_node < 1 || spec->num_gpu_p_node > 32)
         return fail(RLGS_ERR_BAD_ARG, "num_gpu_p_node must be 1..32 (got %d)", spec->num_gpu_p_node);
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
-    if (opts->schedule != RLGS_SCHED_FIFO)
-        return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", opts->schedule);
-    if (opts->placement != RLGS_PLACE_YARN)
-        return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for this schedule", opts->placement);
+    const int sched = opts->schedule;
+    if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU)
+        return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
+    if ((sched == RLGS_SCHED_FIFO || sched == RLGS_SCHED_SJF) && opts->placement != RLGS_PLACE_YARN)
+        return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
+    if (sched == RLGS_SCHED_DLAS_GPU) {
+        if (opts->num_queue < 1 || opts->num_queue > RLGS_MAX_QUEUES) return fail(RLGS_ERR_BAD_ARG, "num_queue must be 1..%d", RLGS_MAX_QUEUES);
+        for (int q = 0; q + 1 < opts->num_queue; ++q)
+            if (opts->queue_limit[q] < 1) return fail(RLGS_ERR_BAD_ARG, "queue_limit[%d] must be >= 1", q);
+    }
+    if (opts->enable_network_costs) return fail(RLGS_ERR_UNSUPPORTED, "network costs are not implemented on the device path yet");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -115,33 +134,44 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     rlgs_sim *s = new (std::nothrow) rlgs_sim();
     if (!s) return fail(RLGS_ERR_OOM, "host allocation failed");
     s->spec = *spec; s->opts = *opts; s->R = opts->n_replicas; s->device = opts->device;
+    s->legacy = sched != RLGS_SCHED_FIFO;
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
     s->cc.D = s->cc.N * s->cc.G;
+    memset(&s->lp, 0, sizeof s->lp);
+    s->lp.nq = sched == RLGS_SCHED_DLAS_GPU ? opts->num_queue : 1;
+    for (int q = 0; q < RLGS_MAX_QUEUES; ++q) s->lp.limit[q] = opts->queue_limit[q];
+    s->lp.total_gpu = s->cc.D; s->lp.num_node = s->cc.N; s->lp.gpus_per_node = s->cc.G; s->lp.max_time = opts->max_ticks;
     s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
     s->slot_cap = (s->slot_cap + 31) & ~31;
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
+    s->h_ldesc.assign(s->R, LegDesc{});
     int ng = opts->n_streams > 0 ? opts->n_streams : (s->R >= 8 * 148 ? 4 : (s->R >= 2 * 148 ? 2 : 1));
     ng = std::max(1, std::min(ng, s->R));
     cudaError_t ce = cudaSuccess;
-    auto ok = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; return e == cudaSuccess; };
+    auto ok = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
     ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    ok(cudaEventCreate(&s->ev_fork)); ok(cudaEventCreate(&s->ev_join));
     ok(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&s->ev_fork));
     for (int g = 0; g < ng; ++g) {
         Group G;
         G.first = (int)((int64_t)s->R * g / ng); G.count = (int)((int64_t)s->R * (g + 1) / ng) - G.first;
         ok(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
-        ok(cudaEventCreate(&G.k_begin)); ok(cudaEventCreate(&G.k_end));
+        ok(cudaEventCreate(&G.k_end));
         s->groups.push_back(G);
     }
     ok(cudaMalloc(&s->d_desc, sizeof(RepDesc) * s->R));
     ok(cudaMalloc(&s->d_state, sizeof(RepState) * s->R));
+    ok(cudaMalloc(&s->d_ldesc, sizeof(LegDesc) * s->R));
+    ok(cudaMalloc(&s->d_lstate, sizeof(LegState) * s->R));
     ok(cudaMalloc(&s->d_returns, sizeof(int64_t) * s->R));
+    ok(cudaMalloc(&s->d_chunk_ptrs, sizeof(rlgs_row *) * MAX_CHUNKS));
     ok(cudaMallocHost(&s->h_returns, sizeof(int64_t) * s->R));
     ok(cudaMallocHost(&s->h_state, sizeof(RepState) * s->R));
     ok(cudaMallocHost(&s->h_init, sizeof(RepState) * s->R));
+    ok(cudaMallocHost(&s->h_lstate, sizeof(LegState) * s->R));
+    ok(cudaMallocHost(&s->h_linit, sizeof(LegState) * s->R));
     if (ce != cudaSuccess) {
         rlgs_destroy(s);
         return fail(ce == cudaErrorMemoryAllocation ? RLGS_ERR_OOM : RLGS_ERR_CUDA, "rlgs_create: %s", cudaGetErrorString(ce));
@@ -156,21 +186,23 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     cudaDeviceSynchronize();
     for (auto &t : s->traces) cudaFree(t.dev);
     for (void *p : s->slabs) cudaFree(p);
-    cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_rows); cudaFree(s->d_jobs); cudaFree(s->d_returns);
-    if (s->h_rows) cudaFreeHost(s->h_rows);
+    for (auto p : s->d_chunks) cudaFree(p);
+    for (auto p : s->h_chunks) if (p) cudaFreeHost(p);
+    cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_ldesc); cudaFree(s->d_lstate); cudaFree(s->d_jobs);
+    cudaFree(s->d_returns); cudaFree(s->d_chunk_ptrs);
     if (s->h_jobs) cudaFreeHost(s->h_jobs);
     if (s->h_returns) cudaFreeHost(s->h_returns);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_init) cudaFreeHost(s->h_init);
+    if (s->h_lstate) cudaFreeHost(s->h_lstate);
+    if (s->h_linit) cudaFreeHost(s->h_linit);
     for (auto &G : s->groups) {
-        if (G.k_begin) cudaEventDestroy(G.k_begin);
         if (G.k_end) cudaEventDestroy(G.k_end);
         if (G.stream) cudaStreamDestroy(G.stream);
     }
     for (auto e : s->ev_pool) cudaEventDestroy(e);
-    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -181,14 +213,12 @@ extern "C" int32_t rlgs_set_stream(rlgs_sim *s, void *cuda_stream) {
     return RLGS_OK;
 }
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
 extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, const rlgs_job *jobs, int32_t n,
                                    const rlgs_netcost_inputs *net) {
     if (!s || !jobs) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (n < 1) return fail(RLGS_ERR_BAD_ARG, "trace has no jobs (the reference asserts on an empty job table, log_manager.py:138)");
     if (first < 0 || count < 1 || first + count > s->R) return fail(RLGS_ERR_BAD_ARG, "replica range [%d,%d) out of 0..%d", first, first + count, s->R);
-    if (net && s->opts.enable_network_costs) return fail(RLGS_ERR_UNSUPPORTED, "network costs are not implemented for this schedule yet");
+    (void)net;
     CU(cudaSetDevice(s->device));
     TraceBuf tb;
     tb.n = n;
@@ -213,7 +243,10 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         if (old.first == first && old.count == count && n <= old.cap_n && tb.log_cap <= old.cap_log) {
             CU(cudaMemcpy(old.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice));
             old.n = n; old.log_cap = tb.log_cap; old.max_arrival = tb.max_arrival;
-            for (int r = 0; r < count; ++r) { s->h_desc[first + r].J = n; s->h_desc[first + r].log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff); }
+            for (int r = 0; r < count; ++r) {
+                s->h_desc[first + r].J = n; s->h_desc[first + r].log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
+                s->h_ldesc[first + r].J = n;
+            }
             s->ran = false;
             return RLGS_OK;
         }
@@ -224,86 +257,122 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     if (e != cudaSuccess) { cudaFree(tb.dev); return fail(RLGS_ERR_CUDA, "trace upload: %s", cudaGetErrorString(e)); }
     int tid = (int)s->traces.size();
     s->traces.push_back(tb);
-    // per-replica working set: stack | place_log | node_save | slot_save
-    int nw = 3 * s->cc.N + (s->cc.N + 31) / 32;
-    size_t per = align_up(sizeof(rlgs_job) * (size_t)n, 256) + align_up(sizeof(int2) * (size_t)std::max<int64_t>(tb.log_cap, 1), 256) +
-                 align_up(4 * (size_t)nw, 256) + align_up(sizeof(int4) * 2 * (size_t)s->slot_cap, 256);
     unsigned char *slab = nullptr;
-    CU(cudaMalloc(&slab, per * (size_t)count));
-    s->slabs.push_back(slab);
-    for (int r = 0; r < count; ++r) {
-        unsigned char *p = slab + per * (size_t)r;
-        RepDesc &D = s->h_desc[first + r];
-        D.trace = tb.dev; D.J = n; D.log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
-        D.stack = reinterpret_cast<rlgs_job *>(p); p += align_up(sizeof(rlgs_job) * (size_t)n, 256);
-        D.place_log = reinterpret_cast<int2 *>(p); p += align_up(sizeof(int2) * (size_t)std::max<int64_t>(tb.log_cap, 1), 256);
-        D.node_save = reinterpret_cast<int32_t *>(p); p += align_up(4 * (size_t)nw, 256);
-        D.slot_save = reinterpret_cast<int4 *>(p);
-        s->rep_trace[first + r] = tid;
+    if (!s->legacy) {
+        // per-replica working set: queue stack | placement log | node_save | slot_save
+        int nw = 3 * s->cc.N + (s->cc.N + 31) / 32;
+        size_t a0 = align_up(sizeof(rlgs_job) * (size_t)n, 256), a1 = align_up(sizeof(int2) * (size_t)std::max<int64_t>(tb.log_cap, 1), 256);
+        size_t a2 = align_up(4 * (size_t)nw, 256), a3 = align_up(sizeof(int4) * 2 * (size_t)s->slot_cap, 256);
+        size_t per = a0 + a1 + a2 + a3;
+        CU(cudaMalloc(&slab, per * (size_t)count));
+        for (int r = 0; r < count; ++r) {
+            unsigned char *p = slab + per * (size_t)r;
+            RepDesc &D = s->h_desc[first + r];
+            D.trace = tb.dev; D.J = n; D.log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
+            D.stack = reinterpret_cast<rlgs_job *>(p); p += a0;
+            D.place_log = reinterpret_cast<int2 *>(p); p += a1;
+            D.node_save = reinterpret_cast<int32_t *>(p); p += a2;
+            D.slot_save = reinterpret_cast<int4 *>(p);
+        }
+    } else {
+        // per-replica working set: 2 entry buffers | pending scratch | 2 demotion scratches | end list | placement scratch
+        size_t ae = align_up(sizeof(Ent) * (size_t)n, 256), al = align_up(4 * (size_t)n, 256), ap = align_up(sizeof(int2) * (size_t)s->cc.N, 256);
+        bool dlas = s->opts.schedule == RLGS_SCHED_DLAS_GPU;
+        size_t per = (dlas ? 5 : 1) * ae + al + ap;
+        CU(cudaMalloc(&slab, per * (size_t)count));
+        for (int r = 0; r < count; ++r) {
+            unsigned char *p = slab + per * (size_t)r;
+            LegDesc &D = s->h_ldesc[first + r];
+            D.trace = tb.dev; D.J = n; D.cap = n;
+            D.buf[0] = reinterpret_cast<Ent *>(p); p += ae;
+            if (dlas) {
+                D.buf[1] = reinterpret_cast<Ent *>(p); p += ae;
+                D.scratch_p = reinterpret_cast<Ent *>(p); p += ae;
+                D.scratch_d[0] = reinterpret_cast<Ent *>(p); p += ae;
+                D.scratch_d[1] = reinterpret_cast<Ent *>(p); p += ae;
+            } else {
+                D.buf[1] = D.scratch_p = D.scratch_d[0] = D.scratch_d[1] = nullptr;
+            }
+            D.end_list = reinterpret_cast<int32_t *>(p); p += al;
+            D.place_scratch = reinterpret_cast<int2 *>(p);
+        }
     }
+    s->slabs.push_back(slab);
+    for (int r = 0; r < count; ++r) s->rep_trace[first + r] = tid;
     s->ran = false;
     return RLGS_OK;
 }
 
-// (re)allocates the [4][R][Jmax] job-output arrays and points every replica at its rows
+// (re)allocates the [N_PLANES][R][Jmax] job-output arrays and points every replica at its rows
 static int32_t setup_job_arrays(rlgs_sim *s) {
     int32_t Jmax = 0;
     for (int r = 0; r < s->R; ++r) {
         if (s->rep_trace[r] < 0) return fail(RLGS_ERR_STATE, "replica %d has no trace (call rlgs_load_trace)", r);
-        Jmax = std::max(Jmax, s->h_desc[r].J);
+        Jmax = std::max(Jmax, s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J);
     }
     if (Jmax != s->Jmax || !s->d_jobs) {
         cudaFree(s->d_jobs); s->d_jobs = nullptr;
         if (s->h_jobs) { cudaFreeHost(s->h_jobs); s->h_jobs = nullptr; }
         s->Jmax = Jmax;
-        s->jobs_bytes = sizeof(int32_t) * 4 * (size_t)s->R * (size_t)Jmax;
+        s->jobs_bytes = sizeof(int32_t) * N_PLANES * (size_t)s->R * (size_t)Jmax;
         CU(cudaMalloc(&s->d_jobs, s->jobs_bytes));
     }
     size_t plane = (size_t)s->R * (size_t)Jmax;
     for (int r = 0; r < s->R; ++r) {
-        RepDesc &D = s->h_desc[r];
-        D.start_tick = s->d_jobs + 0 * plane + (size_t)r * Jmax;
-        D.end_tick = s->d_jobs + 1 * plane + (size_t)r * Jmax;
-        D.finish_order = s->d_jobs + 2 * plane + (size_t)r * Jmax;
-        D.place_off = s->d_jobs + 3 * plane + (size_t)r * Jmax;
+        if (!s->legacy) {
+            RepDesc &D = s->h_desc[r];
+            D.start_tick = s->d_jobs + 0 * plane + (size_t)r * Jmax;
+            D.end_tick = s->d_jobs + 1 * plane + (size_t)r * Jmax;
+            D.finish_order = s->d_jobs + 2 * plane + (size_t)r * Jmax;
+            D.place_off = s->d_jobs + 3 * plane + (size_t)r * Jmax;
+        } else {
+            for (int k = 0; k < N_PLANES; ++k) s->h_ldesc[r].planes[k] = s->d_jobs + k * plane + (size_t)r * Jmax;
+        }
     }
     return RLGS_OK;
 }
 
-// grows the device row store to `cap` ticks per replica, keeping the first `keep` rows of each replica
-static int32_t grow_device_rows(rlgs_sim *s, int64_t cap, int64_t keep) {
-    rlgs_row *nw = nullptr;
-    CU(cudaMalloc(&nw, sizeof(rlgs_row) * (size_t)cap * (size_t)s->R));
-    if (s->d_rows && keep > 0)
-        CU(cudaMemcpy2D(nw, sizeof(rlgs_row) * (size_t)cap, s->d_rows, sizeof(rlgs_row) * (size_t)s->rows_cap,
-                        sizeof(rlgs_row) * (size_t)keep, (size_t)s->R, cudaMemcpyDeviceToDevice));
-    cudaFree(s->d_rows);
-    s->d_rows = nw; s->rows_cap = cap;
-    return RLGS_OK;
-}
-
-static int32_t ensure_host_rows(rlgs_sim *s, int64_t cap) {
-    if (cap <= s->h_cap) return RLGS_OK;
-    if (s->h_rows) cudaFreeHost(s->h_rows);
-    s->h_rows = nullptr; s->h_cap = 0;
-    CU(cudaMallocHost(&s->h_rows, sizeof(rlgs_row) * (size_t)cap * (size_t)s->R));
-    s->h_cap = cap;
-    return RLGS_OK;
-}
-
-// enqueue the device->host copies of one group's results on its stream
-static int32_t enqueue_fetch(rlgs_sim *s, const Group &G, bool rows, bool jobs, int64_t width) {
-    if (rows && width > 0)
-        CU(cudaMemcpy2DAsync(s->h_rows + (size_t)G.first * s->h_cap, sizeof(rlgs_row) * (size_t)s->h_cap,
-                             s->d_rows + (size_t)G.first * s->rows_cap, sizeof(rlgs_row) * (size_t)s->rows_cap,
-                             sizeof(rlgs_row) * (size_t)width, (size_t)G.count, cudaMemcpyDeviceToHost, G.stream));
-    if (jobs) {
-        size_t plane = (size_t)s->R * (size_t)s->Jmax;
-        for (int k = 0; k < 4; ++k)
-            CU(cudaMemcpyAsync(s->h_jobs + k * plane + (size_t)G.first * s->Jmax, s->d_jobs + k * plane + (size_t)G.first * s->Jmax,
-                               sizeof(int32_t) * (size_t)G.count * (size_t)s->Jmax, cudaMemcpyDeviceToHost, G.stream));
+static int32_t add_chunks(rlgs_sim *s, int upto, bool host_too) {
+    if (upto > MAX_CHUNKS) return fail(RLGS_ERR_CAPACITY, "row store would exceed %d chunks", MAX_CHUNKS);
+    bool grew = false;
+    while ((int)s->d_chunks.size() < upto) {
+        rlgs_row *p = nullptr;
+        CU(cudaMalloc(&p, chunk_bytes(s)));
+        s->d_chunks.push_back(p); s->h_chunks.push_back(nullptr); s->h_chunk_valid.push_back(0);
+        grew = true;
     }
+    if (host_too)
+        for (int k = 0; k < upto; ++k)
+            if (!s->h_chunks[k]) CU(cudaMallocHost(&s->h_chunks[k], chunk_bytes(s)));
+    if (grew) CU(cudaMemcpy(s->d_chunk_ptrs, s->d_chunks.data(), sizeof(rlgs_row *) * s->d_chunks.size(), cudaMemcpyHostToDevice));
     return RLGS_OK;
+}
+
+static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cudaStream_t st) {
+    RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
+    if (!s->legacy) {
+        fifo_yarn_kernel<<<count, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, budget,
+                                                                                  rs, s->d_returns + first, s->opts.max_ticks);
+    } else {
+        LegParams lp = s->lp; lp.event_budget = budget;
+        if (s->opts.schedule == RLGS_SCHED_DLAS_GPU)
+            dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
+        else
+            sjf_yarn_kernel<<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
+    }
+}
+
+static Progress progress_of(const rlgs_sim *s, int r) {
+    Progress p;
+    if (!s->legacy) { p.rows = s->h_state[r].d; p.done = s->h_state[r].done; p.status = s->h_state[r].status; }
+    else { p.rows = s->h_lstate[r].n_rows; p.done = s->h_lstate[r].done; p.status = s->h_lstate[r].status; }
+    return p;
+}
+
+static cudaError_t get_event(rlgs_sim *s, size_t i, cudaEvent_t *out) {
+    while (s->ev_pool.size() <= i) { cudaEvent_t e; cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) return ce; s->ev_pool.push_back(e); }
+    *out = s->ev_pool[i];
+    return cudaSuccess;
 }
 
 extern "C" int32_t rlgs_run(rlgs_sim *s) {
@@ -315,165 +384,131 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     const int mode = s->opts.rows_mode;
     const bool rows = mode != RLGS_ROWS_NONE, eager_rows = mode == RLGS_ROWS_FULL, eager_jobs = s->opts.fetch_jobs != 0;
     const int R = s->R;
-    size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
-    if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
-    CU(cudaFuncSetAttribute(fifo_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
+    if (!s->legacy) {
+        size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
+        if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else if (s->opts.schedule == RLGS_SCHED_SJF) {
+        CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
+    }
     int32_t max_arrival = 0;
     for (int r = 0; r < R; ++r) {
-        RepState z; memset(&z, 0, sizeof z);
-        z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
-        z.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
-        z.free_hint = -1;
-        s->h_init[r] = z;
+        if (!s->legacy) {
+            RepState z; memset(&z, 0, sizeof z);
+            z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
+            z.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
+            z.free_hint = -1;
+            s->h_init[r] = z;
+        } else {
+            LegState z; memset(&z, 0, sizeof z);
+            z.next_end = RLGS_NEVER; z.next_jump = RLGS_NEVER;
+            s->h_linit[r] = z;
+        }
         max_arrival = std::max(max_arrival, s->traces[s->rep_trace[r]].max_arrival);
     }
-    if (rows && !s->d_rows) {
+    if (rows) {
         int64_t cap = s->opts.rows_cap > 0 ? s->opts.rows_cap : (int64_t)max_arrival + 4096;
-        rc = grow_device_rows(s, cap, 0);
+        int want = (int)std::max<int64_t>(1, (cap + RLGS_ROW_CHUNK - 1) / RLGS_ROW_CHUNK);
+        rc = add_chunks(s, std::max(want, (int)s->d_chunks.size()), eager_rows);
         if (rc) return rc;
     }
-    if (eager_rows) { rc = ensure_host_rows(s, s->rows_cap); if (rc) return rc; }
     if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
-    s->jobs_fetched = false; s->jobs_partial = false; s->rows_fetched = false; s->ran = false;
+    std::fill(s->h_chunk_valid.begin(), s->h_chunk_valid.end(), 0);
+    s->planes_on_host = 0; s->ran = false;
 
-    CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
-    CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, main_st));
+    if (!s->legacy) {
+        CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
+        CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, main_st));
+    } else {
+        CU(cudaMemcpyAsync(s->d_lstate, s->h_linit, sizeof(LegState) * R, cudaMemcpyHostToDevice, main_st));
+        CU(cudaMemcpyAsync(s->d_ldesc, s->h_ldesc.data(), sizeof(LegDesc) * R, cudaMemcpyHostToDevice, main_st));
+    }
     CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, main_st));
 
-    if (eager_rows && s->opts.ticks_per_launch == 0) {
-        // ---- pipelined path: launches bounded to PIPE_TICKS ticks; the rows of chunk k travel to the
-        // pinned host store on the copy stream while chunk k+1 is being simulated.  Nothing here waits
-        // on the host until every chunk is enqueued.
-        const int PIPE_TICKS = 8192;
-        size_t plane = (size_t)s->R * (size_t)s->Jmax;
-        int64_t next_tick = 0;
-        int launches = 0;
-        float total_ms = 0.f;
-        auto get_event = [&](size_t i, cudaEvent_t *out) -> cudaError_t {
-            while (s->ev_pool.size() <= i) { cudaEvent_t e; cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) return ce; s->ev_pool.push_back(e); }
-            *out = s->ev_pool[i];
-            return cudaSuccess;
-        };
-        for (;;) {
-            size_t ev_i = 0;
-            cudaEvent_t e_begin, e_last = nullptr;
-            CU(get_event(ev_i++, &e_begin));
+    const bool pipelined = eager_rows && s->opts.ticks_per_launch == 0;
+    const int budget = pipelined ? RLGS_ROW_CHUNK : (s->opts.ticks_per_launch > 0 ? s->opts.ticks_per_launch : (1 << 30));
+    float total_ms = 0.f;
+    int launches = 0;
+    int next_chunk = 0;   // pipelined: first chunk whose rows have not been sent to the host yet
+    for (;;) {
+        size_t ev_i = 0;
+        cudaEvent_t e_begin = nullptr, e_last = nullptr;
+        if (pipelined) {
+            // launches bounded to one row chunk; chunk k travels to the pinned host mirror on the copy stream
+            // while chunk k+1 is being simulated.  The host does not wait until everything is enqueued.
+            CU(get_event(s, ev_i++, &e_begin));
             CU(cudaEventRecord(e_begin, main_st));
-            for (; next_tick < s->rows_cap; next_tick += PIPE_TICKS) {
-                fifo_yarn_kernel<<<R, 32, smem, main_st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, PIPE_TICKS, s->d_rows, s->rows_cap,
-                                                          s->d_returns, s->opts.max_ticks);
+            for (; next_chunk < (int)s->d_chunks.size(); ++next_chunk) {
+                launch(s, 0, R, budget, true, main_st);
                 CU(cudaGetLastError());
                 launches++;
-                CU(get_event(ev_i++, &e_last));
+                CU(get_event(s, ev_i++, &e_last));
                 CU(cudaEventRecord(e_last, main_st));
                 CU(cudaStreamWaitEvent(s->copy_stream, e_last, 0));
-                int64_t w = std::min<int64_t>(PIPE_TICKS, s->rows_cap - next_tick);
-                CU(cudaMemcpy2DAsync(s->h_rows + next_tick, sizeof(rlgs_row) * (size_t)s->h_cap, s->d_rows + next_tick,
-                                     sizeof(rlgs_row) * (size_t)s->rows_cap, sizeof(rlgs_row) * (size_t)w, (size_t)R,
-                                     cudaMemcpyDeviceToHost, s->copy_stream));
+                CU(cudaMemcpyAsync(s->h_chunks[next_chunk], s->d_chunks[next_chunk], chunk_bytes(s), cudaMemcpyDeviceToHost, s->copy_stream));
+                s->h_chunk_valid[next_chunk] = 1;
             }
-            CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, main_st));
-            CU(cudaStreamSynchronize(main_st));
+        } else {
+            CU(cudaEventRecord(s->ev_fork, main_st));
+            for (auto &G : s->groups) {
+                CU(cudaStreamWaitEvent(G.stream, s->ev_fork, 0));
+                launch(s, G.first, G.count, budget, rows, G.stream);
+                CU(cudaGetLastError());
+                launches++;
+                CU(cudaEventRecord(G.k_end, G.stream));
+                CU(cudaStreamWaitEvent(main_st, G.k_end, 0));
+            }
+        }
+        if (!s->legacy) CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, main_st));
+        else CU(cudaMemcpyAsync(s->h_lstate, s->d_lstate, sizeof(LegState) * R, cudaMemcpyDeviceToHost, main_st));
+        CU(cudaStreamSynchronize(main_st));
+        if (pipelined) {
             float ms = 0.f;
             if (e_last) CU(cudaEventElapsedTime(&ms, e_begin, e_last));
             total_ms += ms;
-            bool all_done = true, overflow = false;
-            for (int r = 0; r < R; ++r) {
-                const RepState &z = s->h_state[r];
-                if (z.status == RLGS_ERR_CAPACITY && !(s->opts.max_ticks > 0 && z.d >= s->opts.max_ticks)) overflow = true;
-                if (!z.done) all_done = false;
-            }
-            if (overflow) { cudaStreamSynchronize(s->copy_stream); return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap); }
-            if (all_done) break;
-            // some replica filled the row store: double it (device and host) and keep going
-            CU(cudaStreamSynchronize(s->copy_stream));
-            int64_t old_cap = s->rows_cap;
-            rc = grow_device_rows(s, old_cap * 2, old_cap);
-            if (rc) return rc;
-            rlgs_row *old_h = s->h_rows; int64_t old_hcap = s->h_cap;
-            s->h_rows = nullptr; s->h_cap = 0;
-            rc = ensure_host_rows(s, s->rows_cap);
-            if (rc) { cudaFreeHost(old_h); return rc; }
-            for (int r = 0; r < R; ++r) memcpy(s->h_rows + (size_t)r * s->h_cap, old_h + (size_t)r * old_hcap, sizeof(rlgs_row) * (size_t)old_cap);
-            cudaFreeHost(old_h);
+        } else {
+            float wave = 0.f;
+            for (auto &G : s->groups) { float t = 0.f; CU(cudaEventElapsedTime(&t, s->ev_fork, G.k_end)); wave = std::max(wave, t); }
+            total_ms += wave;
         }
-        if (eager_jobs)
-            for (int k = 0; k < 3; ++k)   // start, end, finish_order (place_off stays on the device)
-                CU(cudaMemcpyAsync(s->h_jobs + k * plane, s->d_jobs + k * plane, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s->copy_stream));
-        CU(cudaStreamSynchronize(s->copy_stream));
-        s->rows_fetched = true; s->jobs_fetched = false; s->jobs_partial = eager_jobs;
-        s->last_ms = total_ms; s->last_launches = launches;
-        for (int r = 0; r < R; ++r) s->h_returns[r] = -s->h_state[r].sum_jct;
-        s->ran = true;
-        for (int r = 0; r < R; ++r)
-            if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
-        return RLGS_OK;
-    }
-    const int budget = s->opts.ticks_per_launch > 0 ? s->opts.ticks_per_launch : (1 << 30);
-    float total_ms = 0.f;
-    int launches = 0;
-    bool all_done = false, clean_single_pass = true;
-    while (!all_done) {
-        CU(cudaEventRecord(s->ev_fork, main_st));
-        for (auto &G : s->groups) {
-            CU(cudaStreamWaitEvent(G.stream, s->ev_fork, 0));
-            CU(cudaEventRecord(G.k_begin, G.stream));
-            fifo_yarn_kernel<<<G.count, 32, smem, G.stream>>>(s->d_desc + G.first, s->d_state + G.first, s->cc, s->slot_cap, budget,
-                                                             rows ? s->d_rows + (size_t)G.first * s->rows_cap : nullptr,
-                                                             s->rows_cap, s->d_returns + G.first, s->opts.max_ticks);
-            CU(cudaGetLastError());
-            CU(cudaEventRecord(G.k_end, G.stream));
-            CU(cudaMemcpyAsync(s->h_state + G.first, s->d_state + G.first, sizeof(RepState) * G.count, cudaMemcpyDeviceToHost, G.stream));
-            if (launches == 0 && s->opts.ticks_per_launch == 0) {
-                // optimistic: results of this group go to the host as soon as its kernel ends, while the
-                // other groups still compute; redone below if a replica had to be continued
-                rc = enqueue_fetch(s, G, eager_rows, eager_jobs, std::min(s->rows_cap, s->h_cap));
-                if (rc) return rc;
-            }
-        }
-        launches++;
-        for (auto &G : s->groups) CU(cudaStreamSynchronize(G.stream));
-        float wave_ms = 0.f;
-        for (auto &G : s->groups) {
-            float t0 = 0.f, t1 = 0.f;
-            CU(cudaEventElapsedTime(&t0, s->ev_fork, G.k_begin));
-            CU(cudaEventElapsedTime(&t1, s->ev_fork, G.k_end));
-            wave_ms = std::max(wave_ms, t1);
-            (void)t0;
-        }
-        total_ms += wave_ms;
-        all_done = true;
-        bool overflow = false, rows_full = false;
+        bool all_done = true, overflow = false, rows_full = false;
+        int bad = -1;
         for (int r = 0; r < R; ++r) {
-            const RepState &z = s->h_state[r];
-            if (z.status == RLGS_ERR_CAPACITY && !(s->opts.max_ticks > 0 && z.d >= s->opts.max_ticks)) overflow = true;
-            if (!z.done) { all_done = false; if (rows && z.d >= s->rows_cap) rows_full = true; }
+            Progress p = progress_of(s, r);
+            if (p.status == RLGS_ERR_CAPACITY) { overflow = true; bad = r; }
+            if (!p.done) { all_done = false; if (rows && p.rows >= (int64_t)s->d_chunks.size() * RLGS_ROW_CHUNK) rows_full = true; }
         }
-        if (overflow) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap);
-        if (!all_done) clean_single_pass = false;
-        if (rows_full) {
-            rc = grow_device_rows(s, s->rows_cap * 2, s->rows_cap);
+        if (overflow) {
+            cudaStreamSynchronize(s->copy_stream);
+            if (s->opts.max_ticks > 0) return fail(RLGS_ERR_CAPACITY, "replica %d reached max_ticks", bad);
+            if (!s->legacy) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap);
+            return fail(RLGS_ERR_CAPACITY, "replica %d: runnable-entry table overflow", bad);
+        }
+        if (all_done) break;
+        if (rows_full) {   // a replica filled the allocated chunks: add some and keep going (state is saved on the device)
+            rc = add_chunks(s, (int)s->d_chunks.size() + std::max(1, (int)s->d_chunks.size() / 2), eager_rows);
             if (rc) return rc;
         }
     }
-    if (!clean_single_pass || s->opts.ticks_per_launch != 0) {
-        // continued run: fetch everything now
-        if (eager_rows) { rc = ensure_host_rows(s, s->rows_cap); if (rc) return rc; }
-        for (auto &G : s->groups) {
-            int64_t w = 0;
-            for (int r = G.first; r < G.first + G.count; ++r) w = std::max<int64_t>(w, s->h_state[r].d);
-            rc = enqueue_fetch(s, G, eager_rows, eager_jobs, w);
-            if (rc) return rc;
+    if (eager_rows && !pipelined) {
+        for (size_t k = 0; k < s->d_chunks.size(); ++k) {
+            CU(cudaMemcpyAsync(s->h_chunks[k], s->d_chunks[k], chunk_bytes(s), cudaMemcpyDeviceToHost, s->copy_stream));
+            s->h_chunk_valid[k] = 1;
         }
-        for (auto &G : s->groups) CU(cudaStreamSynchronize(G.stream));
     }
-    s->rows_fetched = eager_rows; s->jobs_fetched = eager_jobs;
-    s->last_ms = total_ms; s->last_launches = launches * (int)s->groups.size();
-    for (int r = 0; r < R; ++r) s->h_returns[r] = -s->h_state[r].sum_jct;
+    if (eager_jobs) {
+        size_t plane = (size_t)R * (size_t)s->Jmax;
+        CU(cudaMemcpyAsync(s->h_jobs, s->d_jobs, sizeof(int32_t) * 3 * plane, cudaMemcpyDeviceToHost, s->copy_stream));  // start, end, finish_order
+        s->planes_on_host = 3;
+    }
+    CU(cudaStreamSynchronize(s->copy_stream));
+    s->last_ms = total_ms; s->last_launches = launches;
+    for (int r = 0; r < R; ++r) s->h_returns[r] = -(s->legacy ? s->h_lstate[r].sum_jct : s->h_state[r].sum_jct);
     s->ran = true;
-    for (int r = 0; r < R; ++r)
-        if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
+    for (int r = 0; r < R; ++r) {
+        Progress p = progress_of(s, r);
+        if (p.status != RLGS_OK) return fail(p.status, "replica %d stopped with status %d after %lld rows", r, p.status, (long long)p.rows);
+    }
     return RLGS_OK;
 }
 
@@ -488,32 +523,42 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
-    const RepState &z = s->h_state[r];
     memset(out, 0, sizeof *out);
-    out->n_ticks = z.d; out->makespan = z.d; out->sum_jct = z.sum_jct; out->sum_queued = z.sumQ; out->sum_running = z.sumR;
-    out->events = z.events; out->n_jobs = s->h_desc[r].J; out->n_arrived = z.cursor; out->n_started = z.start_seq;
-    out->n_finished = z.F; out->max_queued = z.max_q; out->max_running = z.max_r; out->status = z.status; out->done = z.done;
+    if (!s->legacy) {
+        const RepState &z = s->h_state[r];
+        out->n_ticks = z.d; out->makespan = z.d; out->sum_jct = z.sum_jct; out->sum_queued = z.sumQ; out->sum_running = z.sumR;
+        out->events = z.events; out->n_jobs = s->h_desc[r].J; out->n_arrived = z.cursor; out->n_started = z.start_seq;
+        out->n_finished = z.F; out->max_queued = z.max_q; out->max_running = z.max_r; out->status = z.status; out->done = z.done;
+    } else {
+        const LegState &z = s->h_lstate[r];
+        out->n_ticks = z.n_rows; out->makespan = z.t_prev; out->sum_jct = z.sum_jct; out->sum_queued = z.sweep_jobs; out->sum_running = z.demotions;
+        out->events = z.events; out->n_jobs = s->h_ldesc[r].J; out->n_arrived = z.cursor; out->n_started = 0;
+        out->n_finished = z.F; out->max_queued = z.max_m; out->max_running = 0; out->status = z.status; out->done = z.done;
+    }
     return RLGS_OK;
 }
 
-static int32_t fetch_jobs(rlgs_sim *s) {
-    if (s->jobs_fetched) return RLGS_OK;
+static int32_t fetch_planes(rlgs_sim *s, int upto) {
+    if (s->planes_on_host >= upto) return RLGS_OK;
     if (!s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
-    CU(cudaMemcpy(s->h_jobs, s->d_jobs, s->jobs_bytes, cudaMemcpyDeviceToHost));
-    s->jobs_fetched = true;
+    size_t plane = (size_t)s->R * (size_t)s->Jmax;
+    CU(cudaMemcpy(s->h_jobs + s->planes_on_host * plane, s->d_jobs + s->planes_on_host * plane,
+                  sizeof(int32_t) * (size_t)(upto - s->planes_on_host) * plane, cudaMemcpyDeviceToHost));
+    s->planes_on_host = upto;
     return RLGS_OK;
 }
 
-static int32_t fetch_rows(rlgs_sim *s) {
-    if (s->rows_fetched) return RLGS_OK;
-    int32_t rc = ensure_host_rows(s, s->rows_cap);
+extern "C" int32_t rlgs_read_job_plane(rlgs_sim *s, int32_t r, int32_t plane_id, int32_t *out) {
+    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
+    if (r < 0 || r >= s->R || plane_id < 0 || plane_id >= N_PLANES) return fail(RLGS_ERR_BAD_ARG, "replica / plane out of range");
+    if (!s->legacy && plane_id > RLGS_PLANE_AUX) return fail(RLGS_ERR_BAD_ARG, "plane %d is only recorded by the preemptive schedules", plane_id);
+    CU(cudaSetDevice(s->device));
+    int32_t rc = fetch_planes(s, plane_id + 1 <= 3 ? 3 : N_PLANES);
     if (rc) return rc;
-    int64_t w = 0;
-    for (int r = 0; r < s->R; ++r) w = std::max<int64_t>(w, s->h_state[r].d);
-    if (w > 0)
-        CU(cudaMemcpy2D(s->h_rows, sizeof(rlgs_row) * (size_t)s->h_cap, s->d_rows, sizeof(rlgs_row) * (size_t)s->rows_cap,
-                        sizeof(rlgs_row) * (size_t)w, (size_t)s->R, cudaMemcpyDeviceToHost));
-    s->rows_fetched = true;
+    size_t plane = (size_t)s->R * (size_t)s->Jmax;
+    int J = s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J;
+    memcpy(out, s->h_jobs + plane_id * plane + (size_t)r * s->Jmax, 4 * (size_t)J);
     return RLGS_OK;
 }
 
@@ -523,46 +568,65 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     CU(cudaSetDevice(s->device));
-    if (!(s->jobs_partial && !first_node)) {
-        int32_t rc = fetch_jobs(s);
-        if (rc) return rc;
-    }
+    int32_t rc = fetch_planes(s, (first_node || (preempt && s->legacy)) ? N_PLANES : 3);
+    if (rc) return rc;
     size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
-    int J = s->h_desc[r].J;
-    const int32_t *st = s->h_jobs + off, *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off, *po = s->h_jobs + 3 * plane + off;
+    int J = s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J;
+    const int32_t *st = s->h_jobs + off, *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off;
     if (start_tick) memcpy(start_tick, st, 4 * (size_t)J);
     if (end_tick) memcpy(end_tick, en, 4 * (size_t)J);
     if (finish_order) memcpy(finish_order, fo, 4 * (size_t)J);
-    if (preempt) for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171, q6)
-    if (first_node) {
-        // first placement-log entry of every started job (node index), for placement parity tests
-        std::vector<int2> log((size_t)std::max(1, s->h_state[r].log_len));
-        if (s->h_state[r].log_len > 0)
-            CU(cudaMemcpy(log.data(), s->h_desc[r].place_log, sizeof(int2) * (size_t)s->h_state[r].log_len, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < J; ++i) first_node[i] = (po[i] >= 0 && po[i] < s->h_state[r].log_len) ? (log[po[i]].x & 0xffff) : -1;
+    if (preempt) {
+        if (s->legacy) memcpy(preempt, s->h_jobs + 4 * plane + off, 4 * (size_t)J);
+        else for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171, q6)
     }
-    return RLGS_OK;
-}
-
-extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, const rlgs_row **rows, int64_t *count) {
-    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
-    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
-    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
-    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
-    CU(cudaSetDevice(s->device));
-    int32_t rc = fetch_rows(s);
-    if (rc) return rc;
-    *rows = s->h_rows + (size_t)r * s->h_cap;
-    *count = s->h_state[r].d;
+    if (first_node) {
+        if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "placements are recomputed at every event under the preemptive schedules");
+        const int32_t *po = s->h_jobs + 3 * plane + off;
+        int ll = s->h_state[r].log_len;
+        std::vector<int2> log((size_t)std::max(1, ll));
+        if (ll > 0) CU(cudaMemcpy(log.data(), s->h_desc[r].place_log, sizeof(int2) * (size_t)ll, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < J; ++i) first_node[i] = (po[i] >= 0 && po[i] < ll) ? (log[po[i]].x & 0xffff) : -1;
+    }
     return RLGS_OK;
 }
 
 extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
-    const rlgs_row *rows; int64_t n;
-    int32_t rc = rlgs_rows_view(s, r, &rows, &n);
-    if (rc) return rc;
-    if (!out || first < 0 || count < 0 || first + count > n) return fail(RLGS_ERR_BAD_ARG, "row range [%lld,%lld) out of 0..%lld", (long long)first, (long long)(first + count), (long long)n);
-    memcpy(out, rows + first, sizeof(rlgs_row) * (size_t)count);
+    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
+    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
+    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
+    int64_t n = progress_of(s, r).rows;
+    if (first < 0 || count < 0 || first + count > n) return fail(RLGS_ERR_BAD_ARG, "row range [%lld,%lld) out of 0..%lld", (long long)first, (long long)(first + count), (long long)n);
+    CU(cudaSetDevice(s->device));
+    int64_t done = 0;
+    while (done < count) {
+        int64_t i = first + done;
+        int k = (int)(i >> RLGS_ROW_CHUNK_LOG);
+        int64_t off = i & (RLGS_ROW_CHUNK - 1), len = std::min<int64_t>(count - done, RLGS_ROW_CHUNK - off);
+        size_t pos = ((size_t)r << RLGS_ROW_CHUNK_LOG) + (size_t)off;
+        if (s->h_chunk_valid[k]) memcpy(out + done, s->h_chunks[k] + pos, sizeof(rlgs_row) * (size_t)len);
+        else CU(cudaMemcpy(out + done, s->d_chunks[k] + pos, sizeof(rlgs_row) * (size_t)len, cudaMemcpyDeviceToHost));
+        done += len;
+    }
+    return RLGS_OK;
+}
+
+extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
+    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
+    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
+    int64_t n = progress_of(s, r).rows;
+    if (chunk < 0 || (int64_t)chunk * RLGS_ROW_CHUNK >= std::max<int64_t>(n, 1)) return fail(RLGS_ERR_BAD_ARG, "chunk %d out of range", chunk);
+    CU(cudaSetDevice(s->device));
+    if (!s->h_chunk_valid[chunk]) {
+        if (!s->h_chunks[chunk]) CU(cudaMallocHost(&s->h_chunks[chunk], chunk_bytes(s)));
+        CU(cudaMemcpy(s->h_chunks[chunk], s->d_chunks[chunk], chunk_bytes(s), cudaMemcpyDeviceToHost));
+        s->h_chunk_valid[chunk] = 1;
+    }
+    *rows = s->h_chunks[chunk] + ((size_t)r << RLGS_ROW_CHUNK_LOG);
+    *count = std::min<int64_t>(RLGS_ROW_CHUNK, n - (int64_t)chunk * RLGS_ROW_CHUNK);
     return RLGS_OK;
 }
 

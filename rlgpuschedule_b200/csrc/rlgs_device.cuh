@@ -58,6 +58,18 @@ struct ClusterConst {
     int32_t D;             // N*G
 };
 
+// chunk-major row store shared by all kernels: row i of replica r lives in chunk i / RLGS_ROW_CHUNK
+#define RLGS_ROW_CHUNK_LOG 13
+#define RLGS_ROW_CHUNK (1 << RLGS_ROW_CHUNK_LOG)
+struct RowStore {
+    rlgs_row *const *chunks;  // device array of chunk base pointers, each [n_replicas][RLGS_ROW_CHUNK]
+    int32_t n_chunks;
+    int32_t replica;          // global replica index of blockIdx.x == 0
+};
+__device__ __forceinline__ rlgs_row *row_ptr(const RowStore &rs, int replica_local, int64_t i) {
+    return rs.chunks[i >> RLGS_ROW_CHUNK_LOG] + ((size_t)(rs.replica + replica_local) << RLGS_ROW_CHUNK_LOG) + (i & (RLGS_ROW_CHUNK - 1));
+}
+
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // mask of the k lowest set bits of `freemask` (devices are taken in device-id order, node.py:209-219)

@@ -119,14 +119,27 @@ class Simulator(object):
             out['first_node'] = fn
         return out
 
-    def rows_view(self, replica=0):
-        """Zero-copy numpy view of the replica's rows in the handle's pinned host store."""
+    def rows(self, replica=0):
+        """All rows of a replica as one numpy array (copied out of the chunk-major store)."""
+        n = self.summary(replica)['n_ticks']
+        out = np.zeros(n, _ffi.ROW_DTYPE)
+        if n:
+            _ffi.check(_ffi.lib().rlgs_read_rows(self._h, replica, 0, n, out.ctypes.data))
+        return out
+
+    rows_view = rows
+
+    def rows_chunk_view(self, replica, chunk):
+        """Zero-copy numpy view of one 8192-row chunk of a replica in the pinned host mirror."""
         p, n = C.c_void_p(), C.c_int64(0)
-        _ffi.check(_ffi.lib().rlgs_rows_view(self._h, replica, C.byref(p), C.byref(n)))
-        if n.value == 0:
-            return np.zeros(0, _ffi.ROW_DTYPE)
+        _ffi.check(_ffi.lib().rlgs_rows_view(self._h, replica, chunk, C.byref(p), C.byref(n)))
         buf = (C.c_char * (n.value * _ffi.ROW_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=_ffi.ROW_DTYPE, count=n.value)
+
+    def job_plane(self, replica, plane):
+        out = np.empty(len(self.trace_of(replica)), np.int32)
+        _ffi.check(_ffi.lib().rlgs_read_job_plane(self._h, replica, plane, out.ctypes.data))
+        return out
 
     def returns(self):
         out = np.empty(self.n_replicas, np.int64)
