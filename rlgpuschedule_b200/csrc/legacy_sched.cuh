@@ -115,6 +115,16 @@ __device__ __forceinline__ unsigned admit_chunk(int g, bool valid, int &free_gpu
     return adm;
 }
 
+// Jobs that never end (they never fit) still report their counters, like LOG would at shutdown.
+__device__ __forceinline__ void flush_unfinished(const LegDesc &D, const Ent *buf, int M, int lane) {
+    for (int i = lane; i < M; i += 32) {
+        Ent e = load_ent(buf + i);
+        D.planes[3][e.job()] = e.b.y;
+        D.planes[4][e.job()] = e.b.z & 0xffff;
+        D.planes[5][e.job()] = (e.b.z >> 16) & 0xffff;
+    }
+}
+
 struct DlasEvent {
     int time, d, q, nq;
     int free_gpu, n_run, n_pend;
@@ -304,9 +314,9 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
         }
         st.events += ev.events + ev.ne + k_arr;
         st.demotions += ev.demotions;
-        st.sweep_jobs += st.M;
         for (int q = 0; q < P.nq; ++q) st.qlen[q] = new_qlen[q];
         st.M = ev.n_run + ev.n_pend;
+        st.sweep_jobs += st.M;   // runnable jobs swept at this event (after ends left and arrivals joined)
         if (st.M > st.max_m) st.max_m = st.M;
         st.cursor += k_arr;
         st.cur ^= 1;
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
         st.n_rows += 1;
         __syncwarp();
     }
+    if (st.done) flush_unfinished(D, D.buf[st.cur], st.M, lane);
     if (lane == 0) {
         states[blockIdx.x] = st;
         if (st.done) returns[blockIdx.x] = -st.sum_jct;
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
             w_out += __popc(kb);
             __syncwarp();
         }
-        st.sweep_jobs += M0;
+        st.sweep_jobs += w_out;  // runnable jobs swept at this event (after ends left and arrivals joined)
         st.M = w_out;
         if (st.M > st.max_m) st.max_m = st.M;
         st.events += n_events;
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
         st.n_rows += 1;
         __syncwarp();
     }
+    if (st.done) flush_unfinished(D, buf, st.M, lane);
     if (lane == 0) {
         states[blockIdx.x] = st;
         if (st.done) returns[blockIdx.x] = -st.sum_jct;

@@ -23,7 +23,7 @@ class Simulator(object):
             raise NotImplementedError('placement scheme %r has no device implementation' % (scheme,))
         self.cluster = cluster
         self.n_replicas = n_replicas
-        self.rows = rows
+        self.rows_mode = rows
         self._kw = dict(schedule=schedule, scheme=scheme, rows=rows, device=device, n_streams=n_streams,
                         ticks_per_launch=ticks_per_launch, rows_cap=rows_cap, fetch_jobs=fetch_jobs,
                         num_queue=num_queue, queue_limit=tuple(queue_limit), max_ticks=max_ticks,
