@@ -187,6 +187,22 @@ int32_t rlgs_returns(rlgs_sim *sim, int64_t *out_n_replicas);
 /* Device pointer to the same int64[n_replicas] buffer (the NCCL all-gather send buffer). */
 int32_t rlgs_returns_device_ptr(rlgs_sim *sim, void **dev_ptr);
 
+/*
+ * Vectorised RL environment: replaces the reference's stub model/env.py:1-6 (Environment.step(action): pass);
+ * semantics are build-defined (DESIGN.md "Environment").  One step = one scheduler tick of every replica of a
+ * fifo/yarn handle; the action picks which of the first `window_k` queued jobs gets the tick's placement
+ * attempt (-1 = none).  policy 0 = queue head, 1 = random window (counter-based RNG keyed by seed, replica,
+ * tick; n_ticks may be > 1 to roll whole episodes on the device), 2 = actions[] (n_ticks = 1).
+ * obs [n_replicas][obs_dim]: free GPUs / free cpu / free mem per node, (gpus, tasks, dur_ticks, pending) of the
+ * window jobs, then queued, running, finished, tick.  reward = -(queued + running) per tick.  All pointers
+ * are DEVICE pointers; calls are asynchronous on the handle's stream until rlgs_env_sync.
+ */
+int32_t rlgs_env_obs_dim(rlgs_sim *sim, int32_t window_k, int32_t *dim);
+int32_t rlgs_env_reset(rlgs_sim *sim);
+int32_t rlgs_env_step(rlgs_sim *sim, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                      int32_t policy, int32_t window_k, uint32_t seed, int32_t n_ticks);
+int32_t rlgs_env_sync(rlgs_sim *sim);
+
 #ifdef __cplusplus
 }
 #endif

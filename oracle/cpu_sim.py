@@ -217,3 +217,31 @@ def format_legacy_job_csv(tr, res, count_scheme):
                int(res['pending'][i]), int(res['preempt'][i])] + ([int(res['resume'][i])] if count_scheme else []) + [0]
         w.writerow(row)
     return buf.getvalue()
+
+
+def run_env_yarn(cluster, tr, policy, window_k=5, seed=0, replica=0, actions=None, rows_cap=None):
+    """Build-defined RL environment semantics on the CPU (oracle_env_yarn). policy: 0 head, 1 random window,
+    2 = `actions` tape (one action per tick).  PARITY UNPINNED (model/env.py is a stub in the reference)."""
+    L = lib()
+    n = len(tr['nt'])
+    fin = np.empty(max(n, 1), np.int32); st = np.empty(max(n, 1), np.int32); en = np.empty(max(n, 1), np.int32)
+    nfin = C.c_int32(0); nticks = C.c_int64(0); counters = np.zeros(4, np.int64)
+    acts = np.ascontiguousarray(actions, np.int32) if actions is not None else np.zeros(1, np.int32)
+    cap = rows_cap or max(4096, 4 * n)
+    while True:
+        rows = np.zeros(cap, ROW_DTYPE)
+        rc = L.oracle_env_yarn(C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
+                               _p(tr['used_gpus'], C.c_double), _p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double),
+                               _p(tr['util_avg'], C.c_double), C.c_int32(policy), C.c_int32(window_k), C.c_uint32(seed),
+                               C.c_uint32(replica), _p(acts, C.c_int32), C.c_int64(len(acts) if actions is not None else 0),
+                               _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32), C.byref(nfin),
+                               rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc != 0:
+            raise RuntimeError('oracle_env_yarn rc=%d' % rc)
+        break
+    k = nfin.value
+    return dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
+                counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]), starts=int(counters[3])))

@@ -1,0 +1,87 @@
+"""Scheduling / placement / post-tick plugin registries with the reference's surface
+(core/scheduling/algorithm.py of the reference):
+
+    scheduling_algorithms[name](scheme, placement_algo, infrastructure, jobs_manager, delta, **kwargs{k})
+        -> (nodes | None, job | None, success | None)                       algorithm.py:189-298, call site schedule.py:45-47
+    placement_algorithms[name](infrastructure, next_job, scheme) -> (nodes, success)      algorithm.py:28-32,182-187
+    plugin_algorithms[name](infrastructure, jobs_manager)                   algorithm.py:420-444, call site schedule.py:200-202
+    score_fn[name](node, task)                                              algorithm.py:9-13
+
+The entries the hot path implements are DevicePolicy objects: Scheduler.start() hands their integer
+id to librlgs and the whole tick / event loop runs on the GPU.  The reference's other keys (horus,
+horus+, gandiva: RNG-driven packing heuristics) are registered as HostOnlyPolicy so the
+key set is unchanged and selecting them fails loudly instead of silently running something else.
+Users may register their own entries; only DevicePolicy entries can be executed by this package.
+"""
+from . import _ffi
+
+
+class DevicePolicy(object):
+    """A policy executed inside the CUDA kernels (rlgpuschedule_b200/csrc)."""
+
+    def __init__(self, name, kind, device_id, reference):
+        self.name, self.kind, self.device_id, self.reference = name, kind, device_id, reference
+
+    def __call__(self, *args, **kwargs):
+        raise RuntimeError('%s policy %r runs on the device as part of Scheduler.start(); it has no per-call '
+                           'host implementation' % (self.kind, self.name))
+
+    def __repr__(self):
+        return 'DevicePolicy(%s %r, id %d, restates %s)' % (self.kind, self.name, self.device_id, self.reference)
+
+
+class HostOnlyPolicy(object):
+    """A reference policy that has no device implementation yet ('what comes next')."""
+
+    def __init__(self, name, kind, reference):
+        self.name, self.kind, self.reference = name, kind, reference
+
+    def __call__(self, *args, **kwargs):
+        raise NotImplementedError('%s policy %r (%s) is not implemented by the device path' % (self.kind, self.name, self.reference))
+
+    def __repr__(self):
+        return 'HostOnlyPolicy(%s %r)' % (self.kind, self.name)
+
+
+scheduling_algorithms = {
+    'fifo': DevicePolicy('fifo', 'schedule', _ffi.SCHED['fifo'], 'core/scheduling/algorithm.py:189-202'),
+    'sjf': DevicePolicy('sjf', 'schedule', _ffi.SCHED['sjf'], 'run_sim.py:162-287 (dead code, restated)'),
+    'dlas-gpu': DevicePolicy('dlas-gpu', 'schedule', _ffi.SCHED['dlas-gpu'], 'run_sim.py:664-947 (dead code, restated)'),
+    'horus': HostOnlyPolicy('horus', 'schedule', 'core/scheduling/algorithm.py:204-240'),
+    'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
+    'gandiva': HostOnlyPolicy('gandiva', 'schedule', 'core/scheduling/algorithm.py:292-298 + time_slice_check :420-440'),
+}
+
+placement_algorithms = {
+    'yarn': DevicePolicy('yarn', 'placement', _ffi.PLACE['yarn'], 'core/scheduling/algorithm.py:28-32,301-417'),
+    'count': DevicePolicy('count', 'placement', _ffi.PLACE['count'], 'run_sim.py:808-823 (free_gpu counting)'),
+    'horus': HostOnlyPolicy('horus', 'placement', 'core/scheduling/algorithm.py:34-180'),
+    'horus+': HostOnlyPolicy('horus+', 'placement', 'core/scheduling/algorithm.py:34-180'),
+    'gandiva': HostOnlyPolicy('gandiva', 'placement', 'core/scheduling/algorithm.py:34-180'),
+}
+
+plugin_algorithms = {
+    'gandiva': HostOnlyPolicy('gandiva', 'post-tick plugin', 'core/scheduling/algorithm.py:420-440'),
+}
+
+score_fn = {
+    'horus': HostOnlyPolicy('horus', 'score', 'core/scheduling/horus.py:28-56'),
+    'horus+': HostOnlyPolicy('horus+', 'score', 'core/scheduling/horus.py:28-56'),
+    'gandiva': HostOnlyPolicy('gandiva', 'score', 'core/scheduling/horus.py:6-25'),
+}
+
+
+def resolve(schedule, scheme):
+    """(schedule name, scheme name) -> (DevicePolicy, DevicePolicy) or raises like the reference would
+    (KeyError for unknown keys, NotImplementedError for host-only ones)."""
+    sched = scheduling_algorithms[schedule]
+    place = placement_algorithms[scheme]
+    for p in (sched, place):
+        if not isinstance(p, DevicePolicy):
+            if isinstance(p, HostOnlyPolicy):
+                p()  # raises NotImplementedError with the reference location
+            raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
+    post = plugin_algorithms.get(schedule, None)
+    if post is not None and not isinstance(post, DevicePolicy):
+        post()
+    return sched, place

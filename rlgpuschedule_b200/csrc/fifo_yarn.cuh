@@ -140,15 +140,42 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
     __syncwarp();
 }
 
+// Inputs / outputs of the vectorised RL environment (ENV instantiation of the kernel).  Build-defined
+// semantics (the reference's model/env.py:1-6 is an empty stub): one step = one scheduler tick; the
+// action picks which of the first `window_k` queued jobs gets this tick's placement attempt
+// (cf. the k-job look-ahead window of schedule_horus, algorithm.py:204-240); -1 = no attempt.
+struct EnvIO {
+    const int32_t *actions;   // [replicas] action of this step (policy 2), device memory
+    float *obs;               // [replicas][obs_dim]
+    float *reward;            // [replicas]  -(queued + running) summed over the ticks of this launch
+    uint8_t *done;            // [replicas]
+    int32_t policy;           // 0 = queue head (fifo), 1 = random window (counter-based RNG), 2 = actions[]
+    int32_t window_k;
+    uint32_t seed;
+    int32_t obs_dim;          // 3N + 4*window_k + 4
+};
+
+__device__ __forceinline__ uint32_t rlgs_hash3(uint32_t seed, uint32_t replica, uint32_t tick) {
+    // splitmix64 finaliser of (seed, replica, tick); same function as oracle/cpu_sim.c
+    uint64_t z = ((uint64_t)seed << 32) ^ ((uint64_t)replica * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)tick * 0xBF58476D1CE4E5B9ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+template <bool ENV>
 __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
                                                        ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
-                                                       int64_t *__restrict__ returns, int64_t max_ticks) {
+                                                       int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
     const RepDesc D = descs[blockIdx.x];
     RepState st = states[blockIdx.x];
-    if (st.done || st.status != RLGS_OK) return;
+    if (st.done || st.status != RLGS_OK) {
+        if (ENV && lane == 0) { env.reward[blockIdx.x] = 0.f; env.done[blockIdx.x] = 1; }
+        return;
+    }
     FifoSmem s = fifo_carve(smem_raw, c.N, slot_cap);
+    float reward_acc = 0.f;
     const bool rows_mode = rs.chunks != nullptr;
     // device-resident chunk-major row store: a launch stops when the allocated chunks are full
     if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
@@ -234,7 +261,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
         }
 
         // ---------------- one scheduling attempt on the queue head (schedule.py:188-190)
-        if (st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked) {
+        if (!ENV && st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked) {
             PlaceResult pr = yarn_place(s.nv, c, h0, lane, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
             if (pr.ok) {
                 int job = h0.index();
@@ -272,6 +299,57 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                 __syncwarp();
             } else if (h0.fits()) {
                 st.head_blocked = 1;  // a failed attempt has no side effect: skip retries until a release
+            }
+        }
+
+        if (ENV && st.Q > 0) {
+            // ---------------- environment: the policy picks a job inside the look-ahead window
+            const int win = min(st.Q, env.window_k);
+            int pick = 0;
+            if (env.policy == 1) pick = (int)(rlgs_hash3(env.seed, (uint32_t)(rs.replica + blockIdx.x), (uint32_t)d) % (uint32_t)win);
+            else if (env.policy == 2) pick = env.actions[blockIdx.x];
+            if (pick >= 0 && pick < win && st.n_free_nodes >= 1) {
+                JobRec hx = load_rec(D.stack + st.head + pick);
+                PlaceResult pr = yarn_place(s.nv, c, hx, lane, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
+                if (pr.ok) {
+                    int job = hx.index();
+                    int ndev = hx.tasks() * hx.gpc();
+                    int sl = st.free_hint;
+                    if (sl < 0) { sl = st.hw; }
+                    if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
+                    if (sl == st.hw) st.hw += 1;
+                    st.free_hint = -1;
+                    if (lane == 0) {
+                        s.sv.end[sl] = d + hx.dur();
+                        s.sv.job[sl] = job;
+                        s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (hx.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
+                        s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
+                        s.sv.seq[sl] = st.start_seq;
+                        s.sv.util[sl] = hx.util();
+                        s.sv.memterm[sl] = hx.mem_term();
+                        D.start_tick[job] = d;
+                        D.place_off[job] = st.log_len;
+                    }
+                    st.log_len += pr.nnodes;
+                    st.start_seq += 1;
+                    st.busy_gpus += ndev;
+                    st.mem_sum += hx.mem_term() * ndev;
+                    int64_t mu = hx.util() & 0xffff, sd = hx.util() >> 16;
+                    st.util_mu_sum += mu * ndev;
+                    st.util_var_sum += sd * sd * ndev;
+                    st.sum_arr -= hx.arrival();
+                    st.sum_jct += (int64_t)(d + hx.dur() - hx.arrival());
+                    // queue.pop(pick): entries in front of it move one place towards the back of the stack
+                    JobRec mv; bool m = lane < pick;
+                    if (m) mv = load_rec(D.stack + st.head + lane);
+                    __syncwarp();
+                    if (m) store_rec(D.stack + st.head + lane + 1, mv);
+                    __syncwarp();
+                    st.R += 1; st.Q -= 1; st.head += 1;
+                    st.events += 1;
+                    if (st.R > st.max_r) st.max_r = st.R;
+                    if (st.Q > 0) st.bottom_arr = D.stack[st.head + st.Q - 1].arrival_tick;
+                }
             }
         }
 
@@ -323,6 +401,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
 
         // ---------------- stats row (schedule.py:204-205)
         st.sumQ += st.Q; st.sumR += st.R;
+        if (ENV) reward_acc -= (float)(st.Q + st.R);
         if (rows_mode && lane == 0) {
             rlgs_row *row = row_ptr(rs, blockIdx.x, st.d - 1);
             int4 w0 = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
@@ -337,6 +416,28 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
         }
     }
 
+    if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;   // the while condition of schedule.py:185
+    if (ENV) {
+        // observation: per node free GPUs / cpu / mem, the look-ahead window, queue statistics
+        float *o = env.obs + (size_t)blockIdx.x * env.obs_dim;
+        for (int i = lane; i < c.N; i += 32) {
+            o[i] = (float)__popc(~s.nv.busy[i] & c.gmask);
+            o[c.N + i] = (float)(c.cpu_cap - s.nv.cpu[i]);
+            o[2 * c.N + i] = (float)(c.mem_cap - s.nv.mem[i]);
+        }
+        for (int i = lane; i < env.window_k; i += 32) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < st.Q) { JobRec r = load_rec(D.stack + st.head + i); w = make_float4((float)r.gpus(), (float)r.tasks(), (float)r.dur(), (float)(st.d - r.arrival())); }
+            float *ow = o + 3 * c.N + 4 * i;
+            ow[0] = w.x; ow[1] = w.y; ow[2] = w.z; ow[3] = w.w;
+        }
+        if (lane == 0) {
+            float *t = o + 3 * c.N + 4 * env.window_k;
+            t[0] = (float)st.Q; t[1] = (float)st.R; t[2] = (float)st.F; t[3] = (float)st.d;
+            env.reward[blockIdx.x] = reward_acc;
+            env.done[blockIdx.x] = (uint8_t)(st.done != 0);
+        }
+    }
     fifo_state_io(D, s, c.N, slot_cap, st.hw, lane, true);
     if (lane == 0) {
         states[blockIdx.x] = st;

@@ -351,8 +351,9 @@ static int32_t add_chunks(rlgs_sim *s, int upto, bool host_too) {
 static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cudaStream_t st) {
     RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
     if (!s->legacy) {
-        fifo_yarn_kernel<<<count, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, budget,
-                                                                                  rs, s->d_returns + first, s->opts.max_ticks);
+        EnvIO none; memset(&none, 0, sizeof none);
+        fifo_yarn_kernel<false><<<count, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, budget,
+                                                                                         rs, s->d_returns + first, s->opts.max_ticks, none);
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->opts.schedule == RLGS_SCHED_DLAS_GPU)
@@ -387,7 +388,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     if (!s->legacy) {
         size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
         if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else if (s->opts.schedule == RLGS_SCHED_SJF) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
@@ -640,5 +641,77 @@ extern "C" int32_t rlgs_returns(rlgs_sim *s, int64_t *out) {
 extern "C" int32_t rlgs_returns_device_ptr(rlgs_sim *s, void **dev_ptr) {
     if (!s || !dev_ptr) return fail(RLGS_ERR_BAD_ARG, "null argument");
     *dev_ptr = s->d_returns;
+    return RLGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vectorised RL environment (replaces the stub model/env.py:1-6 of the reference; semantics are
+// build-defined, see fifo_yarn.cuh EnvIO).  All pointers are DEVICE pointers (torch tensors);
+// calls are asynchronous on the handle's stream (rlgs_set_stream) until rlgs_env_sync.
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t rlgs_env_obs_dim(rlgs_sim *s, int32_t window_k, int32_t *dim) {
+    if (!s || !dim) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
+    *dim = 3 * s->cc.N + 4 * window_k + 4;
+    return RLGS_OK;
+}
+
+extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
+    if (!s) return fail(RLGS_ERR_BAD_ARG, "null handle");
+    if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
+    CU(cudaSetDevice(s->device));
+    int32_t rc = setup_job_arrays(s);
+    if (rc) return rc;
+    size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
+    if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica", smem);
+    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    for (int r = 0; r < s->R; ++r) {
+        RepState z; memset(&z, 0, sizeof z);
+        z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
+        z.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
+        z.free_hint = -1;
+        s->h_init[r] = z;
+    }
+    CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * s->R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * s->R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, st));
+    CU(cudaStreamSynchronize(st));   // h_init / h_desc may be rewritten by the caller's next call
+    s->planes_on_host = 0; s->ran = false;
+    return RLGS_OK;
+}
+
+extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                                 int32_t policy, int32_t window_k, uint32_t seed, int32_t n_ticks) {
+    if (!s || !obs || !reward || !done) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
+    if (policy < 0 || policy > 2 || (policy == 2 && !actions)) return fail(RLGS_ERR_BAD_ARG, "policy must be 0, 1 or 2 (2 needs actions)");
+    if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
+    if (n_ticks < 1 || (policy == 2 && n_ticks != 1)) return fail(RLGS_ERR_BAD_ARG, "n_ticks must be >= 1 (exactly 1 with external actions)");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    EnvIO io; io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.policy = policy; io.window_k = window_k;
+    io.seed = seed; io.obs_dim = 3 * s->cc.N + 4 * window_k + 4;
+    RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
+    fifo_yarn_kernel<true><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
+                                                                                s->d_returns, s->opts.max_ticks, io);
+    CU(cudaGetLastError());
+    return RLGS_OK;
+}
+
+// Waits for the enqueued steps and refreshes the host copy of the replica states, so that
+// rlgs_get_summary / rlgs_read_jobs / rlgs_returns describe the environment's current state.
+extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
+    if (!s) return fail(RLGS_ERR_BAD_ARG, "null handle");
+    if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * s->R, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < s->R; ++r) {
+        s->h_returns[r] = -s->h_state[r].sum_jct;
+        if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
+    }
+    s->planes_on_host = 0; s->ran = true;
     return RLGS_OK;
 }

@@ -25,6 +25,13 @@ JOB_HEADER = ['job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'ori
               'actual_duration', 'jct', 'preempt']
 
 
+LEGACY_CLUSTER_HEADER = ['time', 'idle_node', 'busy_node', 'full_node', 'idle_gpu', 'busy_gpu', 'pending_job',
+                         'running_job', 'completed_job']                                  # log.py:43-45
+LEGACY_JOB_HEADER_COUNT = ['time', 'job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'executed_time', 'JCT',
+                           'duration', 'pending_time', 'preempt', 'resume', 'promote']        # log.py:86
+LEGACY_JOB_HEADER = [h for h in LEGACY_JOB_HEADER_COUNT if h != 'resume']                  # log.py:88
+
+
 class LogInfo(object):
     """Same fields as the reference's LogInfo (log_manager.py:5-30)."""
 
@@ -123,9 +130,18 @@ class LogManager(object):
         self.cluster_stats_header = list(CLUSTER_HEADER)
         self.job_stats_header = list(JOB_HEADER)
 
-    def init(self, infrastructure):
+    def init(self, infrastructure, legacy=None):
+        """legacy=True writes the headers of the Tiresias-era logger (log.py:30-88 of the reference), the
+        format the sjf / dlas-gpu loops logged in; default: decided from flags.schedule."""
         self.log_cluster = os.path.join(self.log_path, 'cluster.csv')
         self.log_job = os.path.join(self.log_path, 'job.csv')
+        if legacy is None:
+            legacy = getattr(self.flags, 'schedule', 'fifo') in ('sjf', 'dlas-gpu')
+        self.legacy = legacy
+        if legacy:
+            self.cluster_stats_header = list(LEGACY_CLUSTER_HEADER)
+            count = getattr(self.flags, 'schedule', '') == 'dlas-gpu' or self.is_count
+            self.job_stats_header = list(LEGACY_JOB_HEADER_COUNT if count else LEGACY_JOB_HEADER)
         n_nodes = infrastructure.num_nodes
         n_gpus = infrastructure.num_gpus
         with open(self.log_cluster, 'w+', newline='') as f:
@@ -159,6 +175,28 @@ class LogManager(object):
     def write_cluster_rows(self, rows, cluster, mem_shift, util_mode='sample', seed=None):
         with open(self.log_cluster, 'a+', newline='') as f:
             f.write(format_cluster_csv(rows, cluster, mem_shift, with_header=False, util_mode=util_mode, seed=seed))
+
+    def write_legacy(self, rows, cluster, trace, jobs, pending, resume, count_scheme):
+        """cluster.csv / job.csv of the event-driven schedules (LOG.checkpoint log.py:137-258, LOG.job_complete
+        log.py:316-330).  rows: _ffi.ROW_DTYPE with the legacy field mapping documented in include/rlgs.h."""
+        N, Dv = cluster.num_nodes, cluster.num_gpus
+        idle = rows['idle_nodes']; full = rows['median_hi']; busy_g = rows['busy_gpus']
+        busy_n = (full if count_scheme else N - idle - full)
+        with open(self.log_cluster, 'a+', newline='') as f:
+            csv.writer(f).writerows(zip(rows['median_lo'].tolist(), idle.tolist(), busy_n.tolist(), full.tolist(),
+                                        (Dv - busy_g).tolist(), busy_g.tolist(), rows['queued'].tolist(),
+                                        rows['running'].tolist(), rows['finished'].tolist()))
+        fo = np.asarray(jobs['finish_order'], dtype=np.int64)
+        sub = trace.records['arrival_tick'][fo].astype(np.int64)
+        st, en = jobs['start'][fo].astype(np.int64), jobs['end'][fo].astype(np.int64)
+        cols = [en.tolist(), [str(x) for x in trace.label[fo].tolist()], trace.records['gpus'][fo].tolist(), sub.tolist(),
+                st.tolist(), en.tolist(), (en - st).tolist(), (en - sub).tolist(), trace.records['dur_ticks'][fo].tolist(),
+                np.asarray(pending)[fo].tolist(), np.asarray(jobs['preempt'])[fo].tolist()]
+        if count_scheme:
+            cols.append(np.asarray(resume)[fo].tolist())
+        cols.append([0] * len(fo))
+        with open(self.log_job, 'a+', newline='') as f:
+            csv.writer(f).writerows(zip(*cols))
 
     def jcts(self, finished_jobs):
         """finished_jobs: dict job_id -> object with the reference Job's attributes, or a tuple

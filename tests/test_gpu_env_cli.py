@@ -1,0 +1,131 @@
+"""Vectorised environment (build-defined, PARITY UNPINNED: model/env.py is a stub in the reference) vs the
+CPU restatement oracle_env_yarn, and the run_sim.py command line end to end."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cpu_sim
+import goldutil
+import tracegen
+import rlgpuschedule_b200 as rl
+from rlgpuschedule_b200.env import Environment
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLAGS = dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)
+
+
+def _setup(n=300, seed=5, span=30):
+    df = tracegen.frame_gen(n, seed, span)
+    cluster = rl.cluster_from_flags(FLAGS)
+    return df, cluster, rl.prepare_trace(df, cluster), cpu_sim.make_cluster(**FLAGS), cpu_sim.prepare_trace(df)
+
+
+def test_env_head_policy_equals_fifo_and_rollout_matches_oracle():
+    df, cluster, tr, oc, otr = _setup()
+    env = Environment(cluster, tr, n_replicas=6, window_k=5, seed=11)
+    env.reset()
+    env.rollout('head')
+    env.sync()
+    fifo = cpu_sim.run_fifo_yarn(oc, otr)
+    j = env.sim.jobs(0)
+    assert np.array_equal(j['end'], fifo['end']) and np.array_equal(j['finish_order'], fifo['finish_order'])
+    assert bool(env.done.cpu().all())
+    # random-window policy: every replica draws its own stream from (seed, replica, tick)
+    env.reset()
+    env.rollout('random')
+    env.sync()
+    rets = env.sim.returns()
+    for r in (0, 3, 5):
+        o = cpu_sim.run_env_yarn(oc, otr, 1, window_k=5, seed=11, replica=r)
+        j = env.sim.jobs(r)
+        assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end'])
+        assert np.array_equal(j['finish_order'], o['finish_order'])
+        assert env.sim.summary(r)['n_ticks'] == o['n_ticks']
+        arr = np.ceil(otr['nt']).astype(np.int64)
+        fin = o['end'] >= 0
+        assert rets[r] == -int((o['end'][fin] - arr[fin]).sum())
+    assert len(set(rets.tolist())) > 1
+    assert np.array_equal(env.returns_tensor().cpu().numpy(), rets)
+    env.close()
+
+
+def test_env_step_by_step_matches_oracle_tape():
+    import torch
+    df, cluster, tr, oc, otr = _setup(120, 9, 40)
+    R, T, K = 4, 90, 4
+    rng = np.random.default_rng(3)
+    tapes = rng.integers(-1, K + 1, size=(R, T)).astype(np.int32)   # includes no-ops and out-of-window picks
+    env = Environment(cluster, tr, n_replicas=R, window_k=K)
+    obs0 = env.reset().clone()
+    assert obs0.shape == (R, env.obs_dim) and float(obs0[0, 0]) == 8.0
+    total_reward = np.zeros(R)
+    for t in range(T):
+        obs, rew, done, _ = env.step(torch.from_numpy(tapes[:, t]).cuda())
+        total_reward += rew.cpu().numpy()
+    env.sync()
+    obs = obs.cpu().numpy()
+    N = cluster.num_nodes
+    for r in range(R):
+        o = cpu_sim.run_env_yarn(oc, otr, 2, window_k=K, actions=tapes[r])
+        assert o['n_ticks'] == T
+        s = env.sim.summary(r)
+        assert s['n_ticks'] == T
+        last = o['rows'][-1]
+        assert obs[r, 3 * N + 4 * K + 0] == last['queued'] and obs[r, 3 * N + 4 * K + 1] == last['running']
+        assert obs[r, 3 * N + 4 * K + 2] == last['finished'] and obs[r, 3 * N + 4 * K + 3] == T
+        assert obs[r, :N].sum() == last['idle_gpus']
+        assert total_reward[r] == -float((o['rows']['queued'] + o['rows']['running']).sum())
+        j = env.sim.jobs(r)
+        started = o['start'] >= 0
+        assert np.array_equal(j['start'][started], o['start'][started]) and (j['start'][~started] == -1).all()
+    env.close()
+
+
+@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec'])
+def test_run_sim_cli_writes_reference_outputs(name, tmp_path):
+    g = goldutil.load(name)
+    args = []
+    for k, v in g['flags'].items():
+        args += ['--' + k, str(v)]
+    trace = g['trace']
+    if trace is None:
+        trace = str(tmp_path / 'trace.csv')
+        g['frame'].to_csv(trace, index=False)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--log_path', 'cli', '--seed', '1'] + args,
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    runs = sorted(os.listdir(tmp_path / 'log' / 'cli'))
+    out = tmp_path / 'log' / 'cli' / runs[-1]
+    assert sorted(os.listdir(out)) == ['cluster.csv', 'cpu.csv', 'gpu.csv', 'job.csv', 'memory.csv', 'network.csv', 'output.log']
+    assert open(out / 'job.csv', newline='').read() == g['job']
+    clu = open(out / 'cluster.csv', newline='').read()
+    noutil = '\r\n'.join(','.join(f[:5] + f[6:]) for f in (l.split(',') for l in clu.split('\r\n') if l)) + '\r\n'
+    assert noutil == g['cluster']
+    util = [l.split(',')[5] for l in clu.split('\r\n')[1:] if l]
+    assert all(u == '0.0' or (u.startswith('[') and u.endswith(']')) for u in util)
+    assert 'Total Time Taken in seconds' in open(out / 'output.log').read()
+
+
+def test_run_sim_cli_legacy_schedules(tmp_path):
+    df = tracegen.frame_gen(300, 5, 30)
+    trace = str(tmp_path / 't.csv')
+    df.to_csv(trace, index=False)
+    for sched, scheme in (('sjf', 'yarn'), ('dlas-gpu', 'count')):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--log_path', sched, '--schedule', sched,
+                            '--scheme', scheme, '--num_switch', '2', '--num_node_p_switch', '4', '--num_queue', '4'], cwd=str(tmp_path), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = tmp_path / 'log' / sched
+        out = out / sorted(os.listdir(out))[-1]
+        oc, ot = cpu_sim.make_cluster(**FLAGS), cpu_sim.prepare_trace(trace)
+        o = cpu_sim.run_sjf_yarn(oc, ot) if sched == 'sjf' else cpu_sim.run_dlas_gpu(oc, ot, (30, 60, 150))
+        assert open(out / 'job.csv', newline='').read() == cpu_sim.format_legacy_job_csv(ot, o, count_scheme=(scheme == 'count'))
+        rows = open(out / 'cluster.csv').read().splitlines()
+        assert rows[0] == 'time,idle_node,busy_node,full_node,idle_gpu,busy_gpu,pending_job,running_job,completed_job'
+        assert len(rows) - 1 == o['n_events']
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--schedule', 'horus', '--scheme', 'horus'],
+                       cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0 and 'not implemented by the device path' in r.stderr

@@ -1,0 +1,115 @@
+"""CPU tests of the host-side mirror: flags, plugin registries, CSV formatting, ingestion."""
+import numpy as np
+import pytest
+
+import cpu_sim
+import goldutil
+import rlgpuschedule_b200 as rl
+from rlgpuschedule_b200 import _ffi, algorithm, flags, log_manager as lm
+
+
+def test_flags_follow_the_reference_conventions():
+    flags.reset_for_tests()
+    for name, default, kind in (('t_int', 3, flags.DEFINE_integer), ('t_str', 'a', flags.DEFINE_string), ('t_f', 0.5, flags.DEFINE_float)):
+        kind(name, default, 'doc')
+    flags.DEFINE_boolean('t_bool', False, 'doc')
+    unknown = flags.FLAGS.parse(['--t_int', '7', '--t_bool', 'True', '--not_a_flag', '1'])
+    assert flags.FLAGS.t_int == 7 and flags.FLAGS.t_bool is True and flags.FLAGS.t_str == 'a' and flags.FLAGS.t_f == 0.5
+    assert unknown == ['--not_a_flag', '1']            # parse_known_args: unknown flags are ignored (core/flags.py:22)
+    flags.reset_for_tests()
+    flags.FLAGS.parse(['--t_bool', 'False'])
+    assert flags.FLAGS.t_bool is False                  # str2bool: only true/t/1 are True (core/flags.py:91-98)
+    flags.reset_for_tests()
+    flags.FLAGS.parse(['--t_bool'])
+    assert flags.FLAGS.t_bool is True
+    flags.reset_for_tests()
+    flags.FLAGS.parse(['--not_bool_flag_prefix', '--not_bool'])
+    flags.reset_for_tests()
+    flags.FLAGS.parse(['--not_bool'.replace('not_', 'not_')])  # unknown again
+    flags.reset_for_tests()
+    flags.FLAGS.parse(['--t_bool', '--not_bool'])
+    flags.FLAGS.t_int = 11
+    assert flags.FLAGS.t_int == 11
+    flags.reset_for_tests()
+
+
+def test_plugin_registries_keep_the_reference_keys():
+    assert {'fifo', 'horus', 'horus+', 'gandiva'} <= set(algorithm.scheduling_algorithms)   # algorithm.py:292-298
+    assert {'yarn', 'horus', 'horus+', 'gandiva'} <= set(algorithm.placement_algorithms)    # algorithm.py:182-187
+    assert set(algorithm.plugin_algorithms) == {'gandiva'} and set(algorithm.score_fn) == {'horus', 'horus+', 'gandiva'}
+    s, p = algorithm.resolve('fifo', 'yarn')
+    assert s.device_id == _ffi.SCHED['fifo'] and p.device_id == _ffi.PLACE['yarn']
+    assert algorithm.resolve('dlas-gpu', 'count')[0].device_id == 2
+    with pytest.raises(NotImplementedError):
+        algorithm.resolve('horus', 'horus')
+    with pytest.raises(NotImplementedError):
+        algorithm.resolve('gandiva', 'yarn')            # its post-tick plugin (time slicing) has no device form
+    with pytest.raises(KeyError):
+        algorithm.resolve('lpjf', 'yarn')
+    algorithm.scheduling_algorithms['mine'] = lambda *a, **k: (None, None, False)
+    with pytest.raises(NotImplementedError):
+        algorithm.resolve('mine', 'yarn')
+    del algorithm.scheduling_algorithms['mine']
+
+
+@pytest.mark.parametrize('name', ['probe100', 'big_mem_leak', 'dense'])
+def test_row_finishing_reproduces_the_reference_floats(name):
+    """Feeds the oracle's per-tick state through the product's integer row format and formatter:
+    the float columns must come out byte-identical to the reference's cluster.csv."""
+    g = goldutil.load(name)
+    ti = goldutil.trace_input(g)
+    cluster = rl.cluster_from_flags(g['flags'])
+    tr = rl.prepare_trace(ti, cluster)
+    otr = cpu_sim.prepare_trace(ti)
+    o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**g['flags']), otr)
+    # rebuild integer sufficient statistics from the oracle run
+    n = o['n_ticks']
+    rows = np.zeros(n, _ffi.ROW_DTYPE)
+    arr = np.ceil(otr['nt']).astype(np.int64)
+    start, end = o['start'].astype(np.int64), o['end'].astype(np.int64)
+    ndev = tr.records['tasks'].astype(np.int64) * tr.records['gpus_per_task']
+    for d in range(1, n + 1):
+        queued = np.nonzero((arr < d) & ((start < 0) | (start >= d)))[0]
+        running = (start >= 0) & (start < d) & ((end < 0) | (end > d))
+        pend = np.sort(d - arr[queued])
+        r = rows[d - 1]
+        r['queued'] = len(queued); r['running'] = running.sum(); r['finished'] = ((end >= 0) & (end <= d)).sum()
+        r['busy_gpus'] = ndev[running].sum(); r['mem_sum'] = (ndev[running] * tr.records['mem_term'][running]).sum()
+        r['sum_pending'] = pend.sum()
+        if len(pend):
+            r['median_lo'] = pend[(len(pend) - 1) // 2]; r['median_hi'] = pend[len(pend) // 2]; r['max_pending'] = pend[-1]
+        r['idle_nodes'] = o['rows']['idle_nodes'][d - 1]
+    assert np.array_equal(rows['busy_gpus'], o['rows']['busy_gpus']) and np.array_equal(rows['queued'], o['rows']['queued'])
+    assert lm.format_cluster_csv(rows, cluster, tr.mem_shift, with_util=False) == g['cluster']
+    assert lm.format_job_csv(tr, o['finish_order'], o['start'], o['end']) == g['job']
+
+
+def test_log_manager_creates_the_six_files_with_reference_headers(tmp_path):
+    class F(object):
+        scheme = 'yarn'; schedule = 'fifo'
+    cluster = rl.Cluster(num_switch=1, num_node_p_switch=2, num_gpu_p_node=2)
+    m = lm.LogManager(str(tmp_path), F())
+    m.init(cluster)
+    assert open(tmp_path / 'cluster.csv', newline='').read() == ','.join(lm.CLUSTER_HEADER) + '\r\n'
+    assert open(tmp_path / 'job.csv', newline='').read() == ','.join(lm.JOB_HEADER) + '\r\n'
+    assert open(tmp_path / 'cpu.csv', newline='').read() == 'time,cpu0,cpu1\r\n'
+    assert open(tmp_path / 'gpu.csv', newline='').read() == 'time,gpu0,gpu1,gpu2,gpu3\r\n'
+    assert open(tmp_path / 'memory.csv', newline='').read() == 'time,max,99th,95th,med\r\n'
+    assert open(tmp_path / 'network.csv', newline='').read() == 'time,in0,out0,in1,out1\r\n'
+    m.step_cluster(lm.LogInfo(1, 1, 2, 2, 0.0, 0.5, 0.0, float('nan'), 0, 1, 0, 0), 1)
+    assert open(tmp_path / 'cluster.csv', newline='').read().split('\r\n')[1] == '1,1,1,2,2,0.0,0.5,0.0,nan,0,1,0,0'
+
+
+def test_ingest_rejects_what_the_reference_would_raise_on():
+    import pandas as pd
+    import tracegen
+    cluster = rl.Cluster()
+    df = tracegen.frame_rows([dict(used_gpus=1.0, gpu_per_container=2)])
+    with pytest.raises(ValueError):
+        rl.prepare_trace(df, cluster)                    # zero tasks: StopIteration at node.py:118 in the reference
+    df = tracegen.frame_rows([dict(used_gpus=2.0, gpu_per_container=1, memory_max=5000000001.5)])
+    t = rl.prepare_trace(df, cluster)
+    assert t.mem_shift == 21 and int(t.records['mem_term'][0]) == int(5000000001.5 * 2)
+    df = tracegen.frame_rows([dict(memory_max=1e9 / 3)])
+    with pytest.raises(ValueError):
+        rl.prepare_trace(df, cluster)                    # not exactly summable in 53 bits
