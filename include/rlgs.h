@@ -159,8 +159,9 @@ int32_t rlgs_load_trace(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas
 int32_t rlgs_run(rlgs_sim *sim);
 /* Device time of the kernels of the last rlgs_run, from CUDA events on the launch stream. */
 int32_t rlgs_last_run_ms(rlgs_sim *sim, float *kernel_ms, int32_t *n_launches);
-/* Launch on a caller-provided cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); NULL = own stream. */
-int32_t rlgs_set_stream(rlgs_sim *sim, void *cuda_stream);
+/* enable != 0: launch on the caller's cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream; NULL is the
+ * legacy default stream); enable == 0: back to the handle's own stream. */
+int32_t rlgs_set_stream(rlgs_sim *sim, void *cuda_stream, int32_t enable);
 
 int32_t rlgs_get_summary(rlgs_sim *sim, int32_t replica, rlgs_summary *out);
 /* Replaces LogManager.jcts' walk over finished_jobs (log_manager.py:137-155): per job (trace order)

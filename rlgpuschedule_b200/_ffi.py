@@ -87,7 +87,7 @@ def lib():
     L.rlgs_load_trace.argtypes = [vp, i32, i32, vp, i32, C.POINTER(NetcostInputs)]
     L.rlgs_run.argtypes = [vp]
     L.rlgs_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
-    L.rlgs_set_stream.argtypes = [vp, vp]
+    L.rlgs_set_stream.argtypes = [vp, vp, i32]
     L.rlgs_get_summary.argtypes = [vp, i32, C.POINTER(Summary)]
     L.rlgs_read_jobs.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.rlgs_read_rows.argtypes = [vp, i32, i64, i64, vp]

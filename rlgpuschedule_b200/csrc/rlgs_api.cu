@@ -69,6 +69,7 @@ struct rlgs_sim {
     bool legacy = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     void *user_stream = nullptr;
+    bool use_user_stream = false;   // NULL is a valid handle: the legacy default stream
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<Group> groups;
@@ -207,9 +208,10 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     delete s;
 }
 
-extern "C" int32_t rlgs_set_stream(rlgs_sim *s, void *cuda_stream) {
+extern "C" int32_t rlgs_set_stream(rlgs_sim *s, void *cuda_stream, int32_t enable) {
     if (!s) return fail(RLGS_ERR_BAD_ARG, "null handle");
     s->user_stream = cuda_stream;
+    s->use_user_stream = enable != 0;
     return RLGS_OK;
 }
 
@@ -381,7 +383,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     CU(cudaSetDevice(s->device));
     int32_t rc = setup_job_arrays(s);
     if (rc) return rc;
-    cudaStream_t main_st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    cudaStream_t main_st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     const int mode = s->opts.rows_mode;
     const bool rows = mode != RLGS_ROWS_NONE, eager_rows = mode == RLGS_ROWS_FULL, eager_jobs = s->opts.fetch_jobs != 0;
     const int R = s->R;
@@ -665,7 +667,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
     if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica", smem);
     CU(cudaFuncSetAttribute(fifo_yarn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     for (int r = 0; r < s->R; ++r) {
         RepState z; memset(&z, 0, sizeof z);
         z.head = s->h_desc[r].J; z.idle_nodes = s->cc.N;
@@ -689,7 +691,7 @@ extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs
     if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
     if (n_ticks < 1 || (policy == 2 && n_ticks != 1)) return fail(RLGS_ERR_BAD_ARG, "n_ticks must be >= 1 (exactly 1 with external actions)");
     CU(cudaSetDevice(s->device));
-    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     EnvIO io; io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.policy = policy; io.window_k = window_k;
     io.seed = seed; io.obs_dim = 3 * s->cc.N + 4 * window_k + 4;
     RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
@@ -705,7 +707,7 @@ extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
     if (!s) return fail(RLGS_ERR_BAD_ARG, "null handle");
     if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
     CU(cudaSetDevice(s->device));
-    cudaStream_t st = s->user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * s->R, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     for (int r = 0; r < s->R; ++r) {

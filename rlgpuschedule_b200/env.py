@@ -42,7 +42,7 @@ class Environment(object):
 
     def _bind_stream(self):
         # kernels are enqueued on torch's current stream so they order with the policy network's work
-        _ffi.check(_ffi.lib().rlgs_set_stream(self.sim._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)))
+        _ffi.check(_ffi.lib().rlgs_set_stream(self.sim._h, C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream), 1))
 
     def reset(self):
         self._bind_stream()
