@@ -188,6 +188,9 @@ int32_t rlgs_returns(rlgs_sim *sim, int64_t *out_n_replicas);
 /* Device pointer to the same int64[n_replicas] buffer (the NCCL all-gather send buffer). */
 int32_t rlgs_returns_device_ptr(rlgs_sim *sim, void **dev_ptr);
 
+/* Per-job duration after network costs (Job.add_network_costs, job.py:196-197); enable_network_costs only. */
+int32_t rlgs_read_durations(rlgs_sim *sim, int32_t replica, double *out);
+
 /*
  * Vectorised RL environment: replaces the reference's stub model/env.py:1-6 (Environment.step(action): pass);
  * semantics are build-defined (DESIGN.md "Environment").  One step = one scheduler tick of every replica of a

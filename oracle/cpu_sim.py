@@ -80,10 +80,19 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def run_fifo_yarn(cluster, tr, rows_cap=None):
-    """Returns dict(finish_order, start, end, rows (ROW_DTYPE), n_ticks, counters)."""
+def run_fifo_yarn(cluster, tr, rows_cap=None, netcost=None):
+    """Returns dict(finish_order, start, end, rows (ROW_DTYPE), n_ticks, counters).
+    netcost = dict(model_mb, iterations, bandwidth, latency) enables the build-defined network-cost model."""
     L = lib()
     n = len(tr['nt'])
+    dur_out = None
+    L.oracle_set_netcost.restype = None
+    if netcost:
+        dur_out = np.zeros(max(n, 1), np.float64)
+        nm = np.ascontiguousarray(netcost['model_mb'], np.float64); ni = np.ascontiguousarray(netcost['iterations'], np.float64)
+        L.oracle_set_netcost(_p(nm, C.c_double), _p(ni, C.c_double), C.c_double(netcost['bandwidth']), C.c_double(netcost['latency']), _p(dur_out, C.c_double))
+    else:
+        L.oracle_set_netcost(None, None, C.c_double(0), C.c_double(0), None)
     fin = np.empty(max(n, 1), np.int32); st = np.empty(max(n, 1), np.int32); en = np.empty(max(n, 1), np.int32)
     nfin = C.c_int32(0); nticks = C.c_int64(0); counters = np.zeros(4, np.int64)
     cap = rows_cap or max(4096, 4 * n)
@@ -101,9 +110,13 @@ def run_fifo_yarn(cluster, tr, rows_cap=None):
             raise RuntimeError('oracle_fifo_yarn rc=%d (the reference would raise on this input)' % rc)
         break
     k = nfin.value
-    return dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
-                counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]),
-                              starts=int(counters[3])))
+    L.oracle_set_netcost(None, None, C.c_double(0), C.c_double(0), None)
+    out = dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
+               counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]),
+                             starts=int(counters[3])))
+    if dur_out is not None:
+        out['actual_duration'] = dur_out[:n]
+    return out
 
 
 def format_job_csv(tr, res):
@@ -117,7 +130,7 @@ def format_job_csv(tr, res):
     for k, i in enumerate(res['finish_order']):
         i = int(i)
         w.writerow([str(int(tr['label'][i])), float(tr['used_gpus'][i]), int(tr['nt'][i]), int(res['start'][i]),
-                    int(res['end'][i]), float(tr['duration'][i]),
+                    int(res['end'][i]), float(dur[i]),   # Job.duration itself carries the network cost (job.py:196-197)
                     float(dur[i]) if dur[i] > 0 else 0,   # Job.get_duration: max(0, d) keeps the int 0 (job.py:206-210)
                     int(res['jct'][i]) if 'jct' in res else int(res['end'][i] - res['start'][i]),
                     int(pre[i]) if pre is not None else 1])

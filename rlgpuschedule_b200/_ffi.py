@@ -58,7 +58,7 @@ assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64
 EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_run',
            'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
            'rlgs_rows_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
-           'rlgs_env_obs_dim', 'rlgs_env_reset', 'rlgs_env_step', 'rlgs_env_sync']
+           'rlgs_read_durations', 'rlgs_env_obs_dim', 'rlgs_env_reset', 'rlgs_env_step', 'rlgs_env_sync']
 
 _lib = None
 
@@ -95,6 +95,7 @@ def lib():
     L.rlgs_read_job_plane.argtypes = [vp, i32, i32, vp]
     L.rlgs_returns.argtypes = [vp, vp]
     L.rlgs_returns_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.rlgs_read_durations.argtypes = [vp, i32, vp]
     L.rlgs_env_obs_dim.argtypes = [vp, i32, C.POINTER(i32)]
     L.rlgs_env_reset.argtypes = [vp]
     L.rlgs_env_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_uint32, i32]

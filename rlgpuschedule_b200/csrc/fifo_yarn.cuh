@@ -162,10 +162,29 @@ __device__ __forceinline__ uint32_t rlgs_hash3(uint32_t seed, uint32_t replica, 
     return (uint32_t)(z >> 32);
 }
 
+// Duration of a job that was just placed on `nodes_used` nodes (restates calculate_network_costs,
+// core/network/network_service.py:3-39, + Job.add_network_costs job.py:196-197).  The reference's own
+// path raises (Job.is_distributed reads a missing attribute, job.py:199-200), so the semantics are
+// build-defined: distributed = more than one task; there are no PS tasks, so the symmetric difference
+// of PS and worker nodes is the set of worker nodes.  Same float64 operation order as the Python.
+__device__ __forceinline__ int netcost_dur_ticks(const RepDesc &D, const NetCost &net, int job, int tasks, int nodes_used, int lane) {
+    const int J = D.J;
+    double dur = D.net_in[job];
+    if (tasks > 1) {
+        double model_per_sec = D.net_in[J + job] / net.bandwidth;
+        double nodes_induced_sec = (double)nodes_used * net.latency;
+        double iteration_round_trip = D.net_in[2 * J + job] * 2.0;
+        dur += (model_per_sec + nodes_induced_sec) * iteration_round_trip;
+    }
+    if (lane == 0) D.dur_out[job] = dur;
+    double c = ceil(dur);
+    return c < 1.0 ? 1 : (c > 1.0e9 ? 1000000000 : (int)c);
+}
+
 template <bool ENV>
 __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
                                                        ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
-                                                       int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env) {
+                                                       int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env, NetCost net) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
     const RepDesc D = descs[blockIdx.x];
@@ -266,13 +285,14 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
             if (pr.ok) {
                 int job = h0.index();
                 int ndev = h0.tasks() * h0.gpc();
+                const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, h0.tasks(), pr.nnodes, lane) : h0.dur();
                 int sl = st.free_hint;
                 if (sl < 0) { sl = st.hw; }
                 if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                 if (sl == st.hw) st.hw += 1;
                 st.free_hint = -1;
                 if (lane == 0) {
-                    s.sv.end[sl] = d + h0.dur();
+                    s.sv.end[sl] = d + dur_ticks;
                     s.sv.job[sl] = job;
                     s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (h0.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
                     s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                 st.util_mu_sum += mu * ndev;
                 st.util_var_sum += sd * sd * ndev;
                 st.sum_arr -= h0.arrival();
-                st.sum_jct += (int64_t)(d + h0.dur() - h0.arrival());  // end is fixed at start (no preemption)
+                st.sum_jct += (int64_t)(d + dur_ticks - h0.arrival());  // end is fixed at start (no preemption)
                 st.R += 1; st.Q -= 1; st.head += 1;
                 st.events += 1;
                 if (st.R > st.max_r) st.max_r = st.R;
@@ -314,13 +334,14 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                 if (pr.ok) {
                     int job = hx.index();
                     int ndev = hx.tasks() * hx.gpc();
+                    const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, lane) : hx.dur();
                     int sl = st.free_hint;
                     if (sl < 0) { sl = st.hw; }
                     if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                     if (sl == st.hw) st.hw += 1;
                     st.free_hint = -1;
                     if (lane == 0) {
-                        s.sv.end[sl] = d + hx.dur();
+                        s.sv.end[sl] = d + dur_ticks;
                         s.sv.job[sl] = job;
                         s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (hx.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
                         s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
@@ -338,7 +359,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                     st.util_mu_sum += mu * ndev;
                     st.util_var_sum += sd * sd * ndev;
                     st.sum_arr -= hx.arrival();
-                    st.sum_jct += (int64_t)(d + hx.dur() - hx.arrival());
+                    st.sum_jct += (int64_t)(d + dur_ticks - hx.arrival());
                     // queue.pop(pick): entries in front of it move one place towards the back of the stack
                     JobRec mv; bool m = lane < pick;
                     if (m) mv = load_rec(D.stack + st.head + lane);

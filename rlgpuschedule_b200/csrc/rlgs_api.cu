@@ -42,6 +42,8 @@ static const int MAX_CHUNKS = 1 << 16;
 
 struct TraceBuf {
     rlgs_job *dev = nullptr;
+    double *net = nullptr;      // [3][cap_n] network-cost inputs
+    double *dur_out = nullptr;  // [count][cap_n]
     int32_t n = 0, cap_n = 0;
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
@@ -125,7 +127,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
         for (int q = 0; q + 1 < opts->num_queue; ++q)
             if (opts->queue_limit[q] < 1) return fail(RLGS_ERR_BAD_ARG, "queue_limit[%d] must be >= 1", q);
     }
-    if (opts->enable_network_costs) return fail(RLGS_ERR_UNSUPPORTED, "network costs are not implemented on the device path yet");
+    if (opts->enable_network_costs && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "network costs are implemented for the fifo tick loop only");
+    if (opts->enable_network_costs && !(opts->bandwidth > 0)) return fail(RLGS_ERR_BAD_ARG, "bandwidth must be > 0");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -185,7 +188,7 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (auto &t : s->traces) cudaFree(t.dev);
+    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); }
     for (void *p : s->slabs) cudaFree(p);
     for (auto p : s->d_chunks) cudaFree(p);
     for (auto p : s->h_chunks) if (p) cudaFreeHost(p);
@@ -220,7 +223,8 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     if (!s || !jobs) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (n < 1) return fail(RLGS_ERR_BAD_ARG, "trace has no jobs (the reference asserts on an empty job table, log_manager.py:138)");
     if (first < 0 || count < 1 || first + count > s->R) return fail(RLGS_ERR_BAD_ARG, "replica range [%d,%d) out of 0..%d", first, first + count, s->R);
-    (void)net;
+    if (s->opts.enable_network_costs && (!net || !net->duration || !net->model_mb || !net->iterations))
+        return fail(RLGS_ERR_BAD_ARG, "enable_network_costs needs duration / model_mb / iterations arrays");
     CU(cudaSetDevice(s->device));
     TraceBuf tb;
     tb.n = n;
@@ -244,6 +248,12 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         TraceBuf &old = s->traces[t];
         if (old.first == first && old.count == count && n <= old.cap_n && tb.log_cap <= old.cap_log) {
             CU(cudaMemcpy(old.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice));
+            if (s->opts.enable_network_costs) {
+                CU(cudaMemcpy(old.net, net->duration, 8 * (size_t)n, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(old.net + n, net->model_mb, 8 * (size_t)n, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(old.net + 2 * (size_t)n, net->iterations, 8 * (size_t)n, cudaMemcpyHostToDevice));
+                for (int r = 0; r < count; ++r) s->h_desc[first + r].dur_out = old.dur_out + (size_t)r * n;
+            }
             old.n = n; old.log_cap = tb.log_cap; old.max_arrival = tb.max_arrival;
             for (int r = 0; r < count; ++r) {
                 s->h_desc[first + r].J = n; s->h_desc[first + r].log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
@@ -257,6 +267,13 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     CU(cudaMalloc(&tb.dev, sizeof(rlgs_job) * (size_t)n));
     cudaError_t e = cudaMemcpy(tb.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(tb.dev); return fail(RLGS_ERR_CUDA, "trace upload: %s", cudaGetErrorString(e)); }
+    if (s->opts.enable_network_costs) {
+        CU(cudaMalloc(&tb.net, 8 * 3 * (size_t)n));
+        CU(cudaMalloc(&tb.dur_out, 8 * (size_t)n * (size_t)count));
+        CU(cudaMemcpy(tb.net, net->duration, 8 * (size_t)n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tb.net + n, net->model_mb, 8 * (size_t)n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(tb.net + 2 * (size_t)n, net->iterations, 8 * (size_t)n, cudaMemcpyHostToDevice));
+    }
     int tid = (int)s->traces.size();
     s->traces.push_back(tb);
     unsigned char *slab = nullptr;
@@ -275,6 +292,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
             D.place_log = reinterpret_cast<int2 *>(p); p += a1;
             D.node_save = reinterpret_cast<int32_t *>(p); p += a2;
             D.slot_save = reinterpret_cast<int4 *>(p);
+            D.net_in = tb.net; D.dur_out = tb.dur_out ? tb.dur_out + (size_t)r * n : nullptr;
         }
     } else {
         // per-replica working set: 2 entry buffers | pending scratch | 2 demotion scratches | end list | placement scratch
@@ -350,12 +368,17 @@ static int32_t add_chunks(rlgs_sim *s, int upto, bool host_too) {
     return RLGS_OK;
 }
 
+static NetCost netcost_of(const rlgs_sim *s) {
+    NetCost n; n.enabled = s->opts.enable_network_costs != 0; n.pad = 0; n.bandwidth = s->opts.bandwidth; n.latency = s->opts.internode_latency;
+    return n;
+}
+
 static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cudaStream_t st) {
     RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
     if (!s->legacy) {
         EnvIO none; memset(&none, 0, sizeof none);
         fifo_yarn_kernel<false><<<count, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, budget,
-                                                                                         rs, s->d_returns + first, s->opts.max_ticks, none);
+                                                                                         rs, s->d_returns + first, s->opts.max_ticks, none, netcost_of(s));
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->opts.schedule == RLGS_SCHED_DLAS_GPU)
@@ -696,7 +719,7 @@ extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs
     io.seed = seed; io.obs_dim = 3 * s->cc.N + 4 * window_k + 4;
     RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
     fifo_yarn_kernel<true><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
-                                                                                s->d_returns, s->opts.max_ticks, io);
+                                                                                s->d_returns, s->opts.max_ticks, io, netcost_of(s));
     CU(cudaGetLastError());
     return RLGS_OK;
 }
@@ -715,5 +738,24 @@ extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
         if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
     }
     s->planes_on_host = 0; s->ran = true;
+    return RLGS_OK;
+}
+
+// Duration of every job after network costs (Job.add_network_costs, job.py:196-197): the value the
+// reference prints in both duration columns of job.csv.  Jobs that never started keep their input duration.
+extern "C" int32_t rlgs_read_durations(rlgs_sim *s, int32_t r, double *out) {
+    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
+    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
+    if (s->legacy || !s->opts.enable_network_costs) return fail(RLGS_ERR_STATE, "network costs are not enabled");
+    CU(cudaSetDevice(s->device));
+    int J = s->h_desc[r].J;
+    std::vector<int32_t> st((size_t)J);
+    int32_t rc = rlgs_read_jobs(s, r, nullptr, st.data(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    std::vector<double> in((size_t)J);
+    CU(cudaMemcpy(in.data(), s->h_desc[r].net_in, 8 * (size_t)J, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, s->h_desc[r].dur_out, 8 * (size_t)J, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < J; ++i) if (st[i] < 0) out[i] = in[i];
     return RLGS_OK;
 }

@@ -47,8 +47,16 @@ struct RepDesc {
     int2 *place_log;        // [log_cap] (node | ntasks<<16, device mask) per (job, node), in node order
     int32_t *node_save;     // [3N + ceil(N/32)] cpu_used, mem_used, busy mask, ever-used bitmap
     int4 *slot_save;        // [2*slot_cap]
+    const double *net_in;   // [3][J]: duration, model MB, iterations (network-cost inputs; may be null)
+    double *dur_out;        // [J] duration after network costs (null unless enabled)
     int32_t J;
     int32_t log_cap;
+};
+
+// PS/worker transfer cost added to a job's duration when it is placed (core/network/network_service.py:3-39).
+struct NetCost {
+    int32_t enabled, pad;
+    double bandwidth, latency;   // --bandwidth (MB/s), --internode_latency (s)
 };
 
 struct ClusterConst {

@@ -103,8 +103,12 @@ class Scheduler(object):
             limits = parse_queue_limit(getattr(flags, 'queue_limit', None))
             kw = dict(num_queue=len(limits) + 1, queue_limit=limits)
             scheme = 'count'   # dlas admits by GPU count (run_sim.py:808-823) whatever --scheme says
-        if getattr(flags, 'enable_network_costs', False):
-            raise NotImplementedError('--enable_network_costs crashes in the reference (job.py:199-200); not available on the device path')
+        net = bool(getattr(flags, 'enable_network_costs', False))
+        if net and self.schedule != 'fifo':
+            raise NotImplementedError('--enable_network_costs is implemented for the fifo tick loop only')
+        if net:
+            kw.update(enable_network_costs=True, bandwidth=self.infrastructure.bandwidth,
+                      internode_latency=self.infrastructure.internode_latency)
         cluster = self.infrastructure.cluster
         trace = self.jobs_manager.trace
         sim = Simulator(cluster, self.schedule, scheme, n_replicas=1, rows=True, device=getattr(flags, 'device', 0), **kw)
@@ -119,7 +123,7 @@ class Scheduler(object):
                                                 util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
             j = sim.jobs(0)
             logging.info('Total Time Taken in seconds: %d' % took)
-            self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt']))
+            self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt'], sim.durations(0) if net else None))
         else:
             from . import _ffi
             j = sim.jobs(0)

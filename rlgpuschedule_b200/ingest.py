@@ -73,6 +73,8 @@ class Trace:
     records: np.ndarray      # _ffi.JOB_DTYPE
     mem_shift: int           # mem_term unit = 2**-mem_shift MiB
     cap_mib: int
+    model_mb: np.ndarray = None      # network-cost inputs (zeros when the trace has no model_name / iterations)
+    iterations: np.ndarray = None
 
     def __len__(self):
         return len(self.records)
@@ -150,5 +152,10 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     rec['util_mu_q'] = np.clip(np.rint(np.minimum(ua, 100.0) * 512), 0, 65535).astype(np.uint16)
     rec['util_sd_q'] = np.clip(np.rint(np.maximum(um - ua, 0.0) / 2 * 512), 0, 65535).astype(np.uint16)
     rec['index'] = np.arange(n)
-    return Trace(label=df.index.to_numpy().astype(np.int64), nt=nt, duration=duration, used_gpus=used,
-                 records=np.ascontiguousarray(rec), mem_shift=shift, cap_mib=cap)
+    from .model_factory import size_mb
+    model_mb = (np.array([size_mb(m) for m in df['model_name']], dtype=np.float64) if 'model_name' in df.columns
+                else np.zeros(n, dtype=np.float64))
+    iters = df['iterations'].to_numpy(dtype=np.float64) if 'iterations' in df.columns else np.zeros(n, dtype=np.float64)
+    return Trace(label=df.index.to_numpy().astype(np.int64), nt=nt, duration=np.ascontiguousarray(duration), used_gpus=used,
+                 records=np.ascontiguousarray(rec), mem_shift=shift, cap_mib=cap,
+                 model_mb=np.ascontiguousarray(model_mb), iterations=np.ascontiguousarray(iters))

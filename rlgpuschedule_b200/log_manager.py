@@ -107,8 +107,9 @@ def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duratio
     if with_header:
         w.writerow(JOB_HEADER)
     fo = np.asarray(finish_order, dtype=np.int64)
-    dur = trace.duration[fo]
-    act = dur if actual_duration is None else np.asarray(actual_duration)[fo]
+    # with network costs Job.duration itself is increased (job.py:196-197), so both columns show the new value
+    dur = trace.duration[fo] if actual_duration is None else np.asarray(actual_duration)[fo]
+    act = dur
     st, en = np.asarray(start)[fo], np.asarray(end)[fo]
     jc = (en - st) if jct is None else np.asarray(jct)[fo]
     pre = np.ones(len(fo), dtype=np.int64) if preempt is None else np.asarray(preempt)[fo]

@@ -67,7 +67,13 @@ class Simulator(object):
     def load_trace(self, trace, first_replica=0, n_replicas=None):
         n_replicas = self.n_replicas - first_replica if n_replicas is None else n_replicas
         rec = np.ascontiguousarray(trace.records)
-        _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec), None))
+        net = None
+        if self._kw['enable_network_costs']:
+            dp = C.POINTER(C.c_double)
+            net = _ffi.NetcostInputs(trace.duration.ctypes.data_as(dp), trace.model_mb.ctypes.data_as(dp),
+                                     trace.iterations.ctypes.data_as(dp))
+        _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
+                                              C.byref(net) if net is not None else None))
         self._traces = [x for x in self._traces if (x[0], x[1]) != (first_replica, n_replicas)]
         self._traces.append((first_replica, n_replicas, trace))
 
@@ -135,6 +141,12 @@ class Simulator(object):
         _ffi.check(_ffi.lib().rlgs_rows_view(self._h, replica, chunk, C.byref(p), C.byref(n)))
         buf = (C.c_char * (n.value * _ffi.ROW_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=_ffi.ROW_DTYPE, count=n.value)
+
+    def durations(self, replica=0):
+        """Per-job duration after network costs (enable_network_costs only)."""
+        out = np.empty(len(self.trace_of(replica)), np.float64)
+        _ffi.check(_ffi.lib().rlgs_read_durations(self._h, replica, out.ctypes.data))
+        return out
 
     def job_plane(self, replica, plane):
         out = np.empty(len(self.trace_of(replica)), np.int32)
