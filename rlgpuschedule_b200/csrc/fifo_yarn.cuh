@@ -26,7 +26,14 @@ struct SlotView {
     int32_t *seq;      // start sequence number
     uint32_t *util;    // util_mu_q | util_sd_q<<16
     int64_t *memterm;
+    int32_t *next;     // calendar bucket chain / free-slot chain
+    int32_t *bkt;      // [RLGS_CAL_W] first slot of the jobs whose end tick == b (mod RLGS_CAL_W), -1 = empty
 };
+
+// Finish detection is a calendar: a started job is filed under its end tick modulo RLGS_CAL_W, so the
+// per-tick finish scan of the reference (jobs_manager.py:243-250, every running job) touches only
+// the bucket of the current tick.
+#define RLGS_CAL_W 128
 
 struct FifoSmem {
     NodeView nv;
@@ -34,9 +41,9 @@ struct FifoSmem {
 };
 
 __host__ __device__ inline size_t fifo_smem_bytes(int N, int slot_cap) {
-    size_t node_words = 3 * (size_t)N + (size_t)((N + 31) / 32);
+    size_t node_words = 4 * (size_t)N + (size_t)((N + 31) / 32);
     node_words = (node_words + 1) & ~(size_t)1;  // keep the int64 array 8-byte aligned
-    return node_words * 4 + (size_t)slot_cap * (6 * 4 + 8);
+    return node_words * 4 + (size_t)slot_cap * (7 * 4 + 8) + RLGS_CAL_W * 4;
 }
 
 __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int slot_cap) {
@@ -46,6 +53,7 @@ __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int s
     s.nv.mem = w; w += N;
     s.nv.busy = reinterpret_cast<uint32_t *>(w); w += N;
     s.nv.ever = reinterpret_cast<uint32_t *>(w); w += (N + 31) / 32;
+    s.nv.key = reinterpret_cast<uint32_t *>(w); w += N;
     if ((w - reinterpret_cast<int32_t *>(smem)) & 1) w += 1;
     s.sv.memterm = reinterpret_cast<int64_t *>(w); w += 2 * slot_cap;
     s.sv.end = w; w += slot_cap;
@@ -54,6 +62,8 @@ __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int s
     s.sv.mask = reinterpret_cast<uint32_t *>(w); w += slot_cap;
     s.sv.seq = w; w += slot_cap;
     s.sv.util = reinterpret_cast<uint32_t *>(w); w += slot_cap;
+    s.sv.next = w; w += slot_cap;
+    s.sv.bkt = w; w += RLGS_CAL_W;
     return s;
 }
 
@@ -72,32 +82,44 @@ __device__ __forceinline__ JobRec shfl_rec(const JobRec &r, int src) {
     return o;
 }
 
-// Saves / restores the shared-memory state of a replica (chunked runs and env steps).
-__device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, int N, int slot_cap, int hw, int lane, bool save) {
+// Saves / restores the shared-memory state of a replica (chunked runs and env steps).  The node keys,
+// the calendar buckets and the free-slot chain are derived data: they are rebuilt on restore.
+__device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, const ClusterConst &c, int slot_cap, RepState &st, int lane, bool save) {
+    const int N = c.N;
     int nw = 3 * N + (N + 31) / 32;
     int32_t *sm = s.nv.cpu;  // cpu, mem, busy, ever are contiguous
     for (int i = lane; i < nw; i += 32) {
         if (save) D.node_save[i] = sm[i]; else sm[i] = D.node_save[i];
     }
-    for (int i = lane; i < slot_cap; i += 32) {
+    const int hw = st.hw;
+    for (int i = lane; i < hw; i += 32) {
         if (save) {
-            if (i < hw) {
-                D.slot_save[2 * i] = make_int4(s.sv.end[i], s.sv.job[i], (int)s.sv.place[i], (int)s.sv.mask[i]);
-                int64_t m = s.sv.memterm[i];
-                D.slot_save[2 * i + 1] = make_int4(s.sv.seq[i], (int)s.sv.util[i], (int)(uint32_t)m, (int)(m >> 32));
-            }
+            D.slot_save[2 * i] = make_int4(s.sv.end[i], s.sv.job[i], (int)s.sv.place[i], (int)s.sv.mask[i]);
+            int64_t m = s.sv.memterm[i];
+            D.slot_save[2 * i + 1] = make_int4(s.sv.seq[i], (int)s.sv.util[i], (int)(uint32_t)m, (int)(m >> 32));
         } else {
-            if (i < hw) {
-                int4 a = D.slot_save[2 * i], b = D.slot_save[2 * i + 1];
-                s.sv.end[i] = a.x; s.sv.job[i] = a.y; s.sv.place[i] = (uint32_t)a.z; s.sv.mask[i] = (uint32_t)a.w;
-                s.sv.seq[i] = b.x; s.sv.util[i] = (uint32_t)b.y;
-                s.sv.memterm[i] = (int64_t)(((uint64_t)(uint32_t)b.w << 32) | (uint32_t)b.z);
-            } else {
-                s.sv.end[i] = RLGS_NEVER;
-            }
+            int4 a = D.slot_save[2 * i], b = D.slot_save[2 * i + 1];
+            s.sv.end[i] = a.x; s.sv.job[i] = a.y; s.sv.place[i] = (uint32_t)a.z; s.sv.mask[i] = (uint32_t)a.w;
+            s.sv.seq[i] = b.x; s.sv.util[i] = (uint32_t)b.y;
+            s.sv.memterm[i] = (int64_t)(((uint64_t)(uint32_t)b.w << 32) | (uint32_t)b.z);
         }
     }
     __syncwarp();
+    if (!save) {
+        for (int i = lane; i < N; i += 32) s.nv.key[i] = node_key(s.nv.cpu[i], s.nv.mem[i], s.nv.busy[i], c);
+        for (int i = lane; i < RLGS_CAL_W; i += 32) s.sv.bkt[i] = -1;
+        __syncwarp();
+        int free_head = -1;
+        if (lane == 0) {
+            for (int i = hw - 1; i >= 0; --i) {
+                int e = s.sv.end[i];
+                if (e == RLGS_NEVER) { s.sv.next[i] = free_head; free_head = i; }
+                else { int b = e & (RLGS_CAL_W - 1); s.sv.next[i] = s.sv.bkt[b]; s.sv.bkt[b] = i; }
+            }
+        }
+        st.free_hint = __shfl_sync(RLGS_FULL, free_head, 0);
+        __syncwarp();
+    }
 }
 
 // Releases the resources of the job in slot `sl` at tick d and records its completion.
@@ -131,11 +153,12 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
     st.util_var_sum -= sd * sd * ndev;
     if (lane == 0) {
         s.sv.end[sl] = RLGS_NEVER;
+        s.sv.next[sl] = st.free_hint;   // push on the free-slot chain
         D.end_tick[job] = st.d;
         D.finish_order[st.F] = job;
     }
+    st.free_hint = sl;
     st.F += 1; st.R -= 1;
-    if (st.free_hint < 0 || sl < st.free_hint) st.free_hint = sl;
     st.head_blocked = 0;  // resources were freed: the queue head may fit now
     __syncwarp();
 }
@@ -202,10 +225,12 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
     if (st.d == 0) {  // first launch of a run: empty cluster, no running jobs
         int nw = 3 * c.N + (c.N + 31) / 32;
         for (int i = lane; i < nw; i += 32) s.nv.cpu[i] = 0;
-        for (int i = lane; i < slot_cap; i += 32) s.sv.end[i] = RLGS_NEVER;
+        const uint32_t empty_key = node_key(0, 0, 0u, c);
+        for (int i = lane; i < c.N; i += 32) s.nv.key[i] = empty_key;
+        for (int i = lane; i < RLGS_CAL_W; i += 32) s.sv.bkt[i] = -1;
         __syncwarp();
     } else {
-        fifo_state_io(D, s, c.N, slot_cap, st.hw, lane, false);
+        fifo_state_io(D, s, c, slot_cap, st, lane, false);
     }
     const int J = D.J;
 
@@ -241,8 +266,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                     int first = st.cursor - ring_base;
                     if (arr) store_rec(D.stack + (st.head - k) + (idx - st.cursor), ring);
                     JobRec n0 = shfl_rec(ring, first);
-                    JobRec n1 = shfl_rec(ring, (first + 1) & 31);
-                    h1 = (k >= 2) ? n1 : h0;
+                    if (k >= 2) h1 = shfl_rec(ring, (first + 1) & 31); else h1 = h0;
                     h0 = n0;
                 } else {
                     // batch runs past the ring: count it from global memory, then copy records
@@ -286,13 +310,14 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                 int job = h0.index();
                 int ndev = h0.tasks() * h0.gpc();
                 const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, h0.tasks(), pr.nnodes, lane) : h0.dur();
-                int sl = st.free_hint;
-                if (sl < 0) { sl = st.hw; }
+                int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
+                if (sl >= 0) st.free_hint = s.sv.next[sl]; else sl = st.hw++;
                 if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
-                if (sl == st.hw) st.hw += 1;
-                st.free_hint = -1;
+                const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
+                const int cal_head = s.sv.bkt[cal];
                 if (lane == 0) {
                     s.sv.end[sl] = d + dur_ticks;
+                    s.sv.next[sl] = cal_head; s.sv.bkt[cal] = sl;      // file under the end tick
                     s.sv.job[sl] = job;
                     s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (h0.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
                     s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
@@ -335,13 +360,14 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
                     int job = hx.index();
                     int ndev = hx.tasks() * hx.gpc();
                     const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, lane) : hx.dur();
-                    int sl = st.free_hint;
-                    if (sl < 0) { sl = st.hw; }
+                    int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
+                    if (sl >= 0) st.free_hint = s.sv.next[sl]; else sl = st.hw++;
                     if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
-                    if (sl == st.hw) st.hw += 1;
-                    st.free_hint = -1;
+                    const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
+                    const int cal_head = s.sv.bkt[cal];
                     if (lane == 0) {
                         s.sv.end[sl] = d + dur_ticks;
+                        s.sv.next[sl] = cal_head; s.sv.bkt[cal] = sl;  // file under the end tick
                         s.sv.job[sl] = job;
                         s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (hx.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
                         s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
@@ -384,39 +410,21 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
         // ---------------- delta_time += 1; step; release finished jobs in start order
         st.d = d + 1;
         {
-            int nfin = 0, first_slot = -1, hole = -1;
-            for (int b = 0; b < st.hw; b += 32) {
-                int i = b + lane;
-                int e = i < st.hw ? s.sv.end[i] : 0;
-                unsigned fb = __ballot_sync(RLGS_FULL, e == st.d);
-                unsigned hb = __ballot_sync(RLGS_FULL, e == RLGS_NEVER);
-                if (fb) { if (first_slot < 0) first_slot = b + __ffs(fb) - 1; nfin += __popc(fb); }
-                if (hb && hole < 0) hole = b + __ffs(hb) - 1;
-            }
-            st.free_hint = hole;  // lowest free slot below hw (at most one start per tick consumes it)
-            if (nfin == 1) {
-                fifo_finish_slot(D, s, c, st, first_slot, lane);
-                st.events += 1;
-            } else if (nfin > 1) {
-                // several jobs finish this tick: running_jobs dict order = start order (schedule.py:144)
-                for (int n = 0; n < nfin; ++n) {
-                    int best_seq = RLGS_NEVER, best_slot = -1;
-                    for (int b = 0; b < st.hw; b += 32) {
-                        int i = b + lane;
-                        if (i < st.hw && s.sv.end[i] == st.d && s.sv.seq[i] < best_seq) { best_seq = s.sv.seq[i]; best_slot = i; }
-                    }
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        int os = __shfl_xor_sync(RLGS_FULL, best_seq, o), ol = __shfl_xor_sync(RLGS_FULL, best_slot, o);
-                        if (os < best_seq) { best_seq = os; best_slot = ol; }
-                    }
-                    fifo_finish_slot(D, s, c, st, best_slot, lane);
+            // calendar bucket of this tick: jobs whose end == d finish, in start order when there are several
+            // (running_jobs dict order, schedule.py:144); the others in the chain end a multiple of RLGS_CAL_W later
+            const int bk = st.d & (RLGS_CAL_W - 1);
+            for (;;) {
+                int sl = s.sv.bkt[bk], prev = -1, best = -1, best_prev = -1, best_seq = RLGS_NEVER;
+                while (sl >= 0) {
+                    int nx = s.sv.next[sl];
+                    if (s.sv.end[sl] == st.d) { int q = s.sv.seq[sl]; if (q < best_seq) { best_seq = q; best = sl; best_prev = prev; } }
+                    prev = sl; sl = nx;
                 }
-                st.events += nfin;
-            }
-            if (nfin) {
-                while (st.hw > 0 && s.sv.end[st.hw - 1] == RLGS_NEVER) st.hw -= 1;
-                if (st.free_hint >= st.hw) st.free_hint = -1;
+                if (best < 0) break;
+                if (lane == 0) { int nx = s.sv.next[best]; if (best_prev < 0) s.sv.bkt[bk] = nx; else s.sv.next[best_prev] = nx; }
+                __syncwarp();
+                fifo_finish_slot(D, s, c, st, best, lane);
+                st.events += 1;
             }
         }
 
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict
             env.done[blockIdx.x] = (uint8_t)(st.done != 0);
         }
     }
-    fifo_state_io(D, s, c.N, slot_cap, st.hw, lane, true);
+    fifo_state_io(D, s, c, slot_cap, st, lane, true);
     if (lane == 0) {
         states[blockIdx.x] = st;
         if (st.done) returns[blockIdx.x] = -st.sum_jct;  // episode return, read by the all-gather

@@ -129,7 +129,16 @@ struct NodeView {
     int32_t *mem;     // mem_used per node
     uint32_t *busy;   // busy-device bitmask per node
     uint32_t *ever;   // bitmap: node ever held a placed job (Node.placed_jobs is never cleared, q3)
+    uint32_t *key;    // idle devices << 16 | tasks the free cpu/mem can take: the two numbers every fit test needs
 };
+
+// key = popc(idle devices) << 16 | min(cpu_free // 12, mem_free // 60) clamped to [0, 65535]
+__device__ __forceinline__ uint32_t node_key(int cpu_used, int mem_used, uint32_t busy, const ClusterConst &c) {
+    int cf = c.cpu_cap - cpu_used, mf = c.mem_cap - mem_used;
+    int b = cf > 0 ? cf / RLGS_CPUS_PER_TASK : 0, m = mf > 0 ? mf / RLGS_MEM_PER_TASK : 0;
+    int t = min(min(b, m), 0xffff);
+    return ((uint32_t)__popc(~busy & c.gmask) << 16) | (uint32_t)t;
+}
 
 __device__ __forceinline__ bool node_is_free(int cpu_used, int mem_used, const ClusterConst &c) {
     return (c.cpu_cap - cpu_used > 0) || (c.mem_cap - mem_used > 0);  // infra/node.py:59-60

@@ -28,7 +28,7 @@ __device__ __forceinline__ void charge_nodes(NodeView nv, const ClusterConst &c,
         was = node_is_free(cu, mu, c);
         cu += RLGS_CPUS_PER_TASK * k; mu += RLGS_MEM_PER_TASK * k;
         now = node_is_free(cu, mu, c);
-        nv.cpu[i] = cu; nv.mem[i] = mu;
+        nv.cpu[i] = cu; nv.mem[i] = mu; nv.key[i] = node_key(cu, mu, nv.busy[i], c);
     }
     n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
 }
@@ -36,12 +36,9 @@ __device__ __forceinline__ void charge_nodes(NodeView nv, const ClusterConst &c,
 __device__ __forceinline__ int node_task_capacity(NodeView nv, const ClusterConst &c, int i, int gpc) {
     // min(free_devices // gpc, cpu_free // 12, mem_free // 60), python floor division; anything <= 0
     // places nothing (Node.can_fit_num_task, infra/node.py:109-127)
-    int fd = __popc(~nv.busy[i] & c.gmask);
-    int cf = c.cpu_cap - nv.cpu[i], mf = c.mem_cap - nv.mem[i];
-    int a = fd / gpc;
-    int b = cf > 0 ? cf / RLGS_CPUS_PER_TASK : 0;
-    int m = mf > 0 ? mf / RLGS_MEM_PER_TASK : 0;
-    return min(a, min(b, m));
+    (void)c;
+    uint32_t k = nv.key[i];
+    return min((int)(k >> 16) / gpc, (int)(k & 0xffff));
 }
 
 // Tries to place job `j` under yarn.  On success the node counters / masks are updated and the
@@ -58,8 +55,11 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
         for (int base = 0; base < c.N; base += 32) {
             int i = base + lane;
             bool ok = false;
-            if (i < c.N)
-                ok = __popc(~nv.busy[i] & c.gmask) >= need_g && (c.cpu_cap - nv.cpu[i]) >= c_need && (c.mem_cap - nv.mem[i]) >= m_need;
+            if (i < c.N) {
+                // idle devices >= gpus and cpu_free >= 12T and mem_free >= 60T (algorithm.py:407-409), from the node key
+                uint32_t k = nv.key[i];
+                ok = (int)(k >> 16) >= need_g && (int)(k & 0xffff) >= T;
+            }
             if (!fits) {  // no device accepts the task: every candidate node leaks T tasks of cpu/mem (q8)
                 charge_nodes(nv, c, i, ok, T, n_free_nodes);
                 continue;
@@ -80,6 +80,7 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
         __syncwarp();
         if (lane == 0) {
             nv.cpu[node] = cu; nv.mem[node] = mu; nv.busy[node] = busy | taken; nv.ever[node >> 5] = ew | bit;
+            nv.key[node] = node_key(cu, mu, busy | taken, c);
             place_log[log_pos] = make_int2(node | (T << 16), (int)taken);
         }
         __syncwarp();
@@ -125,7 +126,7 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
             was = node_is_free(cu, mu, c);
             cu += RLGS_CPUS_PER_TASK * take; mu += RLGS_MEM_PER_TASK * take;
             now = node_is_free(cu, mu, c);
-            nv.cpu[i] = cu; nv.mem[i] = mu; nv.busy[i] = busy | taken;
+            nv.cpu[i] = cu; nv.mem[i] = mu; nv.busy[i] = busy | taken; nv.key[i] = node_key(cu, mu, busy | taken, c);
             place_log[log_pos + written + __popc(tb & ((1u << lane) - 1))] = make_int2(i | (take << 16), (int)taken);
         }
         n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
@@ -151,7 +152,8 @@ __device__ __forceinline__ void release_entry(NodeView nv, const ClusterConst &c
         was = node_is_free(cu, mu, c);
         cu -= RLGS_CPUS_PER_TASK * tasks; mu -= RLGS_MEM_PER_TASK * tasks;
         now = node_is_free(cu, mu, c);
-        nv.cpu[node] = cu; nv.mem[node] = mu; nv.busy[node] &= ~(uint32_t)e.y;
+        uint32_t busy = nv.busy[node] & ~(uint32_t)e.y;
+        nv.cpu[node] = cu; nv.mem[node] = mu; nv.busy[node] = busy; nv.key[node] = node_key(cu, mu, busy, c);
     }
     n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
 }
