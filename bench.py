@@ -259,7 +259,10 @@ def main():
         j0 = sim2.jobs(0)
         assert len(rows0) == summ[0]['n_ticks'] and int(rows0['finished'][-1]) == len(j0['finish_order'])
         h2d = sum(len(tr.records) * 32 for tr in traces)
-        d2h = int(ticks_step * 64 + 4 * 4 * sum(len(traces[i].records) * (bounds[i + 1] - bounds[i]) for i in range(N_TRACES)) + R * 176)
+        from rlgpuschedule_b200 import _ffi
+        n_chunks = -(-max(s_['n_ticks'] for s_ in summ) // _ffi.ROWS_PER_CHUNK)        # whole chunks travel (chunk-major row store)
+        jmax = max(len(tr.records) for tr in traces)
+        d2h = int(n_chunks * R * _ffi.ROWS_PER_CHUNK * 64 + 3 * 4 * R * jmax + R * 264)
         e2e = {'value': events_all * args.steps / t2.item(), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'ms_per_step': 1e3 * t2.item() / args.steps}
         sim2.close()

@@ -175,7 +175,7 @@ int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t co
 /* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
  * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
  * valid until the next rlgs_run / destroy. */
-#define RLGS_ROWS_PER_CHUNK 8192
+#define RLGS_ROWS_PER_CHUNK 4096
 int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */

@@ -9,14 +9,14 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, 'librlgs.so')
+SO_PATH = os.environ.get('RLGS_LIB') or os.path.join(HERE, 'librlgs.so')   # RLGS_LIB: development override
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2}
 PLACE = {'yarn': 0, 'count': 1}
 ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
 MAX_QUEUES = 8
-ROWS_PER_CHUNK = 8192
+ROWS_PER_CHUNK = 4096
 PLANE_START, PLANE_END, PLANE_FINISH_ORDER, PLANE_AUX, PLANE_PREEMPT, PLANE_RESUME = range(6)
 
 

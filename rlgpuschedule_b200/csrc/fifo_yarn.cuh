@@ -204,8 +204,11 @@ __device__ __forceinline__ int netcost_dur_ticks(const RepDesc &D, const NetCost
     return c < 1.0 ? 1 : (c > 1.0e9 ? 1000000000 : (int)c);
 }
 
+#ifndef RLGS_FIFO_MIN_BLOCKS
+#define RLGS_FIFO_MIN_BLOCKS 16
+#endif
 template <bool ENV>
-__global__ void __launch_bounds__(32) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
+__global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
                                                        ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
                                                        int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env, NetCost net) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

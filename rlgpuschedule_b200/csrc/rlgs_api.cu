@@ -1,7 +1,7 @@
 // rlgs_api.cu — host side of the C ABI declared in include/rlgs.h (librlgs.so).
 //
 // Owns device memory, launches the simulation kernels, keeps the per-tick / per-event rows in a
-// chunk-major device store (chunk k = rows [k*8192, (k+1)*8192) of every replica, contiguous) and,
+// chunk-major device store (chunk k = rows [k*4096, (k+1)*4096) of every replica, contiguous) and,
 // in rows_mode FULL, streams chunk k to a pinned host mirror on a copy stream while chunk k+1 is
 // being simulated.  No torch types, no CPU fallback: every entry point fails with RLGS_ERR_CUDA
 // when no device is usable.
@@ -100,6 +100,7 @@ struct rlgs_sim {
     bool ran = false;
     float last_ms = 0.f;
     int last_launches = 0;
+    int64_t rows_hint = 0;   // rows of the longest replica in the previous run: sizes the speculative pipeline
 };
 
 extern "C" int32_t rlgs_version(void) { return RLGS_VERSION; }
@@ -432,10 +433,11 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         }
         max_arrival = std::max(max_arrival, s->traces[s->rep_trace[r]].max_arrival);
     }
+    int target_chunks = 0;   // chunks launched (and copied) before the host looks at the replica states
     if (rows) {
-        int64_t cap = s->opts.rows_cap > 0 ? s->opts.rows_cap : (int64_t)max_arrival + 4096;
-        int want = (int)std::max<int64_t>(1, (cap + RLGS_ROW_CHUNK - 1) / RLGS_ROW_CHUNK);
-        rc = add_chunks(s, std::max(want, (int)s->d_chunks.size()), eager_rows);
+        int64_t cap = s->opts.rows_cap > 0 ? s->opts.rows_cap : (s->rows_hint > 0 ? s->rows_hint : (int64_t)max_arrival + 4096);
+        target_chunks = (int)std::max<int64_t>(1, (cap + RLGS_ROW_CHUNK - 1) / RLGS_ROW_CHUNK);
+        rc = add_chunks(s, std::max(target_chunks, (int)s->d_chunks.size()), eager_rows);
         if (rc) return rc;
     }
     if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
@@ -464,7 +466,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
             // while chunk k+1 is being simulated.  The host does not wait until everything is enqueued.
             CU(get_event(s, ev_i++, &e_begin));
             CU(cudaEventRecord(e_begin, main_st));
-            for (; next_chunk < (int)s->d_chunks.size(); ++next_chunk) {
+            for (; next_chunk < target_chunks; ++next_chunk) {
                 launch(s, 0, R, budget, true, main_st);
                 CU(cudaGetLastError());
                 launches++;
@@ -511,8 +513,12 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
             return fail(RLGS_ERR_CAPACITY, "replica %d: runnable-entry table overflow", bad);
         }
         if (all_done) break;
-        if (rows_full) {   // a replica filled the allocated chunks: add some and keep going (state is saved on the device)
-            rc = add_chunks(s, (int)s->d_chunks.size() + std::max(1, (int)s->d_chunks.size() / 2), eager_rows);
+        if (pipelined) {   // the estimate was short: continue one chunk at a time
+            target_chunks += 1;
+            rc = add_chunks(s, std::max(target_chunks, (int)s->d_chunks.size()), true);
+            if (rc) return rc;
+        } else if (rows_full) {   // a replica filled the allocated chunks: add some and keep going (state is saved on the device)
+            rc = add_chunks(s, (int)s->d_chunks.size() + std::max(1, (int)s->d_chunks.size() / 8), eager_rows);
             if (rc) return rc;
         }
     }
@@ -528,7 +534,22 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         s->planes_on_host = 3;
     }
     CU(cudaStreamSynchronize(s->copy_stream));
+    if (getenv("RLGS_DEBUG")) {
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        // re-time one chunk copy in isolation to compare with the pipelined run
+        if (eager_rows && !s->d_chunks.empty()) {
+            cudaEventRecord(a, s->copy_stream);
+            cudaMemcpyAsync(s->h_chunks[0], s->d_chunks[0], chunk_bytes(s), cudaMemcpyDeviceToHost, s->copy_stream);
+            cudaEventRecord(b, s->copy_stream); cudaEventSynchronize(b);
+            float ms = 0; cudaEventElapsedTime(&ms, a, b);
+            fprintf(stderr, "[rlgs] chunk copy alone: %.1f MB in %.2f ms = %.1f GB/s; kernels %.1f ms, %d launches, %zu chunks\n",
+                    chunk_bytes(s) / 1e6, ms, chunk_bytes(s) / 1e6 / ms, total_ms, launches, s->d_chunks.size());
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+    }
     s->last_ms = total_ms; s->last_launches = launches;
+    s->rows_hint = 0;
+    for (int r = 0; r < R; ++r) s->rows_hint = std::max<int64_t>(s->rows_hint, progress_of(s, r).rows);
     for (int r = 0; r < R; ++r) s->h_returns[r] = -(s->legacy ? s->h_lstate[r].sum_jct : s->h_state[r].sum_jct);
     s->ran = true;
     for (int r = 0; r < R; ++r) {

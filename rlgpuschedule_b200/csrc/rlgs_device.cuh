@@ -67,7 +67,7 @@ struct ClusterConst {
 };
 
 // chunk-major row store shared by all kernels: row i of replica r lives in chunk i / RLGS_ROW_CHUNK
-#define RLGS_ROW_CHUNK_LOG 13
+#define RLGS_ROW_CHUNK_LOG 12
 #define RLGS_ROW_CHUNK (1 << RLGS_ROW_CHUNK_LOG)
 struct RowStore {
     rlgs_row *const *chunks;  // device array of chunk base pointers, each [n_replicas][RLGS_ROW_CHUNK]
