@@ -276,6 +276,13 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         per_launch_s = kern_s / args.steps
         achieved = alg_bytes_step / per_launch_s / 1e9
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one step's kernel work, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_traffic.json')))
+            if R == 2368:
+                traffic = tj['traffic_bytes_per_launch']
+        except Exception:
+            pass
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': 1e3 * dt_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -286,8 +293,9 @@ def main():
                        'parallelism': 'replicas: %d GPU x %d warps (1 warp = 1 replica)' % (world, R)},
             'jobs_per_sec': jobs_all * args.steps / dt_max, 'ticks_per_sec': ticks_all * args.steps / dt_max,
             'gpu_launches': launches, 'kernel_ms_per_step': 1e3 * per_launch_s,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                         'launch': 'one step = %d concurrent launches of fifo_yarn_kernel<false> (one per replica group / CUDA stream); bytes and time are per step' % (launches // max(args.steps, 1)),
                          'note': 'achieved = SURVEY 8(d) algorithmic bytes (8Q+12R+12N+8D+64 per tick) / kernel time; that state is held in '
                                  'shared memory / registers, so it is not DRAM traffic. hbm_stream_GBps = bytes this layout must move through HBM '
                                  '(records in, queue stack write+read, job tables, 64 B row per tick) / kernel time',

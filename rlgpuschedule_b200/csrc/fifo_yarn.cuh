@@ -19,14 +19,9 @@
 #include "yarn_place.cuh"
 
 struct SlotView {
-    int32_t *end;      // finish tick, RLGS_NEVER = free slot
-    int32_t *job;
-    uint32_t *place;   // node | tasks<<16, or 0xffff | nnodes<<16 for a multi-node job
-    uint32_t *mask;    // device mask, or first placement-log entry for a multi-node job
-    int32_t *seq;      // start sequence number
-    uint32_t *util;    // util_mu_q | util_sd_q<<16
+    int4 *a;           // end tick (RLGS_NEVER = free) | start sequence | next slot in the calendar / free chain | job
+    int4 *b;           // node | tasks<<16 (or 0xffff | nnodes<<16) | device mask (or first log entry) | util_mu_q|util_sd_q<<16 | -
     int64_t *memterm;
-    int32_t *next;     // calendar bucket chain / free-slot chain
     int32_t *bkt;      // [RLGS_CAL_W] first slot of the jobs whose end tick == b (mod RLGS_CAL_W), -1 = empty
 };
 
@@ -42,8 +37,8 @@ struct FifoSmem {
 
 __host__ __device__ inline size_t fifo_smem_bytes(int N, int slot_cap) {
     size_t node_words = 4 * (size_t)N + (size_t)((N + 31) / 32);
-    node_words = (node_words + 1) & ~(size_t)1;  // keep the int64 array 8-byte aligned
-    return node_words * 4 + (size_t)slot_cap * (7 * 4 + 8) + RLGS_CAL_W * 4;
+    node_words = (node_words + 3) & ~(size_t)3;  // 16-byte alignment of the int4 slot arrays
+    return node_words * 4 + (size_t)slot_cap * (16 + 16 + 8) + RLGS_CAL_W * 4;
 }
 
 __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int slot_cap) {
@@ -54,15 +49,10 @@ __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int s
     s.nv.busy = reinterpret_cast<uint32_t *>(w); w += N;
     s.nv.ever = reinterpret_cast<uint32_t *>(w); w += (N + 31) / 32;
     s.nv.key = reinterpret_cast<uint32_t *>(w); w += N;
-    if ((w - reinterpret_cast<int32_t *>(smem)) & 1) w += 1;
+    while ((w - reinterpret_cast<int32_t *>(smem)) & 3) w += 1;
+    s.sv.a = reinterpret_cast<int4 *>(w); w += 4 * slot_cap;
+    s.sv.b = reinterpret_cast<int4 *>(w); w += 4 * slot_cap;
     s.sv.memterm = reinterpret_cast<int64_t *>(w); w += 2 * slot_cap;
-    s.sv.end = w; w += slot_cap;
-    s.sv.job = w; w += slot_cap;
-    s.sv.place = reinterpret_cast<uint32_t *>(w); w += slot_cap;
-    s.sv.mask = reinterpret_cast<uint32_t *>(w); w += slot_cap;
-    s.sv.seq = w; w += slot_cap;
-    s.sv.util = reinterpret_cast<uint32_t *>(w); w += slot_cap;
-    s.sv.next = w; w += slot_cap;
     s.sv.bkt = w; w += RLGS_CAL_W;
     return s;
 }
@@ -94,14 +84,15 @@ __device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, cons
     const int hw = st.hw;
     for (int i = lane; i < hw; i += 32) {
         if (save) {
-            D.slot_save[2 * i] = make_int4(s.sv.end[i], s.sv.job[i], (int)s.sv.place[i], (int)s.sv.mask[i]);
+            int4 a = s.sv.a[i], b = s.sv.b[i];
             int64_t m = s.sv.memterm[i];
-            D.slot_save[2 * i + 1] = make_int4(s.sv.seq[i], (int)s.sv.util[i], (int)(uint32_t)m, (int)(m >> 32));
+            D.slot_save[2 * i] = make_int4(a.x, a.w, b.x, b.y);
+            D.slot_save[2 * i + 1] = make_int4(a.y, b.z, (int)(uint32_t)m, (int)(m >> 32));
         } else {
-            int4 a = D.slot_save[2 * i], b = D.slot_save[2 * i + 1];
-            s.sv.end[i] = a.x; s.sv.job[i] = a.y; s.sv.place[i] = (uint32_t)a.z; s.sv.mask[i] = (uint32_t)a.w;
-            s.sv.seq[i] = b.x; s.sv.util[i] = (uint32_t)b.y;
-            s.sv.memterm[i] = (int64_t)(((uint64_t)(uint32_t)b.w << 32) | (uint32_t)b.z);
+            int4 x = D.slot_save[2 * i], y = D.slot_save[2 * i + 1];
+            s.sv.a[i] = make_int4(x.x, y.x, -1, x.y);
+            s.sv.b[i] = make_int4(x.z, x.w, y.y, 0);
+            s.sv.memterm[i] = (int64_t)(((uint64_t)(uint32_t)y.w << 32) | (uint32_t)y.z);
         }
     }
     __syncwarp();
@@ -112,9 +103,9 @@ __device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, cons
         int free_head = -1;
         if (lane == 0) {
             for (int i = hw - 1; i >= 0; --i) {
-                int e = s.sv.end[i];
-                if (e == RLGS_NEVER) { s.sv.next[i] = free_head; free_head = i; }
-                else { int b = e & (RLGS_CAL_W - 1); s.sv.next[i] = s.sv.bkt[b]; s.sv.bkt[b] = i; }
+                int e = s.sv.a[i].x;
+                if (e == RLGS_NEVER) { s.sv.a[i].z = free_head; free_head = i; }
+                else { int b = e & (RLGS_CAL_W - 1); s.sv.a[i].z = s.sv.bkt[b]; s.sv.bkt[b] = i; }
             }
         }
         st.free_hint = __shfl_sync(RLGS_FULL, free_head, 0);
@@ -124,10 +115,10 @@ __device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, cons
 
 // Releases the resources of the job in slot `sl` at tick d and records its completion.
 __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, const ClusterConst &c, RepState &st, int sl, int lane) {
-    int job = s.sv.job[sl];
-    uint32_t place = s.sv.place[sl], mask = s.sv.mask[sl];
-    uint32_t util = s.sv.util[sl];
-    int64_t mterm = s.sv.memterm[sl];
+    const int4 sb = s.sv.b[sl];
+    const int job = s.sv.a[sl].w;
+    const uint32_t place = (uint32_t)sb.x, mask = (uint32_t)sb.y, util = (uint32_t)sb.z;
+    const int64_t mterm = s.sv.memterm[sl];
     int ndev;
     if ((place & 0xffff) != 0xffff) {
         release_entry(s.nv, c, lane == 0, make_int2((int)place, (int)mask), st.n_free_nodes);
@@ -152,8 +143,7 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
     st.util_mu_sum -= mu * ndev;
     st.util_var_sum -= sd * sd * ndev;
     if (lane == 0) {
-        s.sv.end[sl] = RLGS_NEVER;
-        s.sv.next[sl] = st.free_hint;   // push on the free-slot chain
+        s.sv.a[sl] = make_int4(RLGS_NEVER, 0, st.free_hint, job);   // push on the free-slot chain
         D.end_tick[job] = st.d;
         D.finish_order[st.F] = job;
     }
@@ -221,6 +211,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
     }
     FifoSmem s = fifo_carve(smem_raw, c.N, slot_cap);
     float reward_acc = 0.f;
+    rlgs_row *row_cur = nullptr;   // next row of this replica inside the current chunk
     const bool rows_mode = rs.chunks != nullptr;
     // device-resident chunk-major row store: a launch stops when the allocated chunks are full
     if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
@@ -294,7 +285,6 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 if (st.Q == 0) st.bottom_arr = d;
                 st.head -= k; st.Q += k; st.cursor += k;
                 st.sum_arr += (int64_t)k * d;
-                st.events += k;
                 st.head_blocked = 0;
                 if (st.Q > st.max_q) st.max_q = st.Q;
                 if (st.cursor >= ring_base + 32) {
@@ -314,18 +304,15 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 int ndev = h0.tasks() * h0.gpc();
                 const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, h0.tasks(), pr.nnodes, lane) : h0.dur();
                 int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
-                if (sl >= 0) st.free_hint = s.sv.next[sl]; else sl = st.hw++;
+                if (sl >= 0) st.free_hint = s.sv.a[sl].z; else sl = st.hw++;
                 if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                 const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
                 const int cal_head = s.sv.bkt[cal];
                 if (lane == 0) {
-                    s.sv.end[sl] = d + dur_ticks;
-                    s.sv.next[sl] = cal_head; s.sv.bkt[cal] = sl;      // file under the end tick
-                    s.sv.job[sl] = job;
-                    s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (h0.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
-                    s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
-                    s.sv.seq[sl] = st.start_seq;
-                    s.sv.util[sl] = h0.util();
+                    s.sv.a[sl] = make_int4(d + dur_ticks, st.start_seq, cal_head, job);
+                    s.sv.bkt[cal] = sl;                                   // file under the end tick
+                    s.sv.b[sl] = make_int4(pr.node >= 0 ? (pr.node | (h0.tasks() << 16)) : (int)(0xffffu | ((uint32_t)pr.nnodes << 16)),
+                                           pr.node >= 0 ? (int)pr.mask : st.log_len, (int)h0.util(), 0);
                     s.sv.memterm[sl] = h0.mem_term();
                     D.start_tick[job] = d;
                     D.place_off[job] = st.log_len;
@@ -340,7 +327,6 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 st.sum_arr -= h0.arrival();
                 st.sum_jct += (int64_t)(d + dur_ticks - h0.arrival());  // end is fixed at start (no preemption)
                 st.R += 1; st.Q -= 1; st.head += 1;
-                st.events += 1;
                 if (st.R > st.max_r) st.max_r = st.R;
                 h0 = h1;
                 if (st.Q > 1) h1 = load_rec(D.stack + st.head + 1);
@@ -364,18 +350,15 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                     int ndev = hx.tasks() * hx.gpc();
                     const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, lane) : hx.dur();
                     int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
-                    if (sl >= 0) st.free_hint = s.sv.next[sl]; else sl = st.hw++;
+                    if (sl >= 0) st.free_hint = s.sv.a[sl].z; else sl = st.hw++;
                     if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                     const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
                     const int cal_head = s.sv.bkt[cal];
                     if (lane == 0) {
-                        s.sv.end[sl] = d + dur_ticks;
-                        s.sv.next[sl] = cal_head; s.sv.bkt[cal] = sl;  // file under the end tick
-                        s.sv.job[sl] = job;
-                        s.sv.place[sl] = pr.node >= 0 ? (uint32_t)(pr.node | (hx.tasks() << 16)) : (0xffffu | ((uint32_t)pr.nnodes << 16));
-                        s.sv.mask[sl] = pr.node >= 0 ? pr.mask : (uint32_t)st.log_len;
-                        s.sv.seq[sl] = st.start_seq;
-                        s.sv.util[sl] = hx.util();
+                        s.sv.a[sl] = make_int4(d + dur_ticks, st.start_seq, cal_head, job);
+                        s.sv.bkt[cal] = sl;                               // file under the end tick
+                        s.sv.b[sl] = make_int4(pr.node >= 0 ? (pr.node | (hx.tasks() << 16)) : (int)(0xffffu | ((uint32_t)pr.nnodes << 16)),
+                                               pr.node >= 0 ? (int)pr.mask : st.log_len, (int)hx.util(), 0);
                         s.sv.memterm[sl] = hx.mem_term();
                         D.start_tick[job] = d;
                         D.place_off[job] = st.log_len;
@@ -396,8 +379,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                     if (m) store_rec(D.stack + st.head + lane + 1, mv);
                     __syncwarp();
                     st.R += 1; st.Q -= 1; st.head += 1;
-                    st.events += 1;
-                    if (st.R > st.max_r) st.max_r = st.R;
+                        if (st.R > st.max_r) st.max_r = st.R;
                     if (st.Q > 0) st.bottom_arr = D.stack[st.head + st.Q - 1].arrival_tick;
                 }
             }
@@ -418,16 +400,16 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
             const int bk = st.d & (RLGS_CAL_W - 1);
             for (;;) {
                 int sl = s.sv.bkt[bk], prev = -1, best = -1, best_prev = -1, best_seq = RLGS_NEVER;
+                int best_next = -1;
                 while (sl >= 0) {
-                    int nx = s.sv.next[sl];
-                    if (s.sv.end[sl] == st.d) { int q = s.sv.seq[sl]; if (q < best_seq) { best_seq = q; best = sl; best_prev = prev; } }
-                    prev = sl; sl = nx;
+                    const int4 e = s.sv.a[sl];                       // one 16-byte load per hop: end, seq, next
+                    if (e.x == st.d && e.y < best_seq) { best_seq = e.y; best = sl; best_prev = prev; best_next = e.z; }
+                    prev = sl; sl = e.z;
                 }
                 if (best < 0) break;
-                if (lane == 0) { int nx = s.sv.next[best]; if (best_prev < 0) s.sv.bkt[bk] = nx; else s.sv.next[best_prev] = nx; }
+                if (lane == 0) { if (best_prev < 0) s.sv.bkt[bk] = best_next; else s.sv.a[best_prev].z = best_next; }
                 __syncwarp();
                 fifo_finish_slot(D, s, c, st, best, lane);
-                st.events += 1;
             }
         }
 
@@ -435,7 +417,8 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
         st.sumQ += st.Q; st.sumR += st.R;
         if (ENV) reward_acc -= (float)(st.Q + st.R);
         if (rows_mode && lane == 0) {
-            rlgs_row *row = row_ptr(rs, blockIdx.x, st.d - 1);
+            if (((st.d - 1) & (RLGS_ROW_CHUNK - 1)) == 0 || row_cur == nullptr) row_cur = row_ptr(rs, blockIdx.x, st.d - 1);
+            rlgs_row *row = row_cur++;
             int4 w0 = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
             int4 w1 = make_int4(st.F, st.Q > 0 ? st.d - med_lo_arr : 0, st.Q > 0 ? st.d - med_hi_arr : 0,
                                 st.Q > 0 ? st.d - st.bottom_arr : 0);
@@ -448,6 +431,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
         }
     }
 
+    st.events = (int64_t)st.cursor + st.start_seq + st.F;   // arrivals + starts + finishes
     if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;   // the while condition of schedule.py:185
     if (ENV) {
         // observation: per node free GPUs / cpu / mem, the look-ahead window, queue statistics

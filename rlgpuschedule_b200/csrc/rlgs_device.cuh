@@ -82,6 +82,7 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // mask of the k lowest set bits of `freemask` (devices are taken in device-id order, node.py:209-219)
 __device__ __forceinline__ uint32_t lowest_bits(uint32_t freemask, int k) {
+    if (k == 1) return freemask & (0u - freemask);   // most jobs take one device
     uint32_t rem = freemask;
     for (int i = 0; i < k; ++i) rem &= rem - 1;
     return freemask ^ rem;
