@@ -23,11 +23,8 @@ def test_flags_follow_the_reference_conventions():
     flags.FLAGS.parse(['--t_bool'])
     assert flags.FLAGS.t_bool is True
     flags.reset_for_tests()
-    flags.FLAGS.parse(['--not_bool_flag_prefix', '--not_bool'])
-    flags.reset_for_tests()
-    flags.FLAGS.parse(['--not_bool'.replace('not_', 'not_')])  # unknown again
-    flags.reset_for_tests()
     flags.FLAGS.parse(['--t_bool', '--not_bool'])
+    assert flags.FLAGS.t_bool is False                  # --no<flag> negation (core/flags.py:100-104)
     flags.FLAGS.t_int = 11
     assert flags.FLAGS.t_int == 11
     flags.reset_for_tests()
