@@ -10,7 +10,7 @@
 //
 // Data movement per replica: job records (32 B) stream in from HBM in arrival order through a
 // register ring (one coalesced 1 KB read per 32 jobs); the queue is a stack of the same records in
-// global memory whose two front entries live in registers; node counters / busy masks and the
+// global memory whose front entry lives in registers; node counters / busy masks and the
 // running-job slots live in shared memory for the whole launch; one 64 B row per tick and
 // start/end ticks per job stream out.  pending_time and time_processed are not stored: a queued
 // job's pending time is d - arrival and a running job's processed time is d - start, so the
@@ -236,10 +236,9 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
         if (idx < J) ring = load_rec(D.trace + idx); else { ring.a = make_int4(RLGS_NEVER, 0, 0, 0); ring.b = make_int4(0, 0, 0, 0); }
     }
     // the two front entries of the queue live in registers
-    JobRec h0, h1;
-    h0.a = h0.b = h1.a = h1.b = make_int4(0, 0, 0, 0);
+    JobRec h0;   // the queue front lives in registers; after a pop the next record is fetched while the tick finishes
+    h0.a = h0.b = make_int4(0, 0, 0, 0);
     if (st.Q > 0) h0 = load_rec(D.stack + st.head);
-    if (st.Q > 1) h1 = load_rec(D.stack + st.head + 1);
 
     const int d_stop = st.d + tick_budget;
     while (true) {
@@ -260,7 +259,6 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                     int first = st.cursor - ring_base;
                     if (arr) store_rec(D.stack + (st.head - k) + (idx - st.cursor), ring);
                     JobRec n0 = shfl_rec(ring, first);
-                    if (k >= 2) h1 = shfl_rec(ring, (first + 1) & 31); else h1 = h0;
                     h0 = n0;
                 } else {
                     // batch runs past the ring: count it from global memory, then copy records
@@ -278,9 +276,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                         if (i2 < k) store_rec(D.stack + (st.head - k) + i2, load_rec(D.trace + st.cursor + i2));
                     }
                     __syncwarp();
-                    JobRec old0 = h0;
                     h0 = load_rec(D.stack + st.head - k);
-                    h1 = (k >= 2) ? load_rec(D.stack + st.head - k + 1) : old0;
                 }
                 if (st.Q == 0) st.bottom_arr = d;
                 st.head -= k; st.Q += k; st.cursor += k;
@@ -328,8 +324,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 st.sum_jct += (int64_t)(d + dur_ticks - h0.arrival());  // end is fixed at start (no preemption)
                 st.R += 1; st.Q -= 1; st.head += 1;
                 if (st.R > st.max_r) st.max_r = st.R;
-                h0 = h1;
-                if (st.Q > 1) h1 = load_rec(D.stack + st.head + 1);
+                if (st.Q > 0) h0 = load_rec(D.stack + st.head);   // consumed by the next tick's attempt
                 __syncwarp();
             } else if (h0.fits()) {
                 st.head_blocked = 1;  // a failed attempt has no side effect: skip retries until a release
