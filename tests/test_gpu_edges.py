@@ -50,7 +50,7 @@ def test_single_job_single_node():
 
 def test_32_gpus_per_node_full_mask():
     rng = np.random.default_rng(2)
-    rows = [dict(normalized_time=float(t), minutes=float(m), used_gpus=float(g), gpu_per_container=int(c))
+    rows = [dict(normalized_time=float(t), minutes=float(m), used_gpus=float(g), gpu_per_container=int(min(c, g)))
             for t, m, g, c in zip(np.sort(rng.uniform(0, 4e5, 80)), rng.uniform(2, 60, 80), rng.choice([1, 8, 16, 32, 40, 64], 80), rng.choice([1, 8], 80))]
     sim, _ = _cmp(tracegen.frame_rows(rows), dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=32, num_cpu_p_node=512, mem_p_node=2048))
     sim.close()
@@ -61,6 +61,7 @@ def test_512_node_cluster_and_slot_table_growth():
     # default 128 on-chip slots, so the handle is rebuilt with a larger table
     df = tracegen.frame_gen(2500, 21, 40)
     df['used_gpus'] = 1.0; df['gpu_per_container'] = 1
+    df['minutes'] = np.random.default_rng(5).uniform(300, 900, len(df))   # long jobs: one start per tick fills > 128 slots
     sim, o = _cmp(df, dict(num_switch=8, num_node_p_switch=64, num_gpu_p_node=2))
     assert sim.summary(0)['max_running'] > 128
     sim.close()
