@@ -146,7 +146,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--replicas', type=int, default=2368, help='replicas per GPU (default 16 warps x 148 SMs)')
+    ap.add_argument('--replicas', type=int, default=2960, help='replicas per GPU (default 20 resident warps x 148 SMs)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -279,8 +279,7 @@ def main():
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one step's kernel work, from the committed ncu capture
         try:
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_traffic.json')))
-            if R == 2368:
-                traffic = tj['traffic_bytes_per_launch']
+            traffic = tj['traffic_bytes_per_launch'] * R / tj.get('replicas', 2368)   # rows + queue stack + job tables scale with the replica count
         except Exception:
             pass
         out = {

@@ -195,7 +195,7 @@ __device__ __forceinline__ int netcost_dur_ticks(const RepDesc &D, const NetCost
 }
 
 #ifndef RLGS_FIFO_MIN_BLOCKS
-#define RLGS_FIFO_MIN_BLOCKS 16
+#define RLGS_FIFO_MIN_BLOCKS 18
 #endif
 template <bool ENV>
 __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
