@@ -197,7 +197,7 @@ __device__ __forceinline__ int netcost_dur_ticks(const RepDesc &D, const NetCost
 #ifndef RLGS_FIFO_MIN_BLOCKS
 #define RLGS_FIFO_MIN_BLOCKS 18
 #endif
-template <bool ENV>
+template <bool ENV, bool ROWS, bool NET>
 __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states,
                                                        ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
                                                        int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env, NetCost net) {
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
     FifoSmem s = fifo_carve(smem_raw, c.N, slot_cap);
     float reward_acc = 0.f;
     rlgs_row *row_cur = nullptr;   // next row of this replica inside the current chunk
-    const bool rows_mode = rs.chunks != nullptr;
+    constexpr bool rows_mode = ROWS;   // compile-time: the row path disappears from the rows-off instantiations
     // device-resident chunk-major row store: a launch stops when the allocated chunks are full
     if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
         tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
             if (pr.ok) {
                 int job = h0.index();
                 int ndev = h0.tasks() * h0.gpc();
-                const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, h0.tasks(), pr.nnodes, lane) : h0.dur();
+                const int dur_ticks = NET ? netcost_dur_ticks(D, net, job, h0.tasks(), pr.nnodes, lane) : h0.dur();
                 int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
                 if (sl >= 0) st.free_hint = s.sv.a[sl].z; else sl = st.hw++;
                 if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 if (pr.ok) {
                     int job = hx.index();
                     int ndev = hx.tasks() * hx.gpc();
-                    const int dur_ticks = net.enabled ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, lane) : hx.dur();
+                    const int dur_ticks = NET ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, lane) : hx.dur();
                     int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
                     if (sl >= 0) st.free_hint = s.sv.a[sl].z; else sl = st.hw++;
                     if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }

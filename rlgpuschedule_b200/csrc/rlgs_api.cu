@@ -378,8 +378,13 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
     RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
     if (!s->legacy) {
         EnvIO none; memset(&none, 0, sizeof none);
-        fifo_yarn_kernel<false><<<count, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, budget,
-                                                                                         rs, s->d_returns + first, s->opts.max_ticks, none, netcost_of(s));
+        const size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
+        const NetCost nc = netcost_of(s);
+#define RLGS_LAUNCH_FIFO(ROWS, NET) fifo_yarn_kernel<false, ROWS, NET><<<count, 32, smem, st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, \
+                                        budget, rs, s->d_returns + first, s->opts.max_ticks, none, nc)
+        if (rows) { if (nc.enabled) RLGS_LAUNCH_FIFO(true, true); else RLGS_LAUNCH_FIFO(true, false); }
+        else { if (nc.enabled) RLGS_LAUNCH_FIFO(false, true); else RLGS_LAUNCH_FIFO(false, false); }
+#undef RLGS_LAUNCH_FIFO
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->opts.schedule == RLGS_SCHED_DLAS_GPU)
@@ -414,7 +419,10 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     if (!s->legacy) {
         size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
         if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else if (s->opts.schedule == RLGS_SCHED_SJF) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
@@ -710,7 +718,8 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     if (rc) return rc;
     size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
     if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica", smem);
-    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     for (int r = 0; r < s->R; ++r) {
         RepState z; memset(&z, 0, sizeof z);
@@ -739,8 +748,13 @@ extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs
     EnvIO io; io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.policy = policy; io.window_k = window_k;
     io.seed = seed; io.obs_dim = 3 * s->cc.N + 4 * window_k + 4;
     RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
-    fifo_yarn_kernel<true><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
-                                                                                s->d_returns, s->opts.max_ticks, io, netcost_of(s));
+    const NetCost nc = netcost_of(s);
+    if (nc.enabled)
+        fifo_yarn_kernel<true, false, true><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
+                                                                                                   s->d_returns, s->opts.max_ticks, io, nc);
+    else
+        fifo_yarn_kernel<true, false, false><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
+                                                                                                    s->d_returns, s->opts.max_ticks, io, nc);
     CU(cudaGetLastError());
     return RLGS_OK;
 }
