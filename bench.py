@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--replicas R]
 
 Workload (BASELINE.json metric "simulated events/sec on 60k-job trace"): R independent replicas per
-GPU of the 60 000-job Philly-style trace (oracle/tracegen.frame_gen(60000, seed, 60000); seed 3 is the
+GPU of the 60 000-job Philly-style trace (rlgpuschedule_b200/synth.py frame_gen(60000, seed, 60000); seed 3 is the
 trace whose reference output is pinned in tests/golden/probe60k) on the 4 switches x 32 nodes x 8 GPUs
 simulated cluster under fifo + yarn.  One "step" = every replica simulated to completion.
 An event = arrival | start | finish: 3 per finished job under non-preemptive fifo.
@@ -26,7 +26,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 
 N_JOBS = 60000
 CLUSTER_FLAGS = dict(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
@@ -37,8 +36,8 @@ WORKLOAD = 'fifo+yarn, 4x32x8 simulated cluster, 60k-job Philly-style trace (gen
 
 
 def frames(rank):
-    import tracegen
-    return [tracegen.frame_gen(N_JOBS, 3 + rank * N_TRACES + i, N_JOBS) for i in range(N_TRACES)]
+    from rlgpuschedule_b200 import synth
+    return [synth.frame_gen(N_JOBS, 3 + rank * N_TRACES + i, N_JOBS) for i in range(N_TRACES)]
 
 
 def algorithmic_bytes(summ, n_nodes, n_gpus):
@@ -89,6 +88,7 @@ def run_reference(args, rank, world):
     """CPU arm: the oracle port on all host cores, a bounded sample of the same workload per step."""
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))   # the only legs that touch oracle/: the CPU baseline
     import cpu_sim
     cores = os.cpu_count() or 1
     cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
@@ -122,6 +122,7 @@ def run_reference(args, rank, world):
 
 def cpu_baseline_sample():
     """Bounded cpu_baseline for the cuda arm's JSON line: a few seconds of the oracle on all cores."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import cpu_sim
     cores = os.cpu_count() or 1
     cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)

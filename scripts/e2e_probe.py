@@ -1,7 +1,8 @@
 import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-import tracegen, torch
+import torch
+from rlgpuschedule_b200 import synth as tracegen
 import rlgpuschedule_b200 as rl
 R = int(sys.argv[1]); NT = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 cluster = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)

@@ -4,7 +4,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
-import tracegen, golden_cases
+import golden_cases
+from rlgpuschedule_b200 import synth as tracegen
 import rlgpuschedule_b200 as rl
 from rlgpuschedule_b200.env import Environment
 import torch

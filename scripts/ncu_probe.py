@@ -2,7 +2,7 @@
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-import tracegen
+from rlgpuschedule_b200 import synth as tracegen
 import rlgpuschedule_b200 as rl
 n = int(sys.argv[1]); R = int(sys.argv[2]); rows = {'0': False, 'd': 'device'}[sys.argv[3]]
 cluster = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)

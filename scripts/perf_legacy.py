@@ -2,7 +2,7 @@
 import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-import tracegen
+from rlgpuschedule_b200 import synth as tracegen
 import rlgpuschedule_b200 as rl
 sched = sys.argv[1]; n = int(sys.argv[2]); span = int(sys.argv[3]); reps = [int(x) for x in sys.argv[4].split(',')]
 cluster = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)

@@ -3,7 +3,7 @@ import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
-import tracegen
+from rlgpuschedule_b200 import synth as tracegen
 import rlgpuschedule_b200 as rl
 
 def main():
