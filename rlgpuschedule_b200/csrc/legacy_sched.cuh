@@ -128,7 +128,8 @@ __device__ __forceinline__ void flush_unfinished(const LegDesc &D, const Ent *bu
 struct DlasEvent {
     int time, d, q, nq;
     int free_gpu, n_run, n_pend;
-    int new_end, new_jump;
+    int lane_end, lane_jump;   // per-lane minima, reduced across the warp once per event
+    int lane_flips;            // per-lane count of resumes + preemptions, reduced once per event
     int wr, wp, nd, ne;
     int64_t events, demotions;
 };
@@ -182,29 +183,24 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
         e.set_status(L_PENDING);
         e.b.z = (e.b.z & ~0xffff) | ((e.b.z + 1) & 0xffff);                   // preempt += 1
     }
-    ev.events += __popc(__ballot_sync(RLGS_FULL, resumed)) + __popc(__ballot_sync(RLGS_FULL, preempted));
+    ev.lane_flips += (int)resumed + (int)preempted;
     // ---- stable partition: RUNNING to dst, PENDING to the scratch (run_sim.py:838-848)
     unsigned rb = __ballot_sync(RLGS_FULL, stay && run), pb = __ballot_sync(RLGS_FULL, stay && !run);
     if (stay && run) store_ent(dst + ev.wr + __popc(rb & ((1u << lane) - 1)), e);
     if (stay && !run) store_ent(D.scratch_p + ev.wp + __popc(pb & ((1u << lane) - 1)), e);
     ev.wr += __popc(rb); ev.wp += __popc(pb);
     ev.n_run += __popc(rb); ev.n_pend += __popc(pb);
-    // ---- next end / next queue jump over RUNNING jobs (run_sim.py:908-943)
-    int my_end = RLGS_NEVER, my_jump = RLGS_NEVER;
+    // ---- next end / next queue jump over RUNNING jobs (run_sim.py:908-943): per-lane minima now, one warp reduction per event
     if (stay && run) {
-        my_end = ev.time + e.a.z - e.a.w;
+        ev.lane_end = min(ev.lane_end, ev.time + e.a.z - e.a.w);
         if (e.q() < ev.nq - 1) {
             int num = P.limit[e.q()] - e.b.x, g = e.gpus();                    // as written: executed_time, not gpu-time
-            int c = num >= 0 ? (num + g - 1) / g : -((-num) / g);              // math.ceil(num / g)
-            my_jump = c + ev.time;
+            int c;                                                             // math.ceil(num / g)
+            if ((g & (g - 1)) == 0) { int sh = 31 - __clz(g); c = num >= 0 ? (num + g - 1) >> sh : -((-num) >> sh); }
+            else c = num >= 0 ? (num + g - 1) / g : -((-num) / g);
+            ev.lane_jump = min(ev.lane_jump, c + ev.time);
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        my_end = min(my_end, __shfl_xor_sync(RLGS_FULL, my_end, o));
-        my_jump = min(my_jump, __shfl_xor_sync(RLGS_FULL, my_jump, o));
-    }
-    ev.new_end = min(ev.new_end, my_end); ev.new_jump = min(ev.new_jump, my_jump);
 }
 
 __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
@@ -216,12 +212,12 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
     const int J = D.J;
     int budget = P.event_budget;
     const bool rows_on = rs.chunks != nullptr;
+    int next_arr = st.cursor < J ? D.trace[st.cursor].arrival_tick : RLGS_NEVER;   // refreshed only when arrivals are consumed
     while (true) {
         if ((J - st.cursor) + st.M == 0) { st.done = 1; break; }                          // run_sim.py:679
         if ((J - st.cursor) == 0 && st.next_end == RLGS_NEVER) { st.done = 1; break; }    // :680-682 cluster too small
         if (budget-- <= 0) break;
         if (rows_on && st.n_rows >= (int64_t)rs.n_chunks * RLGS_ROW_CHUNK) break;
-        const int next_arr = st.cursor < J ? D.trace[st.cursor].arrival_tick : RLGS_NEVER;
         int event_time = min(next_arr, st.next_end);                                      // :684-713
         bool has_start = next_arr <= st.next_end;
         if (event_time > st.next_jump) { event_time = st.next_jump; has_start = false; }  // :715-717
@@ -242,7 +238,7 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
         if (st.M + k_arr > D.cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
         DlasEvent ev;
         ev.time = event_time; ev.d = event_time - st.t_prev; ev.nq = P.nq;
-        ev.free_gpu = P.total_gpu; ev.n_run = ev.n_pend = 0; ev.new_end = ev.new_jump = RLGS_NEVER;
+        ev.free_gpu = P.total_gpu; ev.n_run = ev.n_pend = 0; ev.lane_end = ev.lane_jump = RLGS_NEVER; ev.lane_flips = 0;
         ev.ne = 0; ev.events = 0; ev.demotions = 0; ev.nd = 0;
         const Ent *src = D.buf[st.cur];
         Ent *dst = D.buf[st.cur ^ 1];
@@ -312,15 +308,22 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
             }
             st.F += ev.ne;
         }
-        st.events += ev.events + ev.ne + k_arr;
+        int new_end = ev.lane_end, new_jump = ev.lane_jump, flips = ev.lane_flips;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            new_end = min(new_end, __shfl_xor_sync(RLGS_FULL, new_end, o));
+            new_jump = min(new_jump, __shfl_xor_sync(RLGS_FULL, new_jump, o));
+            flips += __shfl_xor_sync(RLGS_FULL, flips, o);
+        }
+        st.events += ev.events + flips + ev.ne + k_arr;
         st.demotions += ev.demotions;
         for (int q = 0; q < P.nq; ++q) st.qlen[q] = new_qlen[q];
         st.M = ev.n_run + ev.n_pend;
         st.sweep_jobs += st.M;   // runnable jobs swept at this event (after ends left and arrivals joined)
         if (st.M > st.max_m) st.max_m = st.M;
-        st.cursor += k_arr;
+        if (k_arr > 0) { st.cursor += k_arr; next_arr = st.cursor < J ? D.trace[st.cursor].arrival_tick : RLGS_NEVER; }
         st.cur ^= 1;
-        st.next_end = ev.new_end; st.next_jump = ev.new_jump;
+        st.next_end = new_end; st.next_jump = new_jump;
         st.t_prev = event_time;
         if (rows_on && lane == 0) {                                                       // LOG.checkpoint, count branch (log.py:225-238)
             int busy = P.total_gpu - ev.free_gpu;
