@@ -262,9 +262,7 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
                     bool valid = b + lane < n_dem_in;
                     Ent e; e.a = e.b = make_int4(0, 0, 0, 0);
                     if (valid) e = load_ent(din + b + lane);
-                    int nd_keep = ev.nd;
                     dlas_chunk(D, P, ev, e, valid, 1, dq, dem_out, st.t_prev, lane);
-                    ev.nd = nd_keep;
                 }
             }
             if (q == 0 && k_arr > 0) {
@@ -417,7 +415,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
         for (int i = lane; i < nw; i += 32) nv.cpu[i] = 0;
         for (int i = lane; i < c.N; i += 32) nv.key[i] = empty_key;
         __syncwarp();
-        int n_free_nodes = (c.cpu_cap > 0 || c.mem_cap > 0) ? c.N : 0, idle_dummy = c.N;
+        int n_free_nodes = (c.cpu_cap > 0 || c.mem_cap > 0) ? c.N : 0, idle_unused = c.N;   // yarn_place's sticky idle-node counter is a fifo statistic
         // ---- one pass in priority order: drop ended jobs, sweep, re-place, flip, minima
         int w_out = 0, n_run = 0, n_pend = 0, new_end = RLGS_NEVER;
         const int M0 = st.M;
@@ -443,7 +441,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
                 if (e.a.y & (1 << 23)) e.a.y &= ~(1 << 23);                               // last_check_time == event_time: nothing to add
                 else if (status == L_RUNNING) e.a.w += d; else e.b.y += d;               // :216-230
                 JobRec jr; jr.a = make_int4(0, e.a.z, e.b.x, e.b.w); jr.b = make_int4(0, 0, 0, job);
-                PlaceResult pr = yarn_place(nv, c, jr, lane, D.place_scratch, 0, n_free_nodes, idle_dummy);   // :246
+                PlaceResult pr = yarn_place(nv, c, jr, lane, D.place_scratch, 0, n_free_nodes, idle_unused);   // :246
                 if (pr.ok) {
                     if (!e.started()) { e.set_started(); if (lane == 0) D.planes[0][job] = event_time; }    // :251-252
                     if (status == L_PENDING) { e.set_status(L_RUNNING); e.b.z += 1 << 16; n_events += 1; }   // :265-267

@@ -542,19 +542,6 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         s->planes_on_host = 3;
     }
     CU(cudaStreamSynchronize(s->copy_stream));
-    if (getenv("RLGS_DEBUG")) {
-        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-        // re-time one chunk copy in isolation to compare with the pipelined run
-        if (eager_rows && !s->d_chunks.empty()) {
-            cudaEventRecord(a, s->copy_stream);
-            cudaMemcpyAsync(s->h_chunks[0], s->d_chunks[0], chunk_bytes(s), cudaMemcpyDeviceToHost, s->copy_stream);
-            cudaEventRecord(b, s->copy_stream); cudaEventSynchronize(b);
-            float ms = 0; cudaEventElapsedTime(&ms, a, b);
-            fprintf(stderr, "[rlgs] chunk copy alone: %.1f MB in %.2f ms = %.1f GB/s; kernels %.1f ms, %d launches, %zu chunks\n",
-                    chunk_bytes(s) / 1e6, ms, chunk_bytes(s) / 1e6 / ms, total_ms, launches, s->d_chunks.size());
-        }
-        cudaEventDestroy(a); cudaEventDestroy(b);
-    }
     s->last_ms = total_ms; s->last_launches = launches;
     s->rows_hint = 0;
     for (int r = 0; r < R; ++r) s->rows_hint = std::max<int64_t>(s->rows_hint, progress_of(s, r).rows);

@@ -97,9 +97,6 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
-__device__ __forceinline__ int4 ld_int4(const void *p) { return *reinterpret_cast<const int4 *>(p); }
-__device__ __forceinline__ void st_int4(void *p, int4 v) { *reinterpret_cast<int4 *>(p) = v; }
-
 __device__ __forceinline__ int4 shfl_int4(int4 v, int src) {
     int4 r;
     r.x = __shfl_sync(RLGS_FULL, v.x, src);
