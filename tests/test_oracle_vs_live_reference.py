@@ -1,0 +1,49 @@
+"""Randomised differential test: oracle/cpu_sim.c vs the UNMODIFIED reference run live (only where
+/root/reference is mounted, i.e. in the build container; skipped on the GPU box).  Complements the fixed
+golden cases with fresh random traces / cluster shapes on every seed listed here."""
+import os
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+import cpu_sim
+import ref_runner
+from rlgpuschedule_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_runner.available(), reason='reference not mounted')
+
+
+def _case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(20, 90))
+    flags = dict(num_switch=int(rng.integers(1, 3)), num_node_p_switch=int(rng.integers(1, 5)),
+                 num_gpu_p_node=int(rng.choice([2, 4, 8])), num_cpu_p_node=int(rng.choice([24, 48, 128])),
+                 mem_p_node=int(rng.choice([120, 256, 512])), gpu_memory_capacity=int(rng.choice([8, 16, 32])))
+    g = rng.choice([1, 2, 3, 4, 6, 8, 16], n)
+    gpc = np.array([int(rng.choice([c for c in (1, 2, 3, 4, 8) if c <= x])) for x in g])
+    rows = [dict(normalized_time=float(t), minutes=float(m), used_gpus=float(a), gpu_per_container=int(b),
+                 memory_max=int(mm), gpu_utilization_avg=float(u), gpu_utilization_max=float(min(100, u + 10)))
+            for t, m, a, b, mm, u in zip(np.sort(rng.uniform(0, 6e5, n)).round(-3 if seed % 2 else 0), rng.uniform(0.5, 60, n), g, gpc,
+                                         rng.uniform(5e8, 1.9e10, n), rng.uniform(1, 90, n))]
+    return synth.frame_rows(rows), flags
+
+
+def _run(seed):
+    df, flags = _case(seed)
+    work = tempfile.mkdtemp(prefix='rlgs_live_%d_' % seed)
+    trace = os.path.join(work, 't.csv')
+    synth.write(df, trace)
+    ref = ref_runner.run_reference(trace, workdir=work, **flags)
+    tr = cpu_sim.prepare_trace(trace)
+    res = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**flags), tr)
+    return seed, ref, cpu_sim.format_job_csv(tr, res), cpu_sim.format_cluster_csv(res)
+
+
+def test_oracle_equals_live_reference_on_random_cases():
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for seed, ref, job, clu in ex.map(_run, range(100, 112)):
+            assert ref['job_csv'] is not None, (seed, ref['stderr'][-500:])
+            assert job == ref['job_csv'], seed
+            assert clu == ref_runner.strip_util_column(ref['cluster_csv']), seed
