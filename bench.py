@@ -304,7 +304,7 @@ def main():
         }
         if e2e:
             out['e2e'] = e2e
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only
             out['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(out))
     if world > 1:
