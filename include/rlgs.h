@@ -95,7 +95,8 @@ typedef struct {
     uint16_t gpus_per_task;/* gpu_per_container */
     uint16_t least_nodes_fits; /* bit15 = an empty device accepts the task (infra/device.py:67-77);
                                   bits0-14 = ceil(used_gpus / num_gpu_p_node) (algorithm.py:310) */
-    int64_t mem_term;      /* min(cap, memory_max MiB) per occupied device in units of 2^-mem_shift MiB */
+    int64_t mem_term;      /* tasks * gpus_per_task * min(cap, memory_max MiB): what the job adds to the
+                              avg_gpu_memory_allocated numerator, in units of 2^-mem_shift MiB */
     uint16_t util_mu_q;    /* gpu_utilization_avg * 512 (statistics of the unseeded RNG column only) */
     uint16_t util_sd_q;    /* (gpu_utilization_max - gpu_utilization_avg)/2 * 512 */
     int32_t index;         /* position of this job in the trace (0..n-1) */
@@ -150,7 +151,7 @@ void rlgs_destroy(rlgs_sim *sim);
 
 /* Replaces JobTraceReader ingestion into JobsManager (jobs_manager.py:16-18,228-241): copies `n` job
  * records to the device once and attaches them to replicas [first_replica, first_replica+n_replicas).
- * mem_shift/mem_cap_term describe the fixed-point unit of rlgs_job.mem_term.  `net` may be NULL. */
+ * `net` may be NULL unless opts.enable_network_costs is set. */
 int32_t rlgs_load_trace(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas, const rlgs_job *jobs, int32_t n,
                         const rlgs_netcost_inputs *net);
 

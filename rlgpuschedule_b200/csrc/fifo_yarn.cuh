@@ -138,7 +138,7 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
     }
     __syncwarp();
     st.busy_gpus -= ndev;
-    st.mem_sum -= mterm * ndev;
+    st.mem_sum -= mterm;   // mem_term already is the job's total over its devices
     int64_t mu = util & 0xffff, sd = util >> 16;
     st.util_mu_sum -= mu * ndev;
     st.util_var_sum -= sd * sd * ndev;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 st.log_len += pr.nnodes;
                 st.start_seq += 1;
                 st.busy_gpus += ndev;
-                st.mem_sum += h0.mem_term() * ndev;
+                st.mem_sum += h0.mem_term();
                 int64_t mu = h0.util() & 0xffff, sd = h0.util() >> 16;
                 st.util_mu_sum += mu * ndev;
                 st.util_var_sum += sd * sd * ndev;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                     st.log_len += pr.nnodes;
                     st.start_seq += 1;
                     st.busy_gpus += ndev;
-                    st.mem_sum += hx.mem_term() * ndev;
+                    st.mem_sum += hx.mem_term();
                     int64_t mu = hx.util() & 0xffff, sd = hx.util() >> 16;
                     st.util_mu_sum += mu * ndev;
                     st.util_var_sum += sd * sd * ndev;
@@ -393,15 +393,15 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
             // calendar bucket of this tick: jobs whose end == d finish, in start order when there are several
             // (running_jobs dict order, schedule.py:144); the others in the chain end a multiple of RLGS_CAL_W later
             const int bk = st.d & (RLGS_CAL_W - 1);
-            for (;;) {
-                int sl = s.sv.bkt[bk], prev = -1, best = -1, best_prev = -1, best_seq = RLGS_NEVER;
-                int best_next = -1;
+            for (int more = 1; more;) {
+                int sl = s.sv.bkt[bk], prev = -1, best = -1, best_prev = -1, best_seq = RLGS_NEVER, best_next = -1, matches = 0;
                 while (sl >= 0) {
                     const int4 e = s.sv.a[sl];                       // one 16-byte load per hop: end, seq, next
-                    if (e.x == st.d && e.y < best_seq) { best_seq = e.y; best = sl; best_prev = prev; best_next = e.z; }
+                    if (e.x == st.d) { matches++; if (e.y < best_seq) { best_seq = e.y; best = sl; best_prev = prev; best_next = e.z; } }
                     prev = sl; sl = e.z;
                 }
                 if (best < 0) break;
+                more = matches > 1;                                  // walk again only if another job finishes this tick
                 if (lane == 0) { if (best_prev < 0) s.sv.bkt[bk] = best_next; else s.sv.a[best_prev].z = best_next; }
                 __syncwarp();
                 fifo_finish_slot(D, s, c, st, best, lane);

@@ -148,7 +148,8 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     if n and (shift > 60 or scaled.max() * max(cluster.num_gpus, 1) >= 2.0 ** 53):
         raise ValueError('memory_max values are not exactly summable in 53 bits; cannot reproduce '
                          'avg_gpu_memory_allocated bit-exactly')
-    rec['mem_term'] = scaled.astype(np.int64)
+    # stored as the job's total over the devices it occupies (tasks * gpus_per_task): the kernel only adds / subtracts it
+    rec['mem_term'] = scaled.astype(np.int64) * (tasks * gpc)
     rec['util_mu_q'] = np.clip(np.rint(np.minimum(ua, 100.0) * 512), 0, 65535).astype(np.uint16)
     rec['util_sd_q'] = np.clip(np.rint(np.maximum(um - ua, 0.0) / 2 * 512), 0, 65535).astype(np.uint16)
     rec['index'] = np.arange(n)

@@ -71,7 +71,7 @@ def test_row_finishing_reproduces_the_reference_floats(name):
         pend = np.sort(d - arr[queued])
         r = rows[d - 1]
         r['queued'] = len(queued); r['running'] = running.sum(); r['finished'] = ((end >= 0) & (end <= d)).sum()
-        r['busy_gpus'] = ndev[running].sum(); r['mem_sum'] = (ndev[running] * tr.records['mem_term'][running]).sum()
+        r['busy_gpus'] = ndev[running].sum(); r['mem_sum'] = tr.records['mem_term'][running].sum()
         r['sum_pending'] = pend.sum()
         if len(pend):
             r['median_lo'] = pend[(len(pend) - 1) // 2]; r['median_hi'] = pend[len(pend) // 2]; r['max_pending'] = pend[-1]
@@ -106,7 +106,7 @@ def test_ingest_rejects_what_the_reference_would_raise_on():
         rl.prepare_trace(df, cluster)                    # zero tasks: StopIteration at node.py:118 in the reference
     df = tracegen.frame_rows([dict(used_gpus=2.0, gpu_per_container=1, memory_max=5000000001.5)])
     t = rl.prepare_trace(df, cluster)
-    assert t.mem_shift == 21 and int(t.records['mem_term'][0]) == int(5000000001.5 * 2)
+    assert t.mem_shift == 21 and int(t.records['mem_term'][0]) == 2 * int(5000000001.5 * 2)
     df = tracegen.frame_rows([dict(memory_max=1e9 / 3)])
     with pytest.raises(ValueError):
         rl.prepare_trace(df, cluster)                    # not exactly summable in 53 bits
