@@ -141,6 +141,25 @@ def cpu_baseline_sample():
             'single_core_value': ev1 / dt1}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host mirrors it
+    allocates are first-touched on the GPU's NUMA node: with several ranks per box the device->host copies
+    otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -165,6 +184,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl cuda needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -304,7 +325,8 @@ def main():
         }
         if e2e:
             out['e2e'] = e2e
-        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only, on every host core
+            os.sched_setaffinity(0, all_cpus)
             out['cpu_baseline'] = cpu_baseline_sample()
         print(json.dumps(out))
     if world > 1:
