@@ -5,6 +5,7 @@ import pytest
 
 import cpu_sim
 import tracegen
+from rlgpuschedule_b200 import synth
 import rlgpuschedule_b200 as rl
 from rlgpuschedule_b200 import _ffi, log_manager as lm
 
@@ -82,3 +83,33 @@ def test_row_store_grows_across_chunks():
         sim.run()                                                   # second run sizes the pipeline from the first
         assert np.array_equal(sim.rows(1), r)
         sim.close()
+
+
+@pytest.mark.parametrize('mode', [True, 'device'])
+def test_replicas_with_different_lengths_across_row_chunks(mode):
+    """Three traces whose makespans straddle the 4096-row chunks differently, reloaded and rerun (the e2e pattern)."""
+    flags = dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=4)
+    cluster = rl.cluster_from_flags(flags)
+
+    def frame(long_minutes, n_extra, seed):
+        rng = np.random.default_rng(seed)
+        rows = [dict(normalized_time=0, minutes=float(long_minutes), used_gpus=2.0, gpu_per_container=1)]
+        rows += [dict(normalized_time=float(t), minutes=float(m), used_gpus=float(g), gpu_per_container=1)
+                 for t, m, g in zip(np.sort(rng.uniform(1e4, 2e7, n_extra)), rng.uniform(1, 300, n_extra), rng.choice([1, 2, 4], n_extra))]
+        return synth.frame_rows(rows)
+    frames = [frame(6000, 40, 1), frame(10000, 60, 2), frame(18500, 80, 3)]
+    traces = [rl.prepare_trace(f, cluster) for f in frames]
+    sim = rl.Simulator(cluster, n_replicas=5, rows=mode, fetch_jobs=True)
+    layout = [(0, 2, 0), (2, 1, 1), (3, 2, 2)]
+    for rep in range(2):
+        for first, count, t in layout:
+            sim.load_trace(traces[t], first, count)
+        sim.run()
+        for first, count, t in layout:
+            o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(frames[t]))
+            for r in (first, first + count - 1):
+                assert sim.summary(r)['n_ticks'] == o['n_ticks']
+                j = sim.jobs(r)
+                assert np.array_equal(j['end'], o['end']) and np.array_equal(j['finish_order'], o['finish_order'])
+                assert lm.format_cluster_csv(sim.rows(r), cluster, traces[t].mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+    sim.close()
