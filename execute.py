@@ -1,56 +1,66 @@
 #!/usr/bin/env python
-"""Experiment sweep driver with the reference's execute.py shape (execute.py:5-55): one run_sim.py
-child process per (scheme, schedule, num_queue, num_buffer, repeat), strictly sequential.
+"""Sequential experiment sweep over run_sim.py, the role execute.py plays in the reference
+(execute.py:5-55 there): every (placement, schedule, queues, look-ahead) combination is run `--repeats`
+times as its own child process and logs under log/thesis_fitted_<k>_nodes_p_s<N>_job_<trace>/<scheme>_<schedule>/.
 
-The reference sweeps horus+/horus/gandiva/yarn; here the default sweep covers the schedules the device
-path implements (fifo, sjf, dlas-gpu).  `--reference-sweep` uses the reference's own list: the
-horus / gandiva combinations then exit with "not implemented by the device path".
+Default sweep = the schedules this package runs on the GPU (fifo, sjf, dlas-gpu).  `--reference-sweep`
+replays the reference's own list (horus+ x3, horus, gandiva, yarn/fifo): the packing heuristics are not
+implemented on the device path, so those children stop with a NotImplementedError.
 """
 import argparse
 import os
+import subprocess
 import sys
-from subprocess import Popen
+from collections import namedtuple
+
+Run = namedtuple('Run', 'scheme schedule num_queue num_buffer')
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+DEVICE_SWEEP = [Run('yarn', 'fifo', 1, 1), Run('yarn', 'sjf', 1, 1), Run('count', 'dlas-gpu', 4, 1)]
+REFERENCE_SWEEP = [Run(s, s, q, b) for s, q in (('horus+', 3), ('horus+', 4), ('horus+', 5), ('horus', 1), ('gandiva', 1))
+                   for b in (15, 15, 15, 1, 1, 1)] + [Run('yarn', 'fifo', 1, b) for b in (15, 15, 15, 1, 1, 1)]
 
 
-def do_once(scheme, schedule, num_queue, num_buffer, trace_file='month', num_nodes_p_switch=32, num_switch=4, data_dir='data'):
-    migrate = True
-    log_sub_dir = 'thesis_fitted_' + str(num_buffer) + '_nodes_p_s' + str(num_nodes_p_switch) + '_job_' + trace_file
-    log_path = os.path.join(log_sub_dir, '%s_%s' % (scheme, schedule))
-    if schedule == 'horus+':
-        log_path = os.path.join(log_path, 'k' + str(num_queue))
-    cmd = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'run_sim.py'),
-           '--num_node_p_switch', str(num_nodes_p_switch), '--num_switch', str(num_switch), '--scheme', scheme,
-           '--trace_file', os.path.join(data_dir, trace_file + '.csv'), '--num_queue', str(num_queue),
-           '--num_buffer', str(num_buffer), '--schedule', schedule, '--enable_network_costs', 'False',
-           '--enable_migration', str(migrate), '--log_path', log_path]
-    p = Popen(cmd)
-    print('process pid %d: ' % p.pid)
+def log_dir_for(run, trace_name, nodes_per_switch):
+    parts = ['thesis_fitted_%d_nodes_p_s%d_job_%s' % (run.num_buffer, nodes_per_switch, trace_name),
+             '%s_%s' % (run.scheme, run.schedule)]
+    if run.schedule == 'horus+':
+        parts.append('k%d' % run.num_queue)
+    return os.path.join(*parts)
+
+
+def launch(run, opts):
+    argv = [sys.executable, os.path.join(HERE, 'run_sim.py'),
+            '--scheme', run.scheme, '--schedule', run.schedule,
+            '--num_queue', str(run.num_queue), '--num_buffer', str(run.num_buffer),
+            '--num_switch', str(opts.num_switch), '--num_node_p_switch', str(opts.num_node_p_switch),
+            '--trace_file', os.path.join(opts.data_dir, opts.trace + '.csv'),
+            '--enable_network_costs', 'False', '--enable_migration', 'True',
+            '--log_path', log_dir_for(run, opts.trace, opts.num_node_p_switch)]
+    child = subprocess.Popen(argv)
+    print('process pid %d: %s' % (child.pid, ' '.join(argv[2:])), flush=True)
     try:
-        return p.wait()
+        return child.wait()
     except KeyboardInterrupt:
-        p.kill()
-        return -1
+        child.kill()
+        raise
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--reference-sweep', action='store_true')
-    ap.add_argument('--trace', default='month')
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    ap.add_argument('--reference-sweep', action='store_true', help="the reference's own combination list")
+    ap.add_argument('--trace', default='month', help='trace name: <data-dir>/<trace>.csv')
     ap.add_argument('--data-dir', default='data')
     ap.add_argument('--repeats', type=int, default=3)
-    a = ap.parse_args()
-    if a.reference_sweep:
-        schemes = ['horus+', 'horus+', 'horus+', 'horus', 'gandiva', 'yarn']
-        queues = [3, 4, 5, 1, 1, 1]
-        schedules = ['horus+', 'horus+', 'horus+', 'horus', 'gandiva', 'fifo']
-        buffers = [15, 15, 15, 1, 1, 1]
-    else:
-        schemes, queues, schedules, buffers = ['yarn', 'yarn', 'count'], [1, 1, 4], ['fifo', 'sjf', 'dlas-gpu'], [1]
-    for scheme, schedule, queue in zip(schemes, schedules, queues):
-        for buff in buffers:
-            for _ in range(a.repeats):
-                do_once(scheme, schedule, queue, buff, trace_file=a.trace, data_dir=a.data_dir)
+    ap.add_argument('--num_switch', type=int, default=4)
+    ap.add_argument('--num_node_p_switch', type=int, default=32)
+    opts = ap.parse_args(argv)
+    failures = 0
+    for run in (REFERENCE_SWEEP if opts.reference_sweep else DEVICE_SWEEP):
+        for _ in range(opts.repeats):
+            failures += launch(run, opts) != 0
+    return failures
 
 
 if __name__ == '__main__':
-    main()
+    sys.exit(1 if main() else 0)

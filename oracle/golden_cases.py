@@ -125,7 +125,7 @@ CASES = {
     'filter_nan': dict(frame=_filter_nan, flags=C148),
     'short_durations': dict(frame=_short, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=4)),
     'ties': dict(frame=_ties, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8)),
-    'cluster_spec': dict(frame=lambda: tg.frame_gen(150, 9, 400), flags=dict(cluster_spec='@cluster_spec.csv')),
+    'cluster_spec': dict(frame=lambda: tg.frame_gen(150, 9, 400), flags=dict(cluster_spec='@examples/cluster_spec_2x8x4.csv')),
     'dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)),
     'probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, big=True),
     'probe10k': dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, big=True),
