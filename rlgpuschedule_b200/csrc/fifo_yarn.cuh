@@ -36,7 +36,7 @@ struct FifoSmem {
 };
 
 __host__ __device__ inline size_t fifo_smem_bytes(int N, int slot_cap) {
-    size_t node_words = 4 * (size_t)N + (size_t)((N + 31) / 32);
+    size_t node_words = 3 * (size_t)N + (size_t)((N + 31) / 32);   // units, busy, key, ever bitmap
     node_words = (node_words + 3) & ~(size_t)3;  // 16-byte alignment of the int4 slot arrays
     return node_words * 4 + (size_t)slot_cap * (16 + 16 + 8) + RLGS_CAL_W * 4;
 }
@@ -44,8 +44,7 @@ __host__ __device__ inline size_t fifo_smem_bytes(int N, int slot_cap) {
 __device__ __forceinline__ FifoSmem fifo_carve(unsigned char *smem, int N, int slot_cap) {
     FifoSmem s;
     int32_t *w = reinterpret_cast<int32_t *>(smem);
-    s.nv.cpu = w; w += N;
-    s.nv.mem = w; w += N;
+    s.nv.units = w; w += N;
     s.nv.busy = reinterpret_cast<uint32_t *>(w); w += N;
     s.nv.ever = reinterpret_cast<uint32_t *>(w); w += (N + 31) / 32;
     s.nv.key = reinterpret_cast<uint32_t *>(w); w += N;
@@ -76,8 +75,8 @@ __device__ __forceinline__ JobRec shfl_rec(const JobRec &r, int src) {
 // the calendar buckets and the free-slot chain are derived data: they are rebuilt on restore.
 __device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, const ClusterConst &c, int slot_cap, RepState &st, int lane, bool save) {
     const int N = c.N;
-    int nw = 3 * N + (N + 31) / 32;
-    int32_t *sm = s.nv.cpu;  // cpu, mem, busy, ever are contiguous
+    int nw = 2 * N + (N + 31) / 32;
+    int32_t *sm = s.nv.units;  // units, busy, ever are contiguous
     for (int i = lane; i < nw; i += 32) {
         if (save) D.node_save[i] = sm[i]; else sm[i] = D.node_save[i];
     }
@@ -97,7 +96,7 @@ __device__ __forceinline__ void fifo_state_io(const RepDesc &D, FifoSmem s, cons
     }
     __syncwarp();
     if (!save) {
-        for (int i = lane; i < N; i += 32) s.nv.key[i] = node_key(s.nv.cpu[i], s.nv.mem[i], s.nv.busy[i], c);
+        for (int i = lane; i < N; i += 32) s.nv.key[i] = node_key(s.nv.units[i], s.nv.busy[i], c);
         for (int i = lane; i < RLGS_CAL_W; i += 32) s.sv.bkt[i] = -1;
         __syncwarp();
         int free_head = -1;
@@ -217,9 +216,9 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
     if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
         tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
     if (st.d == 0) {  // first launch of a run: empty cluster, no running jobs
-        int nw = 3 * c.N + (c.N + 31) / 32;
-        for (int i = lane; i < nw; i += 32) s.nv.cpu[i] = 0;
-        const uint32_t empty_key = node_key(0, 0, 0u, c);
+        int nw = 2 * c.N + (c.N + 31) / 32;
+        for (int i = lane; i < nw; i += 32) s.nv.units[i] = 0;
+        const uint32_t empty_key = node_key(0, 0u, c);
         for (int i = lane; i < c.N; i += 32) s.nv.key[i] = empty_key;
         for (int i = lane; i < RLGS_CAL_W; i += 32) s.sv.bkt[i] = -1;
         __syncwarp();
@@ -433,8 +432,8 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
         float *o = env.obs + (size_t)blockIdx.x * env.obs_dim;
         for (int i = lane; i < c.N; i += 32) {
             o[i] = (float)__popc(~s.nv.busy[i] & c.gmask);
-            o[c.N + i] = (float)(c.cpu_cap - s.nv.cpu[i]);
-            o[2 * c.N + i] = (float)(c.mem_cap - s.nv.mem[i]);
+            o[c.N + i] = (float)(c.cpu_cap - RLGS_CPUS_PER_TASK * s.nv.units[i]);
+            o[2 * c.N + i] = (float)(c.mem_cap - RLGS_MEM_PER_TASK * s.nv.units[i]);
         }
         for (int i = lane; i < env.window_k; i += 32) {
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
 //                      b = {attr0 (gpus|tasks<<16), pending_time, preempt|resume<<16, attr1 (gpc|least<<16|fits<<31)}
 struct SjfSmem { NodeView nv; };
 
-__host__ __device__ inline size_t sjf_smem_bytes(int N) { return (4 * (size_t)N + (size_t)((N + 31) / 32)) * 4; }
+__host__ __device__ inline size_t sjf_smem_bytes(int N) { return (3 * (size_t)N + (size_t)((N + 31) / 32)) * 4; }
 
 __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
                                                       ClusterConst c, RowStore rs, int64_t *__restrict__ returns) {
@@ -358,11 +358,11 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
     NodeView nv;
     {
         int32_t *w = reinterpret_cast<int32_t *>(smem_raw);
-        nv.cpu = w; w += c.N; nv.mem = w; w += c.N; nv.busy = reinterpret_cast<uint32_t *>(w); w += c.N; nv.ever = reinterpret_cast<uint32_t *>(w);
+        nv.units = w; w += c.N; nv.busy = reinterpret_cast<uint32_t *>(w); w += c.N; nv.ever = reinterpret_cast<uint32_t *>(w);
         w += (c.N + 31) / 32; nv.key = reinterpret_cast<uint32_t *>(w);
     }
-    const int nw = 3 * c.N + (c.N + 31) / 32;
-    const uint32_t empty_key = node_key(0, 0, 0u, c);
+    const int nw = 2 * c.N + (c.N + 31) / 32;
+    const uint32_t empty_key = node_key(0, 0u, c);
     const int J = D.J;
     Ent *buf = D.buf[0];
     int budget = P.event_budget;
@@ -412,10 +412,10 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
             if (st.status != RLGS_OK) break;
         }
         // ---- CLUSTER.empty_infra() (run_sim.py:241)
-        for (int i = lane; i < nw; i += 32) nv.cpu[i] = 0;
+        for (int i = lane; i < nw; i += 32) nv.units[i] = 0;
         for (int i = lane; i < c.N; i += 32) nv.key[i] = empty_key;
         __syncwarp();
-        int n_free_nodes = (c.cpu_cap > 0 || c.mem_cap > 0) ? c.N : 0, idle_unused = c.N;   // yarn_place's sticky idle-node counter is a fifo statistic
+        int n_free_nodes = c.free_limit > 0 ? c.N : 0, idle_unused = c.N;   // yarn_place's sticky idle-node counter is a fifo statistic
         // ---- one pass in priority order: drop ended jobs, sweep, re-place, flip, minima
         int w_out = 0, n_run = 0, n_pend = 0, new_end = RLGS_NEVER;
         const int M0 = st.M;

@@ -143,6 +143,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
     s->cc.D = s->cc.N * s->cc.G;
+    s->cc.base_units = std::max(0, std::min(s->cc.cpu_cap > 0 ? s->cc.cpu_cap / RLGS_CPUS_PER_TASK : 0, s->cc.mem_cap > 0 ? s->cc.mem_cap / RLGS_MEM_PER_TASK : 0));
+    s->cc.free_limit = std::max(rlgs_ceil_div_pos(s->cc.cpu_cap, RLGS_CPUS_PER_TASK), rlgs_ceil_div_pos(s->cc.mem_cap, RLGS_MEM_PER_TASK));
     memset(&s->lp, 0, sizeof s->lp);
     s->lp.nq = sched == RLGS_SCHED_DLAS_GPU ? opts->num_queue : 1;
     for (int q = 0; q < RLGS_MAX_QUEUES; ++q) s->lp.limit[q] = opts->queue_limit[q];

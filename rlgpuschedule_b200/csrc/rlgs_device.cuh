@@ -62,6 +62,8 @@ struct NetCost {
 struct ClusterConst {
     int32_t N, G;          // nodes, GPUs per node
     int32_t cpu_cap, mem_cap;
+    int32_t base_units;    // min(cpu_cap // 12, mem_cap // 60): tasks an empty node's cpu and mem can take
+    int32_t free_limit;    // a node is "free" (cpu_free > 0 or mem_free > 0, node.py:59) while its charged units < this
     uint32_t gmask;        // G low bits set
     int32_t D;             // N*G
 };
@@ -122,22 +124,26 @@ struct JobRec {
 };
 
 // Shared-memory view of the simulated cluster of one replica.
+// Every task charges exactly 12 cpus and 60 memory units to its node (core/jobs/job.py:105-106) — also on the
+// q8 leak path — so cpu_used = 12 u and mem_used = 60 u for one per-node counter u ("units"):
+//   cpu_free // 12 = cpu_cap // 12 - u,  mem_free // 60 = mem_cap // 60 - u   (both clamp at <= 0 the same way)
+//   is_free  <=>  u < max(ceil(cpu_cap / 12), ceil(mem_cap / 60))
+// which removes every division from the per-tick path.
 struct NodeView {
-    int32_t *cpu;     // cpu_used per node
-    int32_t *mem;     // mem_used per node
+    int32_t *units;   // tasks charged to the node (placed + leaked)
     uint32_t *busy;   // busy-device bitmask per node
     uint32_t *ever;   // bitmap: node ever held a placed job (Node.placed_jobs is never cleared, q3)
     uint32_t *key;    // idle devices << 16 | tasks the free cpu/mem can take: the two numbers every fit test needs
 };
 
+__host__ __device__ inline int rlgs_ceil_div_pos(int x, int d) { return x > 0 ? (x + d - 1) / d : 0; }
+
 // key = popc(idle devices) << 16 | min(cpu_free // 12, mem_free // 60) clamped to [0, 65535]
-__device__ __forceinline__ uint32_t node_key(int cpu_used, int mem_used, uint32_t busy, const ClusterConst &c) {
-    int cf = c.cpu_cap - cpu_used, mf = c.mem_cap - mem_used;
-    int b = cf > 0 ? cf / RLGS_CPUS_PER_TASK : 0, m = mf > 0 ? mf / RLGS_MEM_PER_TASK : 0;
-    int t = min(min(b, m), 0xffff);
+__device__ __forceinline__ uint32_t node_key(int units, uint32_t busy, const ClusterConst &c) {
+    int t = min(max(c.base_units - units, 0), 0xffff);
     return ((uint32_t)__popc(~busy & c.gmask) << 16) | (uint32_t)t;
 }
 
-__device__ __forceinline__ bool node_is_free(int cpu_used, int mem_used, const ClusterConst &c) {
-    return (c.cpu_cap - cpu_used > 0) || (c.mem_cap - mem_used > 0);  // infra/node.py:59-60
+__device__ __forceinline__ bool node_is_free(int units, const ClusterConst &c) {
+    return units < c.free_limit;  // cpu_free > 0 or mem_free > 0 (infra/node.py:59-60)
 }

@@ -7,6 +7,7 @@
 //   try_cross_node_alloc_ms      core/scheduling/algorithm.py:301-393  (q11: tries fit+1 tasks, no side effect)
 //   Node.try_reserve_and_placed_task  infra/node.py:200-221  (q8: cpu/mem charged before the device loop,
 //                                     never undone when no device accepts the task)
+// Node state = charged task units + busy-device mask + the derived fit key (see NodeView in rlgs_device.cuh).
 // Lane l owns nodes l, l+32, ...; node ids ascend with the index, so "first node in id order" is
 // the lowest set bit of the first non-empty ballot.
 #pragma once
@@ -24,11 +25,11 @@ struct PlaceResult {
 __device__ __forceinline__ void charge_nodes(NodeView nv, const ClusterConst &c, int i, bool pred, int k, int &n_free_nodes) {
     bool was = false, now = false;
     if (pred) {
-        int cu = nv.cpu[i], mu = nv.mem[i];
-        was = node_is_free(cu, mu, c);
-        cu += RLGS_CPUS_PER_TASK * k; mu += RLGS_MEM_PER_TASK * k;
-        now = node_is_free(cu, mu, c);
-        nv.cpu[i] = cu; nv.mem[i] = mu; nv.key[i] = node_key(cu, mu, nv.busy[i], c);
+        int u = nv.units[i];
+        was = node_is_free(u, c);
+        u += k;
+        now = node_is_free(u, c);
+        nv.units[i] = u; nv.key[i] = node_key(u, nv.busy[i], c);
     }
     n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
 }
@@ -50,7 +51,6 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
     const bool fits = j.fits();
     if (need_g <= c.G) {
         // ---- single node: first node (id order) with enough idle devices, cpu and mem ----
-        const int c_need = RLGS_CPUS_PER_TASK * T, m_need = RLGS_MEM_PER_TASK * T;
         int node = -1;
         for (int base = 0; base < c.N; base += 32) {
             int i = base + lane;
@@ -69,18 +69,18 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
         }
         __syncwarp();
         if (node < 0) return r;
-        int cu = nv.cpu[node], mu = nv.mem[node];
+        int u = nv.units[node];
         uint32_t busy = nv.busy[node];
         uint32_t taken = lowest_bits(~busy & c.gmask, T * gpc);
-        bool was = node_is_free(cu, mu, c);
-        cu += c_need; mu += m_need;
-        n_free_nodes += (int)node_is_free(cu, mu, c) - (int)was;
+        bool was = node_is_free(u, c);
+        u += T;
+        n_free_nodes += (int)node_is_free(u, c) - (int)was;
         uint32_t ew = nv.ever[node >> 5], bit = 1u << (node & 31);
         if (!(ew & bit)) idle_nodes--;
         __syncwarp();
         if (lane == 0) {
-            nv.cpu[node] = cu; nv.mem[node] = mu; nv.busy[node] = busy | taken; nv.ever[node >> 5] = ew | bit;
-            nv.key[node] = node_key(cu, mu, busy | taken, c);
+            nv.units[node] = u; nv.busy[node] = busy | taken; nv.ever[node >> 5] = ew | bit;
+            nv.key[node] = node_key(u, busy | taken, c);
             place_log[log_pos] = make_int2(node | (T << 16), (int)taken);
         }
         __syncwarp();
@@ -120,13 +120,13 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
         unsigned tb = __ballot_sync(RLGS_FULL, take > 0);
         bool was = false, now = false;
         if (take > 0) {
-            int cu = nv.cpu[i], mu = nv.mem[i];
+            int u = nv.units[i];
             uint32_t busy = nv.busy[i];
             uint32_t taken = lowest_bits(~busy & c.gmask, take * gpc);
-            was = node_is_free(cu, mu, c);
-            cu += RLGS_CPUS_PER_TASK * take; mu += RLGS_MEM_PER_TASK * take;
-            now = node_is_free(cu, mu, c);
-            nv.cpu[i] = cu; nv.mem[i] = mu; nv.busy[i] = busy | taken; nv.key[i] = node_key(cu, mu, busy | taken, c);
+            was = node_is_free(u, c);
+            u += take;
+            now = node_is_free(u, c);
+            nv.units[i] = u; nv.busy[i] = busy | taken; nv.key[i] = node_key(u, busy | taken, c);
             place_log[log_pos + written + __popc(tb & ((1u << lane) - 1))] = make_int2(i | (take << 16), (int)taken);
         }
         n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
@@ -148,12 +148,12 @@ __device__ __forceinline__ void release_entry(NodeView nv, const ClusterConst &c
     bool was = false, now = false;
     if (active) {
         int node = e.x & 0xffff, tasks = (e.x >> 16) & 0xffff;
-        int cu = nv.cpu[node], mu = nv.mem[node];
-        was = node_is_free(cu, mu, c);
-        cu -= RLGS_CPUS_PER_TASK * tasks; mu -= RLGS_MEM_PER_TASK * tasks;
-        now = node_is_free(cu, mu, c);
+        int u = nv.units[node];
+        was = node_is_free(u, c);
+        u -= tasks;
+        now = node_is_free(u, c);
         uint32_t busy = nv.busy[node] & ~(uint32_t)e.y;
-        nv.cpu[node] = cu; nv.mem[node] = mu; nv.busy[node] = busy; nv.key[node] = node_key(cu, mu, busy, c);
+        nv.units[node] = u; nv.busy[node] = busy; nv.key[node] = node_key(u, busy, c);
     }
     n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
 }
