@@ -120,7 +120,7 @@ __device__ __forceinline__ void fifo_finish_slot(const RepDesc &D, FifoSmem s, c
     const int64_t mterm = s.sv.memterm[sl];
     int ndev;
     if ((place & 0xffff) != 0xffff) {
-        release_entry(s.nv, c, lane == 0, make_int2((int)place, (int)mask), st.n_free_nodes);
+        release_single(s.nv, c, (int)(place & 0xffff), (int)(place >> 16), mask, lane, st.n_free_nodes);
         ndev = __popc(mask);
     } else {
         int nn = (int)(place >> 16), off = (int)mask;

@@ -157,3 +157,14 @@ __device__ __forceinline__ void release_entry(NodeView nv, const ClusterConst &c
     }
     n_free_nodes += __popc(__ballot_sync(RLGS_FULL, now)) - __popc(__ballot_sync(RLGS_FULL, was));
 }
+
+// Same release for a single-node job: every lane computes the same values, lane 0 stores them.
+__device__ __forceinline__ void release_single(NodeView nv, const ClusterConst &c, int node, int tasks, uint32_t mask, int lane, int &n_free_nodes) {
+    int u = nv.units[node];
+    const bool was = node_is_free(u, c);
+    u -= tasks;
+    n_free_nodes += (int)node_is_free(u, c) - (int)was;
+    const uint32_t busy = nv.busy[node] & ~mask;
+    __syncwarp();
+    if (lane == 0) { nv.units[node] = u; nv.busy[node] = busy; nv.key[node] = node_key(u, busy, c); }
+}
