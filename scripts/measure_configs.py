@@ -26,7 +26,7 @@ out['C1 fifo+yarn 1x4x8 100 jobs, 1 replica'] = dict(wall_ms=w * 1e3, kernel_ms=
 sim.close()
 # C2 sjf + yarn 10k
 tr = rl.prepare_trace(tracegen.frame_gen(10000, 2, 10000), C4)
-for R in (1, 1184):
+for R in (1, 2960):
     sim = rl.Simulator(C4, 'sjf', 'yarn', n_replicas=R, rows='device'); sim.load_trace(tr)
     w = timed(sim.run, 2); s = sim.summary(0); ms, _ = sim.kernel_ms()
     out['C2 sjf+yarn 4x32x8 10k jobs, %d replica(s)' % R] = dict(wall_ms=w * 1e3, kernel_ms=ms, event_rows=s['n_ticks'], events=s['events'], events_per_s=s['events'] * R / w,
@@ -34,7 +34,7 @@ for R in (1, 1184):
     sim.close()
 # C3 dlas-gpu 60k
 tr60 = rl.prepare_trace(tracegen.frame_gen(60000, 3, 60000), C4)
-for R in (1, 2368):
+for R in (1, 2960):
     sim = rl.Simulator(C4, 'dlas-gpu', 'count', n_replicas=R, rows='device', num_queue=4, queue_limit=(30, 60, 150)); sim.load_trace(tr60)
     w = timed(sim.run, 2); s = sim.summary(0); ms, _ = sim.kernel_ms()
     out['C3 dlas-gpu 4 queues 4x32x8 60k jobs, %d replica(s)' % R] = dict(wall_ms=w * 1e3, kernel_ms=ms, event_rows=s['n_ticks'], events=s['events'], events_per_s=s['events'] * R / w,
