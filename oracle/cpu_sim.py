@@ -208,10 +208,11 @@ def run_sjf_yarn(cluster, tr, rows_cap=None):
     return _run_legacy('oracle_sjf_yarn', cluster, tr, [_p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double)], rows_cap)
 
 
-def run_dlas_gpu(cluster, tr, queue_limit=(30, 60, 150), rows_cap=None):
-    """Restated dlas_sim_jobs(gputime=True) (run_sim.py:664-947), count-based admission.  PARITY UNPINNED."""
+def run_dlas_gpu(cluster, tr, queue_limit=(30, 60, 150), rows_cap=None, gputime=True):
+    """Restated dlas_sim_jobs (run_sim.py:664-947), count-based admission; gputime=False is `--schedule dlas`.
+    PARITY UNPINNED."""
     ql = np.asarray(queue_limit, np.int32)
-    return _run_legacy('oracle_dlas_gpu', cluster, tr, [C.c_int32(len(ql) + 1), _p(ql, C.c_int32)], rows_cap)
+    return _run_legacy('oracle_dlas', cluster, tr, [C.c_int32(int(gputime)), C.c_int32(len(ql) + 1), _p(ql, C.c_int32)], rows_cap)
 
 
 def format_legacy_job_csv(tr, res, count_scheme):

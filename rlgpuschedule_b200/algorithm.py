@@ -47,6 +47,7 @@ scheduling_algorithms = {
     'fifo': DevicePolicy('fifo', 'schedule', _ffi.SCHED['fifo'], 'core/scheduling/algorithm.py:189-202'),
     'sjf': DevicePolicy('sjf', 'schedule', _ffi.SCHED['sjf'], 'run_sim.py:162-287 (dead code, restated)'),
     'dlas-gpu': DevicePolicy('dlas-gpu', 'schedule', _ffi.SCHED['dlas-gpu'], 'run_sim.py:664-947 (dead code, restated)'),
+    'dlas': DevicePolicy('dlas', 'schedule', _ffi.SCHED['dlas'], 'run_sim.py:664-947 with gputime=False (dead code, restated)'),
     'horus': HostOnlyPolicy('horus', 'schedule', 'core/scheduling/algorithm.py:204-240'),
     'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
     'gandiva': HostOnlyPolicy('gandiva', 'schedule', 'core/scheduling/algorithm.py:292-298 + time_slice_check :420-440'),

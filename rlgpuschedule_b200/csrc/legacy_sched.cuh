@@ -64,6 +64,7 @@ struct LegParams {
     int32_t nq;
     int32_t limit[RLGS_MAX_QUEUES];
     int32_t total_gpu, num_node, gpus_per_node;
+    int32_t gputime;      // 1 = dlas-gpu (attained service in GPU-ticks), 0 = dlas (ticks)
     int32_t event_budget;
     int64_t max_time;
 };
@@ -145,7 +146,7 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
             ended = t_prev + e.a.z - e.a.w == ev.time;
             if (!ended) {
                 e.a.w += ev.d; e.b.x += ev.d;                                  // total_executed, executed (:741-744)
-                if (ev.q < ev.nq - 1 && (int64_t)e.b.x * e.gpus() >= P.limit[ev.q]) demote = true;  // :747-759
+                if (ev.q < ev.nq - 1 && (P.gputime ? (int64_t)e.b.x * e.gpus() : (int64_t)e.b.x) >= P.limit[ev.q]) demote = true;  // :747-759
             }
         } else {
             e.b.y += ev.d;                                                     // pending_time (:765-767)
@@ -195,8 +196,9 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
         ev.lane_end = min(ev.lane_end, ev.time + e.a.z - e.a.w);
         if (e.q() < ev.nq - 1) {
             int num = P.limit[e.q()] - e.b.x, g = e.gpus();                    // as written: executed_time, not gpu-time
-            int c;                                                             // math.ceil(num / g)
-            if ((g & (g - 1)) == 0) { int sh = 31 - __clz(g); c = num >= 0 ? (num + g - 1) >> sh : -((-num) >> sh); }
+            int c;                                                             // math.ceil(num / g); plain `num` for time-based dlas (:932)
+            if (!P.gputime) c = num;
+            else if ((g & (g - 1)) == 0) { int sh = 31 - __clz(g); c = num >= 0 ? (num + g - 1) >> sh : -((-num) >> sh); }
             else c = num >= 0 ? (num + g - 1) / g : -((-num) / g);
             ev.lane_jump = min(ev.lane_jump, c + ev.time);
         }

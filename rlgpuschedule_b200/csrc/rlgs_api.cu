@@ -119,11 +119,12 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
         return fail(RLGS_ERR_BAD_ARG, "num_gpu_p_node must be 1..32 (got %d)", spec->num_gpu_p_node);
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
     const int sched = opts->schedule;
-    if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU)
+    if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS)
         return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
     if ((sched == RLGS_SCHED_FIFO || sched == RLGS_SCHED_SJF) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
-    if (sched == RLGS_SCHED_DLAS_GPU) {
+    const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
+    if (is_dlas) {
         if (opts->num_queue < 1 || opts->num_queue > RLGS_MAX_QUEUES) return fail(RLGS_ERR_BAD_ARG, "num_queue must be 1..%d", RLGS_MAX_QUEUES);
         for (int q = 0; q + 1 < opts->num_queue; ++q)
             if (opts->queue_limit[q] < 1) return fail(RLGS_ERR_BAD_ARG, "queue_limit[%d] must be >= 1", q);
@@ -146,7 +147,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->cc.base_units = std::max(0, std::min(s->cc.cpu_cap > 0 ? s->cc.cpu_cap / RLGS_CPUS_PER_TASK : 0, s->cc.mem_cap > 0 ? s->cc.mem_cap / RLGS_MEM_PER_TASK : 0));
     s->cc.free_limit = std::max(rlgs_ceil_div_pos(s->cc.cpu_cap, RLGS_CPUS_PER_TASK), rlgs_ceil_div_pos(s->cc.mem_cap, RLGS_MEM_PER_TASK));
     memset(&s->lp, 0, sizeof s->lp);
-    s->lp.nq = sched == RLGS_SCHED_DLAS_GPU ? opts->num_queue : 1;
+    s->lp.nq = is_dlas ? opts->num_queue : 1;
+    s->lp.gputime = sched == RLGS_SCHED_DLAS_GPU;
     for (int q = 0; q < RLGS_MAX_QUEUES; ++q) s->lp.limit[q] = opts->queue_limit[q];
     s->lp.total_gpu = s->cc.D; s->lp.num_node = s->cc.N; s->lp.gpus_per_node = s->cc.G; s->lp.max_time = opts->max_ticks;
     s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
@@ -300,7 +302,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     } else {
         // per-replica working set: 2 entry buffers | pending scratch | 2 demotion scratches | end list | placement scratch
         size_t ae = align_up(sizeof(Ent) * (size_t)n, 256), al = align_up(4 * (size_t)n, 256), ap = align_up(sizeof(int2) * (size_t)s->cc.N, 256);
-        bool dlas = s->opts.schedule == RLGS_SCHED_DLAS_GPU;
+        bool dlas = s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS;
         size_t per = (dlas ? 5 : 1) * ae + al + ap;
         CU(cudaMalloc(&slab, per * (size_t)count));
         for (int r = 0; r < count; ++r) {
@@ -389,7 +391,7 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
 #undef RLGS_LAUNCH_FIFO
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
-        if (s->opts.schedule == RLGS_SCHED_DLAS_GPU)
+        if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         else
             sjf_yarn_kernel<<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);

@@ -99,7 +99,7 @@ class Scheduler(object):
         sched, place = algorithm.resolve(self.schedule, self.placement)
         scheme = self.placement
         kw = {}
-        if self.schedule == 'dlas-gpu':
+        if self.schedule in ('dlas-gpu', 'dlas'):
             limits = parse_queue_limit(getattr(flags, 'queue_limit', None))
             kw = dict(num_queue=len(limits) + 1, queue_limit=limits)
             scheme = 'count'   # dlas admits by GPU count (run_sim.py:808-823) whatever --scheme says

@@ -137,11 +137,11 @@ class LogManager(object):
         self.log_cluster = os.path.join(self.log_path, 'cluster.csv')
         self.log_job = os.path.join(self.log_path, 'job.csv')
         if legacy is None:
-            legacy = getattr(self.flags, 'schedule', 'fifo') in ('sjf', 'dlas-gpu')
+            legacy = getattr(self.flags, 'schedule', 'fifo') in ('sjf', 'dlas-gpu', 'dlas')
         self.legacy = legacy
         if legacy:
             self.cluster_stats_header = list(LEGACY_CLUSTER_HEADER)
-            count = getattr(self.flags, 'schedule', '') == 'dlas-gpu' or self.is_count
+            count = getattr(self.flags, 'schedule', '') in ('dlas-gpu', 'dlas') or self.is_count
             self.job_stats_header = list(LEGACY_JOB_HEADER_COUNT if count else LEGACY_JOB_HEADER)
         n_nodes = infrastructure.num_nodes
         n_gpus = infrastructure.num_gpus

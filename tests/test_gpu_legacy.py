@@ -73,13 +73,14 @@ def test_dlas_gpu_matches_restated_oracle(name, limits):
     df = frame()
     cluster = rl.cluster_from_flags(flags)
     tr = rl.prepare_trace(df, cluster)
-    sim = rl.Simulator(cluster, 'dlas-gpu', 'count', n_replicas=2, rows=True, num_queue=len(limits) + 1, queue_limit=limits)
-    sim.load_trace(tr)
-    sim.run()
-    ores = cpu_sim.run_dlas_gpu(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df), limits)
-    compare(sim, tr, ores)
-    assert sim.summary(0)['sum_running'] == ores['counters']['demotions']
-    sim.close()
+    for sched, gputime in (('dlas-gpu', True), ('dlas', False)):
+        sim = rl.Simulator(cluster, sched, 'count', n_replicas=2, rows=True, num_queue=len(limits) + 1, queue_limit=limits)
+        sim.load_trace(tr)
+        sim.run()
+        ores = cpu_sim.run_dlas_gpu(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df), limits, gputime=gputime)
+        compare(sim, tr, ores)
+        assert sim.summary(0)['sum_running'] == ores['counters']['demotions']
+        sim.close()
 
 
 def test_legacy_bounded_launches_resume_exactly():

@@ -36,7 +36,7 @@ def test_plugin_registries_keep_the_reference_keys():
     assert set(algorithm.plugin_algorithms) == {'gandiva'} and set(algorithm.score_fn) == {'horus', 'horus+', 'gandiva'}
     s, p = algorithm.resolve('fifo', 'yarn')
     assert s.device_id == _ffi.SCHED['fifo'] and p.device_id == _ffi.PLACE['yarn']
-    assert algorithm.resolve('dlas-gpu', 'count')[0].device_id == 2
+    assert algorithm.resolve('dlas-gpu', 'count')[0].device_id == 2 and algorithm.resolve('dlas', 'count')[0].device_id == 3
     with pytest.raises(NotImplementedError):
         algorithm.resolve('horus', 'horus')
     with pytest.raises(NotImplementedError):
