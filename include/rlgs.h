@@ -39,7 +39,9 @@ enum {
 /* --schedule (run_sim.py:38-49); live fifo = core/scheduling/algorithm.py:189-202,
  * sjf = run_sim.py:162-287 (dead code, restated), dlas-gpu = run_sim.py:664-947 (dead code, restated) */
 enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2,
-       RLGS_SCHED_DLAS = 3 /* dlas_sim_jobs(gputime=False): thresholds on attained time instead of GPU-time */ };
+       RLGS_SCHED_DLAS = 3, /* dlas_sim_jobs(gputime=False): thresholds on attained time instead of GPU-time */
+       RLGS_SCHED_SHORTEST = 4,     /* shortest_first_sim_jobs, run_sim.py:299-431: shortest remaining time first */
+       RLGS_SCHED_SHORTEST_GPU = 5  /* ... shortest remaining GPU-time first */ };
 /* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
  * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
 enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1 };

@@ -203,9 +203,10 @@ def _run_legacy(fn_name, cluster, tr, extra_args, rows_cap=None):
                 counters=dict(sweep_jobs=int(counters[0]), events=int(counters[1]), demotions=int(counters[2])))
 
 
-def run_sjf_yarn(cluster, tr, rows_cap=None):
-    """Restated smallest_first_sim_jobs (run_sim.py:162-287) with the live yarn fit.  PARITY UNPINNED."""
-    return _run_legacy('oracle_sjf_yarn', cluster, tr, [_p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double)], rows_cap)
+def run_sjf_yarn(cluster, tr, rows_cap=None, sort_mode=0):
+    """Restated smallest_first_sim_jobs (run_sim.py:162-287; sort_mode 0) / shortest_first_sim_jobs
+    (run_sim.py:299-431; 1 = shortest, 2 = shortest-gpu) with the live yarn fit.  PARITY UNPINNED."""
+    return _run_legacy('oracle_sjf_yarn', cluster, tr, [_p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double), C.c_int32(sort_mode)], rows_cap)
 
 
 def run_dlas_gpu(cluster, tr, queue_limit=(30, 60, 150), rows_cap=None, gputime=True):

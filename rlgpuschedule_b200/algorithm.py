@@ -48,6 +48,8 @@ scheduling_algorithms = {
     'sjf': DevicePolicy('sjf', 'schedule', _ffi.SCHED['sjf'], 'run_sim.py:162-287 (dead code, restated)'),
     'dlas-gpu': DevicePolicy('dlas-gpu', 'schedule', _ffi.SCHED['dlas-gpu'], 'run_sim.py:664-947 (dead code, restated)'),
     'dlas': DevicePolicy('dlas', 'schedule', _ffi.SCHED['dlas'], 'run_sim.py:664-947 with gputime=False (dead code, restated)'),
+    'shortest': DevicePolicy('shortest', 'schedule', _ffi.SCHED['shortest'], 'run_sim.py:299-431 (dead code, restated)'),
+    'shortest-gpu': DevicePolicy('shortest-gpu', 'schedule', _ffi.SCHED['shortest-gpu'], 'run_sim.py:299-431 with gputime (dead code, restated)'),
     'horus': HostOnlyPolicy('horus', 'schedule', 'core/scheduling/algorithm.py:204-240'),
     'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
     'gandiva': HostOnlyPolicy('gandiva', 'schedule', 'core/scheduling/algorithm.py:292-298 + time_slice_check :420-440'),

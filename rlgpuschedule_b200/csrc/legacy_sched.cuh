@@ -65,6 +65,7 @@ struct LegParams {
     int32_t limit[RLGS_MAX_QUEUES];
     int32_t total_gpu, num_node, gpus_per_node;
     int32_t gputime;      // 1 = dlas-gpu (attained service in GPU-ticks), 0 = dlas (ticks)
+    int32_t sort_mode;    // sjf kernel: 0 = num_gpu (sjf), 1 = remaining_time (shortest), 2 = remaining_gputime (shortest-gpu)
     int32_t event_budget;
     int64_t max_time;
 };
@@ -386,12 +387,15 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
                 rlgs_job jr = D.trace[st.cursor];
                 if (jr.arrival_tick != event_time) break;
                 if (st.M + 1 > D.cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
-                // position = number of entries with num_gpu <= this job's
+                // static key (sjf): position = number of entries with num_gpu <= this job's; dynamic keys
+                // (shortest / shortest-gpu): append, the stable sort below finds the place (run_sim.py:343-352,380-385)
                 int pos = 0;
-                for (int b = 0; b < st.M; b += 32) {
-                    bool le = b + lane < st.M && (buf[b + lane].a.y & 0xffff) <= (int)jr.gpus;
-                    pos += __popc(__ballot_sync(RLGS_FULL, le));
-                }
+                if (P.sort_mode == 0) {
+                    for (int b = 0; b < st.M; b += 32) {
+                        bool le = b + lane < st.M && (buf[b + lane].a.y & 0xffff) <= (int)jr.gpus;
+                        pos += __popc(__ballot_sync(RLGS_FULL, le));
+                    }
+                } else pos = st.M;
                 // shift [pos, M) up by one, from the back
                 for (int hi = st.M; hi > pos; hi -= 32) {
                     int i = hi - 1 - lane;
@@ -418,30 +422,88 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
         for (int i = lane; i < c.N; i += 32) nv.key[i] = empty_key;
         __syncwarp();
         int n_free_nodes = c.free_limit > 0 ? c.N : 0, idle_unused = c.N;   // yarn_place's sticky idle-node counter is a fifo statistic
-        // ---- one pass in priority order: drop ended jobs, sweep, re-place, flip, minima
         int w_out = 0, n_run = 0, n_pend = 0, new_end = RLGS_NEVER;
+        const Ent *src = buf;
+        const bool fused = P.sort_mode == 0;   // static key: end / sweep / re-place in one pass over the sorted array
+        if (!fused) {
+            // ---- pass A: ended jobs leave (logged in the previous event's order), sweep (run_sim.py:333-364)
+            int w = 0;
+            for (int b = 0; b < st.M; b += 32) {
+                bool valid = b + lane < st.M;
+                Ent e; e.a = e.b = make_int4(0, 0, 0, 0);
+                if (valid) e = load_ent(buf + b + lane);
+                bool ended = valid && e.status() == L_RUNNING && st.t_prev + e.a.z - e.a.w == event_time;
+                unsigned eb = __ballot_sync(RLGS_FULL, ended);
+                if (ended) {
+                    int job = e.job();
+                    D.planes[1][job] = event_time; D.planes[3][job] = e.b.y;
+                    D.planes[4][job] = e.b.z & 0xffff; D.planes[5][job] = (e.b.z >> 16) & 0xffff;
+                    D.planes[2][st.F + __popc(eb & ((1u << lane) - 1))] = job;
+                }
+                int64_t jct = ended ? event_time - D.trace[e.job()].arrival_tick : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) jct += __shfl_xor_sync(RLGS_FULL, jct, o);
+                st.sum_jct += jct; st.F += __popc(eb); n_events += __popc(eb);
+                bool stay = valid && !ended;
+                if (stay) {
+                    if (e.a.y & (1 << 23)) e.a.y &= ~(1 << 23);
+                    else if (e.status() == L_RUNNING) e.a.w += d; else e.b.y += d;
+                }
+                unsigned sb = __ballot_sync(RLGS_FULL, stay);
+                __syncwarp();
+                if (stay) store_ent(buf + w + __popc(sb & ((1u << lane) - 1)), e);
+                w += __popc(sb);
+                __syncwarp();
+            }
+            st.M = w;
+            // ---- pass B: stable sort by the dynamic key (Python list.sort: ties keep the previous order)
+            for (int bi = 0; bi < st.M; bi += 32) {
+                bool vi = bi + lane < st.M;
+                Ent ei; ei.a = ei.b = make_int4(0, 0, 0, 0);
+                if (vi) ei = load_ent(buf + bi + lane);
+                const int64_t rem_i = ei.a.z - ei.a.w;
+                const int64_t key_i = P.sort_mode == 1 ? rem_i : rem_i * ei.gpus();
+                int rank = 0;
+                for (int bj = 0; bj < st.M; bj += 32) {
+                    bool vj = bj + lane < st.M;
+                    int64_t key_j = 0x7fffffffffffffffll;
+                    if (vj) { int4 a = buf[bj + lane].a; int64_t r = a.z - a.w; key_j = P.sort_mode == 1 ? r : r * (a.y & 0xffff); }
+                    for (int k = 0; k < 32; ++k) {
+                        int64_t kk = __shfl_sync(RLGS_FULL, key_j, k);
+                        int pj = bj + k;
+                        rank += (pj < st.M) && (kk < key_i || (kk == key_i && pj < bi + lane));
+                    }
+                }
+                if (vi) store_ent(D.scratch_p + rank, ei);
+            }
+            __syncwarp();
+            src = D.scratch_p;
+        }
+        // ---- pass in priority order: (fused: drop ended jobs, sweep,) re-place, flip, minima
         const int M0 = st.M;
         for (int b = 0; b < M0; b += 32) {
             const int cnt = min(32, M0 - b);
             Ent mine; mine.a = mine.b = make_int4(0, 0, 0, 0);
-            if (lane < cnt) mine = load_ent(buf + b + lane);
+            if (lane < cnt) mine = load_ent(src + b + lane);
             bool keep = false;
             for (int k = 0; k < cnt; ++k) {
                 Ent e; e.a = shfl_int4(mine.a, k); e.b = shfl_int4(mine.b, k);
                 const int job = e.job();
                 int status = e.status();
-                if (status == L_RUNNING && st.t_prev + e.a.z - e.a.w == event_time) {     // :198-204 end job
-                    if (lane == 0) {
-                        D.planes[1][job] = event_time; D.planes[3][job] = e.b.y;
-                        D.planes[4][job] = e.b.z & 0xffff; D.planes[5][job] = (e.b.z >> 16) & 0xffff;
-                        D.planes[2][st.F] = job;
+                if (fused) {
+                    if (status == L_RUNNING && st.t_prev + e.a.z - e.a.w == event_time) {     // :198-204 end job
+                        if (lane == 0) {
+                            D.planes[1][job] = event_time; D.planes[3][job] = e.b.y;
+                            D.planes[4][job] = e.b.z & 0xffff; D.planes[5][job] = (e.b.z >> 16) & 0xffff;
+                            D.planes[2][st.F] = job;
+                        }
+                        st.sum_jct += event_time - D.trace[job].arrival_tick;
+                        st.F += 1; n_events += 1;
+                        continue;
                     }
-                    st.sum_jct += event_time - D.trace[job].arrival_tick;
-                    st.F += 1; n_events += 1;
-                    continue;
+                    if (e.a.y & (1 << 23)) e.a.y &= ~(1 << 23);                               // last_check_time == event_time: nothing to add
+                    else if (status == L_RUNNING) e.a.w += d; else e.b.y += d;               // :216-230
                 }
-                if (e.a.y & (1 << 23)) e.a.y &= ~(1 << 23);                               // last_check_time == event_time: nothing to add
-                else if (status == L_RUNNING) e.a.w += d; else e.b.y += d;               // :216-230
                 JobRec jr; jr.a = make_int4(0, e.a.z, e.b.x, e.b.w); jr.b = make_int4(0, 0, 0, job);
                 PlaceResult pr = yarn_place(nv, c, jr, lane, D.place_scratch, 0, n_free_nodes, idle_unused);   // :246
                 if (pr.ok) {

@@ -119,9 +119,11 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
         return fail(RLGS_ERR_BAD_ARG, "num_gpu_p_node must be 1..32 (got %d)", spec->num_gpu_p_node);
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
     const int sched = opts->schedule;
-    if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS)
+    if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS &&
+        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU)
         return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
-    if ((sched == RLGS_SCHED_FIFO || sched == RLGS_SCHED_SJF) && opts->placement != RLGS_PLACE_YARN)
+    const bool is_sjf_family = sched == RLGS_SCHED_SJF || sched == RLGS_SCHED_SHORTEST || sched == RLGS_SCHED_SHORTEST_GPU;
+    if ((sched == RLGS_SCHED_FIFO || is_sjf_family) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
     const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
     if (is_dlas) {
@@ -149,6 +151,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     memset(&s->lp, 0, sizeof s->lp);
     s->lp.nq = is_dlas ? opts->num_queue : 1;
     s->lp.gputime = sched == RLGS_SCHED_DLAS_GPU;
+    s->lp.sort_mode = sched == RLGS_SCHED_SHORTEST ? 1 : (sched == RLGS_SCHED_SHORTEST_GPU ? 2 : 0);
     for (int q = 0; q < RLGS_MAX_QUEUES; ++q) s->lp.limit[q] = opts->queue_limit[q];
     s->lp.total_gpu = s->cc.D; s->lp.num_node = s->cc.N; s->lp.gpus_per_node = s->cc.G; s->lp.max_time = opts->max_ticks;
     s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
@@ -303,7 +306,8 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         // per-replica working set: 2 entry buffers | pending scratch | 2 demotion scratches | end list | placement scratch
         size_t ae = align_up(sizeof(Ent) * (size_t)n, 256), al = align_up(4 * (size_t)n, 256), ap = align_up(sizeof(int2) * (size_t)s->cc.N, 256);
         bool dlas = s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS;
-        size_t per = (dlas ? 5 : 1) * ae + al + ap;
+        const bool sorts = s->lp.sort_mode != 0;   // shortest / shortest-gpu need one scratch buffer for the stable sort
+        size_t per = (dlas ? 5 : (sorts ? 2 : 1)) * ae + al + ap;
         CU(cudaMalloc(&slab, per * (size_t)count));
         for (int r = 0; r < count; ++r) {
             unsigned char *p = slab + per * (size_t)r;
@@ -317,6 +321,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
                 D.scratch_d[1] = reinterpret_cast<Ent *>(p); p += ae;
             } else {
                 D.buf[1] = D.scratch_p = D.scratch_d[0] = D.scratch_d[1] = nullptr;
+                if (sorts) { D.scratch_p = reinterpret_cast<Ent *>(p); p += ae; }
             }
             D.end_list = reinterpret_cast<int32_t *>(p); p += al;
             D.place_scratch = reinterpret_cast<int2 *>(p);
@@ -427,7 +432,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else if (s->opts.schedule == RLGS_SCHED_SJF) {
+    } else if (s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
     int32_t max_arrival = 0;

@@ -137,7 +137,7 @@ class LogManager(object):
         self.log_cluster = os.path.join(self.log_path, 'cluster.csv')
         self.log_job = os.path.join(self.log_path, 'job.csv')
         if legacy is None:
-            legacy = getattr(self.flags, 'schedule', 'fifo') in ('sjf', 'dlas-gpu', 'dlas')
+            legacy = getattr(self.flags, 'schedule', 'fifo') in ('sjf', 'shortest', 'shortest-gpu', 'dlas-gpu', 'dlas')
         self.legacy = legacy
         if legacy:
             self.cluster_stats_header = list(LEGACY_CLUSTER_HEADER)

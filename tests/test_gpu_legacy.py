@@ -52,15 +52,16 @@ def compare(sim, tr, ores, check_rows=True):
 
 
 @pytest.mark.parametrize('name', list(CASES))
-def test_sjf_matches_restated_oracle(name):
+@pytest.mark.parametrize('sched,mode', [('sjf', 0), ('shortest', 1), ('shortest-gpu', 2)])
+def test_sjf_family_matches_restated_oracle(name, sched, mode):
     frame, flags = CASES[name]
     df = frame()
     cluster = rl.cluster_from_flags(flags)
     tr = rl.prepare_trace(df, cluster)
-    sim = rl.Simulator(cluster, 'sjf', 'yarn', n_replicas=3, rows=True)
+    sim = rl.Simulator(cluster, sched, 'yarn', n_replicas=3, rows=True)
     sim.load_trace(tr)
     sim.run()
-    ores = cpu_sim.run_sjf_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df))
+    ores = cpu_sim.run_sjf_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df), sort_mode=mode)
     compare(sim, tr, ores)
     assert ores['preempt'].sum() > 0 or name not in ('dense', 'dense2')   # the dense cases must exercise preemption
     sim.close()

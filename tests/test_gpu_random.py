@@ -28,6 +28,9 @@ def test_random_cases_all_schedules(block):
         assert lm.format_cluster_csv(sim.rows(1), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o), seed
         sim.close()
         for sched, scheme, kw, run in (('sjf', 'yarn', {}, lambda: cpu_sim.run_sjf_yarn(oc, otr)),
+                                       ('shortest', 'yarn', {}, lambda: cpu_sim.run_sjf_yarn(oc, otr, sort_mode=1)),
+                                       ('shortest-gpu', 'yarn', {}, lambda: cpu_sim.run_sjf_yarn(oc, otr, sort_mode=2)),
+                                       ('dlas', 'count', dict(num_queue=3, queue_limit=(3, 11)), lambda: cpu_sim.run_dlas_gpu(oc, otr, (3, 11), gputime=False)),
                                        ('dlas-gpu', 'count', dict(num_queue=3, queue_limit=(6, 40)), lambda: cpu_sim.run_dlas_gpu(oc, otr, (6, 40)))):
             sim = rl.Simulator(cluster, sched, scheme, n_replicas=1, rows=True, **kw)
             sim.load_trace(tr); sim.run()
