@@ -119,6 +119,38 @@ def run_fifo_yarn(cluster, tr, rows_cap=None, netcost=None):
     return out
 
 
+def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, rows_cap=None):
+    """Restated `--schedule horus|gandiva` with horus_placement (oracle_pack).  seed=None pins every utilisation draw
+    to its mean (the reference's behaviour on traces with gpu_utilization_max == gpu_utilization_avg: PINNED); a seed
+    enables the build-defined counter-based draw (UNPINNED)."""
+    L = lib()
+    n = len(tr['nt'])
+    fin = np.empty(max(n, 1), np.int32); st = np.empty(max(n, 1), np.int32); en = np.empty(max(n, 1), np.int32)
+    dur = np.zeros(max(n, 1), np.float64)
+    nfin = C.c_int32(0); nticks = C.c_int64(0); counters = np.zeros(4, np.int64)
+    cap = rows_cap or max(4096, 4 * n)
+    while True:
+        rows = np.zeros(cap, ROW_DTYPE)
+        rc = L.oracle_pack(C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
+                           _p(tr['used_gpus'], C.c_double), _p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double),
+                           _p(tr['util_avg'], C.c_double), _p(tr['util_max'], C.c_double),
+                           C.c_int32(1 if schedule == 'gandiva' else 0), C.c_int32(num_buffer),
+                           C.c_int32(0 if seed is None else 1), C.c_uint32(seed or 0), C.c_uint32(replica),
+                           _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32), C.byref(nfin), _p(dur, C.c_double),
+                           rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc != 0:
+            raise RuntimeError('oracle_pack rc=%d (the reference would raise on this input)' % rc)
+        break
+    k = nfin.value
+    return dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
+                actual_duration=dur[:n], orig_duration=tr['duration'],
+                counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]),
+                              starts=int(counters[3])))
+
+
 def format_job_csv(tr, res):
     """job.csv as LogManager.jcts writes it (/root/reference/log_manager.py:45-54,137-155)."""
     buf = io.StringIO(newline='')
@@ -130,7 +162,7 @@ def format_job_csv(tr, res):
     for k, i in enumerate(res['finish_order']):
         i = int(i)
         w.writerow([str(int(tr['label'][i])), float(tr['used_gpus'][i]), int(tr['nt'][i]), int(res['start'][i]),
-                    int(res['end'][i]), float(dur[i]),   # Job.duration itself carries the network cost (job.py:196-197)
+                    int(res['end'][i]), float(res['orig_duration'][i] if 'orig_duration' in res else dur[i]),   # Job.duration itself carries the network cost (job.py:196-197)
                     float(dur[i]) if dur[i] > 0 else 0,   # Job.get_duration: max(0, d) keeps the int 0 (job.py:206-210)
                     int(res['jct'][i]) if 'jct' in res else int(res['end'][i] - res['start'][i]),
                     int(pre[i]) if pre is not None else 1])
