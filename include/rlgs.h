@@ -41,10 +41,14 @@ enum {
 enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2,
        RLGS_SCHED_DLAS = 3, /* dlas_sim_jobs(gputime=False): thresholds on attained time instead of GPU-time */
        RLGS_SCHED_SHORTEST = 4,     /* shortest_first_sim_jobs, run_sim.py:299-431: shortest remaining time first */
-       RLGS_SCHED_SHORTEST_GPU = 5  /* ... shortest remaining GPU-time first */ };
+       RLGS_SCHED_SHORTEST_GPU = 5, /* ... shortest remaining GPU-time first */
+       RLGS_SCHED_HORUS = 6         /* schedule_horus, core/scheduling/algorithm.py:204-240: utilisation-ordered heap queue
+                                       (core/jobs/base_factory.py:1-12) + look-ahead window of opts.num_buffer jobs */ };
 /* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
  * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
-enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1 };
+enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1,
+       RLGS_PLACE_HORUS = 2 /* horus_placement, core/scheduling/algorithm.py:34-180 with horus_score (horus.py:28-56):
+                               packs up to 4 tasks per device; what --scheme horus|horus+|gandiva select under --schedule horus */ };
 /* rows_mode: NONE = no per-tick rows; FULL = one row per tick kept in a device-resident store and
  * copied to the handle's pinned host store inside rlgs_run (overlapped with compute, one stream per
  * replica group); DEVICE = rows stay in HBM until rlgs_read_rows / rlgs_rows_view asks for them. */
@@ -76,12 +80,15 @@ typedef struct {
     int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES */
     int32_t enable_network_costs; /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
     int32_t fetch_jobs;    /* 1 = copy the per-job tables to the host inside rlgs_run as well */
-    int32_t reserved0;
+    int32_t num_buffer;    /* horus: look-ahead window, --num_buffer (run_sim.py:76); 0 = the reference default 5 */
     int32_t queue_limit[RLGS_MAX_QUEUES]; /* dlas-gpu demotion thresholds in GPU-ticks */
     double bandwidth;          /* --bandwidth MB/s (run_sim.py:59) */
     double internode_latency;  /* --internode_latency s (run_sim.py:65) */
     int64_t max_ticks;         /* safety stop; 0 = none */
     int64_t rows_cap;          /* initial capacity (ticks) of the row store; 0 = auto; grown when a replica fills it */
+    int32_t pack_rng;          /* horus: 0 = every utilisation draw of infra/device.py:52 returns its mean (the reference on
+                                  traces with gpu_utilization_max == gpu_utilization_avg); 1 = build-defined counter-based draw */
+    uint32_t pack_seed;        /* seed of that draw */
 } rlgs_opts;
 
 /*
@@ -158,6 +165,19 @@ void rlgs_destroy(rlgs_sim *sim);
 int32_t rlgs_load_trace(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas, const rlgs_job *jobs, int32_t n,
                         const rlgs_netcost_inputs *net);
 
+/* Per-job inputs of the pack placement (RLGS_PLACE_HORUS), arrays of n entries in trace order; attach them with
+ * rlgs_load_pack_inputs after rlgs_load_trace of the same replica range.  Memory amounts are integers in units of
+ * 2^-mem_shift MiB (the shift rlgs_job.mem_term uses). */
+typedef struct {
+    const double *util_avg;     /* gpu_utilization_avg (Task.gpu_utilization_avg, core/jobs/job.py:30) */
+    const double *util_sd;      /* (gpu_utilization_max - gpu_utilization_avg) / 2 (infra/device.py:52) */
+    const int64_t *task_mem;    /* memory_max of one task, not clamped (Task.gpu_memory_max) */
+    const int32_t *heap_cap;    /* floor(used_gpus): size of horus_placement's node heap (algorithm.py:64) */
+    int32_t mem_shift;
+    int32_t gpu_mem_cap_mib;    /* --gpu_memory_capacity * 1024 (infra/infrastructure.py:36) */
+} rlgs_pack_inputs;
+int32_t rlgs_load_pack_inputs(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas, const rlgs_pack_inputs *in, int32_t n);
+
 /* Replaces Scheduler.start() (core/scheduling/schedule.py:178-216): runs every replica to completion.
  * Blocking.  Resets replica state first, so it can be called repeatedly (bench steps). */
 int32_t rlgs_run(rlgs_sim *sim);
@@ -184,7 +204,8 @@ int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,
-       RLGS_PLANE_AUX = 3,      /* fifo: first placement-log entry; sjf/dlas-gpu: pending_time */
+       RLGS_PLANE_AUX = 3,      /* fifo: first placement-log entry; sjf/dlas-gpu: pending_time;
+                                   horus: 1 = Job.get_duration() is original + 5 (a task was de-interfered), 0 = original */
        RLGS_PLANE_PREEMPT = 4, RLGS_PLANE_RESUME = 5 };
 int32_t rlgs_read_job_plane(rlgs_sim *sim, int32_t replica, int32_t plane, int32_t *out);
 /* Episode return per replica: -(sum of job completion times), the reward of the vectorised Environment. */

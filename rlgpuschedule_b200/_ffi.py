@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get('RLGS_LIB') or os.path.join(HERE, 'librlgs.so')   # RLGS_LIB: development override
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
-SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2, 'dlas': 3, 'shortest': 4, 'shortest-gpu': 5}
-PLACE = {'yarn': 0, 'count': 1}
+SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2, 'dlas': 3, 'shortest': 4, 'shortest-gpu': 5, 'horus': 6}
+PLACE = {'yarn': 0, 'count': 1, 'horus': 2, 'horus+': 2, 'gandiva': 2}   # the three pack names share horus_placement (algorithm.py:182-187)
 ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
 MAX_QUEUES = 8
 ROWS_PER_CHUNK = 4096
@@ -29,9 +29,14 @@ class Opts(C.Structure):
     _fields_ = [('device', C.c_int32), ('n_replicas', C.c_int32), ('schedule', C.c_int32), ('placement', C.c_int32),
                 ('rows_mode', C.c_int32), ('slot_cap', C.c_int32), ('n_streams', C.c_int32),
                 ('ticks_per_launch', C.c_int32), ('num_queue', C.c_int32), ('enable_network_costs', C.c_int32),
-                ('fetch_jobs', C.c_int32), ('reserved0', C.c_int32), ('queue_limit', C.c_int32 * MAX_QUEUES),
+                ('fetch_jobs', C.c_int32), ('num_buffer', C.c_int32), ('queue_limit', C.c_int32 * MAX_QUEUES),
                 ('bandwidth', C.c_double), ('internode_latency', C.c_double), ('max_ticks', C.c_int64),
-                ('rows_cap', C.c_int64)]
+                ('rows_cap', C.c_int64), ('pack_rng', C.c_int32), ('pack_seed', C.c_uint32)]
+
+
+class PackInputs(C.Structure):
+    _fields_ = [('util_avg', C.POINTER(C.c_double)), ('util_sd', C.POINTER(C.c_double)), ('task_mem', C.POINTER(C.c_int64)),
+                ('heap_cap', C.POINTER(C.c_int32)), ('mem_shift', C.c_int32), ('gpu_mem_cap_mib', C.c_int32)]
 
 
 class NetcostInputs(C.Structure):
@@ -55,7 +60,7 @@ ROW_DTYPE = np.dtype([('idle_nodes', '<i4'), ('busy_gpus', '<i4'), ('running', '
                       ('sum_pending', '<i8'), ('mem_sum', '<i8'), ('util_mu_sum', '<i8'), ('util_var_sum', '<i8')])
 assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64
 
-EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_run',
+EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_load_pack_inputs', 'rlgs_run',
            'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
            'rlgs_rows_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
            'rlgs_read_durations', 'rlgs_env_obs_dim', 'rlgs_env_reset', 'rlgs_env_step', 'rlgs_env_sync']
@@ -85,6 +90,7 @@ def lib():
     L.rlgs_destroy.argtypes = [vp]
     L.rlgs_destroy.restype = None
     L.rlgs_load_trace.argtypes = [vp, i32, i32, vp, i32, C.POINTER(NetcostInputs)]
+    L.rlgs_load_pack_inputs.argtypes = [vp, i32, i32, C.POINTER(PackInputs), i32]
     L.rlgs_run.argtypes = [vp]
     L.rlgs_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
     L.rlgs_set_stream.argtypes = [vp, vp, i32]

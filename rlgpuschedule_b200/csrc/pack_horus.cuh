@@ -1,0 +1,580 @@
+// pack_horus.cuh — `--schedule horus` with horus_placement on the device, one warp per replica.
+//
+// Restates (reference paths):
+//   Scheduler.start tick loop            core/scheduling/schedule.py:178-216
+//   schedule_horus (look-ahead window)   core/scheduling/algorithm.py:204-240
+//   horus_placement                      core/scheduling/algorithm.py:34-180   (heap of scored nodes, trial placement per
+//                                        heap entry with rack walk + backtracking, fewest-nodes plan wins)
+//   horus_score                          core/scheduling/horus.py:28-56        (float64, np.polyval Horner form)
+//   Node / Device pack=True branches     infra/node.py:146-221, infra/device.py:19-77 (<= 4 tasks per device, 500 MiB margin,
+//                                        cpu/mem and accepting devices stay charged when a task finds too few devices)
+//   utilisation-ordered job queue        core/jobs/base_factory.py:1-12 + job_queue_manager.py:129-154 (stdlib heapq)
+//   interference bookkeeping             infra/node.py:71-91, core/jobs/jobs_manager.py:175-187 (+5 ticks once a flagged
+//                                        task is left alone on a device)
+//
+// Everything order-dependent in the reference (heapq sift order, stable sorts, dict insertion order, the order of
+// release calls) is kept, because ties are the common case (all idle nodes score the same).  Scalar phases (heap
+// sifts, list walks) run warp-uniform: every lane executes the same loads and stores; device scans, node scoring
+// and the rack pre-filter are lane-parallel.  State lives in global memory (L1/L2 resident per replica) so that a
+// bounded launch can stop and resume at any tick.
+//
+// Memory amounts are integers in units of 2^-shift MiB (exact: ingest picks the shift), scores are float64 with the
+// reference's operation order (the library is built with --fmad=false).
+#pragma once
+#include "rlgs_device.cuh"
+
+#define PACK_DEV_SLOTS 4      // infra/device.py:72
+#define PACK_CAL_W 128
+#define PACK_MAX_TASKS 32
+#define PACK_MAX_HEAP 255
+
+struct PackJob {              // per job of a trace, shared by the replicas that replay it
+    double util_avg;          // gpu_utilization_avg
+    double util_sd;           // (gpu_utilization_max - gpu_utilization_avg) / 2   (device.py:52)
+    int64_t mem;              // memory_max of one task, units of 2^-shift MiB
+    int32_t heap_cap;         // floor(used_gpus): `len(nodes_stack) > gpu_demand` (algorithm.py:64)
+    int32_t task_off;         // first entry of the job in tnode[]
+};
+
+struct PackDesc {
+    const rlgs_job *trace;
+    const PackJob *pj;
+    int32_t *planes[6];       // start, end, finish_order, aux (bit0: a task got +5 ticks), interfered-task mask, unused
+    int32_t *units;           // [N] tasks charged to the node (cpu = 12u, mem = 60u)
+    int32_t *ntk;             // [N] len(placed_tasks) << 16 | len(running_tasks)
+    int32_t *npj;             // [N] len(placed_jobs)
+    int32_t *dn;              // [D] len(device.running_tasks)
+    int64_t *dm;              // [D] sum of min(cap, memory_max) of the tasks on the device
+    int2 *ent;                // [D][4] (job, task) in insertion order
+    uint32_t *pjbits;         // [J][W] node.placed_jobs membership of each job
+    double *qkey; int32_t *qjob;      // [J] the job queue: a heapq array ordered by utilisation
+    int32_t *lprev, *lnext;   // [J] queued jobs in arrival order (pending-time statistics)
+    int32_t *pend;            // [J] tick at which the running job finishes
+    int32_t *cnext;           // [J] calendar chain
+    int32_t *chead;           // [PACK_CAL_W]
+    int16_t *tnode;           // [sum of tasks] node of each placed task (tasks_running_on)
+    double *score;            // [N] scratch: min_cost of each node, < 0 = node cannot take the task
+    double *hscore; int32_t *hnode;   // [PACK_MAX_HEAP + 1] horus_placement's nodes_stack
+    int32_t *fin;             // [J] jobs finishing at this tick
+    int64_t cap_units, margin_units;  // gpu memory capacity and the 500 MiB margin in units
+    double cap_mib, unit_mib; // capacity in MiB, 2^-shift
+    int32_t J, W;
+};
+
+struct PackState {
+    int32_t d, cursor, F, Q, R;
+    int32_t n_free_nodes, idle_nodes, busy_gpus, start_seq;
+    int32_t lhead, ltail, mlo, mrank;
+    int32_t done, status, max_q, max_r, pad;
+    int64_t mem_sum, util_mu_sum, util_var_sum, sum_arr, sum_jct, sumQ, sumR, events;
+};
+
+struct PackParams {
+    int32_t num_buffer;       // --num_buffer (run_sim.py:76): look-ahead window
+    int32_t rng_on;           // 0: every utilisation draw returns its mean
+    uint32_t seed;
+    int32_t nodes_per_rack, racks;
+    int32_t tick_budget;
+    int64_t max_ticks;
+};
+
+// ---- build-defined stand-in for np.random.normal (the reference's RNG is unseeded): Irwin-Hall sum of twelve
+// 16-bit uniforms keyed by (seed, replica, tick, look-ahead position, task pass, device, slot)
+__device__ __forceinline__ uint64_t pack_mix64(uint64_t z) { z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+__device__ __forceinline__ double pack_draw(uint32_t seed, uint32_t replica, uint32_t tick, uint32_t attempt, uint32_t pass, uint32_t dev, uint32_t slot) {
+    uint64_t h = pack_mix64((((uint64_t)seed << 32) | replica) + 0x9E3779B97F4A7C15ull);
+    h = pack_mix64(h ^ (((uint64_t)tick << 32) | ((uint64_t)attempt << 16) | pass));
+    h = pack_mix64(h ^ (((uint64_t)dev << 8) | slot));
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) { uint64_t w = pack_mix64(h + (uint64_t)k * 0x9E3779B97F4A7C15ull); sum += (uint32_t)(w & 0xffff) + (uint32_t)((w >> 16) & 0xffff) + (uint32_t)((w >> 32) & 0xffff) + (uint32_t)(w >> 48); }
+    return ((double)sum - 393210.0) / 65536.0;
+}
+
+// CompareAbleByUtilization.__lt__ (base_factory.py:8-12)
+__device__ __forceinline__ bool pack_lt_util(double a, double b) { return a != 0.0 ? a < b : false; }
+
+// heapq.heappush / heappop on (qkey, qjob): lane 0 walks the heap, the others wait at the __syncwarp
+__device__ __forceinline__ void pack_q_siftdown(const PackDesc &D, int pos, double key, int job) {
+    while (pos > 0) {
+        int pp = (pos - 1) >> 1; double pk = D.qkey[pp];
+        if (!pack_lt_util(key, pk)) break;
+        D.qkey[pos] = pk; D.qjob[pos] = D.qjob[pp]; pos = pp;
+    }
+    D.qkey[pos] = key; D.qjob[pos] = job;
+}
+__device__ __forceinline__ void pack_q_push(const PackDesc &D, int lane, int &q, double key, int job) {
+    if (lane == 0) pack_q_siftdown(D, q, key, job);
+    q += 1;
+    __syncwarp();
+}
+__device__ __forceinline__ void pack_q_pop(const PackDesc &D, int lane, int &q, double &key, int &job) {
+    q -= 1;
+    if (lane == 0) {
+        double lk = D.qkey[q]; int lj = D.qjob[q];
+        if (q == 0) { key = lk; job = lj; }
+        else {
+            key = D.qkey[0]; job = D.qjob[0];
+            int pos = 0, child = 1;
+            while (child < q) {                           // _siftup: bubble the smaller child up to a leaf ...
+                int right = child + 1;
+                double ck = D.qkey[child];
+                if (right < q) { double rk = D.qkey[right]; if (!pack_lt_util(ck, rk)) { child = right; ck = rk; } }
+                D.qkey[pos] = ck; D.qjob[pos] = D.qjob[child];
+                pos = child; child = 2 * pos + 1;
+            }
+            pack_q_siftdown(D, pos, lk, lj);              // ... then sift the displaced last item down from there
+        }
+    }
+    __syncwarp();
+    key = __shfl_sync(RLGS_FULL, key, 0); job = __shfl_sync(RLGS_FULL, job, 0);
+}
+
+// nodes_stack of horus_placement: NodeDeviceInfo.__lt__ is `self.min_score > other.min_score` (algorithm.py:25-26)
+__device__ __forceinline__ void pack_h_siftdown(const PackDesc &D, int pos, double sc, int node) {
+    while (pos > 0) {
+        int pp = (pos - 1) >> 1; double ps = D.hscore[pp];
+        if (!(sc > ps)) break;
+        D.hscore[pos] = ps; D.hnode[pos] = D.hnode[pp]; pos = pp;
+    }
+    D.hscore[pos] = sc; D.hnode[pos] = node;
+}
+__device__ __forceinline__ void pack_h_pop(const PackDesc &D, int len) {   // len = length after the pop
+    double ls = D.hscore[len]; int ln = D.hnode[len];
+    if (len == 0) return;
+    int pos = 0, child = 1;
+    while (child < len) {
+        int right = child + 1;
+        double cs = D.hscore[child];
+        if (right < len) { double rs = D.hscore[right]; if (!(cs > rs)) { child = right; cs = rs; } }
+        D.hscore[pos] = cs; D.hnode[pos] = D.hnode[child];
+        pos = child; child = 2 * pos + 1;
+    }
+    pack_h_siftdown(D, pos, ls, ln);
+}
+
+__device__ __forceinline__ bool pack_dev_fits(const PackDesc &D, int dev, int64_t m) {   // Device.can_fit (device.py:67-77)
+    int n = D.dn[dev];
+    int64_t cur = min(D.dm[dev], D.cap_units);
+    return n < PACK_DEV_SLOTS && D.cap_units - (cur + m) > D.margin_units;
+}
+
+struct PackCtx {              // registers shared by the placement helpers
+    int lane;
+    int job, T, gpc;
+    int64_t m;                // memory_max of one task of the job being placed
+    int mu_q, sd_q;           // quantised utilisation statistics of the job (cluster.csv's RNG column)
+    uint32_t interf;          // Task.interfered of the job's tasks, bit per task
+};
+
+__device__ __forceinline__ void pack_idle_delta(PackState &st, bool was_idle, bool now_idle) { st.idle_nodes += (int)now_idle - (int)was_idle; }
+__device__ __forceinline__ bool pack_node_idle(const PackDesc &D, int i) { return D.ntk[i] == 0 && D.npj[i] == 0; }   // Node.is_idle (node.py:93-97)
+
+__device__ __forceinline__ void pack_pj_set(const PackDesc &D, PackState &st, int node, int job) {
+    uint32_t *w = &D.pjbits[(size_t)job * D.W + (node >> 5)]; const uint32_t b = 1u << (node & 31), v = *w;
+    if (!(v & b)) { const bool was = pack_node_idle(D, node); const int np = D.npj[node]; __syncwarp(); *w = v | b; D.npj[node] = np + 1; pack_idle_delta(st, was, false); }
+    __syncwarp();
+}
+__device__ __forceinline__ void pack_pj_pop(const PackDesc &D, PackState &st, int node, int job) {
+    uint32_t *w = &D.pjbits[(size_t)job * D.W + (node >> 5)]; const uint32_t b = 1u << (node & 31), v = *w;
+    if (v & b) { const int np = D.npj[node] - 1; const int tk = D.ntk[node]; __syncwarp(); *w = v & ~b; D.npj[node] = np; pack_idle_delta(st, false, np == 0 && tk == 0); }
+    __syncwarp();
+}
+
+// Node.try_reserve_and_placed_task(pack=True) (node.py:200-221).  0 = node cannot take the task (no side effect),
+// 1 = placed, 2 = too few devices accepted it: cpu/mem and those devices stay charged.
+__device__ __forceinline__ int pack_try_reserve(const PackDesc &D, const ClusterConst &c, PackState &st, PackCtx &x, int node, int t) {
+    const int u = D.units[node];
+    if (u >= c.base_units) return 0;                                   // cpu_free - 12 < 0 or mem_free - 60 < 0
+    const int dev = node * c.G + x.lane;
+    const bool fit = x.lane < c.G && pack_dev_fits(D, dev, x.m);
+    const unsigned fb = __ballot_sync(RLGS_FULL, fit);
+    if (!fb) return 0;
+    st.n_free_nodes += (int)node_is_free(u + 1, c) - (int)node_is_free(u, c);
+    const int have = __popc(fb);
+    const unsigned taken = have <= x.gpc ? fb : lowest_bits(fb, x.gpc);
+    int n_before = 0; int64_t dmem = 0; int newly_busy = 0, added = 0;
+    if ((taken >> x.lane) & 1) {
+        n_before = D.dn[dev];
+        bool present = false;                                          // dict overwrite of an entry leaked earlier
+        for (int k = 0; k < n_before; ++k) { int2 e = D.ent[dev * PACK_DEV_SLOTS + k]; present |= (e.x == x.job && e.y == t); }
+        if (!present) {
+            const int64_t before = D.dm[dev], after = before + min(x.m, D.cap_units);
+            D.ent[dev * PACK_DEV_SLOTS + n_before] = make_int2(x.job, t);
+            D.dn[dev] = n_before + 1; D.dm[dev] = after;
+            dmem = min(after, D.cap_units) - min(before, D.cap_units);
+            newly_busy = n_before == 0; added = 1;
+        }
+    }
+    __syncwarp();
+    const int hi = 31 - __clz(taken);                                  // Task.interfered is rewritten by every add_task: the last device wins
+    const int nb_hi = __shfl_sync(RLGS_FULL, n_before, hi);
+    x.interf = (x.interf & ~(1u << t)) | ((nb_hi >= 2 ? 1u : 0u) << t);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { dmem += __shfl_xor_sync(RLGS_FULL, dmem, o); newly_busy += __shfl_xor_sync(RLGS_FULL, newly_busy, o); added += __shfl_xor_sync(RLGS_FULL, added, o); }
+    st.mem_sum += dmem; st.busy_gpus += newly_busy;
+    st.util_mu_sum += (int64_t)added * x.mu_q; st.util_var_sum += (int64_t)added * x.sd_q * x.sd_q;
+    D.units[node] = u + 1;
+    if (have < x.gpc) { __syncwarp(); return 2; }
+    const bool was = pack_node_idle(D, node);
+    const int tk = D.ntk[node];
+    __syncwarp();
+    D.ntk[node] = tk + (1 << 16);
+    pack_idle_delta(st, was, false);
+    __syncwarp();
+    return 1;
+}
+
+// Node.release_allocated_resources (node.py:71-91) for one task; `running` = the task sits in node.running_tasks
+// (completion) instead of node.placed_tasks (backtracking).  On completion the devices of the node that are left with
+// at most one task hand their flagged task to JobsManager.reset_interference (jobs_manager.py:175-187).
+__device__ __forceinline__ void pack_release(const PackDesc &D, const ClusterConst &c, PackState &st, int lane, int node, int job, int t, bool running) {
+    const int u = D.units[node];
+    st.n_free_nodes += (int)node_is_free(u - 1, c) - (int)node_is_free(u, c);
+    const int tk = D.ntk[node] - (running ? 1 : (1 << 16));
+    const int np = D.npj[node];
+    const PackJob pj = D.pj[job];
+    const rlgs_job rec = D.trace[job];
+    const int dev = node * c.G + lane;
+    int64_t dmem = 0; int now_idle = 0, removed = 0, n_after = -1;
+    if (lane < c.G) {
+        int n = D.dn[dev], at = -1;
+        for (int k = 0; k < n; ++k) { int2 e = D.ent[dev * PACK_DEV_SLOTS + k]; if (e.x == job && e.y == t) at = k; }
+        if (at >= 0) {
+            for (int k = at; k + 1 < n; ++k) D.ent[dev * PACK_DEV_SLOTS + k] = D.ent[dev * PACK_DEV_SLOTS + k + 1];
+            const int64_t before = D.dm[dev], after = before - min(pj.mem, D.cap_units);
+            D.dn[dev] = n - 1; D.dm[dev] = after;
+            dmem = min(after, D.cap_units) - min(before, D.cap_units);
+            now_idle = n == 1; removed = 1; n -= 1;
+        }
+        n_after = n;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { dmem += __shfl_xor_sync(RLGS_FULL, dmem, o); now_idle += __shfl_xor_sync(RLGS_FULL, now_idle, o); removed += __shfl_xor_sync(RLGS_FULL, removed, o); }
+    st.mem_sum += dmem; st.busy_gpus -= now_idle;
+    st.util_mu_sum -= (int64_t)removed * rec.util_mu_q; st.util_var_sum -= (int64_t)removed * rec.util_sd_q * rec.util_sd_q;
+    D.units[node] = u - 1; D.ntk[node] = tk;
+    pack_idle_delta(st, false, tk == 0 && np == 0);
+    __syncwarp();
+    if (!running) return;
+    // reduce_interference_set: flagged tasks alone on a device of this node, whose job is in running_jobs
+    int oj = -1, ot = 0;
+    if (n_after == 1) {
+        int2 e = D.ent[dev * PACK_DEV_SLOTS];
+        if (((uint32_t)D.planes[4][e.x] >> e.y) & 1) if (D.planes[0][e.x] >= 0 && D.planes[1][e.x] < 0) { oj = e.x; ot = e.y; }
+    }
+    unsigned cand = __ballot_sync(RLGS_FULL, oj >= 0);
+    while (cand) {
+        const int src = __ffs(cand) - 1; cand &= cand - 1;
+        const int j2 = __shfl_sync(RLGS_FULL, oj, src), t2 = __shfl_sync(RLGS_FULL, ot, src);
+        const uint32_t mk = (uint32_t)D.planes[4][j2];
+        if ((mk >> t2) & 1) {
+            const int aux = D.planes[3][j2]; const int pe = D.pend[j2];
+            __syncwarp();
+            D.planes[4][j2] = (int)(mk & ~(1u << t2));
+            if (!(aux & 1)) { D.planes[3][j2] = aux | 1; D.pend[j2] = pe + 5; }     // duration = original + max(int(0 / 2), 5)
+        }
+        __syncwarp();
+    }
+}
+
+// horus_score of every node for one task of the job (horus.py:28-56); score < 0 marks a node that is not free or
+// cannot take the task (get_free_nodes + Node.can_fit(pack=True), algorithm.py:52-56)
+__device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const ClusterConst &c, const PackParams &P, const PackCtx &x,
+                                                 uint32_t replica, uint32_t tick, uint32_t attempt, uint32_t pass, double job_util) {
+    for (int base = 0; base < c.N; base += 32) {
+        const int i = base + x.lane;
+        double best = -1.0;
+        if (i < c.N) {
+            const int u = D.units[i];
+            if (node_is_free(u, c) && u < c.base_units) {
+                double min_cost = 999.0; bool any = false;
+                for (int g = 0; g < c.G; ++g) {
+                    const int dev = i * c.G + g;
+                    const int n = D.dn[dev];
+                    const int64_t cur = min(D.dm[dev], D.cap_units);
+                    if (!(n < PACK_DEV_SLOTS && D.cap_units - (cur + x.m) > D.margin_units)) continue;
+                    any = true;
+                    double util = 0.0;                                  // Device.get_current_utilization (device.py:48-54)
+                    for (int k = 0; k < n; ++k) {
+                        const int oj = D.ent[dev * PACK_DEV_SLOTS + k].x;
+                        const PackJob o = D.pj[oj];
+                        double v = o.util_avg;
+                        if (P.rng_on && o.util_sd != 0.0) v = o.util_avg + o.util_sd * pack_draw(P.seed, replica, tick, attempt, pass, (uint32_t)dev, (uint32_t)k);
+                        util += (v < 100.0) ? v : 100.0;
+                        util = (util < 100.0) ? util : 100.0;
+                    }
+                    const double mem_cost = ((double)(cur + x.m) * D.unit_mib) / D.cap_mib;
+                    const double xx = util + job_util;
+                    double y = 0.0 * xx + 4E-5; y = y * xx + -0.00302; y = y * xx + 1.16664;   // np.polyval(NV_2080_COEF, .)
+                    const double cost = (mem_cost * 0.5) + (y * 0.5) + (double)n;
+                    if (cost < min_cost) min_cost = cost;
+                }
+                if (any) best = min_cost;
+            }
+            D.score[i] = best;
+        }
+    }
+    __syncwarp();
+}
+
+// horus_placement (algorithm.py:34-180).  1 = placed (tnode / planes[4] written), 0 = not placed, < 0 = error status.
+__device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst &c, const PackParams &P, PackState &st, PackCtx &x,
+                                          uint32_t replica, uint32_t attempt) {
+    const PackJob pj = D.pj[x.job];
+    const int cap = pj.heap_cap;
+    // ---- score the nodes, keep the `cap` best in a heap (one pass per task: the reference re-scores per task)
+    int hlen = 0;
+    for (int pass = 0; pass < x.T; ++pass) {
+        if (pass == 0 || P.rng_on) pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
+        for (int base = 0; base < c.N; base += 32) {
+            const int i = base + x.lane;
+            const double sc = i < c.N ? D.score[i] : -1.0;
+            unsigned fb = __ballot_sync(RLGS_FULL, sc >= 0.0);
+            while (fb) {
+                const int src = __ffs(fb) - 1; fb &= fb - 1;
+                const double s1 = __shfl_sync(RLGS_FULL, sc, src);
+                if (x.lane == 0) pack_h_siftdown(D, hlen, s1, base + src);     // heappush (only lane 0 touches the heap arrays)
+                hlen += 1;
+                if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(D, hlen); }   // heappop: drop the worst
+            }
+        }
+    }
+    if (hlen == 0) return 0;
+    // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array
+    if (x.lane == 0) for (int a = 1; a < hlen; ++a) {
+        const double vs = D.hscore[a]; const int vn = D.hnode[a];
+        int b = a - 1;
+        while (b >= 0 && D.hscore[b] > vs) { D.hscore[b + 1] = D.hscore[b]; D.hnode[b + 1] = D.hnode[b]; --b; }
+        D.hscore[b + 1] = vs; D.hnode[b + 1] = vn;
+    }
+    __syncwarp();
+    // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
+    int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
+    for (int e = 0; e < hlen; ++e) {
+        const int home = D.hnode[e];
+        int cnt = 0;
+        for (int t = 0; t < x.T; ++t) {
+            const int r = pack_try_reserve(D, c, st, x, home, t);
+            if (r == 1) { if (t != cnt) return RLGS_ERR_STATE; pack_pj_set(D, st, home, x.job); if (x.lane == cnt) cur_map = home; cnt++; }
+            else if (r == 0) break;                                             // later tasks fail the same way, without side effects
+        }
+        // racks by distance from the home rack, ties towards the lower id (infrastructure.py:135-147)
+        const int hr = home / P.nodes_per_rack;
+        for (int dist = 0; dist < P.racks && cnt < x.T; ++dist) {
+            for (int side = 0; side < (dist == 0 ? 1 : 2) && cnt < x.T; ++side) {
+                const int rk = side == 0 ? hr - dist : hr + dist;
+                if (rk < 0 || rk >= P.racks) continue;
+                const int n0 = rk * P.nodes_per_rack, n1 = n0 + P.nodes_per_rack;
+                for (int base = n0; base < n1 && cnt < x.T; base += 32) {
+                    const int i = base + x.lane;
+                    bool can = false;                                            // pre-filter: Node.can_fit(pack=True)
+                    if (i < n1 && D.units[i] < c.base_units)
+                        for (int g = 0; g < c.G; ++g) can |= pack_dev_fits(D, i * c.G + g, x.m);
+                    unsigned cb = __ballot_sync(RLGS_FULL, can);
+                    while (cb && cnt < x.T) {
+                        const int node = base + __ffs(cb) - 1; cb &= cb - 1;
+                        for (int t = cnt; t < x.T; ++t) {                        // every unmapped task tries this node
+                            const int r = pack_try_reserve(D, c, st, x, node, t);
+                            if (r == 1) { if (t != cnt) return RLGS_ERR_STATE; pack_pj_set(D, st, node, x.job); if (x.lane == cnt) cur_map = node; cnt++; }
+                            else if (r == 0) break;
+                            if (cnt >= x.T) break;
+                        }
+                    }
+                }
+            }
+        }
+        // distinct nodes of the plan (tasks fill node after node) and backtracking (algorithm.py:122-133)
+        const int prev = __shfl_up_sync(RLGS_FULL, cur_map, 1);
+        const int nn = __popc(__ballot_sync(RLGS_FULL, x.lane < cnt && (x.lane == 0 || prev != cur_map)));
+        for (int t = 0; t < cnt; ++t) {
+            const int node = __shfl_sync(RLGS_FULL, cur_map, t);
+            if (t == 0) pack_pj_pop(D, st, node, x.job);
+            pack_release(D, c, st, x.lane, node, x.job, t, false);
+        }
+        if (cnt >= x.T && nn < best_nn) { best_nn = nn; best_map = cur_map; }   // stable sort by len(nodes): first minimum
+    }
+    if (best_nn == RLGS_NEVER) return 0;
+    // ---- place for real (algorithm.py:163-178)
+    for (int t = 0; t < x.T; ++t) {
+        const int node = __shfl_sync(RLGS_FULL, best_map, t);
+        if (pack_try_reserve(D, c, st, x, node, t) != 1) return RLGS_ERR_UNSUPPORTED;   // the reference's `assert cnt == len(tasks)` fails
+        pack_pj_set(D, st, node, x.job);
+        D.tnode[pj.task_off + t] = (int16_t)node;
+    }
+    D.planes[4][x.job] = (int)x.interf;
+    __syncwarp();
+    return 1;
+}
+
+__global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
+                                                        RowStore rs, int64_t *returns) {
+    const int lane = lane_id();
+    const PackDesc D = descs[blockIdx.x];
+    PackState st = states[blockIdx.x];
+    if (st.done) return;
+    const bool rows_mode = rs.chunks != nullptr;
+    const uint32_t replica = (uint32_t)(rs.replica + blockIdx.x);
+    int tick_budget = P.tick_budget;
+    if (rows_mode && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)
+        tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
+    const int J = D.J;
+    if (st.d == 0 && st.cursor == 0) {                     // first launch of a run: empty cluster
+        for (int i = lane; i < c.N; i += 32) { D.units[i] = 0; D.ntk[i] = 0; D.npj[i] = 0; }
+        for (int i = lane; i < c.D; i += 32) { D.dn[i] = 0; D.dm[i] = 0; }
+        for (int i = lane; i < PACK_CAL_W; i += 32) D.chead[i] = -1;
+        for (size_t i = lane; i < (size_t)J * D.W; i += 32) D.pjbits[i] = 0;
+        __syncwarp();
+    }
+    const int d_stop = st.d + tick_budget;
+    while (true) {
+        if ((J - st.cursor) + st.R == 0) { st.done = 1; break; }   // schedule.py:185 (the queue is not consulted, q2)
+        if (st.d == d_stop) break;
+        if (P.max_ticks > 0 && st.d >= P.max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
+        const int d = st.d;
+
+        // ---------------- arrivals: heappush in trace order (jobs_manager.py:228-241, job_queue_manager.py:147-152)
+        while (st.cursor < J) {
+            const int job = st.cursor;
+            const int arr = D.trace[job].arrival_tick;
+            if (arr > d) break;
+            pack_q_push(D, lane, st.Q, D.pj[job].util_avg, job);
+            if (lane == 0) { D.lprev[job] = st.ltail; D.lnext[job] = -1; if (st.ltail >= 0) D.lnext[st.ltail] = job; }
+            if (st.ltail < 0) st.lhead = job;
+            st.ltail = job;
+            __syncwarp();
+            const int ql = st.Q;                              // queued jobs = heap length here (no look-ahead is out)
+            if (ql == 1) { st.mlo = job; st.mrank = 0; }
+            else if ((ql - 1) / 2 > st.mrank) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
+            st.sum_arr += arr;
+            st.cursor += 1;
+            if (st.Q > st.max_q) st.max_q = st.Q;
+            __syncwarp();
+        }
+
+        // ---------------- _schedule -> schedule_horus (schedule.py:40-60, algorithm.py:204-240)
+        if (st.Q > 0 && st.n_free_nodes >= 1) {
+            const int k = min(max(P.num_buffer, 0), st.Q);
+            int my_job = -1; double my_key = 0.0;
+            for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
+            __syncwarp();
+            int pos = -1, err = 0;
+            for (int a = 0; a < k && pos < 0; ++a) {
+                PackCtx x;
+                x.lane = lane; x.job = __shfl_sync(RLGS_FULL, my_job, a);
+                const rlgs_job rec = D.trace[x.job];
+                x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q; x.interf = 0;
+                if (x.T > PACK_MAX_TASKS || D.pj[x.job].heap_cap > PACK_MAX_HEAP || D.pj[x.job].heap_cap < 0) { err = RLGS_ERR_UNSUPPORTED; break; }
+                const int r = pack_place(D, c, P, st, x, replica, (uint32_t)a);
+                if (r < 0) { err = r; break; }
+                if (r) pos = a;
+            }
+            if (err) { st.status = err; st.done = 1; break; }
+            for (int a = 0; a < k; ++a) {                     // jobs_manager.insert(look_ahead): heappush the rest in order
+                const int job = __shfl_sync(RLGS_FULL, my_job, a); const double key = __shfl_sync(RLGS_FULL, my_key, a);
+                if (a != pos) pack_q_push(D, lane, st.Q, key, job);
+            }
+            __syncwarp();
+            if (pos >= 0) {                                   // add_to_running -> start_job (schedule.py:164-167, jobs_manager.py:189-207)
+                const int job = __shfl_sync(RLGS_FULL, my_job, pos);
+                const rlgs_job rec = D.trace[job];
+                const PackJob pj = D.pj[job];
+                const int p = D.lprev[job], n = D.lnext[job];
+                const int hb = D.chead[(d + rec.dur_ticks) & (PACK_CAL_W - 1)];
+                int tn = -1;
+                if (lane < rec.tasks) tn = D.tnode[pj.task_off + lane];
+                __syncwarp();
+                if (p >= 0) D.lnext[p] = n; else st.lhead = n;
+                if (n >= 0) D.lprev[n] = p; else st.ltail = p;
+                if (job == st.mlo) { if (n >= 0) st.mlo = n; else { st.mlo = p; st.mrank -= 1; } }
+                else if (job < st.mlo) st.mrank -= 1;
+                __syncwarp();
+                const int ql = st.Q;                          // queued jobs after the start
+                if (ql > 0) {
+                    const int target = (ql - 1) / 2;
+                    if (st.mrank < target) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
+                    else if (st.mrank > target) { st.mlo = D.lprev[st.mlo]; st.mrank -= 1; }
+                }
+                st.sum_arr -= rec.arrival_tick;
+                D.planes[0][job] = d; D.planes[3][job] = 0;
+                D.pend[job] = d + rec.dur_ticks;
+                D.cnext[job] = hb; D.chead[(d + rec.dur_ticks) & (PACK_CAL_W - 1)] = job;
+                // placed_tasks -> running_tasks on every node of the job (node.py:173-198); several tasks may share a node
+                for (int t = 0; t < rec.tasks; ++t) {
+                    const int node = __shfl_sync(RLGS_FULL, tn, t);
+                    const int v = D.ntk[node];
+                    __syncwarp();
+                    D.ntk[node] = v - (1 << 16) + 1;
+                    __syncwarp();
+                }
+                st.R += 1; st.start_seq += 1;
+                if (st.R > st.max_r) st.max_r = st.R;
+                __syncwarp();
+            }
+        }
+
+        // ---------------- delta_time += 1; step; release_finished_jobs in running_jobs (= start) order
+        st.d = d + 1;
+        {
+            const int bk = st.d & (PACK_CAL_W - 1);
+            int nf = 0;
+            if (lane == 0) {                                   // jobs_to_finish is fixed before any release (jobs_manager.py:243-250)
+                int prev = -1, cur = D.chead[bk];
+                while (cur >= 0) {
+                    const int nx = D.cnext[cur], pe = D.pend[cur];
+                    if (pe == st.d || (pe & (PACK_CAL_W - 1)) != bk) {
+                        if (prev < 0) D.chead[bk] = nx; else D.cnext[prev] = nx;
+                        if (pe == st.d) { D.fin[nf] = cur; nf += 1; }
+                        else { const int b2 = pe & (PACK_CAL_W - 1); D.cnext[cur] = D.chead[b2]; D.chead[b2] = cur; }   // +5 moved it to another bucket
+                    } else prev = cur;
+                    cur = nx;
+                }
+            }
+            __syncwarp();
+            nf = __shfl_sync(RLGS_FULL, nf, 0);
+            for (int done_n = 0; done_n < nf; ++done_n) {
+                // next finisher in start order (one start per tick: start ticks are distinct)
+                int best = -1, best_start = RLGS_NEVER, best_at = -1;
+                for (int i = 0; i < nf; ++i) { const int jb = D.fin[i]; if (jb < 0) continue; const int s0 = D.planes[0][jb]; if (s0 < best_start) { best_start = s0; best = jb; best_at = i; } }
+                __syncwarp();
+                D.fin[best_at] = -1;
+                const rlgs_job rec = D.trace[best];
+                const int off = D.pj[best].task_off;
+                for (int t = 0; t < rec.tasks; ++t) pack_release(D, c, st, lane, (int)D.tnode[off + t], best, t, true);
+                D.planes[1][best] = st.d;
+                D.planes[2][st.F] = best;
+                st.F += 1; st.R -= 1;
+                st.sum_jct += (int64_t)(st.d - rec.arrival_tick);
+                __syncwarp();
+            }
+        }
+
+        // ---------------- stats row (schedule.py:95-133, 204-205)
+        st.sumQ += st.Q; st.sumR += st.R;
+        if (rows_mode) {
+            int lo = 0, hi = 0, mx = 0;
+            if (st.Q > 0) {
+                const int a0 = D.trace[st.mlo].arrival_tick;
+                const int a1 = (st.Q & 1) ? a0 : D.trace[D.lnext[st.mlo]].arrival_tick;
+                lo = st.d - a1; hi = st.d - a0; mx = st.d - D.trace[st.lhead].arrival_tick;
+            }
+            if (lane == 0) {
+                rlgs_row *row = row_ptr(rs, blockIdx.x, st.d - 1);
+                const int64_t sp = (int64_t)st.Q * st.d - st.sum_arr;
+                int4 *o = reinterpret_cast<int4 *>(row);
+                o[0] = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
+                o[1] = make_int4(st.F, lo, hi, mx);
+                o[2] = make_int4((int)(uint32_t)sp, (int)(sp >> 32), (int)(uint32_t)st.mem_sum, (int)(st.mem_sum >> 32));
+                o[3] = make_int4((int)(uint32_t)st.util_mu_sum, (int)(st.util_mu_sum >> 32), (int)(uint32_t)st.util_var_sum, (int)(st.util_var_sum >> 32));
+            }
+        }
+    }
+    st.events = (int64_t)st.cursor + st.start_seq + st.F;
+    if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;
+    __syncwarp();
+    if (lane == 0) {
+        states[blockIdx.x] = st;
+        if (st.done) returns[blockIdx.x] = -st.sum_jct;
+    }
+}

@@ -18,6 +18,7 @@
 #include "../../include/rlgs.h"
 #include "fifo_yarn.cuh"
 #include "legacy_sched.cuh"
+#include "pack_horus.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -44,6 +45,7 @@ struct TraceBuf {
     rlgs_job *dev = nullptr;
     double *net = nullptr;      // [3][cap_n] network-cost inputs
     double *dur_out = nullptr;  // [count][cap_n]
+    PackJob *pack = nullptr;    // [n] horus placement inputs
     int32_t n = 0, cap_n = 0;
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
@@ -69,6 +71,8 @@ struct rlgs_sim {
     LegParams lp;
     int R = 0, device = 0;
     bool legacy = false;
+    bool pack = false;      // horus schedule + horus placement (pack_horus.cuh)
+    PackParams pp;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     void *user_stream = nullptr;
     bool use_user_stream = false;   // NULL is a valid handle: the legacy default stream
@@ -85,6 +89,10 @@ struct rlgs_sim {
     std::vector<LegDesc> h_ldesc;
     LegDesc *d_ldesc = nullptr;
     LegState *d_lstate = nullptr, *h_lstate = nullptr, *h_linit = nullptr;
+    // pack
+    std::vector<PackDesc> h_pdesc;
+    PackDesc *d_pdesc = nullptr;
+    PackState *d_pstate = nullptr, *h_pstate = nullptr, *h_pinit = nullptr;
     std::vector<void *> slabs;
     int slot_cap = 0;
     // chunk-major row store
@@ -120,11 +128,15 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
     const int sched = opts->schedule;
     if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS &&
-        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU)
+        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU && sched != RLGS_SCHED_HORUS)
         return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
     const bool is_sjf_family = sched == RLGS_SCHED_SJF || sched == RLGS_SCHED_SHORTEST || sched == RLGS_SCHED_SHORTEST_GPU;
     if ((sched == RLGS_SCHED_FIFO || is_sjf_family) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
+    if ((sched == RLGS_SCHED_HORUS) != (opts->placement == RLGS_PLACE_HORUS))
+        return fail(RLGS_ERR_UNSUPPORTED, "the horus schedule and the horus placement go together (schedule.py:47 passes the schedule "
+                    "name to the placement's score table, so fifo + horus raises KeyError in the reference)");
+    if (sched == RLGS_SCHED_HORUS && (opts->num_buffer < 0 || opts->num_buffer > 32)) return fail(RLGS_ERR_BAD_ARG, "num_buffer must be 0..32");
     const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
     if (is_dlas) {
         if (opts->num_queue < 1 || opts->num_queue > RLGS_MAX_QUEUES) return fail(RLGS_ERR_BAD_ARG, "num_queue must be 1..%d", RLGS_MAX_QUEUES);
@@ -143,6 +155,11 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (!s) return fail(RLGS_ERR_OOM, "host allocation failed");
     s->spec = *spec; s->opts = *opts; s->R = opts->n_replicas; s->device = opts->device;
     s->legacy = sched != RLGS_SCHED_FIFO;
+    s->pack = sched == RLGS_SCHED_HORUS;
+    memset(&s->pp, 0, sizeof s->pp);
+    s->pp.num_buffer = opts->num_buffer > 0 ? opts->num_buffer : 5;
+    s->pp.rng_on = opts->pack_rng != 0; s->pp.seed = opts->pack_seed;
+    s->pp.nodes_per_rack = spec->num_node_p_switch; s->pp.racks = spec->num_switch; s->pp.max_ticks = opts->max_ticks;
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
     s->cc.D = s->cc.N * s->cc.G;
@@ -159,6 +176,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
     s->h_ldesc.assign(s->R, LegDesc{});
+    if (s->pack) s->h_pdesc.assign(s->R, PackDesc{});
     int ng = opts->n_streams > 0 ? opts->n_streams : (s->R >= 8 * 148 ? 4 : (s->R >= 2 * 148 ? 2 : 1));
     ng = std::max(1, std::min(ng, s->R));
     cudaError_t ce = cudaSuccess;
@@ -184,6 +202,12 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     ok(cudaMallocHost(&s->h_init, sizeof(RepState) * s->R));
     ok(cudaMallocHost(&s->h_lstate, sizeof(LegState) * s->R));
     ok(cudaMallocHost(&s->h_linit, sizeof(LegState) * s->R));
+    if (s->pack) {
+        ok(cudaMalloc(&s->d_pdesc, sizeof(PackDesc) * s->R));
+        ok(cudaMalloc(&s->d_pstate, sizeof(PackState) * s->R));
+        ok(cudaMallocHost(&s->h_pstate, sizeof(PackState) * s->R));
+        ok(cudaMallocHost(&s->h_pinit, sizeof(PackState) * s->R));
+    }
     if (ce != cudaSuccess) {
         rlgs_destroy(s);
         return fail(ce == cudaErrorMemoryAllocation ? RLGS_ERR_OOM : RLGS_ERR_CUDA, "rlgs_create: %s", cudaGetErrorString(ce));
@@ -196,7 +220,10 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); }
+    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); }
+    cudaFree(s->d_pdesc); cudaFree(s->d_pstate);
+    if (s->h_pstate) cudaFreeHost(s->h_pstate);
+    if (s->h_pinit) cudaFreeHost(s->h_pinit);
     for (void *p : s->slabs) cudaFree(p);
     for (auto p : s->d_chunks) cudaFree(p);
     for (auto p : s->h_chunks) if (p) cudaFreeHost(p);
@@ -252,7 +279,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     tb.max_arrival = prev; tb.first = first; tb.count = count;
     // a reload of the same replica range with a trace that fits the existing buffers only re-uploads
     // the records (the e2e path: one host->device copy per step, no allocation)
-    for (size_t t = 0; t < s->traces.size(); ++t) {
+    for (size_t t = 0; t < s->traces.size() && !s->pack; ++t) {
         TraceBuf &old = s->traces[t];
         if (old.first == first && old.count == count && n <= old.cap_n && tb.log_cap <= old.cap_log) {
             CU(cudaMemcpy(old.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice));
@@ -285,7 +312,9 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     int tid = (int)s->traces.size();
     s->traces.push_back(tb);
     unsigned char *slab = nullptr;
-    if (!s->legacy) {
+    if (s->pack) {
+        for (int r = 0; r < count; ++r) { s->h_pdesc[first + r] = PackDesc{}; s->h_pdesc[first + r].trace = tb.dev; s->h_pdesc[first + r].J = n; s->h_ldesc[first + r].J = n; }
+    } else if (!s->legacy) {
         // per-replica working set: queue stack | placement log | node_save | slot_save
         int nw = 3 * s->cc.N + (s->cc.N + 31) / 32;
         size_t a0 = align_up(sizeof(rlgs_job) * (size_t)n, 256), a1 = align_up(sizeof(int2) * (size_t)std::max<int64_t>(tb.log_cap, 1), 256);
@@ -333,6 +362,56 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     return RLGS_OK;
 }
 
+extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t count, const rlgs_pack_inputs *in, int32_t n) {
+    if (!s || !in || !in->util_avg || !in->util_sd || !in->task_mem || !in->heap_cap) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->pack) return fail(RLGS_ERR_STATE, "pack inputs belong to the horus placement");
+    if (in->mem_shift < 0 || in->mem_shift > 30 || in->gpu_mem_cap_mib < 1) return fail(RLGS_ERR_BAD_ARG, "mem_shift must be 0..30 and gpu_mem_cap_mib >= 1");
+    TraceBuf *tb = nullptr;
+    for (auto &t : s->traces) if (t.first == first && t.count == count && t.n == n && !t.pack) tb = &t;
+    if (!tb) return fail(RLGS_ERR_STATE, "no trace of %d jobs loaded for replicas [%d,%d) without pack inputs", n, first, first + count);
+    CU(cudaSetDevice(s->device));
+    std::vector<rlgs_job> jobs((size_t)n);
+    CU(cudaMemcpy(jobs.data(), tb->dev, sizeof(rlgs_job) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<PackJob> pj((size_t)n);
+    int64_t sum_tasks = 0;
+    for (int i = 0; i < n; ++i) {
+        if (jobs[i].tasks > PACK_MAX_TASKS) return fail(RLGS_ERR_UNSUPPORTED, "job %d has %d tasks; the pack placement handles up to %d per job", i, (int)jobs[i].tasks, PACK_MAX_TASKS);
+        if (in->heap_cap[i] < 0 || in->heap_cap[i] > PACK_MAX_HEAP) return fail(RLGS_ERR_UNSUPPORTED, "job %d: used_gpus %d outside 0..%d", i, in->heap_cap[i], PACK_MAX_HEAP);
+        if (in->task_mem[i] < 0) return fail(RLGS_ERR_BAD_ARG, "job %d: negative memory", i);
+        pj[i].util_avg = in->util_avg[i]; pj[i].util_sd = in->util_sd[i]; pj[i].mem = in->task_mem[i];
+        pj[i].heap_cap = in->heap_cap[i]; pj[i].task_off = (int32_t)sum_tasks;
+        sum_tasks += jobs[i].tasks;
+    }
+    CU(cudaMalloc(&tb->pack, sizeof(PackJob) * (size_t)n));
+    CU(cudaMemcpy(tb->pack, pj.data(), sizeof(PackJob) * (size_t)n, cudaMemcpyHostToDevice));
+    const size_t N = (size_t)s->cc.N, Dv = (size_t)s->cc.D, J = (size_t)n, W = (N + 31) / 32;
+    // per-replica working set, 256-byte aligned pieces in this order
+    const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J,
+                         4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 8 * N, 8 * (PACK_MAX_HEAP + 1), 4 * (PACK_MAX_HEAP + 1), 4 * J};
+    size_t per = 0;
+    for (size_t v : sz) per += align_up(v, 256);
+    unsigned char *slab = nullptr;
+    CU(cudaMalloc(&slab, per * (size_t)count));
+    s->slabs.push_back(slab);
+    const int64_t unit = (int64_t)1 << in->mem_shift;
+    for (int r = 0; r < count; ++r) {
+        unsigned char *p = slab + per * (size_t)r;
+        PackDesc &D = s->h_pdesc[first + r];
+        int k = 0;
+        auto take = [&](size_t) { unsigned char *q = p; p += align_up(sz[k++], 256); return q; };
+        D.trace = tb->dev; D.pj = tb->pack; D.J = n; D.W = (int32_t)W;
+        D.units = (int32_t *)take(0); D.ntk = (int32_t *)take(0); D.npj = (int32_t *)take(0); D.dn = (int32_t *)take(0);
+        D.dm = (int64_t *)take(0); D.ent = (int2 *)take(0); D.pjbits = (uint32_t *)take(0); D.qkey = (double *)take(0);
+        D.qjob = (int32_t *)take(0); D.lprev = (int32_t *)take(0); D.lnext = (int32_t *)take(0); D.pend = (int32_t *)take(0);
+        D.cnext = (int32_t *)take(0); D.chead = (int32_t *)take(0); D.tnode = (int16_t *)take(0); D.score = (double *)take(0);
+        D.hscore = (double *)take(0); D.hnode = (int32_t *)take(0); D.fin = (int32_t *)take(0);
+        D.cap_units = (int64_t)in->gpu_mem_cap_mib * unit; D.margin_units = 500 * unit;
+        D.cap_mib = (double)in->gpu_mem_cap_mib; D.unit_mib = 1.0 / (double)unit;
+    }
+    s->ran = false;
+    return RLGS_OK;
+}
+
 // (re)allocates the [N_PLANES][R][Jmax] job-output arrays and points every replica at its rows
 static int32_t setup_job_arrays(rlgs_sim *s) {
     int32_t Jmax = 0;
@@ -357,6 +436,10 @@ static int32_t setup_job_arrays(rlgs_sim *s) {
             D.place_off = s->d_jobs + 3 * plane + (size_t)r * Jmax;
         } else {
             for (int k = 0; k < N_PLANES; ++k) s->h_ldesc[r].planes[k] = s->d_jobs + k * plane + (size_t)r * Jmax;
+            if (s->pack) {
+                if (!s->h_pdesc[r].pj) return fail(RLGS_ERR_STATE, "replica %d has no pack inputs (call rlgs_load_pack_inputs)", r);
+                for (int k = 0; k < N_PLANES; ++k) s->h_pdesc[r].planes[k] = s->h_ldesc[r].planes[k];
+            }
         }
     }
     return RLGS_OK;
@@ -396,7 +479,10 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
 #undef RLGS_LAUNCH_FIFO
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
-        if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
+        if (s->pack) {
+            PackParams pp = s->pp; pp.tick_budget = budget;
+            pack_horus_kernel<<<count, 32, 0, st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
+        } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         else
             sjf_yarn_kernel<<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
@@ -405,7 +491,8 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
 
 static Progress progress_of(const rlgs_sim *s, int r) {
     Progress p;
-    if (!s->legacy) { p.rows = s->h_state[r].d; p.done = s->h_state[r].done; p.status = s->h_state[r].status; }
+    if (s->pack) { p.rows = s->h_pstate[r].d; p.done = s->h_pstate[r].done; p.status = s->h_pstate[r].status; }
+    else if (!s->legacy) { p.rows = s->h_state[r].d; p.done = s->h_state[r].done; p.status = s->h_state[r].status; }
     else { p.rows = s->h_lstate[r].n_rows; p.done = s->h_lstate[r].done; p.status = s->h_lstate[r].status; }
     return p;
 }
@@ -432,7 +519,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else if (s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
+    } else if (!s->pack && s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
     int32_t max_arrival = 0;
@@ -447,6 +534,12 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
             LegState z; memset(&z, 0, sizeof z);
             z.next_end = RLGS_NEVER; z.next_jump = RLGS_NEVER;
             s->h_linit[r] = z;
+            if (s->pack) {
+                PackState q; memset(&q, 0, sizeof q);
+                q.idle_nodes = s->cc.N; q.n_free_nodes = (s->cc.cpu_cap > 0 || s->cc.mem_cap > 0) ? s->cc.N : 0;
+                q.lhead = q.ltail = q.mlo = -1;
+                s->h_pinit[r] = q;
+            }
         }
         max_arrival = std::max(max_arrival, s->traces[s->rep_trace[r]].max_arrival);
     }
@@ -464,6 +557,9 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     if (!s->legacy) {
         CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
         CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * R, cudaMemcpyHostToDevice, main_st));
+    } else if (s->pack) {
+        CU(cudaMemcpyAsync(s->d_pstate, s->h_pinit, sizeof(PackState) * R, cudaMemcpyHostToDevice, main_st));
+        CU(cudaMemcpyAsync(s->d_pdesc, s->h_pdesc.data(), sizeof(PackDesc) * R, cudaMemcpyHostToDevice, main_st));
     } else {
         CU(cudaMemcpyAsync(s->d_lstate, s->h_linit, sizeof(LegState) * R, cudaMemcpyHostToDevice, main_st));
         CU(cudaMemcpyAsync(s->d_ldesc, s->h_ldesc.data(), sizeof(LegDesc) * R, cudaMemcpyHostToDevice, main_st));
@@ -504,7 +600,8 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
                 CU(cudaStreamWaitEvent(main_st, G.k_end, 0));
             }
         }
-        if (!s->legacy) CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, main_st));
+        if (s->pack) CU(cudaMemcpyAsync(s->h_pstate, s->d_pstate, sizeof(PackState) * R, cudaMemcpyDeviceToHost, main_st));
+        else if (!s->legacy) CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * R, cudaMemcpyDeviceToHost, main_st));
         else CU(cudaMemcpyAsync(s->h_lstate, s->d_lstate, sizeof(LegState) * R, cudaMemcpyDeviceToHost, main_st));
         CU(cudaStreamSynchronize(main_st));
         if (pipelined) {
@@ -526,6 +623,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         if (overflow) {
             cudaStreamSynchronize(s->copy_stream);
             if (s->opts.max_ticks > 0) return fail(RLGS_ERR_CAPACITY, "replica %d reached max_ticks", bad);
+            if (s->pack) return fail(RLGS_ERR_CAPACITY, "replica %d stopped on a capacity limit", bad);
             if (!s->legacy) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap);
             return fail(RLGS_ERR_CAPACITY, "replica %d: runnable-entry table overflow", bad);
         }
@@ -554,7 +652,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     s->last_ms = total_ms; s->last_launches = launches;
     s->rows_hint = 0;
     for (int r = 0; r < R; ++r) s->rows_hint = std::max<int64_t>(s->rows_hint, progress_of(s, r).rows);
-    for (int r = 0; r < R; ++r) s->h_returns[r] = -(s->legacy ? s->h_lstate[r].sum_jct : s->h_state[r].sum_jct);
+    for (int r = 0; r < R; ++r) s->h_returns[r] = -(s->pack ? s->h_pstate[r].sum_jct : (s->legacy ? s->h_lstate[r].sum_jct : s->h_state[r].sum_jct));
     s->ran = true;
     for (int r = 0; r < R; ++r) {
         Progress p = progress_of(s, r);
@@ -575,7 +673,12 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     memset(out, 0, sizeof *out);
-    if (!s->legacy) {
+    if (s->pack) {
+        const PackState &z = s->h_pstate[r];
+        out->n_ticks = z.d; out->makespan = z.d; out->sum_jct = z.sum_jct; out->sum_queued = z.sumQ; out->sum_running = z.sumR;
+        out->events = z.events; out->n_jobs = s->h_pdesc[r].J; out->n_arrived = z.cursor; out->n_started = z.start_seq;
+        out->n_finished = z.F; out->max_queued = z.max_q; out->max_running = z.max_r; out->status = z.status; out->done = z.done;
+    } else if (!s->legacy) {
         const RepState &z = s->h_state[r];
         out->n_ticks = z.d; out->makespan = z.d; out->sum_jct = z.sum_jct; out->sum_queued = z.sumQ; out->sum_running = z.sumR;
         out->events = z.events; out->n_jobs = s->h_desc[r].J; out->n_arrived = z.cursor; out->n_started = z.start_seq;
@@ -628,7 +731,8 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (end_tick) memcpy(end_tick, en, 4 * (size_t)J);
     if (finish_order) memcpy(finish_order, fo, 4 * (size_t)J);
     if (preempt) {
-        if (s->legacy) memcpy(preempt, s->h_jobs + 4 * plane + off, 4 * (size_t)J);
+        if (s->pack) for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171)
+        else if (s->legacy) memcpy(preempt, s->h_jobs + 4 * plane + off, 4 * (size_t)J);
         else for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171, q6)
     }
     if (first_node) {

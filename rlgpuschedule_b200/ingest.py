@@ -75,6 +75,20 @@ class Trace:
     cap_mib: int
     model_mb: np.ndarray = None      # network-cost inputs (zeros when the trace has no model_name / iterations)
     iterations: np.ndarray = None
+    util_avg: np.ndarray = None      # gpu_utilization_avg / _max and memory_max in MiB: inputs of the pack placement
+    util_max: np.ndarray = None
+    mem_mib: np.ndarray = None
+
+    def pack_inputs(self):
+        """Arrays of rlgs_pack_inputs (include/rlgs.h): what horus_score / Device.can_fit read from a Task
+        (core/scheduling/horus.py:28-56, infra/device.py:48-77)."""
+        mem = self.mem_mib * float(2 ** self.mem_shift)
+        if len(mem) and (np.any(mem != np.floor(mem)) or mem.max() >= 2.0 ** 52):
+            raise ValueError('memory_max is not an exact multiple of 2**-%d MiB' % self.mem_shift)
+        return dict(util_avg=np.ascontiguousarray(self.util_avg, np.float64),
+                    util_sd=np.ascontiguousarray((self.util_max - self.util_avg) / 2, np.float64),
+                    task_mem=np.ascontiguousarray(mem.astype(np.int64)),
+                    heap_cap=np.ascontiguousarray(np.floor(self.used_gpus).astype(np.int32)))
 
     def __len__(self):
         return len(self.records)
@@ -143,7 +157,7 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     # is a dyadic rational, so with a common unit 2**-s MiB the float64 running sum of the reference
     # (schedule.py:109-121) is exact and equals an integer sum as long as it stays below 2**53.
     term = np.where(mem_mib < cap, mem_mib, float(cap))
-    shift = _dyadic_shift(term)
+    shift = max(_dyadic_shift(term), _dyadic_shift(mem_mib))   # the pack placement also adds un-clamped amounts
     scaled = term * float(2 ** shift)
     if n and (shift > 60 or scaled.max() * max(cluster.num_gpus, 1) >= 2.0 ** 53):
         raise ValueError('memory_max values are not exactly summable in 53 bits; cannot reproduce '
@@ -159,4 +173,5 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     iters = df['iterations'].to_numpy(dtype=np.float64) if 'iterations' in df.columns else np.zeros(n, dtype=np.float64)
     return Trace(label=df.index.to_numpy().astype(np.int64), nt=nt, duration=np.ascontiguousarray(duration), used_gpus=used,
                  records=np.ascontiguousarray(rec), mem_shift=shift, cap_mib=cap,
-                 model_mb=np.ascontiguousarray(model_mb), iterations=np.ascontiguousarray(iters))
+                 model_mb=np.ascontiguousarray(model_mb), iterations=np.ascontiguousarray(iters),
+                 util_avg=np.ascontiguousarray(ua), util_max=np.ascontiguousarray(um), mem_mib=np.ascontiguousarray(mem_mib))

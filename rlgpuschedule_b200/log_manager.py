@@ -100,7 +100,8 @@ def format_cluster_csv(rows, cluster, mem_shift, with_header=True, with_util=Tru
     return buf.getvalue()
 
 
-def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duration=None, jct=None, with_header=True):
+def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duration=None, jct=None, with_header=True,
+                   get_duration=None):
     """job.csv text: one row per finished job in finish order (finished_jobs dict order, log_manager.py:141-153)."""
     buf = io.StringIO(newline='')
     w = csv.writer(buf)
@@ -109,7 +110,8 @@ def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duratio
     fo = np.asarray(finish_order, dtype=np.int64)
     # with network costs Job.duration itself is increased (job.py:196-197), so both columns show the new value
     dur = trace.duration[fo] if actual_duration is None else np.asarray(actual_duration)[fo]
-    act = dur
+    # horus: Job.duration stays, Job.get_duration() grows by 5 when a task was de-interfered (jobs_manager.py:184-185)
+    act = dur if get_duration is None else np.asarray(get_duration)[fo]
     st, en = np.asarray(start)[fo], np.asarray(end)[fo]
     jc = (en - st) if jct is None else np.asarray(jct)[fo]
     pre = np.ones(len(fo), dtype=np.int64) if preempt is None else np.asarray(preempt)[fo]

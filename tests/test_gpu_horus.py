@@ -1,0 +1,80 @@
+"""horus schedule + horus placement on the device vs the CPU restatement (oracle_pack), which is pinned byte-for-byte
+against the real reference on zero-spread traces (tests/golden/horus_*, tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+import rlgpuschedule_b200 as rl
+from rlgpuschedule_b200 import _ffi, log_manager as lm
+from oracle import cpu_sim, tracegen
+
+pytestmark = pytest.mark.gpu
+
+
+def zero_spread(df):
+    df = df.copy()
+    df['gpu_utilization_max'] = df['gpu_utilization_avg']
+    return df
+
+
+CASES = {
+    'probe100_1x4x8': (lambda: zero_spread(tracegen.frame_probe100()), dict(num_switch=1, num_node_p_switch=4, num_gpu_p_node=8), 5),
+    'probe100_2x2x8_k3': (lambda: zero_spread(tracegen.frame_probe100()), dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8), 3),
+    'gen300_2x4x8': (lambda: zero_spread(tracegen.frame_gen(300, 11, 150)), dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), 5),
+    'gen300_3x2x4': (lambda: zero_spread(tracegen.frame_gen(300, 12, 60)), dict(num_switch=3, num_node_p_switch=2, num_gpu_p_node=4), 5),
+    'gen2000_4x8x8_spread': (lambda: tracegen.frame_gen(2000, 13, 1000), dict(num_switch=4, num_node_p_switch=8, num_gpu_p_node=8), 5),
+}
+
+
+def run_device(df, flags, k, seed=None, **kw):
+    cluster = rl.cluster_from_flags(flags)
+    tr = rl.prepare_trace(df, cluster)
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, **kw)
+    sim.load_trace(tr)
+    sim.run()
+    return sim, cluster, tr
+
+
+def check(sim, cluster, tr, o, otr, replica):
+    j = sim.jobs(replica)
+    aux = sim.job_plane(replica, _ffi.PLANE_AUX)
+    dur = tr.duration + 5.0 * (aux == 1)
+    assert np.array_equal(j['finish_order'], o['finish_order'])
+    assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end'])
+    assert np.array_equal(dur, o['actual_duration'])
+    got = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur)
+    assert got == cpu_sim.format_job_csv(otr, o)
+    assert lm.format_cluster_csv(sim.rows(replica), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_horus_matches_oracle_mean_draws(name):
+    frame, flags, k = CASES[name]
+    df = frame()
+    sim, cluster, tr = run_device(df, flags, k)
+    otr = cpu_sim.prepare_trace(df)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k)
+    for r in range(2):
+        check(sim, cluster, tr, o, otr, r)
+    sim.close()
+
+
+@pytest.mark.parametrize('name', ['probe100_1x4x8', 'gen300_2x4x8', 'gen2000_4x8x8_spread'])
+def test_horus_matches_oracle_seeded_draws(name):
+    frame, flags, k = CASES[name]
+    df = tracegen.frame_probe100() if name.startswith('probe') else (tracegen.frame_gen(300, 11, 150) if name.startswith('gen300') else frame())
+    sim, cluster, tr = run_device(df, flags, k, seed=1234)
+    otr = cpu_sim.prepare_trace(df)
+    for r in range(2):
+        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k, seed=1234, replica=r)
+        check(sim, cluster, tr, o, otr, r)
+    sim.close()
+
+
+def test_horus_bounded_launches_resume():
+    frame, flags, k = CASES['gen300_2x4x8']
+    df = frame()
+    sim, cluster, tr = run_device(df, flags, k, ticks_per_launch=37)
+    otr = cpu_sim.prepare_trace(df)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k)
+    check(sim, cluster, tr, o, otr, 1)
+    sim.close()
