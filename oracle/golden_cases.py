@@ -112,6 +112,16 @@ def _ties():
     return tg.frame_rows(rows)
 
 
+def _zs(frame):
+    """Zero utilisation spread: gpu_utilization_max = gpu_utilization_avg makes every np.random.normal(loc, 0) of
+    infra/device.py:30,52 return loc, so the reference's horus path is deterministic and can be pinned."""
+    def f():
+        df = frame().copy()
+        df['gpu_utilization_max'] = df['gpu_utilization_avg']
+        return df
+    return f
+
+
 CASES = {
     'kat6': dict(frame=_kat6, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8)),
     'kat5_early': dict(frame=lambda: _kat6(True), flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8)),
@@ -131,4 +141,16 @@ CASES = {
     'probe10k': dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, big=True),
     'loaded10k': dict(frame=lambda: tg.frame_gen(10000, 4, 2500), flags=C4328, big=True),
     'probe60k': dict(frame=lambda: tg.frame_gen(60000, 3, 60000), flags=C4328, big=True, huge=True),
+    # --schedule horus --scheme horus (schedule_horus + horus_placement), zero-spread traces
+    'horus_probe100': dict(frame=_zs(tg.frame_probe100), flags=C148, schedule='horus'),
+    'horus_racks_k3': dict(frame=_zs(tg.frame_probe100), flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8), schedule='horus', num_buffer=3),
+    'horus_multi_node': dict(frame=_zs(_multi_node), flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus'),
+    'horus_big_mem_leak': dict(frame=_zs(_big_mem), flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4, num_cpu_p_node=64, mem_p_node=256), schedule='horus'),
+    'horus_gpu_cap16': dict(frame=_zs(lambda: tg.frame_gen(120, 7, 150)), flags=dict(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8, gpu_memory_capacity=12), schedule='horus'),
+    'horus_ties': dict(frame=_zs(_ties), flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='horus'),
+    'horus_mem_bound': dict(frame=_zs(lambda: _resource_bound(22)), flags=dict(num_switch=2, num_node_p_switch=3, num_gpu_p_node=8, mem_p_node=130), schedule='horus'),
+    'horus_early_stop': dict(frame=_zs(lambda: tg.frame_gen(300, 12, 60)), flags=dict(num_switch=3, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus'),
+    'horus_gen300': dict(frame=_zs(lambda: tg.frame_gen(300, 11, 150)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus', big=True),
+    'horus_dense': dict(frame=_zs(lambda: tg.frame_gen(300, 5, 30)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus', num_buffer=8, big=True),
+    'horus_probe2k': dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='horus', big=True),
 }

@@ -8,9 +8,10 @@
     score_fn[name](node, task)                                              algorithm.py:9-13
 
 The entries the hot path implements are DevicePolicy objects: Scheduler.start() hands their integer
-id to librlgs and the whole tick / event loop runs on the GPU.  The reference's other keys (horus,
-horus+, gandiva: RNG-driven packing heuristics) are registered as HostOnlyPolicy so the
-key set is unchanged and selecting them fails loudly instead of silently running something else.
+id to librlgs and the whole tick / event loop runs on the GPU.  `horus` (schedule_horus + horus_placement
+with horus_score) is one of them; the reference's remaining keys (horus+: k-means queues, gandiva: time
+slicing) are registered as HostOnlyPolicy so the key set is unchanged and selecting them fails loudly
+instead of silently running something else.
 Users may register their own entries; only DevicePolicy entries can be executed by this package.
 """
 from . import _ffi
@@ -50,7 +51,7 @@ scheduling_algorithms = {
     'dlas': DevicePolicy('dlas', 'schedule', _ffi.SCHED['dlas'], 'run_sim.py:664-947 with gputime=False (dead code, restated)'),
     'shortest': DevicePolicy('shortest', 'schedule', _ffi.SCHED['shortest'], 'run_sim.py:299-431 (dead code, restated)'),
     'shortest-gpu': DevicePolicy('shortest-gpu', 'schedule', _ffi.SCHED['shortest-gpu'], 'run_sim.py:299-431 with gputime (dead code, restated)'),
-    'horus': HostOnlyPolicy('horus', 'schedule', 'core/scheduling/algorithm.py:204-240'),
+    'horus': DevicePolicy('horus', 'schedule', _ffi.SCHED['horus'], 'core/scheduling/algorithm.py:204-240'),
     'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
     'gandiva': HostOnlyPolicy('gandiva', 'schedule', 'core/scheduling/algorithm.py:292-298 + time_slice_check :420-440'),
 }
@@ -58,9 +59,11 @@ scheduling_algorithms = {
 placement_algorithms = {
     'yarn': DevicePolicy('yarn', 'placement', _ffi.PLACE['yarn'], 'core/scheduling/algorithm.py:28-32,301-417'),
     'count': DevicePolicy('count', 'placement', _ffi.PLACE['count'], 'run_sim.py:808-823 (free_gpu counting)'),
-    'horus': HostOnlyPolicy('horus', 'placement', 'core/scheduling/algorithm.py:34-180'),
-    'horus+': HostOnlyPolicy('horus+', 'placement', 'core/scheduling/algorithm.py:34-180'),
-    'gandiva': HostOnlyPolicy('gandiva', 'placement', 'core/scheduling/algorithm.py:34-180'),
+    # one function under three names in the reference (algorithm.py:182-187); its score table is keyed by the SCHEDULE
+    # name (schedule.py:47), so all three behave the same under --schedule horus
+    'horus': DevicePolicy('horus', 'placement', _ffi.PLACE['horus'], 'core/scheduling/algorithm.py:34-180'),
+    'horus+': DevicePolicy('horus+', 'placement', _ffi.PLACE['horus+'], 'core/scheduling/algorithm.py:34-180'),
+    'gandiva': DevicePolicy('gandiva', 'placement', _ffi.PLACE['gandiva'], 'core/scheduling/algorithm.py:34-180'),
 }
 
 plugin_algorithms = {
@@ -68,7 +71,7 @@ plugin_algorithms = {
 }
 
 score_fn = {
-    'horus': HostOnlyPolicy('horus', 'score', 'core/scheduling/horus.py:28-56'),
+    'horus': DevicePolicy('horus', 'score', 0, 'core/scheduling/horus.py:28-56'),
     'horus+': HostOnlyPolicy('horus+', 'score', 'core/scheduling/horus.py:28-56'),
     'gandiva': HostOnlyPolicy('gandiva', 'score', 'core/scheduling/horus.py:6-25'),
 }
@@ -84,6 +87,10 @@ def resolve(schedule, scheme):
             if isinstance(p, HostOnlyPolicy):
                 p()  # raises NotImplementedError with the reference location
             raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
+    if (schedule == 'horus') != (place.device_id == _ffi.PLACE['horus']):
+        # fifo + horus: KeyError 'fifo' in the reference's score table (algorithm.py:58); horus + yarn is a valid
+        # reference combination that this package does not implement
+        raise NotImplementedError('schedule %r with scheme %r is not implemented by the device path' % (schedule, scheme))
     post = plugin_algorithms.get(schedule, None)
     if post is not None and not isinstance(post, DevicePolicy):
         post()

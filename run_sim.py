@@ -20,8 +20,8 @@ from rlgpuschedule_b200.host import Infrastructure, JobQueueManager, JobsManager
 flags.DEFINE_string('trace_file', 'tf_job.csv', 'job trace file (*.csv) in the Philly-style schema')
 flags.DEFINE_string('log_path', 'result-' + time.strftime('%Y%m%d-%H-%M-%S', time.localtime()),
                     'simulation output folder under log/; default result-[time]')
-flags.DEFINE_string('scheme', 'yarn', 'job placement scheme: yarn | count (device); horus | horus+ | gandiva (not on the device path)')
-flags.DEFINE_string('schedule', 'fifo', 'job schedule: fifo | sjf | shortest | shortest-gpu | dlas | dlas-gpu (device); horus | horus+ | gandiva (not on the device path)')
+flags.DEFINE_string('scheme', 'yarn', 'job placement scheme: yarn | count | horus (= horus+ = gandiva, with --schedule horus)')
+flags.DEFINE_string('schedule', 'fifo', 'job schedule: fifo | horus | sjf | shortest | shortest-gpu | dlas | dlas-gpu (device); horus+ | gandiva (not on the device path)')
 flags.DEFINE_boolean('pack', False, 'enable packing for gpu jobs (stored, not consulted by yarn)')
 flags.DEFINE_integer('num_switch', 1, 'cluster spec: number of switches')
 flags.DEFINE_integer('num_node_p_switch', 32, 'cluster spec: nodes under one switch')
@@ -41,7 +41,7 @@ flags.DEFINE_boolean('flush_stdout', True, 'flush stdout')
 # additions of this implementation
 flags.DEFINE_string('queue_limit', '30,60,150', 'dlas-gpu: MLFQ demotion thresholds in GPU-ticks (README.md:57-62), comma separated')
 flags.DEFINE_string('util_mode', 'sample', "avg_gpu_utilization column: 'sample' (seedable normal draw) or 'mean'")
-flags.DEFINE_integer('seed', None, 'seed of the avg_gpu_utilization draw (the reference draws unseeded)')
+flags.DEFINE_integer('seed', None, 'seed of the utilisation draws: the avg_gpu_utilization column and the horus score (the reference draws unseeded)')
 flags.DEFINE_integer('device', 0, 'CUDA device ordinal')
 flags.DEFINE_version('0.1')
 

@@ -15,10 +15,10 @@ def sha(s):
     return hashlib.sha256(s.encode() if isinstance(s, str) else s).hexdigest()
 
 
-def case_names(kind='small'):
+def case_names(kind='small', schedule='fifo'):
     out = []
     for n, c in golden_cases.CASES.items():
-        if not os.path.exists(os.path.join(GOLD, n, 'meta.json')):
+        if not os.path.exists(os.path.join(GOLD, n, 'meta.json')) or c.get('schedule', 'fifo') != schedule:
             continue
         k = 'huge' if c.get('huge') else ('big' if c.get('big') else 'small')
         if kind == 'all' or k == kind:
@@ -34,7 +34,7 @@ def load(name):
     for k, v in list(flags.items()):
         if isinstance(v, str) and v.startswith('@'):
             flags[k] = os.path.join(ROOT, v[1:])
-    out = dict(meta=meta, flags=flags, job=None, cluster=None)
+    out = dict(meta=meta, flags=flags, job=None, cluster=None, schedule=case.get('schedule', 'fifo'), num_buffer=case.get('num_buffer', 5))
     if os.path.exists(os.path.join(d, 'trace.csv')):
         out['trace'] = os.path.join(d, 'trace.csv')
         out['frame'] = None

@@ -85,10 +85,12 @@ def test_env_step_by_step_matches_oracle_tape():
     env.close()
 
 
-@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec'])
+@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec', 'horus_multi_node', 'horus_ties'])
 def test_run_sim_cli_writes_reference_outputs(name, tmp_path):
     g = goldutil.load(name)
     args = []
+    if g['schedule'] != 'fifo':
+        args += ['--schedule', g['schedule'], '--scheme', g['schedule'], '--num_buffer', str(g['num_buffer'])]
     for k, v in g['flags'].items():
         args += ['--' + k, str(v)]
     trace = g['trace']
@@ -126,6 +128,6 @@ def test_run_sim_cli_legacy_schedules(tmp_path):
         rows = open(out / 'cluster.csv').read().splitlines()
         assert rows[0] == 'time,idle_node,busy_node,full_node,idle_gpu,busy_gpu,pending_job,running_job,completed_job'
         assert len(rows) - 1 == o['n_events']
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--schedule', 'horus', '--scheme', 'horus'],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--schedule', 'horus+', '--scheme', 'horus+'],
                        cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode != 0 and 'not implemented by the device path' in r.stderr

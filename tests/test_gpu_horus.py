@@ -6,6 +6,7 @@ import pytest
 import rlgpuschedule_b200 as rl
 from rlgpuschedule_b200 import _ffi, log_manager as lm
 from oracle import cpu_sim, tracegen
+import goldutil
 
 pytestmark = pytest.mark.gpu
 
@@ -77,4 +78,24 @@ def test_horus_bounded_launches_resume():
     otr = cpu_sim.prepare_trace(df)
     o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k)
     check(sim, cluster, tr, o, otr, 1)
+    sim.close()
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('big', 'horus'))
+def test_horus_matches_the_reference_golden(name):
+    """Device outputs vs the files the UNMODIFIED reference wrote for `--schedule horus --scheme horus` (tests/golden)."""
+    g = goldutil.load(name)
+    cluster = rl.cluster_from_flags(g['flags'])
+    tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=3, rows=True, num_buffer=g['num_buffer'])
+    sim.load_trace(tr)
+    sim.run()
+    for r in (0, 2):
+        j = sim.jobs(r)
+        dur = tr.duration + 5.0 * (sim.job_plane(r, _ffi.PLANE_AUX) == 1)
+        job = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur)
+        clu = lm.format_cluster_csv(sim.rows(r), cluster, tr.mem_shift, with_util=False)
+        if g['job'] is not None:
+            assert job == g['job'] and clu == g['cluster']
+        assert goldutil.sha(job) == g['meta']['job_sha256'] and goldutil.sha(clu) == g['meta']['cluster_noutil_sha256']
     sim.close()

@@ -37,8 +37,13 @@ def test_plugin_registries_keep_the_reference_keys():
     s, p = algorithm.resolve('fifo', 'yarn')
     assert s.device_id == _ffi.SCHED['fifo'] and p.device_id == _ffi.PLACE['yarn']
     assert algorithm.resolve('dlas-gpu', 'count')[0].device_id == 2 and algorithm.resolve('dlas', 'count')[0].device_id == 3
+    assert algorithm.resolve('horus', 'gandiva')[0].device_id == _ffi.SCHED['horus']   # three names, one placement
     with pytest.raises(NotImplementedError):
-        algorithm.resolve('horus', 'horus')
+        algorithm.resolve('horus+', 'horus+')           # k-means queues: not on the device path
+    with pytest.raises(NotImplementedError):
+        algorithm.resolve('fifo', 'horus')              # KeyError 'fifo' in the reference (algorithm.py:58)
+    with pytest.raises(NotImplementedError):
+        algorithm.resolve('horus', 'yarn')
     with pytest.raises(NotImplementedError):
         algorithm.resolve('gandiva', 'yarn')            # its post-tick plugin (time slicing) has no device form
     with pytest.raises(KeyError):

@@ -27,3 +27,26 @@ def test_oracle_matches_reference_big(name):
     g, tr, res = _run(name)
     assert goldutil.sha(cpu_sim.format_job_csv(tr, res)) == g['meta']['job_sha256']
     assert goldutil.sha(cpu_sim.format_cluster_csv(res)) == g['meta']['cluster_noutil_sha256']
+
+
+# ---- horus schedule + horus_placement (oracle_pack) on zero-spread traces
+def _run_pack(name):
+    g = goldutil.load(name)
+    tr = cpu_sim.prepare_trace(goldutil.trace_input(g))
+    res = cpu_sim.run_pack(cpu_sim.make_cluster(**g['flags']), tr, g['schedule'], g['num_buffer'])
+    return g, tr, res
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus'))
+def test_pack_oracle_matches_reference_small(name):
+    g, tr, res = _run_pack(name)
+    assert cpu_sim.format_job_csv(tr, res) == g['job']
+    assert cpu_sim.format_cluster_csv(res) == g['cluster']
+    assert res['n_ticks'] == g['meta']['n_ticks']
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus'))
+def test_pack_oracle_matches_reference_big(name):
+    g, tr, res = _run_pack(name)
+    assert goldutil.sha(cpu_sim.format_job_csv(tr, res)) == g['meta']['job_sha256']
+    assert goldutil.sha(cpu_sim.format_cluster_csv(res)) == g['meta']['cluster_noutil_sha256']
