@@ -67,7 +67,17 @@ struct PackState {
     int32_t lhead, ltail, mlo, mrank;
     int32_t done, status, max_q, max_r, pad;
     int64_t mem_sum, util_mu_sum, util_var_sum, sum_arr, sum_jct, sumQ, sumR, events;
+#ifdef PACK_PROFILE
+    int64_t prof[12];   // cycles: 0 arrivals, 1 queue pops, 2 score, 3 heap, 4 sort, 5 trials, 6 real place, 7 re-push, 8 start, 9 finish, 10 row, 11 attempts
+#endif
 };
+#ifdef PACK_PROFILE
+#define PACK_T0 long long _t0 = clock64()
+#define PACK_T(i) do { long long _t1 = clock64(); st.prof[i] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define PACK_T0
+#define PACK_T(i)
+#endif
 
 struct PackParams {
     int32_t num_buffer;       // --num_buffer (run_sim.py:76): look-ahead window
@@ -324,10 +334,15 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
                                           uint32_t replica, uint32_t attempt) {
     const PackJob pj = D.pj[x.job];
     const int cap = pj.heap_cap;
+    PACK_T0;
+#ifdef PACK_PROFILE
+    st.prof[11] += 1;
+#endif
     // ---- score the nodes, keep the `cap` best in a heap (one pass per task: the reference re-scores per task)
     int hlen = 0;
     for (int pass = 0; pass < x.T; ++pass) {
         if (pass == 0 || P.rng_on) pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
+        PACK_T(2);
         for (int base = 0; base < c.N; base += 32) {
             const int i = base + x.lane;
             const double sc = i < c.N ? D.score[i] : -1.0;
@@ -340,6 +355,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
                 if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(D, hlen); }   // heappop: drop the worst
             }
         }
+        PACK_T(3);
     }
     if (hlen == 0) return 0;
     // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array
@@ -350,6 +366,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
         D.hscore[b + 1] = vs; D.hnode[b + 1] = vn;
     }
     __syncwarp();
+    PACK_T(4);
     // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
     int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
     for (int e = 0; e < hlen; ++e) {
@@ -395,6 +412,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
         }
         if (cnt >= x.T && nn < best_nn) { best_nn = nn; best_map = cur_map; }   // stable sort by len(nodes): first minimum
     }
+    PACK_T(5);
     if (best_nn == RLGS_NEVER) return 0;
     // ---- place for real (algorithm.py:163-178)
     for (int t = 0; t < x.T; ++t) {
@@ -405,6 +423,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     }
     D.planes[4][x.job] = (int)x.interf;
     __syncwarp();
+    PACK_T(6);
     return 1;
 }
 
@@ -433,6 +452,7 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
         if (st.d == d_stop) break;
         if (P.max_ticks > 0 && st.d >= P.max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
         const int d = st.d;
+        PACK_T0;
 
         // ---------------- arrivals: heappush in trace order (jobs_manager.py:228-241, job_queue_manager.py:147-152)
         while (st.cursor < J) {
@@ -453,12 +473,14 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
             __syncwarp();
         }
 
+        PACK_T(0);
         // ---------------- _schedule -> schedule_horus (schedule.py:40-60, algorithm.py:204-240)
         if (st.Q > 0 && st.n_free_nodes >= 1) {
             const int k = min(max(P.num_buffer, 0), st.Q);
             int my_job = -1; double my_key = 0.0;
             for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
             __syncwarp();
+            PACK_T(1);
             int pos = -1, err = 0;
             for (int a = 0; a < k && pos < 0; ++a) {
                 PackCtx x;
@@ -471,11 +493,15 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
                 if (r) pos = a;
             }
             if (err) { st.status = err; st.done = 1; break; }
+#ifdef PACK_PROFILE
+            _t0 = clock64();
+#endif
             for (int a = 0; a < k; ++a) {                     // jobs_manager.insert(look_ahead): heappush the rest in order
                 const int job = __shfl_sync(RLGS_FULL, my_job, a); const double key = __shfl_sync(RLGS_FULL, my_key, a);
                 if (a != pos) pack_q_push(D, lane, st.Q, key, job);
             }
             __syncwarp();
+            PACK_T(7);
             if (pos >= 0) {                                   // add_to_running -> start_job (schedule.py:164-167, jobs_manager.py:189-207)
                 const int job = __shfl_sync(RLGS_FULL, my_job, pos);
                 const rlgs_job rec = D.trace[job];
@@ -514,6 +540,7 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
             }
         }
 
+        PACK_T(8);
         // ---------------- delta_time += 1; step; release_finished_jobs in running_jobs (= start) order
         st.d = d + 1;
         {
@@ -550,6 +577,7 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
             }
         }
 
+        PACK_T(9);
         // ---------------- stats row (schedule.py:95-133, 204-205)
         st.sumQ += st.Q; st.sumR += st.R;
         if (rows_mode) {
@@ -569,6 +597,7 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
                 o[3] = make_int4((int)(uint32_t)st.util_mu_sum, (int)(st.util_mu_sum >> 32), (int)(uint32_t)st.util_var_sum, (int)(st.util_var_sum >> 32));
             }
         }
+        PACK_T(10);
     }
     st.events = (int64_t)st.cursor + st.start_seq + st.F;
     if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;

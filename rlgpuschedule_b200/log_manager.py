@@ -205,8 +205,9 @@ class LogManager(object):
         """finished_jobs: dict job_id -> object with the reference Job's attributes, or a tuple
         (trace, finish_order, start, end[, preempt]) from the device backend."""
         if isinstance(finished_jobs, tuple):
-            kw = finished_jobs[-1] if isinstance(finished_jobs[-1], dict) else {}
-            args = finished_jobs[:-1] if kw else finished_jobs
+            has_kw = isinstance(finished_jobs[-1], dict)
+            kw = finished_jobs[-1] if has_kw else {}
+            args = finished_jobs[:-1] if has_kw else finished_jobs
             text = format_job_csv(*args, with_header=False, **kw)
             assert len(finished_jobs[1]) > 0, ValueError("No finished jobs")
             with open(self.log_job, 'a+', newline='') as f:
