@@ -53,8 +53,6 @@ struct PackDesc {
     int32_t *cnext;           // [J] calendar chain
     int32_t *chead;           // [PACK_CAL_W]
     int16_t *tnode;           // [sum of tasks] node of each placed task (tasks_running_on)
-    double *score;            // [N] scratch: min_cost of each node, < 0 = node cannot take the task
-    double *hscore; int32_t *hnode;   // [PACK_MAX_HEAP + 1] horus_placement's nodes_stack
     int32_t *fin;             // [J] jobs finishing at this tick
     int64_t cap_units, margin_units;  // gpu memory capacity and the 500 MiB margin in units
     double cap_mib, unit_mib; // capacity in MiB, 2^-shift
@@ -141,26 +139,26 @@ __device__ __forceinline__ void pack_q_pop(const PackDesc &D, int lane, int &q, 
 }
 
 // nodes_stack of horus_placement: NodeDeviceInfo.__lt__ is `self.min_score > other.min_score` (algorithm.py:25-26)
-__device__ __forceinline__ void pack_h_siftdown(const PackDesc &D, int pos, double sc, int node) {
+__device__ __forceinline__ void pack_h_siftdown(double *hscore, int32_t *hnode, int pos, double sc, int node) {
     while (pos > 0) {
-        int pp = (pos - 1) >> 1; double ps = D.hscore[pp];
+        int pp = (pos - 1) >> 1; double ps = hscore[pp];
         if (!(sc > ps)) break;
-        D.hscore[pos] = ps; D.hnode[pos] = D.hnode[pp]; pos = pp;
+        hscore[pos] = ps; hnode[pos] = hnode[pp]; pos = pp;
     }
-    D.hscore[pos] = sc; D.hnode[pos] = node;
+    hscore[pos] = sc; hnode[pos] = node;
 }
-__device__ __forceinline__ void pack_h_pop(const PackDesc &D, int len) {   // len = length after the pop
-    double ls = D.hscore[len]; int ln = D.hnode[len];
+__device__ __forceinline__ void pack_h_pop(double *hscore, int32_t *hnode, int len) {   // len = length after the pop
+    double ls = hscore[len]; int ln = hnode[len];
     if (len == 0) return;
     int pos = 0, child = 1;
     while (child < len) {
         int right = child + 1;
-        double cs = D.hscore[child];
-        if (right < len) { double rs = D.hscore[right]; if (!(cs > rs)) { child = right; cs = rs; } }
-        D.hscore[pos] = cs; D.hnode[pos] = D.hnode[child];
+        double cs = hscore[child];
+        if (right < len) { double rs = hscore[right]; if (!(cs > rs)) { child = right; cs = rs; } }
+        hscore[pos] = cs; hnode[pos] = hnode[child];
         pos = child; child = 2 * pos + 1;
     }
-    pack_h_siftdown(D, pos, ls, ln);
+    pack_h_siftdown(hscore, hnode, pos, ls, ln);
 }
 
 __device__ __forceinline__ bool pack_dev_fits(const PackDesc &D, int dev, int64_t m) {   // Device.can_fit (device.py:67-77)
@@ -175,7 +173,10 @@ struct PackCtx {              // registers shared by the placement helpers
     int64_t m;                // memory_max of one task of the job being placed
     int mu_q, sd_q;           // quantised utilisation statistics of the job (cluster.csv's RNG column)
     uint32_t interf;          // Task.interfered of the job's tasks, bit per task
+    double *score;            // shared memory [N]: min_cost of each node, < 0 = node cannot take the task
+    double *hscore; int32_t *hnode;   // shared memory [PACK_MAX_HEAP + 1]: horus_placement's nodes_stack
 };
+__host__ __device__ inline size_t pack_smem_bytes(int n_nodes) { return 8 * (size_t)((n_nodes + 1) & ~1) + 12 * (size_t)(PACK_MAX_HEAP + 1); }
 
 __device__ __forceinline__ void pack_idle_delta(PackState &st, bool was_idle, bool now_idle) { st.idle_nodes += (int)now_idle - (int)was_idle; }
 __device__ __forceinline__ bool pack_node_idle(const PackDesc &D, int i) { return D.ntk[i] == 0 && D.npj[i] == 0; }   // Node.is_idle (node.py:93-97)
@@ -323,7 +324,7 @@ __device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const Cluste
                 }
                 if (any) best = min_cost;
             }
-            D.score[i] = best;
+            x.score[i] = best;
         }
     }
     __syncwarp();
@@ -340,19 +341,34 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
 #endif
     // ---- score the nodes, keep the `cap` best in a heap (one pass per task: the reference re-scores per task)
     int hlen = 0;
+    if (x.T == 1 && cap == 1) {
+        // a heap of one slot keeps, of the nodes with the lowest score, the one pushed last (a push with an equal or lower
+        // score displaces the resident): arg-min with ties to the higher node id, no sifting needed
+        pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, 0u, pj.util_avg);
+        PACK_T(2);
+        double bs = 1e300; int bn = -1;
+        for (int i = x.lane; i < c.N; i += 32) { const double sc = x.score[i]; if (sc >= 0.0 && sc <= bs) { bs = sc; bn = i; } }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double os = __shfl_xor_sync(RLGS_FULL, bs, o); const int on = __shfl_xor_sync(RLGS_FULL, bn, o);
+            if (on >= 0 && (bn < 0 || os < bs || (os == bs && on > bn))) { bs = os; bn = on; }
+        }
+        if (bn >= 0) { hlen = 1; if (x.lane == 0) { x.hscore[0] = bs; x.hnode[0] = bn; } }
+        PACK_T(3);
+    } else
     for (int pass = 0; pass < x.T; ++pass) {
         if (pass == 0 || P.rng_on) pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
         PACK_T(2);
         for (int base = 0; base < c.N; base += 32) {
             const int i = base + x.lane;
-            const double sc = i < c.N ? D.score[i] : -1.0;
+            const double sc = i < c.N ? x.score[i] : -1.0;
             unsigned fb = __ballot_sync(RLGS_FULL, sc >= 0.0);
             while (fb) {
                 const int src = __ffs(fb) - 1; fb &= fb - 1;
                 const double s1 = __shfl_sync(RLGS_FULL, sc, src);
-                if (x.lane == 0) pack_h_siftdown(D, hlen, s1, base + src);     // heappush (only lane 0 touches the heap arrays)
+                if (x.lane == 0) pack_h_siftdown(x.hscore, x.hnode, hlen, s1, base + src);     // heappush (only lane 0 touches the heap arrays)
                 hlen += 1;
-                if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(D, hlen); }   // heappop: drop the worst
+                if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(x.hscore, x.hnode, hlen); }   // heappop: drop the worst
             }
         }
         PACK_T(3);
@@ -360,17 +376,17 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     if (hlen == 0) return 0;
     // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array
     if (x.lane == 0) for (int a = 1; a < hlen; ++a) {
-        const double vs = D.hscore[a]; const int vn = D.hnode[a];
+        const double vs = x.hscore[a]; const int vn = x.hnode[a];
         int b = a - 1;
-        while (b >= 0 && D.hscore[b] > vs) { D.hscore[b + 1] = D.hscore[b]; D.hnode[b + 1] = D.hnode[b]; --b; }
-        D.hscore[b + 1] = vs; D.hnode[b + 1] = vn;
+        while (b >= 0 && x.hscore[b] > vs) { x.hscore[b + 1] = x.hscore[b]; x.hnode[b + 1] = x.hnode[b]; --b; }
+        x.hscore[b + 1] = vs; x.hnode[b + 1] = vn;
     }
     __syncwarp();
     PACK_T(4);
     // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
     int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
     for (int e = 0; e < hlen; ++e) {
-        const int home = D.hnode[e];
+        const int home = x.hnode[e];
         int cnt = 0;
         for (int t = 0; t < x.T; ++t) {
             const int r = pack_try_reserve(D, c, st, x, home, t);
@@ -427,8 +443,12 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     return 1;
 }
 
-__global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
+__global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
                                                         RowStore rs, int64_t *returns) {
+    extern __shared__ __align__(16) unsigned char pack_smem[];
+    double *sm_score = reinterpret_cast<double *>(pack_smem);
+    double *sm_hscore = sm_score + ((c.N + 1) & ~1);
+    int32_t *sm_hnode = reinterpret_cast<int32_t *>(sm_hscore + PACK_MAX_HEAP + 1);
     const int lane = lane_id();
     const PackDesc D = descs[blockIdx.x];
     PackState st = states[blockIdx.x];
@@ -485,6 +505,7 @@ __global__ void __launch_bounds__(32) pack_horus_kernel(const PackDesc *descs, P
             for (int a = 0; a < k && pos < 0; ++a) {
                 PackCtx x;
                 x.lane = lane; x.job = __shfl_sync(RLGS_FULL, my_job, a);
+                x.score = sm_score; x.hscore = sm_hscore; x.hnode = sm_hnode;
                 const rlgs_job rec = D.trace[x.job];
                 x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q; x.interf = 0;
                 if (x.T > PACK_MAX_TASKS || D.pj[x.job].heap_cap > PACK_MAX_HEAP || D.pj[x.job].heap_cap < 0) { err = RLGS_ERR_UNSUPPORTED; break; }

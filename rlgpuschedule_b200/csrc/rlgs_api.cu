@@ -387,7 +387,7 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
     const size_t N = (size_t)s->cc.N, Dv = (size_t)s->cc.D, J = (size_t)n, W = (N + 31) / 32;
     // per-replica working set, 256-byte aligned pieces in this order
     const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J,
-                         4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 8 * N, 8 * (PACK_MAX_HEAP + 1), 4 * (PACK_MAX_HEAP + 1), 4 * J};
+                         4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J};
     size_t per = 0;
     for (size_t v : sz) per += align_up(v, 256);
     unsigned char *slab = nullptr;
@@ -403,8 +403,7 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
         D.units = (int32_t *)take(0); D.ntk = (int32_t *)take(0); D.npj = (int32_t *)take(0); D.dn = (int32_t *)take(0);
         D.dm = (int64_t *)take(0); D.ent = (int2 *)take(0); D.pjbits = (uint32_t *)take(0); D.qkey = (double *)take(0);
         D.qjob = (int32_t *)take(0); D.lprev = (int32_t *)take(0); D.lnext = (int32_t *)take(0); D.pend = (int32_t *)take(0);
-        D.cnext = (int32_t *)take(0); D.chead = (int32_t *)take(0); D.tnode = (int16_t *)take(0); D.score = (double *)take(0);
-        D.hscore = (double *)take(0); D.hnode = (int32_t *)take(0); D.fin = (int32_t *)take(0);
+        D.cnext = (int32_t *)take(0); D.chead = (int32_t *)take(0); D.tnode = (int16_t *)take(0); D.fin = (int32_t *)take(0);
         D.cap_units = (int64_t)in->gpu_mem_cap_mib * unit; D.margin_units = 500 * unit;
         D.cap_mib = (double)in->gpu_mem_cap_mib; D.unit_mib = 1.0 / (double)unit;
     }
@@ -481,7 +480,7 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
             PackParams pp = s->pp; pp.tick_budget = budget;
-            pack_horus_kernel<<<count, 32, 0, st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
+            pack_horus_kernel<<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
         } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         else

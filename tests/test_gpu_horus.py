@@ -29,7 +29,7 @@ CASES = {
 def run_device(df, flags, k, seed=None, **kw):
     cluster = rl.cluster_from_flags(flags)
     tr = rl.prepare_trace(df, cluster)
-    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, **kw)
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, max_ticks=400000, **kw)
     sim.load_trace(tr)
     sim.run()
     return sim, cluster, tr
@@ -87,7 +87,7 @@ def test_horus_matches_the_reference_golden(name):
     g = goldutil.load(name)
     cluster = rl.cluster_from_flags(g['flags'])
     tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
-    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=3, rows=True, num_buffer=g['num_buffer'])
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
     sim.load_trace(tr)
     sim.run()
     for r in (0, 2):
