@@ -39,7 +39,7 @@ struct PackJob {              // per job of a trace, shared by the replicas that
 struct PackDesc {
     const rlgs_job *trace;
     const PackJob *pj;
-    int32_t *planes[6];       // start, end, finish_order, aux (bit0: a task got +5 ticks), interfered-task mask, unused
+    int32_t *planes[6];       // start, end, finish_order, aux (bit0: a task got +5 ticks), interfered-task mask, 1 = the job has leaked entries
     int32_t *units;           // [N] tasks charged to the node (cpu = 12u, mem = 60u)
     int32_t *ntk;             // [N] len(placed_tasks) << 16 | len(running_tasks)
     int32_t *npj;             // [N] len(placed_jobs)
@@ -226,7 +226,7 @@ __device__ __forceinline__ int pack_try_reserve(const PackDesc &D, const Cluster
     st.mem_sum += dmem; st.busy_gpus += newly_busy;
     st.util_mu_sum += (int64_t)added * x.mu_q; st.util_var_sum += (int64_t)added * x.sd_q * x.sd_q;
     D.units[node] = u + 1;
-    if (have < x.gpc) { __syncwarp(); return 2; }
+    if (have < x.gpc) { D.planes[5][x.job] = 1; __syncwarp(); return 2; }   // remember that the job has leaked entries
     const bool was = pack_node_idle(D, node);
     const int tk = D.ntk[node];
     __syncwarp();
@@ -330,6 +330,33 @@ __device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const Cluste
     __syncwarp();
 }
 
+// Tasks of the job that node i accepts one after another (try_reserve_and_placed_task in a loop), and whether the attempt
+// after the last accepted task would leak: the node still passes Node.can_fit but fewer than task.gpu devices accept.
+__device__ __forceinline__ int pack_node_capacity(const PackDesc &D, const ClusterConst &c, const PackCtx &x, int i, bool &leak) {
+    leak = false;
+    int r = c.base_units - D.units[i];
+    if (r <= 0) return 0;
+    int s[32], tot = 0;
+    for (int g = 0; g < c.G; ++g) {
+        const int dev = i * c.G + g, n = D.dn[dev];
+        const int64_t room = D.cap_units - D.margin_units - min(D.dm[dev], D.cap_units);   // a task fits while cur + m < cap - margin
+        int k = 0;
+        if (n < PACK_DEV_SLOTS && x.m < room) k = x.m > 0 ? (int)min((room - 1) / x.m, (int64_t)(PACK_DEV_SLOTS - n)) : PACK_DEV_SLOTS - n;
+        s[g] = k; tot += k;
+    }
+    if (x.gpc == 1) return min(r, tot);                                // one device per task: never too few devices
+    int cap = 0;
+    while (r > 0) {
+        int have = 0;
+        for (int g = 0; g < c.G; ++g) have += s[g] > 0;
+        if (have < x.gpc) { leak = have >= 1; break; }
+        int need = x.gpc;
+        for (int g = 0; g < c.G && need > 0; ++g) if (s[g] > 0) { s[g] -= 1; need -= 1; }
+        cap += 1; r -= 1;
+    }
+    return cap;
+}
+
 // horus_placement (algorithm.py:34-180).  1 = placed (tnode / planes[4] written), 0 = not placed, < 0 = error status.
 __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst &c, const PackParams &P, PackState &st, PackCtx &x,
                                           uint32_t replica, uint32_t attempt) {
@@ -383,6 +410,31 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     }
     __syncwarp();
     PACK_T(4);
+    // ---- a placement that is bound to fail and cannot leak: every trial walks every rack, maps the same tasks on every node
+    // with capacity and undoes them; all that stays is placed_jobs[job] on those nodes, popped from the home of the trial
+    // (algorithm.py:122-127), so after the last trial only that home lacks the key.  Same end state without the trials.
+    {
+        int tot = 0; bool leak_any = false;
+        for (int base = 0; base < c.N; base += 32) {
+            const int i = base + x.lane;
+            bool lk = false;
+            const int cp = i < c.N ? pack_node_capacity(D, c, x, i, lk) : 0;
+            tot += cp; leak_any |= lk;
+            if (i < c.N) x.score[i] = cp > 0 ? 1.0 : 0.0;              // the scores are spent: reuse the array as the node set
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(RLGS_FULL, tot, o);
+        leak_any = __any_sync(RLGS_FULL, leak_any);
+        __syncwarp();
+        // (a job with leaked entries is excluded: re-adding a task over its own leaked entry takes no slot, and undoing the
+        // trial removes the leaked entry as well)
+        if (tot < x.T && !leak_any && D.planes[5][x.job] != 1) {
+            for (int i = 0; i < c.N; ++i) if (x.score[i] > 0.0) pack_pj_set(D, st, i, x.job);
+            pack_pj_pop(D, st, x.hnode[hlen - 1], x.job);
+            PACK_T(5);
+            return 0;
+        }
+    }
     // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
     int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
     for (int e = 0; e < hlen; ++e) {
