@@ -14,9 +14,9 @@
 //
 // Everything order-dependent in the reference (heapq sift order, stable sorts, dict insertion order, the order of
 // release calls) is kept, because ties are the common case (all idle nodes score the same).  Scalar phases (heap
-// sifts, list walks) run warp-uniform: every lane executes the same loads and stores; device scans, node scoring
-// and the rack pre-filter are lane-parallel.  State lives in global memory (L1/L2 resident per replica) so that a
-// bounded launch can stop and resume at any tick.
+// sifts, calendar walks) run on lane 0 between __syncwarp()s; device scans, node scoring, the rack pre-filter and the
+// per-node capacity are lane-parallel.  State lives in global memory (L1/L2 resident per replica) so that a bounded
+// launch can stop and resume at any tick; node scores and the node heap are shared-memory scratch.
 //
 // Memory amounts are integers in units of 2^-shift MiB (exact: ingest picks the shift), scores are float64 with the
 // reference's operation order (the library is built with --fmad=false).

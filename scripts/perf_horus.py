@@ -7,12 +7,11 @@ from rlgpuschedule_b200 import synth
 
 C = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
 out = {}
-for name, n, seed, span, reps in (('probe2k', 2000, 1, 2000, (1, 592, 2368)), ('probe10k', 10000, 2, 10000, (1, 592, 2368)),
-                                  ('probe60k', 60000, 3, 60000, (1, 592))):
+for name, n, seed, span, reps in (('probe2k', 2000, 1, 2000, (1, 1776, 3552)), ('probe10k', 10000, 2, 10000, (1, 1776))):
     df = synth.frame_gen(n, seed, span)
     tr = rl.prepare_trace(df, C)
     for R in reps:
-        for seedp in (None, 7):
+        for seedp in ((None, 7) if R == 1 else (None,)):
             sim = rl.Simulator(C, 'horus', 'horus', n_replicas=R, rows='device', pack_seed=seedp)
             sim.load_trace(tr)
             t0 = time.time(); sim.run(); wall = time.time() - t0
