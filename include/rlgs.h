@@ -42,13 +42,15 @@ enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2,
        RLGS_SCHED_DLAS = 3, /* dlas_sim_jobs(gputime=False): thresholds on attained time instead of GPU-time */
        RLGS_SCHED_SHORTEST = 4,     /* shortest_first_sim_jobs, run_sim.py:299-431: shortest remaining time first */
        RLGS_SCHED_SHORTEST_GPU = 5, /* ... shortest remaining GPU-time first */
-       RLGS_SCHED_HORUS = 6         /* schedule_horus, core/scheduling/algorithm.py:204-240: utilisation-ordered heap queue
-                                       (core/jobs/base_factory.py:1-12) + look-ahead window of opts.num_buffer jobs */ };
+       RLGS_SCHED_HORUS = 6,        /* schedule_horus, core/scheduling/algorithm.py:204-240: utilisation-ordered heap queue
+                                       (core/jobs/base_factory.py:1-12) + look-ahead window of opts.num_buffer jobs */
+       RLGS_SCHED_GANDIVA = 7       /* algorithm.py:292-298: schedule_fifo on a plain list + gandiva_score (horus.py:6-25) +
+                                       time_slice_check (algorithm.py:420-440): preempt every 100 processed ticks */ };
 /* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
  * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
 enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1,
        RLGS_PLACE_HORUS = 2 /* horus_placement, core/scheduling/algorithm.py:34-180 with horus_score (horus.py:28-56):
-                               packs up to 4 tasks per device; what --scheme horus|horus+|gandiva select under --schedule horus */ };
+                               packs up to 4 tasks per device; what --scheme horus|horus+|gandiva select under --schedule horus|gandiva */ };
 /* rows_mode: NONE = no per-tick rows; FULL = one row per tick kept in a device-resident store and
  * copied to the handle's pinned host store inside rlgs_run (overlapped with compute, one stream per
  * replica group); DEVICE = rows stay in HBM until rlgs_read_rows / rlgs_rows_view asks for them. */
@@ -206,7 +208,8 @@ int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,
        RLGS_PLANE_AUX = 3,      /* fifo: first placement-log entry; sjf/dlas-gpu: pending_time;
                                    horus: 1 = Job.get_duration() is original + 5 (a task was de-interfered), 0 = original */
-       RLGS_PLANE_PREEMPT = 4, RLGS_PLANE_RESUME = 5 };
+       RLGS_PLANE_PREEMPT = 4,  /* horus / gandiva: Job.time_processed() of a finished job (the jct column) */
+       RLGS_PLANE_RESUME = 5 }; /* horus / gandiva: Job.migration_count of a finished job (the preempt column) */
 int32_t rlgs_read_job_plane(rlgs_sim *sim, int32_t replica, int32_t plane, int32_t *out);
 /* Episode return per replica: -(sum of job completion times), the reward of the vectorised Environment. */
 int32_t rlgs_returns(rlgs_sim *sim, int64_t *out_n_replicas);

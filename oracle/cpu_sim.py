@@ -127,6 +127,7 @@ def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, 
     n = len(tr['nt'])
     fin = np.empty(max(n, 1), np.int32); st = np.empty(max(n, 1), np.int32); en = np.empty(max(n, 1), np.int32)
     dur = np.zeros(max(n, 1), np.float64)
+    jct = np.zeros(max(n, 1), np.int32); starts = np.zeros(max(n, 1), np.int32)
     nfin = C.c_int32(0); nticks = C.c_int64(0); counters = np.zeros(4, np.int64)
     cap = rows_cap or max(4096, 4 * n)
     while True:
@@ -137,7 +138,7 @@ def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, 
                            C.c_int32(1 if schedule == 'gandiva' else 0), C.c_int32(num_buffer),
                            C.c_int32(0 if seed is None else 1), C.c_uint32(seed or 0), C.c_uint32(replica),
                            _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32), C.byref(nfin), _p(dur, C.c_double),
-                           rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
+                           _p(jct, C.c_int32), _p(starts, C.c_int32), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
         if rc == -1:
             cap *= 4
             continue
@@ -146,7 +147,7 @@ def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, 
         break
     k = nfin.value
     return dict(finish_order=fin[:k].copy(), start=st[:n], end=en[:n], rows=rows[:nticks.value], n_ticks=nticks.value,
-                actual_duration=dur[:n], orig_duration=tr['duration'],
+                actual_duration=dur[:n], orig_duration=tr['duration'], jct=jct[:n], preempt=starts[:n],
                 counters=dict(sum_queued=int(counters[0]), sum_running=int(counters[1]), ticks=int(counters[2]),
                               starts=int(counters[3])))
 

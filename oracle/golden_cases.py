@@ -153,4 +153,13 @@ CASES = {
     'horus_gen300': dict(frame=_zs(lambda: tg.frame_gen(300, 11, 150)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus', big=True),
     'horus_dense': dict(frame=_zs(lambda: tg.frame_gen(300, 5, 30)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus', num_buffer=8, big=True),
     'horus_probe2k': dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='horus', big=True),
+    # --schedule gandiva --scheme gandiva (schedule_fifo + horus_placement with gandiva_score + time_slice_check), zero-spread traces
+    'gandiva_probe100': dict(frame=_zs(tg.frame_probe100), flags=C148, schedule='gandiva'),
+    'gandiva_racks': dict(frame=_zs(tg.frame_probe100), flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8), schedule='gandiva'),
+    'gandiva_multi_node': dict(frame=_zs(_multi_node), flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='gandiva'),
+    'gandiva_gpu_cap16': dict(frame=_zs(lambda: tg.frame_gen(120, 7, 150)), flags=dict(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8, gpu_memory_capacity=12), schedule='gandiva'),
+    'gandiva_ties': dict(frame=_zs(_ties), flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='gandiva'),
+    'gandiva_cluster_spec': dict(frame=_zs(lambda: tg.frame_gen(150, 9, 400)), flags=dict(cluster_spec='@examples/cluster_spec_2x8x4.csv'), schedule='gandiva', big=True),
+    'gandiva_gen300': dict(frame=_zs(lambda: tg.frame_gen(300, 11, 150)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='gandiva', big=True),
+    'gandiva_probe2k': dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='gandiva', big=True),
 }

@@ -9,9 +9,10 @@
 
 The entries the hot path implements are DevicePolicy objects: Scheduler.start() hands their integer
 id to librlgs and the whole tick / event loop runs on the GPU.  `horus` (schedule_horus + horus_placement
-with horus_score) is one of them; the reference's remaining keys (horus+: k-means queues, gandiva: time
-slicing) are registered as HostOnlyPolicy so the key set is unchanged and selecting them fails loudly
-instead of silently running something else.
+with horus_score) and `gandiva` (schedule_fifo + gandiva_score + the time-slice plugin) are among them; the
+reference's remaining key (horus+: k-means queues with an unseeded random init) is registered as
+HostOnlyPolicy so the key set is unchanged and selecting it fails loudly instead of silently running
+something else.
 Users may register their own entries; only DevicePolicy entries can be executed by this package.
 """
 from . import _ffi
@@ -53,7 +54,7 @@ scheduling_algorithms = {
     'shortest-gpu': DevicePolicy('shortest-gpu', 'schedule', _ffi.SCHED['shortest-gpu'], 'run_sim.py:299-431 with gputime (dead code, restated)'),
     'horus': DevicePolicy('horus', 'schedule', _ffi.SCHED['horus'], 'core/scheduling/algorithm.py:204-240'),
     'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
-    'gandiva': HostOnlyPolicy('gandiva', 'schedule', 'core/scheduling/algorithm.py:292-298 + time_slice_check :420-440'),
+    'gandiva': DevicePolicy('gandiva', 'schedule', _ffi.SCHED['gandiva'], 'core/scheduling/algorithm.py:292-298 (schedule_fifo) + time_slice_check :420-440'),
 }
 
 placement_algorithms = {
@@ -67,13 +68,13 @@ placement_algorithms = {
 }
 
 plugin_algorithms = {
-    'gandiva': HostOnlyPolicy('gandiva', 'post-tick plugin', 'core/scheduling/algorithm.py:420-440'),
+    'gandiva': DevicePolicy('gandiva', 'post-tick plugin', _ffi.SCHED['gandiva'], 'core/scheduling/algorithm.py:420-440'),
 }
 
 score_fn = {
     'horus': DevicePolicy('horus', 'score', 0, 'core/scheduling/horus.py:28-56'),
     'horus+': HostOnlyPolicy('horus+', 'score', 'core/scheduling/horus.py:28-56'),
-    'gandiva': HostOnlyPolicy('gandiva', 'score', 'core/scheduling/horus.py:6-25'),
+    'gandiva': DevicePolicy('gandiva', 'score', 1, 'core/scheduling/horus.py:6-25'),
 }
 
 
@@ -87,7 +88,7 @@ def resolve(schedule, scheme):
             if isinstance(p, HostOnlyPolicy):
                 p()  # raises NotImplementedError with the reference location
             raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
-    if (schedule == 'horus') != (place.device_id == _ffi.PLACE['horus']):
+    if (schedule in ('horus', 'gandiva')) != (place.device_id == _ffi.PLACE['horus']):
         # fifo + horus: KeyError 'fifo' in the reference's score table (algorithm.py:58); horus + yarn is a valid
         # reference combination that this package does not implement
         raise NotImplementedError('schedule %r with scheme %r is not implemented by the device path' % (schedule, scheme))

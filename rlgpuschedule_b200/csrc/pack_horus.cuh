@@ -39,7 +39,7 @@ struct PackJob {              // per job of a trace, shared by the replicas that
 struct PackDesc {
     const rlgs_job *trace;
     const PackJob *pj;
-    int32_t *planes[6];       // start, end, finish_order, aux (bit0: a task got +5 ticks), interfered-task mask, 1 = the job has leaked entries
+    int32_t *planes[6];       // start (of the last run), end, finish_order, 1 = get_duration() is duration + 5, ticks processed (jct), number of starts
     int32_t *units;           // [N] tasks charged to the node (cpu = 12u, mem = 60u)
     int32_t *ntk;             // [N] len(placed_tasks) << 16 | len(running_tasks)
     int32_t *npj;             // [N] len(placed_jobs)
@@ -53,7 +53,15 @@ struct PackDesc {
     int32_t *cnext;           // [J] calendar chain
     int32_t *chead;           // [PACK_CAL_W]
     int16_t *tnode;           // [sum of tasks] node of each placed task (tasks_running_on)
-    int32_t *fin;             // [J] jobs finishing at this tick
+    int32_t *fin;             // [J] jobs finishing (or losing their time slice) at this tick
+    uint32_t *imask;          // [J] Task.interfered, bit per task
+    uint32_t *bmask;          // [J] Task.duration == original + 5, bit per task
+    int32_t *jflag;           // [J] bit0: the job has leaked device entries
+    int32_t *pproc;           // [J] ticks processed in earlier runs (gandiva time slices)
+    int32_t *nstart;          // [J] Job.migration_count: number of starts
+    int32_t *qtick;           // [J] gandiva: tick the job entered the queue (arrival or preemption): pending_time = d - qtick
+    int32_t *cbk;             // [J] calendar bucket the running job is chained in
+    int32_t *snext, *shead, *sat;     // gandiva: calendar of time-slice ticks ([J], [PACK_CAL_W], [J])
     int64_t cap_units, margin_units;  // gpu memory capacity and the 500 MiB margin in units
     double cap_mib, unit_mib; // capacity in MiB, 2^-shift
     int32_t J, W;
@@ -63,7 +71,7 @@ struct PackState {
     int32_t d, cursor, F, Q, R;
     int32_t n_free_nodes, idle_nodes, busy_gpus, start_seq;
     int32_t lhead, ltail, mlo, mrank;
-    int32_t done, status, max_q, max_r, pad;
+    int32_t done, status, max_q, max_r, r_pre, preempts;   // r_pre: running jobs before the post-tick plugin (schedule.py:195)
     int64_t mem_sum, util_mu_sum, util_var_sum, sum_arr, sum_jct, sumQ, sumR, events;
 #ifdef PACK_PROFILE
     int64_t prof[12];   // cycles: 0 arrivals, 1 queue pops, 2 score, 3 heap, 4 sort, 5 trials, 6 real place, 7 re-push, 8 start, 9 finish, 10 row, 11 attempts
@@ -83,8 +91,10 @@ struct PackParams {
     uint32_t seed;
     int32_t nodes_per_rack, racks;
     int32_t tick_budget;
+    int32_t gandiva;          // 1: --schedule gandiva = fifo queue + gandiva_score + time slicing (algorithm.py:292-298,420-444)
     int64_t max_ticks;
 };
+#define PACK_QUANTA 100       // time_slice_check, algorithm.py:427
 
 // ---- build-defined stand-in for np.random.normal (the reference's RNG is unseeded): Irwin-Hall sum of twelve
 // 16-bit uniforms keyed by (seed, replica, tick, look-ahead position, task pass, device, slot)
@@ -173,6 +183,7 @@ struct PackCtx {              // registers shared by the placement helpers
     int64_t m;                // memory_max of one task of the job being placed
     int mu_q, sd_q;           // quantised utilisation statistics of the job (cluster.csv's RNG column)
     uint32_t interf;          // Task.interfered of the job's tasks, bit per task
+    uint32_t bump;            // Task.duration == original + 5, bit per task (reset by add_task on a device with < 2 tasks)
     double *score;            // shared memory [N]: min_cost of each node, < 0 = node cannot take the task
     double *hscore; int32_t *hnode;   // shared memory [PACK_MAX_HEAP + 1]: horus_placement's nodes_stack
 };
@@ -221,12 +232,13 @@ __device__ __forceinline__ int pack_try_reserve(const PackDesc &D, const Cluster
     const int hi = 31 - __clz(taken);                                  // Task.interfered is rewritten by every add_task: the last device wins
     const int nb_hi = __shfl_sync(RLGS_FULL, n_before, hi);
     x.interf = (x.interf & ~(1u << t)) | ((nb_hi >= 2 ? 1u : 0u) << t);
+    if (x.bump && __any_sync(RLGS_FULL, ((taken >> x.lane) & 1) && n_before < 2)) x.bump &= ~(1u << t);   // task.duration = original (device.py:39-41)
 #pragma unroll
     for (int o = 16; o; o >>= 1) { dmem += __shfl_xor_sync(RLGS_FULL, dmem, o); newly_busy += __shfl_xor_sync(RLGS_FULL, newly_busy, o); added += __shfl_xor_sync(RLGS_FULL, added, o); }
     st.mem_sum += dmem; st.busy_gpus += newly_busy;
     st.util_mu_sum += (int64_t)added * x.mu_q; st.util_var_sum += (int64_t)added * x.sd_q * x.sd_q;
     D.units[node] = u + 1;
-    if (have < x.gpc) { D.planes[5][x.job] = 1; __syncwarp(); return 2; }   // remember that the job has leaked entries
+    if (have < x.gpc) { D.jflag[x.job] = 1; __syncwarp(); return 2; }   // remember that the job has leaked entries
     const bool was = pack_node_idle(D, node);
     const int tk = D.ntk[node];
     __syncwarp();
@@ -273,18 +285,19 @@ __device__ __forceinline__ void pack_release(const PackDesc &D, const ClusterCon
     int oj = -1, ot = 0;
     if (n_after == 1) {
         int2 e = D.ent[dev * PACK_DEV_SLOTS];
-        if (((uint32_t)D.planes[4][e.x] >> e.y) & 1) if (D.planes[0][e.x] >= 0 && D.planes[1][e.x] < 0) { oj = e.x; ot = e.y; }
+        if ((D.imask[e.x] >> e.y) & 1) if (D.pend[e.x] > 0) { oj = e.x; ot = e.y; }      // pend > 0 <=> the job is in running_jobs
     }
     unsigned cand = __ballot_sync(RLGS_FULL, oj >= 0);
     while (cand) {
         const int src = __ffs(cand) - 1; cand &= cand - 1;
         const int j2 = __shfl_sync(RLGS_FULL, oj, src), t2 = __shfl_sync(RLGS_FULL, ot, src);
-        const uint32_t mk = (uint32_t)D.planes[4][j2];
+        const uint32_t mk = D.imask[j2];
         if ((mk >> t2) & 1) {
-            const int aux = D.planes[3][j2]; const int pe = D.pend[j2];
+            const uint32_t bm = D.bmask[j2]; const int pe = D.pend[j2];
             __syncwarp();
-            D.planes[4][j2] = (int)(mk & ~(1u << t2));
-            if (!(aux & 1)) { D.planes[3][j2] = aux | 1; D.pend[j2] = pe + 5; }     // duration = original + max(int(0 / 2), 5)
+            D.imask[j2] = mk & ~(1u << t2);
+            D.bmask[j2] = bm | (1u << t2);                              // duration = original + max(int(diff / 2), 5), diff = 0 or 5
+            if (bm == 0) D.pend[j2] = pe + 5;                           // Job.get_duration() is the max over the tasks
         }
         __syncwarp();
     }
@@ -316,10 +329,16 @@ __device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const Cluste
                         util += (v < 100.0) ? v : 100.0;
                         util = (util < 100.0) ? util : 100.0;
                     }
-                    const double mem_cost = ((double)(cur + x.m) * D.unit_mib) / D.cap_mib;
-                    const double xx = util + job_util;
-                    double y = 0.0 * xx + 4E-5; y = y * xx + -0.00302; y = y * xx + 1.16664;   // np.polyval(NV_2080_COEF, .)
-                    const double cost = (mem_cost * 0.5) + (y * 0.5) + (double)n;
+                    double cost;
+                    if (!P.gandiva) {
+                        const double mem_cost = ((double)(cur + x.m) * D.unit_mib) / D.cap_mib;
+                        const double xx = util + job_util;
+                        double y = 0.0 * xx + 4E-5; y = y * xx + -0.00302; y = y * xx + 1.16664;   // np.polyval(NV_2080_COEF, .)
+                        cost = (mem_cost * 0.5) + (y * 0.5) + (double)n;
+                    } else {                                            // gandiva_score (horus.py:6-25): current memory in MiB + the task's share
+                        const double mem_cost = (double)cur * D.unit_mib + ((double)x.m * D.unit_mib) / D.cap_mib;
+                        cost = (mem_cost * 0.5) + (util / 100) + (double)n;
+                    }
                     if (cost < min_cost) min_cost = cost;
                 }
                 if (any) best = min_cost;
@@ -428,7 +447,8 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
         __syncwarp();
         // (a job with leaked entries is excluded: re-adding a task over its own leaked entry takes no slot, and undoing the
         // trial removes the leaked entry as well)
-        if (tot < x.T && !leak_any && D.planes[5][x.job] != 1) {
+        // (and a job with +5 tasks: the skipped add_task calls would have reset them)
+        if (tot < x.T && !leak_any && D.jflag[x.job] == 0 && x.bump == 0) {
             for (int i = 0; i < c.N; ++i) if (x.score[i] > 0.0) pack_pj_set(D, st, i, x.job);
             pack_pj_pop(D, st, x.hnode[hlen - 1], x.job);
             PACK_T(5);
@@ -489,10 +509,18 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
         pack_pj_set(D, st, node, x.job);
         D.tnode[pj.task_off + t] = (int16_t)node;
     }
-    D.planes[4][x.job] = (int)x.interf;
+    D.imask[x.job] = x.interf;
     __syncwarp();
     PACK_T(6);
     return 1;
+}
+
+// removes `job` from a singly linked calendar bucket (lane 0)
+__device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, int bucket, int job) {
+    int prev = -1, cur = head[bucket];
+    while (cur >= 0 && cur != job) { prev = cur; cur = next[cur]; }
+    if (cur < 0) return;
+    if (prev < 0) head[bucket] = next[cur]; else next[prev] = next[cur];
 }
 
 __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
@@ -514,43 +542,59 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
     if (st.d == 0 && st.cursor == 0) {                     // first launch of a run: empty cluster
         for (int i = lane; i < c.N; i += 32) { D.units[i] = 0; D.ntk[i] = 0; D.npj[i] = 0; }
         for (int i = lane; i < c.D; i += 32) { D.dn[i] = 0; D.dm[i] = 0; }
-        for (int i = lane; i < PACK_CAL_W; i += 32) D.chead[i] = -1;
+        for (int i = lane; i < PACK_CAL_W; i += 32) { D.chead[i] = -1; D.shead[i] = -1; }
         for (size_t i = lane; i < (size_t)J * D.W; i += 32) D.pjbits[i] = 0;
+        for (int i = lane; i < J; i += 32) { D.pend[i] = 0; D.imask[i] = 0; D.bmask[i] = 0; D.jflag[i] = 0; D.pproc[i] = 0; D.nstart[i] = 0; }
         __syncwarp();
     }
     const int d_stop = st.d + tick_budget;
     while (true) {
-        if ((J - st.cursor) + st.R == 0) { st.done = 1; break; }   // schedule.py:185 (the queue is not consulted, q2)
+        if ((J - st.cursor) + st.r_pre == 0 && st.d > 0) { st.done = 1; break; }   // schedule.py:185 (the queue is not consulted, q2)
         if (st.d == d_stop) break;
         if (P.max_ticks > 0 && st.d >= P.max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
         const int d = st.d;
         PACK_T0;
 
-        // ---------------- arrivals: heappush in trace order (jobs_manager.py:228-241, job_queue_manager.py:147-152)
-        while (st.cursor < J) {
-            const int job = st.cursor;
-            const int arr = D.trace[job].arrival_tick;
-            if (arr > d) break;
-            pack_q_push(D, lane, st.Q, D.pj[job].util_avg, job);
-            if (lane == 0) { D.lprev[job] = st.ltail; D.lnext[job] = -1; if (st.ltail >= 0) D.lnext[st.ltail] = job; }
-            if (st.ltail < 0) st.lhead = job;
-            st.ltail = job;
-            __syncwarp();
-            const int ql = st.Q;                              // queued jobs = heap length here (no look-ahead is out)
-            if (ql == 1) { st.mlo = job; st.mrank = 0; }
-            else if ((ql - 1) / 2 > st.mrank) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
-            st.sum_arr += arr;
-            st.cursor += 1;
+        // ---------------- arrivals (jobs_manager.py:228-241)
+        if (!P.gandiva) {
+            // horus: heappush in trace order (job_queue_manager.py:147-152)
+            while (st.cursor < J) {
+                const int job = st.cursor;
+                const int arr = D.trace[job].arrival_tick;
+                if (arr > d) break;
+                pack_q_push(D, lane, st.Q, D.pj[job].util_avg, job);
+                if (lane == 0) { D.lprev[job] = st.ltail; D.lnext[job] = -1; if (st.ltail >= 0) D.lnext[st.ltail] = job; }
+                if (st.ltail < 0) st.lhead = job;
+                st.ltail = job;
+                __syncwarp();
+                const int ql = st.Q;                              // queued jobs = heap length here (no look-ahead is out)
+                if (ql == 1) { st.mlo = job; st.mrank = 0; }
+                else if ((ql - 1) / 2 > st.mrank) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
+                st.sum_arr += arr;
+                st.cursor += 1;
+                if (st.Q > st.max_q) st.max_q = st.Q;
+                __syncwarp();
+            }
+        } else {
+            // gandiva: a plain list, queue.insert(i, job_i): the batch goes to the front in order (q1).  The queue is a stack
+            // whose top (index Q - 1) is the front, so the batch is pushed last-to-first.
+            int c1 = st.cursor;
+            while (c1 < J && D.trace[c1].arrival_tick <= d) c1 += 1;
+            const int k = c1 - st.cursor;
+            for (int i = lane; i < k; i += 32) { const int job = c1 - 1 - i; D.qjob[st.Q + i] = job; D.qtick[job] = d; }
+            st.sum_arr += (int64_t)k * d;
+            st.Q += k; st.cursor = c1;
             if (st.Q > st.max_q) st.max_q = st.Q;
             __syncwarp();
         }
 
         PACK_T(0);
-        // ---------------- _schedule -> schedule_horus (schedule.py:40-60, algorithm.py:204-240)
+        // ---------------- _schedule (schedule.py:40-60) -> schedule_horus (algorithm.py:204-240) | schedule_fifo (:189-202)
         if (st.Q > 0 && st.n_free_nodes >= 1) {
-            const int k = min(max(P.num_buffer, 0), st.Q);
+            const int k = P.gandiva ? 1 : min(max(P.num_buffer, 0), st.Q);
             int my_job = -1; double my_key = 0.0;
-            for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
+            if (!P.gandiva) for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
+            else my_job = D.qjob[st.Q - 1];                   // the head of the list stays queued unless it is placed
             __syncwarp();
             PACK_T(1);
             int pos = -1, err = 0;
@@ -559,17 +603,21 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 x.lane = lane; x.job = __shfl_sync(RLGS_FULL, my_job, a);
                 x.score = sm_score; x.hscore = sm_hscore; x.hnode = sm_hnode;
                 const rlgs_job rec = D.trace[x.job];
-                x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q; x.interf = 0;
+                x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q;
+                x.interf = D.imask[x.job]; x.bump = D.bmask[x.job];
                 if (x.T > PACK_MAX_TASKS || D.pj[x.job].heap_cap > PACK_MAX_HEAP || D.pj[x.job].heap_cap < 0) { err = RLGS_ERR_UNSUPPORTED; break; }
                 const int r = pack_place(D, c, P, st, x, replica, (uint32_t)a);
                 if (r < 0) { err = r; break; }
+                __syncwarp();
+                D.bmask[x.job] = x.bump;                      // trial add_task calls reset Task.duration even when the plan fails
+                __syncwarp();
                 if (r) pos = a;
             }
             if (err) { st.status = err; st.done = 1; break; }
 #ifdef PACK_PROFILE
             _t0 = clock64();
 #endif
-            for (int a = 0; a < k; ++a) {                     // jobs_manager.insert(look_ahead): heappush the rest in order
+            if (!P.gandiva) for (int a = 0; a < k; ++a) {     // jobs_manager.insert(look_ahead): heappush the rest in order
                 const int job = __shfl_sync(RLGS_FULL, my_job, a); const double key = __shfl_sync(RLGS_FULL, my_key, a);
                 if (a != pos) pack_q_push(D, lane, st.Q, key, job);
             }
@@ -579,26 +627,40 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 const int job = __shfl_sync(RLGS_FULL, my_job, pos);
                 const rlgs_job rec = D.trace[job];
                 const PackJob pj = D.pj[job];
-                const int p = D.lprev[job], n = D.lnext[job];
-                const int hb = D.chead[(d + rec.dur_ticks) & (PACK_CAL_W - 1)];
                 int tn = -1;
                 if (lane < rec.tasks) tn = D.tnode[pj.task_off + lane];
-                __syncwarp();
-                if (p >= 0) D.lnext[p] = n; else st.lhead = n;
-                if (n >= 0) D.lprev[n] = p; else st.ltail = p;
-                if (job == st.mlo) { if (n >= 0) st.mlo = n; else { st.mlo = p; st.mrank -= 1; } }
-                else if (job < st.mlo) st.mrank -= 1;
-                __syncwarp();
-                const int ql = st.Q;                          // queued jobs after the start
-                if (ql > 0) {
-                    const int target = (ql - 1) / 2;
-                    if (st.mrank < target) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
-                    else if (st.mrank > target) { st.mlo = D.lprev[st.mlo]; st.mrank -= 1; }
+                if (!P.gandiva) {
+                    const int p = D.lprev[job], n = D.lnext[job];
+                    __syncwarp();
+                    if (p >= 0) D.lnext[p] = n; else st.lhead = n;
+                    if (n >= 0) D.lprev[n] = p; else st.ltail = p;
+                    if (job == st.mlo) { if (n >= 0) st.mlo = n; else { st.mlo = p; st.mrank -= 1; } }
+                    else if (job < st.mlo) st.mrank -= 1;
+                    __syncwarp();
+                    const int ql = st.Q;                      // queued jobs after the start
+                    if (ql > 0) {
+                        const int target = (ql - 1) / 2;
+                        if (st.mrank < target) { st.mlo = D.lnext[st.mlo]; st.mrank += 1; }
+                        else if (st.mrank > target) { st.mlo = D.lprev[st.mlo]; st.mrank -= 1; }
+                    }
+                    st.sum_arr -= rec.arrival_tick;
+                } else {
+                    st.sum_arr -= D.qtick[job];
+                    st.Q -= 1;                                // queues[0].pop(0)
                 }
-                st.sum_arr -= rec.arrival_tick;
-                D.planes[0][job] = d; D.planes[3][job] = 0;
-                D.pend[job] = d + rec.dur_ticks;
-                D.cnext[job] = hb; D.chead[(d + rec.dur_ticks) & (PACK_CAL_W - 1)] = job;
+                // the job runs until time_processed >= get_duration(): ticks still to do = duration (+5) - processed so far
+                const int pb = D.pproc[job], ns = D.nstart[job];
+                const int end = d + max(1, rec.dur_ticks + (D.bmask[job] ? 5 : 0) - pb);
+                const int bk = end & (PACK_CAL_W - 1);
+                const int hb = D.chead[bk];
+                const int slice = d + PACK_QUANTA - pb % PACK_QUANTA;         // next tick with time_processed % 100 == 0
+                const int sb = slice & (PACK_CAL_W - 1);
+                const int hs = D.shead[sb];
+                __syncwarp();
+                D.planes[0][job] = d; D.nstart[job] = ns + 1;
+                D.pend[job] = end; D.cbk[job] = bk;
+                D.cnext[job] = hb; D.chead[bk] = job;
+                if (P.gandiva) { D.sat[job] = slice; D.snext[job] = hs; D.shead[sb] = job; }
                 // placed_tasks -> running_tasks on every node of the job (node.py:173-198); several tasks may share a node
                 for (int t = 0; t < rec.tasks; ++t) {
                     const int node = __shfl_sync(RLGS_FULL, tn, t);
@@ -626,7 +688,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                     if (pe == st.d || (pe & (PACK_CAL_W - 1)) != bk) {
                         if (prev < 0) D.chead[bk] = nx; else D.cnext[prev] = nx;
                         if (pe == st.d) { D.fin[nf] = cur; nf += 1; }
-                        else { const int b2 = pe & (PACK_CAL_W - 1); D.cnext[cur] = D.chead[b2]; D.chead[b2] = cur; }   // +5 moved it to another bucket
+                        else { const int b2 = pe & (PACK_CAL_W - 1); D.cnext[cur] = D.chead[b2]; D.chead[b2] = cur; D.cbk[cur] = b2; }   // +5 moved it to another bucket
                     } else prev = cur;
                     cur = nx;
                 }
@@ -642,10 +704,64 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 const rlgs_job rec = D.trace[best];
                 const int off = D.pj[best].task_off;
                 for (int t = 0; t < rec.tasks; ++t) pack_release(D, c, st, lane, (int)D.tnode[off + t], best, t, true);
+                if (P.gandiva && lane == 0) pack_chain_unlink(D.shead, D.snext, D.sat[best] & (PACK_CAL_W - 1), best);
+                __syncwarp();
                 D.planes[1][best] = st.d;
                 D.planes[2][st.F] = best;
+                D.planes[3][best] = D.bmask[best] != 0;                         // Job.get_duration() - Job.duration = 5
+                D.planes[4][best] = D.pproc[best] + (st.d - best_start);       // Job.time_processed()
+                D.planes[5][best] = D.nstart[best];                            // Job.migration_count
+                D.pend[best] = 0;                                              // running_jobs.pop
                 st.F += 1; st.R -= 1;
                 st.sum_jct += (int64_t)(st.d - rec.arrival_tick);
+                __syncwarp();
+            }
+        }
+        st.r_pre = st.R;                                       // schedule.py:195: counted before the post-tick plugin
+
+        // ---------------- time_slice_check (algorithm.py:420-440): with a non-empty queue, every running job whose processed time
+        // reached a multiple of 100 is preempted (jobs_manager.py:150-173) and re-queued at the front
+        if (P.gandiva) {
+            const int sb = st.d & (PACK_CAL_W - 1);
+            const bool slicing = st.Q > 0;
+            int nt = 0;
+            if (lane == 0) {
+                int prev = -1, cur = D.shead[sb];
+                while (cur >= 0) {
+                    const int nx = D.snext[cur];
+                    if (D.sat[cur] == st.d) {
+                        if (prev < 0) D.shead[sb] = nx; else D.snext[prev] = nx;
+                        if (slicing) { D.fin[nt] = cur; nt += 1; }
+                        else { const int s2 = st.d + PACK_QUANTA, b2 = s2 & (PACK_CAL_W - 1); D.sat[cur] = s2; D.snext[cur] = D.shead[b2]; D.shead[b2] = cur; }
+                    } else prev = cur;
+                    cur = nx;
+                }
+            }
+            __syncwarp();
+            nt = __shfl_sync(RLGS_FULL, nt, 0);
+            for (int k2 = 0; k2 < nt; ++k2) {                  // every job of the todo list leaves running_jobs as its turn comes
+                int best = -1, best_start = RLGS_NEVER, best_at = -1;
+                for (int i = 0; i < nt; ++i) { const int jb = D.fin[i]; if (jb < 0) continue; const int s0 = D.planes[0][jb]; if (s0 < best_start) { best_start = s0; best = jb; best_at = i; } }
+                __syncwarp();
+                D.fin[best_at] = -1;
+                const rlgs_job rec = D.trace[best];
+                const int off = D.pj[best].task_off;
+                const int pb = D.pproc[best];
+                if (lane == 0) pack_chain_unlink(D.chead, D.cnext, D.cbk[best], best);
+                __syncwarp();
+                D.pend[best] = 0;                              // running_jobs.pop(job_id) comes first
+                D.pproc[best] = pb + (st.d - best_start);
+                __syncwarp();
+                for (int t = 0; t < rec.tasks; ++t) {
+                    const int node = (int)D.tnode[off + t];
+                    pack_pj_pop(D, st, node, best);            // placed_jobs.pop(job_id), once per node
+                    pack_release(D, c, st, lane, node, best, t, true);
+                }
+                const int qn = st.Q;
+                __syncwarp();
+                D.qjob[qn] = best; D.qtick[best] = st.d;       // Job.preempted(): pending_time = 0; insert([job]) at the front
+                st.Q = qn + 1; st.sum_arr += st.d; st.R -= 1; st.preempts += 1;
+                if (st.Q > st.max_q) st.max_q = st.Q;
                 __syncwarp();
             }
         }
@@ -656,9 +772,15 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
         if (rows_mode) {
             int lo = 0, hi = 0, mx = 0;
             if (st.Q > 0) {
-                const int a0 = D.trace[st.mlo].arrival_tick;
-                const int a1 = (st.Q & 1) ? a0 : D.trace[D.lnext[st.mlo]].arrival_tick;
-                lo = st.d - a1; hi = st.d - a0; mx = st.d - D.trace[st.lhead].arrival_tick;
+                if (!P.gandiva) {
+                    const int a0 = D.trace[st.mlo].arrival_tick;
+                    const int a1 = (st.Q & 1) ? a0 : D.trace[D.lnext[st.mlo]].arrival_tick;
+                    lo = st.d - a1; hi = st.d - a0; mx = st.d - D.trace[st.lhead].arrival_tick;
+                } else {                                       // the stack is ordered by entry tick: positions give the order statistics
+                    lo = st.d - D.qtick[D.qjob[st.Q - 1 - (st.Q - 1) / 2]];
+                    hi = st.d - D.qtick[D.qjob[st.Q - 1 - st.Q / 2]];
+                    mx = st.d - D.qtick[D.qjob[0]];
+                }
             }
             if (lane == 0) {
                 rlgs_row *row = row_ptr(rs, blockIdx.x, st.d - 1);
@@ -672,8 +794,8 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
         }
         PACK_T(10);
     }
-    st.events = (int64_t)st.cursor + st.start_seq + st.F;
-    if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;
+    st.events = (int64_t)st.cursor + st.start_seq + st.F + st.preempts;
+    if (!st.done && st.status == RLGS_OK && st.d > 0 && (J - st.cursor) + st.r_pre == 0) st.done = 1;
     __syncwarp();
     if (lane == 0) {
         states[blockIdx.x] = st;

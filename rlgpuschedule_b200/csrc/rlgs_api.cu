@@ -128,14 +128,15 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
     const int sched = opts->schedule;
     if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS &&
-        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU && sched != RLGS_SCHED_HORUS)
+        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU && sched != RLGS_SCHED_HORUS && sched != RLGS_SCHED_GANDIVA)
         return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
     const bool is_sjf_family = sched == RLGS_SCHED_SJF || sched == RLGS_SCHED_SHORTEST || sched == RLGS_SCHED_SHORTEST_GPU;
     if ((sched == RLGS_SCHED_FIFO || is_sjf_family) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
-    if ((sched == RLGS_SCHED_HORUS) != (opts->placement == RLGS_PLACE_HORUS))
-        return fail(RLGS_ERR_UNSUPPORTED, "the horus schedule and the horus placement go together (schedule.py:47 passes the schedule "
-                    "name to the placement's score table, so fifo + horus raises KeyError in the reference)");
+    const bool is_pack = sched == RLGS_SCHED_HORUS || sched == RLGS_SCHED_GANDIVA;
+    if (is_pack != (opts->placement == RLGS_PLACE_HORUS))
+        return fail(RLGS_ERR_UNSUPPORTED, "the horus / gandiva schedules and the pack placement go together (schedule.py:47 passes the "
+                    "schedule name to the placement's score table, so fifo + horus raises KeyError in the reference)");
     if (sched == RLGS_SCHED_HORUS && (opts->num_buffer < 0 || opts->num_buffer > 32)) return fail(RLGS_ERR_BAD_ARG, "num_buffer must be 0..32");
     const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
     if (is_dlas) {
@@ -155,10 +156,10 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (!s) return fail(RLGS_ERR_OOM, "host allocation failed");
     s->spec = *spec; s->opts = *opts; s->R = opts->n_replicas; s->device = opts->device;
     s->legacy = sched != RLGS_SCHED_FIFO;
-    s->pack = sched == RLGS_SCHED_HORUS;
+    s->pack = is_pack;
     memset(&s->pp, 0, sizeof s->pp);
     s->pp.num_buffer = opts->num_buffer > 0 ? opts->num_buffer : 5;
-    s->pp.rng_on = opts->pack_rng != 0; s->pp.seed = opts->pack_seed;
+    s->pp.rng_on = opts->pack_rng != 0; s->pp.seed = opts->pack_seed; s->pp.gandiva = sched == RLGS_SCHED_GANDIVA;
     s->pp.nodes_per_rack = spec->num_node_p_switch; s->pp.racks = spec->num_switch; s->pp.max_ticks = opts->max_ticks;
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
@@ -387,7 +388,8 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
     const size_t N = (size_t)s->cc.N, Dv = (size_t)s->cc.D, J = (size_t)n, W = (N + 31) / 32;
     // per-replica working set, 256-byte aligned pieces in this order
     const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J,
-                         4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J};
+                         4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J,
+                         4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * PACK_CAL_W, 4 * J};
     size_t per = 0;
     for (size_t v : sz) per += align_up(v, 256);
     unsigned char *slab = nullptr;
@@ -404,6 +406,9 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
         D.dm = (int64_t *)take(0); D.ent = (int2 *)take(0); D.pjbits = (uint32_t *)take(0); D.qkey = (double *)take(0);
         D.qjob = (int32_t *)take(0); D.lprev = (int32_t *)take(0); D.lnext = (int32_t *)take(0); D.pend = (int32_t *)take(0);
         D.cnext = (int32_t *)take(0); D.chead = (int32_t *)take(0); D.tnode = (int16_t *)take(0); D.fin = (int32_t *)take(0);
+        D.imask = (uint32_t *)take(0); D.bmask = (uint32_t *)take(0); D.jflag = (int32_t *)take(0); D.pproc = (int32_t *)take(0);
+        D.nstart = (int32_t *)take(0); D.qtick = (int32_t *)take(0); D.cbk = (int32_t *)take(0); D.snext = (int32_t *)take(0);
+        D.shead = (int32_t *)take(0); D.sat = (int32_t *)take(0);
         D.cap_units = (int64_t)in->gpu_mem_cap_mib * unit; D.margin_units = 500 * unit;
         D.cap_mib = (double)in->gpu_mem_cap_mib; D.unit_mib = 1.0 / (double)unit;
     }
@@ -725,7 +730,7 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     CU(cudaSetDevice(s->device));
-    int32_t rc = fetch_planes(s, (first_node || (preempt && s->legacy)) ? N_PLANES : 3);
+    int32_t rc = fetch_planes(s, (first_node || (preempt && s->legacy)) ? N_PLANES : 3);   // pack is a legacy-layout family
     if (rc) return rc;
     size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
     int J = s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J;
@@ -734,7 +739,7 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (end_tick) memcpy(end_tick, en, 4 * (size_t)J);
     if (finish_order) memcpy(finish_order, fo, 4 * (size_t)J);
     if (preempt) {
-        if (s->pack) for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171)
+        if (s->pack) { const int32_t *ns = s->h_jobs + 5 * plane + off; for (int i = 0; i < J; ++i) preempt[i] = ns[i] >= 0 ? ns[i] : (st[i] >= 0 ? 1 : 0); }  // Job.migration_count
         else if (s->legacy) memcpy(preempt, s->h_jobs + 4 * plane + off, 4 * (size_t)J);
         else for (int i = 0; i < J; ++i) preempt[i] = st[i] >= 0 ? 1 : 0;  // Job.migration_count (job.py:171, q6)
     }

@@ -103,8 +103,8 @@ class Scheduler(object):
             limits = parse_queue_limit(getattr(flags, 'queue_limit', None))
             kw = dict(num_queue=len(limits) + 1, queue_limit=limits)
             scheme = 'count'   # dlas admits by GPU count (run_sim.py:808-823) whatever --scheme says
-        if self.schedule == 'horus':
-            # horus_score draws device utilisations from an unseeded normal (infra/device.py:52); here the draw is
+        if self.schedule in ('horus', 'gandiva'):
+            # horus_score / gandiva_score draw device utilisations from an unseeded normal (infra/device.py:52); here the draw is
             # counter-based: --seed fixes it, --util_mode mean replaces every draw by its mean
             seed = getattr(flags, 'seed', None)
             if seed is None and getattr(flags, 'util_mode', 'sample') != 'mean':
@@ -124,16 +124,18 @@ class Scheduler(object):
         sim.run()
         took = time.time() - t0
         summ = sim.summary(0)
-        legacy = self.schedule not in ('fifo', 'horus')
+        legacy = self.schedule not in ('fifo', 'horus', 'gandiva')
         if not legacy:
             self.log_manager.write_cluster_rows(sim.rows(0), cluster, trace.mem_shift,
                                                 util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
             j = sim.jobs(0)
             logging.info('Total Time Taken in seconds: %d' % took)
             extra = {}
-            if self.schedule == 'horus':   # Job.get_duration() = original + 5 once a task was de-interfered (jobs_manager.py:184-185)
+            if self.schedule in ('horus', 'gandiva'):
+                # Job.get_duration() = original + 5 once a task was de-interfered (jobs_manager.py:184-185); jct = Job.time_processed()
                 from . import _ffi
-                extra = dict(get_duration=trace.duration + 5.0 * (sim.job_plane(0, _ffi.PLANE_AUX) == 1))
+                extra = dict(get_duration=trace.duration + 5.0 * (sim.job_plane(0, _ffi.PLANE_AUX) == 1),
+                             jct=sim.job_plane(0, _ffi.PLANE_PREEMPT))
             self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt'], sim.durations(0) if net else None, extra))
         else:
             from . import _ffi

@@ -78,7 +78,7 @@ class Simulator(object):
                                      trace.iterations.ctypes.data_as(dp))
         _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
                                               C.byref(net) if net is not None else None))
-        if self._kw['schedule'] == 'horus':
+        if self._kw['schedule'] in ('horus', 'gandiva'):
             pi = trace.pack_inputs()
             dp = C.POINTER(C.c_double)
             inp = _ffi.PackInputs(pi['util_avg'].ctypes.data_as(dp), pi['util_sd'].ctypes.data_as(dp),

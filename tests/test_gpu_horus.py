@@ -26,10 +26,10 @@ CASES = {
 }
 
 
-def run_device(df, flags, k, seed=None, **kw):
+def run_device(df, flags, k, seed=None, schedule='horus', **kw):
     cluster = rl.cluster_from_flags(flags)
     tr = rl.prepare_trace(df, cluster)
-    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, max_ticks=400000, **kw)
+    sim = rl.Simulator(cluster, schedule, schedule, n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, max_ticks=400000, **kw)
     sim.load_trace(tr)
     sim.run()
     return sim, cluster, tr
@@ -42,58 +42,65 @@ def check(sim, cluster, tr, o, otr, replica):
     assert np.array_equal(j['finish_order'], o['finish_order'])
     assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end'])
     assert np.array_equal(dur, o['actual_duration'])
-    got = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur)
+    jct = sim.job_plane(replica, _ffi.PLANE_PREEMPT)
+    assert np.array_equal(jct[j['finish_order']], o['jct'][o['finish_order']]) and np.array_equal(j['preempt'][j['finish_order']], o['preempt'][o['finish_order']])
+    got = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur, jct=jct)
     assert got == cpu_sim.format_job_csv(otr, o)
     assert lm.format_cluster_csv(sim.rows(replica), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
 
 
+@pytest.mark.parametrize('schedule', ['horus', 'gandiva'])
 @pytest.mark.parametrize('name', list(CASES))
-def test_horus_matches_oracle_mean_draws(name):
+def test_horus_matches_oracle_mean_draws(name, schedule):
     frame, flags, k = CASES[name]
     df = frame()
-    sim, cluster, tr = run_device(df, flags, k)
+    sim, cluster, tr = run_device(df, flags, k, schedule=schedule)
     otr = cpu_sim.prepare_trace(df)
-    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, schedule, k)
     for r in range(2):
         check(sim, cluster, tr, o, otr, r)
     sim.close()
 
 
+@pytest.mark.parametrize('schedule', ['horus', 'gandiva'])
 @pytest.mark.parametrize('name', ['probe100_1x4x8', 'gen300_2x4x8', 'gen2000_4x8x8_spread'])
-def test_horus_matches_oracle_seeded_draws(name):
+def test_horus_matches_oracle_seeded_draws(name, schedule):
     frame, flags, k = CASES[name]
     df = tracegen.frame_probe100() if name.startswith('probe') else (tracegen.frame_gen(300, 11, 150) if name.startswith('gen300') else frame())
-    sim, cluster, tr = run_device(df, flags, k, seed=1234)
+    sim, cluster, tr = run_device(df, flags, k, seed=1234, schedule=schedule)
     otr = cpu_sim.prepare_trace(df)
     for r in range(2):
-        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k, seed=1234, replica=r)
+        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, schedule, k, seed=1234, replica=r)
         check(sim, cluster, tr, o, otr, r)
     sim.close()
 
 
-def test_horus_bounded_launches_resume():
+@pytest.mark.parametrize('schedule', ['horus', 'gandiva'])
+def test_horus_bounded_launches_resume(schedule):
     frame, flags, k = CASES['gen300_2x4x8']
     df = frame()
-    sim, cluster, tr = run_device(df, flags, k, ticks_per_launch=37)
+    sim, cluster, tr = run_device(df, flags, k, ticks_per_launch=37, schedule=schedule)
     otr = cpu_sim.prepare_trace(df)
-    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, schedule, k)
     check(sim, cluster, tr, o, otr, 1)
     sim.close()
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('big', 'horus'))
+@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('big', 'horus') +
+                         goldutil.case_names('small', 'gandiva') + goldutil.case_names('big', 'gandiva'))
 def test_horus_matches_the_reference_golden(name):
     """Device outputs vs the files the UNMODIFIED reference wrote for `--schedule horus --scheme horus` (tests/golden)."""
     g = goldutil.load(name)
     cluster = rl.cluster_from_flags(g['flags'])
     tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
-    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
+    sim = rl.Simulator(cluster, g['schedule'], g['schedule'], n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
     sim.load_trace(tr)
     sim.run()
     for r in (0, 2):
         j = sim.jobs(r)
         dur = tr.duration + 5.0 * (sim.job_plane(r, _ffi.PLANE_AUX) == 1)
-        job = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur)
+        job = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur,
+                                jct=sim.job_plane(r, _ffi.PLANE_PREEMPT))
         clu = lm.format_cluster_csv(sim.rows(r), cluster, tr.mem_shift, with_util=False)
         if g['job'] is not None:
             assert job == g['job'] and clu == g['cluster']

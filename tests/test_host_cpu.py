@@ -44,8 +44,9 @@ def test_plugin_registries_keep_the_reference_keys():
         algorithm.resolve('fifo', 'horus')              # KeyError 'fifo' in the reference (algorithm.py:58)
     with pytest.raises(NotImplementedError):
         algorithm.resolve('horus', 'yarn')
+    assert algorithm.resolve('gandiva', 'gandiva')[0].device_id == _ffi.SCHED['gandiva']
     with pytest.raises(NotImplementedError):
-        algorithm.resolve('gandiva', 'yarn')            # its post-tick plugin (time slicing) has no device form
+        algorithm.resolve('gandiva', 'yarn')            # fifo + time slicing over the yarn fit: not on the device path
     with pytest.raises(KeyError):
         algorithm.resolve('lpjf', 'yarn')
     algorithm.scheduling_algorithms['mine'] = lambda *a, **k: (None, None, False)
