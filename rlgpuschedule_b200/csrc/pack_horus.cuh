@@ -751,6 +751,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 __syncwarp();
                 D.pend[best] = 0;                              // running_jobs.pop(job_id) comes first
                 D.pproc[best] = pb + (st.d - best_start);
+                D.planes[0][best] = -1;                        // the start column belongs to the run that finishes the job
                 __syncwarp();
                 for (int t = 0; t < rec.tasks; ++t) {
                     const int node = (int)D.tnode[off + t];

@@ -85,7 +85,7 @@ def test_env_step_by_step_matches_oracle_tape():
     env.close()
 
 
-@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec', 'horus_multi_node', 'horus_ties'])
+@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec', 'horus_multi_node', 'horus_ties', 'gandiva_multi_node', 'gandiva_ties'])
 def test_run_sim_cli_writes_reference_outputs(name, tmp_path):
     g = goldutil.load(name)
     args = []
