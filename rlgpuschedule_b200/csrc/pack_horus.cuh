@@ -305,6 +305,7 @@ __device__ __forceinline__ void pack_release(const PackDesc &D, const ClusterCon
 
 // horus_score of every node for one task of the job (horus.py:28-56); score < 0 marks a node that is not free or
 // cannot take the task (get_free_nodes + Node.can_fit(pack=True), algorithm.py:52-56)
+template <bool GANDIVA>
 __device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const ClusterConst &c, const PackParams &P, const PackCtx &x,
                                                  uint32_t replica, uint32_t tick, uint32_t attempt, uint32_t pass, double job_util) {
     for (int base = 0; base < c.N; base += 32) {
@@ -330,7 +331,7 @@ __device__ __forceinline__ void pack_score_nodes(const PackDesc &D, const Cluste
                         util = (util < 100.0) ? util : 100.0;
                     }
                     double cost;
-                    if (!P.gandiva) {
+                    if (!GANDIVA) {
                         const double mem_cost = ((double)(cur + x.m) * D.unit_mib) / D.cap_mib;
                         const double xx = util + job_util;
                         double y = 0.0 * xx + 4E-5; y = y * xx + -0.00302; y = y * xx + 1.16664;   // np.polyval(NV_2080_COEF, .)
@@ -377,6 +378,7 @@ __device__ __forceinline__ int pack_node_capacity(const PackDesc &D, const Clust
 }
 
 // horus_placement (algorithm.py:34-180).  1 = placed (tnode / planes[4] written), 0 = not placed, < 0 = error status.
+template <bool GANDIVA>
 __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst &c, const PackParams &P, PackState &st, PackCtx &x,
                                           uint32_t replica, uint32_t attempt) {
     const PackJob pj = D.pj[x.job];
@@ -390,7 +392,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     if (x.T == 1 && cap == 1) {
         // a heap of one slot keeps, of the nodes with the lowest score, the one pushed last (a push with an equal or lower
         // score displaces the resident): arg-min with ties to the higher node id, no sifting needed
-        pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, 0u, pj.util_avg);
+        pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, 0u, pj.util_avg);
         PACK_T(2);
         double bs = 1e300; int bn = -1;
         for (int i = x.lane; i < c.N; i += 32) { const double sc = x.score[i]; if (sc >= 0.0 && sc <= bs) { bs = sc; bn = i; } }
@@ -403,7 +405,7 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
         PACK_T(3);
     } else
     for (int pass = 0; pass < x.T; ++pass) {
-        if (pass == 0 || P.rng_on) pack_score_nodes(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
+        if (pass == 0 || P.rng_on) pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
         PACK_T(2);
         for (int base = 0; base < c.N; base += 32) {
             const int i = base + x.lane;
@@ -523,7 +525,8 @@ __device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, 
     if (prev < 0) head[bucket] = next[cur]; else next[prev] = next[cur];
 }
 
-__global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
+template <bool GANDIVA>
+__global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
                                                         RowStore rs, int64_t *returns) {
     extern __shared__ __align__(16) unsigned char pack_smem[];
     double *sm_score = reinterpret_cast<double *>(pack_smem);
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
         PACK_T0;
 
         // ---------------- arrivals (jobs_manager.py:228-241)
-        if (!P.gandiva) {
+        if (!GANDIVA) {
             // horus: heappush in trace order (job_queue_manager.py:147-152)
             while (st.cursor < J) {
                 const int job = st.cursor;
@@ -591,9 +594,9 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
         PACK_T(0);
         // ---------------- _schedule (schedule.py:40-60) -> schedule_horus (algorithm.py:204-240) | schedule_fifo (:189-202)
         if (st.Q > 0 && st.n_free_nodes >= 1) {
-            const int k = P.gandiva ? 1 : min(max(P.num_buffer, 0), st.Q);
+            const int k = GANDIVA ? 1 : min(max(P.num_buffer, 0), st.Q);
             int my_job = -1; double my_key = 0.0;
-            if (!P.gandiva) for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
+            if (!GANDIVA) for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
             else my_job = D.qjob[st.Q - 1];                   // the head of the list stays queued unless it is placed
             __syncwarp();
             PACK_T(1);
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q;
                 x.interf = D.imask[x.job]; x.bump = D.bmask[x.job];
                 if (x.T > PACK_MAX_TASKS || D.pj[x.job].heap_cap > PACK_MAX_HEAP || D.pj[x.job].heap_cap < 0) { err = RLGS_ERR_UNSUPPORTED; break; }
-                const int r = pack_place(D, c, P, st, x, replica, (uint32_t)a);
+                const int r = pack_place<GANDIVA>(D, c, P, st, x, replica, (uint32_t)a);
                 if (r < 0) { err = r; break; }
                 __syncwarp();
                 D.bmask[x.job] = x.bump;                      // trial add_task calls reset Task.duration even when the plan fails
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
 #ifdef PACK_PROFILE
             _t0 = clock64();
 #endif
-            if (!P.gandiva) for (int a = 0; a < k; ++a) {     // jobs_manager.insert(look_ahead): heappush the rest in order
+            if (!GANDIVA) for (int a = 0; a < k; ++a) {     // jobs_manager.insert(look_ahead): heappush the rest in order
                 const int job = __shfl_sync(RLGS_FULL, my_job, a); const double key = __shfl_sync(RLGS_FULL, my_key, a);
                 if (a != pos) pack_q_push(D, lane, st.Q, key, job);
             }
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 const PackJob pj = D.pj[job];
                 int tn = -1;
                 if (lane < rec.tasks) tn = D.tnode[pj.task_off + lane];
-                if (!P.gandiva) {
+                if (!GANDIVA) {
                     const int p = D.lprev[job], n = D.lnext[job];
                     __syncwarp();
                     if (p >= 0) D.lnext[p] = n; else st.lhead = n;
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 D.planes[0][job] = d; D.nstart[job] = ns + 1;
                 D.pend[job] = end; D.cbk[job] = bk;
                 D.cnext[job] = hb; D.chead[bk] = job;
-                if (P.gandiva) { D.sat[job] = slice; D.snext[job] = hs; D.shead[sb] = job; }
+                if (GANDIVA) { D.sat[job] = slice; D.snext[job] = hs; D.shead[sb] = job; }
                 // placed_tasks -> running_tasks on every node of the job (node.py:173-198); several tasks may share a node
                 for (int t = 0; t < rec.tasks; ++t) {
                     const int node = __shfl_sync(RLGS_FULL, tn, t);
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
                 const rlgs_job rec = D.trace[best];
                 const int off = D.pj[best].task_off;
                 for (int t = 0; t < rec.tasks; ++t) pack_release(D, c, st, lane, (int)D.tnode[off + t], best, t, true);
-                if (P.gandiva && lane == 0) pack_chain_unlink(D.shead, D.snext, D.sat[best] & (PACK_CAL_W - 1), best);
+                if (GANDIVA && lane == 0) pack_chain_unlink(D.shead, D.snext, D.sat[best] & (PACK_CAL_W - 1), best);
                 __syncwarp();
                 D.planes[1][best] = st.d;
                 D.planes[2][st.F] = best;
@@ -721,7 +724,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
 
         // ---------------- time_slice_check (algorithm.py:420-440): with a non-empty queue, every running job whose processed time
         // reached a multiple of 100 is preempted (jobs_manager.py:150-173) and re-queued at the front
-        if (P.gandiva) {
+        if (GANDIVA) {
             const int sb = st.d & (PACK_CAL_W - 1);
             const bool slicing = st.Q > 0;
             int nt = 0;
@@ -773,7 +776,7 @@ __global__ void __launch_bounds__(32, 12) pack_horus_kernel(const PackDesc *desc
         if (rows_mode) {
             int lo = 0, hi = 0, mx = 0;
             if (st.Q > 0) {
-                if (!P.gandiva) {
+                if (!GANDIVA) {
                     const int a0 = D.trace[st.mlo].arrival_tick;
                     const int a1 = (st.Q & 1) ? a0 : D.trace[D.lnext[st.mlo]].arrival_tick;
                     lo = st.d - a1; hi = st.d - a0; mx = st.d - D.trace[st.lhead].arrival_tick;

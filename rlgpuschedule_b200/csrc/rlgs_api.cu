@@ -485,7 +485,8 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
             PackParams pp = s->pp; pp.tick_budget = budget;
-            pack_horus_kernel<<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
+            if (pp.gandiva) pack_horus_kernel<true><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
+            else pack_horus_kernel<false><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
         } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         else
