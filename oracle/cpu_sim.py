@@ -119,7 +119,7 @@ def run_fifo_yarn(cluster, tr, rows_cap=None, netcost=None):
     return out
 
 
-def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, rows_cap=None):
+def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, rows_cap=None, scheme=None):
     """Restated `--schedule horus|gandiva` with horus_placement (oracle_pack).  seed=None pins every utilisation draw
     to its mean (the reference's behaviour on traces with gpu_utilization_max == gpu_utilization_avg: PINNED); a seed
     enables the build-defined counter-based draw (UNPINNED)."""
@@ -135,7 +135,7 @@ def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, 
         rc = L.oracle_pack(C.byref(cluster), C.c_int32(n), _p(tr['nt'], C.c_double), _p(tr['duration'], C.c_double),
                            _p(tr['used_gpus'], C.c_double), _p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double),
                            _p(tr['util_avg'], C.c_double), _p(tr['util_max'], C.c_double),
-                           C.c_int32(1 if schedule == 'gandiva' else 0), C.c_int32(num_buffer),
+                           C.c_int32(1 if schedule == 'gandiva' else 0), C.c_int32(1 if scheme == 'yarn' else 0), C.c_int32(num_buffer),
                            C.c_int32(0 if seed is None else 1), C.c_uint32(seed or 0), C.c_uint32(replica),
                            _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32), C.byref(nfin), _p(dur, C.c_double),
                            _p(jct, C.c_int32), _p(starts, C.c_int32), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))

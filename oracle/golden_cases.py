@@ -162,4 +162,15 @@ CASES = {
     'gandiva_cluster_spec': dict(frame=_zs(lambda: tg.frame_gen(150, 9, 400)), flags=dict(cluster_spec='@examples/cluster_spec_2x8x4.csv'), schedule='gandiva', big=True),
     'gandiva_gen300': dict(frame=_zs(lambda: tg.frame_gen(300, 11, 150)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='gandiva', big=True),
     'gandiva_probe2k': dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='gandiva', big=True),
+    # the same two schedules over --scheme yarn (ms_yarn_placement never reads utilisation: traces keep their spread)
+    'horusyarn_probe100': dict(frame=tg.frame_probe100, flags=C148, schedule='horus', scheme='yarn'),
+    'horusyarn_big_mem_leak': dict(frame=_big_mem, flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4, num_cpu_p_node=64, mem_p_node=256), schedule='horus', scheme='yarn', num_buffer=3),
+    'horusyarn_cluster_spec': dict(frame=lambda: tg.frame_gen(150, 9, 400), flags=dict(cluster_spec='@examples/cluster_spec_2x8x4.csv'), schedule='horus', scheme='yarn', big=True),
+    'horusyarn_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus', scheme='yarn', big=True),
+    'horusyarn_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='horus', scheme='yarn', big=True),
+    'gandivayarn_probe100': dict(frame=tg.frame_probe100, flags=C148, schedule='gandiva', scheme='yarn'),
+    'gandivayarn_multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='gandiva', scheme='yarn'),
+    'gandivayarn_cluster_spec': dict(frame=lambda: tg.frame_gen(150, 9, 400), flags=dict(cluster_spec='@examples/cluster_spec_2x8x4.csv'), schedule='gandiva', scheme='yarn', big=True),
+    'gandivayarn_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='gandiva', scheme='yarn', big=True),
+    'gandivayarn_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='gandiva', scheme='yarn', big=True),
 }

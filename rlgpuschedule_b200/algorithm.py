@@ -88,9 +88,9 @@ def resolve(schedule, scheme):
             if isinstance(p, HostOnlyPolicy):
                 p()  # raises NotImplementedError with the reference location
             raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
-    if (schedule in ('horus', 'gandiva')) != (place.device_id == _ffi.PLACE['horus']):
-        # fifo + horus: KeyError 'fifo' in the reference's score table (algorithm.py:58); horus + yarn is a valid
-        # reference combination that this package does not implement
+    packs = place.device_id == _ffi.PLACE['horus']
+    if (packs and schedule not in ('horus', 'gandiva')) or (schedule in ('horus', 'gandiva') and not packs and scheme != 'yarn'):
+        # fifo + horus: KeyError 'fifo' in the reference's score table (algorithm.py:58)
         raise NotImplementedError('schedule %r with scheme %r is not implemented by the device path' % (schedule, scheme))
     post = plugin_algorithms.get(schedule, None)
     if post is not None and not isinstance(post, DevicePolicy):

@@ -21,7 +21,7 @@
 // Memory amounts are integers in units of 2^-shift MiB (exact: ingest picks the shift), scores are float64 with the
 // reference's operation order (the library is built with --fmad=false).
 #pragma once
-#include "rlgs_device.cuh"
+#include "yarn_place.cuh"
 
 #define PACK_DEV_SLOTS 4      // infra/device.py:72
 #define PACK_CAL_W 128
@@ -62,6 +62,10 @@ struct PackDesc {
     int32_t *qtick;           // [J] gandiva: tick the job entered the queue (arrival or preemption): pending_time = d - qtick
     int32_t *cbk;             // [J] calendar bucket the running job is chained in
     int32_t *snext, *shead, *sat;     // gandiva: calendar of time-slice ticks ([J], [PACK_CAL_W], [J])
+    // --scheme yarn under these schedules: the node view of yarn_place.cuh and the placement of every running job
+    uint32_t *ybusy, *ykey, *yever;   // [N], [N], [ceil(N/32)]
+    int2 *plog;               // [sum of tasks] (node | tasks << 16, device mask) entries of job j at plog[task_off ..]
+    int32_t *pcnt;            // [J] entries of the job's placement
     int64_t cap_units, margin_units;  // gpu memory capacity and the 500 MiB margin in units
     double cap_mib, unit_mib; // capacity in MiB, 2^-shift
     int32_t J, W;
@@ -517,6 +521,64 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     return 1;
 }
 
+// ---- --scheme yarn (ms_yarn_placement, algorithm.py:28-32) under the horus / gandiva schedules: the fit of yarn_place.cuh on a
+// node view in global memory; devices are never shared, so there is no interference and no trial placement
+__device__ __forceinline__ NodeView pack_yarn_view(const PackDesc &D) { NodeView nv; nv.units = D.units; nv.busy = D.ybusy; nv.ever = D.yever; nv.key = D.ykey; return nv; }
+__device__ __forceinline__ int pack_yarn_attempt(const PackDesc &D, const ClusterConst &c, PackState &st, int lane, int job) {
+    JobRec jr; { const int4 *q = reinterpret_cast<const int4 *>(D.trace + job); jr.a = q[0]; jr.b = q[1]; }
+    const int off = D.pj[job].task_off;
+    int sticky_idle = 0;                                               // yarn_place's own idle count assumes keys are never popped
+    const PlaceResult pr = yarn_place(pack_yarn_view(D), c, jr, lane, D.plog, off, st.n_free_nodes, sticky_idle);
+    if (!pr.ok) return 0;
+    __syncwarp();
+    int went_busy = 0;
+    for (int base = 0; base < pr.nnodes; base += 32) {                  // one entry per node: tasks start running, placed_jobs gets the key
+        const int e = base + lane;
+        bool was = false;
+        if (e < pr.nnodes) {
+            const int2 en = D.plog[off + e];
+            const int node = en.x & 0xffff, tasks = (en.x >> 16) & 0xffff;
+            const int tk = D.ntk[node], np = D.npj[node];
+            was = tk == 0 && np == 0;
+            D.ntk[node] = tk + tasks; D.npj[node] = np + 1;
+        }
+        went_busy += __popc(__ballot_sync(RLGS_FULL, was));
+    }
+    st.idle_nodes -= went_busy;
+    const int ndev = jr.tasks() * jr.gpc();
+    const int64_t mu = jr.util() & 0xffff, sd = jr.util() >> 16;
+    st.busy_gpus += ndev; st.mem_sum += jr.mem_term(); st.util_mu_sum += mu * ndev; st.util_var_sum += sd * sd * ndev;
+    if (lane == 0) D.pcnt[job] = pr.nnodes;
+    __syncwarp();
+    return 1;
+}
+// completion (placed_jobs keeps the key, q3) or preemption (jobs_manager.py:150-173 pops it)
+__device__ __forceinline__ void pack_yarn_release(const PackDesc &D, const ClusterConst &c, PackState &st, int lane, int job, bool preempt) {
+    JobRec jr; { const int4 *q = reinterpret_cast<const int4 *>(D.trace + job); jr.a = q[0]; jr.b = q[1]; }
+    const int off = D.pj[job].task_off, cnt = D.pcnt[job];
+    int went_idle = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int e = base + lane;
+        const bool active = e < cnt;
+        int2 en = make_int2(0, 0);
+        if (active) en = D.plog[off + e];
+        release_entry(pack_yarn_view(D), c, active, en, st.n_free_nodes);
+        bool now = false;
+        if (active) {
+            const int node = en.x & 0xffff, tasks = (en.x >> 16) & 0xffff;
+            const int tk = D.ntk[node] - tasks, np = D.npj[node] - (preempt ? 1 : 0);
+            D.ntk[node] = tk; D.npj[node] = np;
+            now = tk == 0 && np == 0;
+        }
+        went_idle += __popc(__ballot_sync(RLGS_FULL, now));
+    }
+    st.idle_nodes += went_idle;
+    const int ndev = jr.tasks() * jr.gpc();
+    const int64_t mu = jr.util() & 0xffff, sd = jr.util() >> 16;
+    st.busy_gpus -= ndev; st.mem_sum -= jr.mem_term(); st.util_mu_sum -= mu * ndev; st.util_var_sum -= sd * sd * ndev;
+    __syncwarp();
+}
+
 // removes `job` from a singly linked calendar bucket (lane 0)
 __device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, int bucket, int job) {
     int prev = -1, cur = head[bucket];
@@ -525,7 +587,7 @@ __device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, 
     if (prev < 0) head[bucket] = next[cur]; else next[prev] = next[cur];
 }
 
-template <bool GANDIVA>
+template <bool GANDIVA, bool YARN>
 __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
                                                         RowStore rs, int64_t *returns) {
     extern __shared__ __align__(16) unsigned char pack_smem[];
@@ -544,6 +606,11 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
     const int J = D.J;
     if (st.d == 0 && st.cursor == 0) {                     // first launch of a run: empty cluster
         for (int i = lane; i < c.N; i += 32) { D.units[i] = 0; D.ntk[i] = 0; D.npj[i] = 0; }
+        if (YARN) {
+            const uint32_t empty_key = node_key(0, 0u, c);
+            for (int i = lane; i < c.N; i += 32) { D.ybusy[i] = 0; D.ykey[i] = empty_key; }
+            for (int i = lane; i < (c.N + 31) / 32; i += 32) D.yever[i] = 0;
+        }
         for (int i = lane; i < c.D; i += 32) { D.dn[i] = 0; D.dm[i] = 0; }
         for (int i = lane; i < PACK_CAL_W; i += 32) { D.chead[i] = -1; D.shead[i] = -1; }
         for (size_t i = lane; i < (size_t)J * D.W; i += 32) D.pjbits[i] = 0;
@@ -609,11 +676,15 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 x.T = rec.tasks; x.gpc = rec.gpus_per_task; x.m = D.pj[x.job].mem; x.mu_q = rec.util_mu_q; x.sd_q = rec.util_sd_q;
                 x.interf = D.imask[x.job]; x.bump = D.bmask[x.job];
                 if (x.T > PACK_MAX_TASKS || D.pj[x.job].heap_cap > PACK_MAX_HEAP || D.pj[x.job].heap_cap < 0) { err = RLGS_ERR_UNSUPPORTED; break; }
-                const int r = pack_place<GANDIVA>(D, c, P, st, x, replica, (uint32_t)a);
-                if (r < 0) { err = r; break; }
-                __syncwarp();
-                D.bmask[x.job] = x.bump;                      // trial add_task calls reset Task.duration even when the plan fails
-                __syncwarp();
+                int r;
+                if (YARN) r = pack_yarn_attempt(D, c, st, lane, x.job);
+                else {
+                    r = pack_place<GANDIVA>(D, c, P, st, x, replica, (uint32_t)a);
+                    if (r < 0) { err = r; break; }
+                    __syncwarp();
+                    D.bmask[x.job] = x.bump;                  // trial add_task calls reset Task.duration even when the plan fails
+                    __syncwarp();
+                }
                 if (r) pos = a;
             }
             if (err) { st.status = err; st.done = 1; break; }
@@ -631,7 +702,7 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 const rlgs_job rec = D.trace[job];
                 const PackJob pj = D.pj[job];
                 int tn = -1;
-                if (lane < rec.tasks) tn = D.tnode[pj.task_off + lane];
+                if (!YARN && lane < rec.tasks) tn = D.tnode[pj.task_off + lane];
                 if (!GANDIVA) {
                     const int p = D.lprev[job], n = D.lnext[job];
                     __syncwarp();
@@ -665,7 +736,7 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 D.cnext[job] = hb; D.chead[bk] = job;
                 if (GANDIVA) { D.sat[job] = slice; D.snext[job] = hs; D.shead[sb] = job; }
                 // placed_tasks -> running_tasks on every node of the job (node.py:173-198); several tasks may share a node
-                for (int t = 0; t < rec.tasks; ++t) {
+                if (!YARN) for (int t = 0; t < rec.tasks; ++t) {
                     const int node = __shfl_sync(RLGS_FULL, tn, t);
                     const int v = D.ntk[node];
                     __syncwarp();
@@ -706,7 +777,8 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 D.fin[best_at] = -1;
                 const rlgs_job rec = D.trace[best];
                 const int off = D.pj[best].task_off;
-                for (int t = 0; t < rec.tasks; ++t) pack_release(D, c, st, lane, (int)D.tnode[off + t], best, t, true);
+                if (YARN) pack_yarn_release(D, c, st, lane, best, false);
+                else for (int t = 0; t < rec.tasks; ++t) pack_release(D, c, st, lane, (int)D.tnode[off + t], best, t, true);
                 if (GANDIVA && lane == 0) pack_chain_unlink(D.shead, D.snext, D.sat[best] & (PACK_CAL_W - 1), best);
                 __syncwarp();
                 D.planes[1][best] = st.d;
@@ -756,7 +828,8 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 D.pproc[best] = pb + (st.d - best_start);
                 D.planes[0][best] = -1;                        // the start column belongs to the run that finishes the job
                 __syncwarp();
-                for (int t = 0; t < rec.tasks; ++t) {
+                if (YARN) pack_yarn_release(D, c, st, lane, best, true);
+                else for (int t = 0; t < rec.tasks; ++t) {
                     const int node = (int)D.tnode[off + t];
                     pack_pj_pop(D, st, node, best);            // placed_jobs.pop(job_id), once per node
                     pack_release(D, c, st, lane, node, best, t, true);

@@ -134,9 +134,11 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if ((sched == RLGS_SCHED_FIFO || is_sjf_family) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
     const bool is_pack = sched == RLGS_SCHED_HORUS || sched == RLGS_SCHED_GANDIVA;
-    if (is_pack != (opts->placement == RLGS_PLACE_HORUS))
-        return fail(RLGS_ERR_UNSUPPORTED, "the horus / gandiva schedules and the pack placement go together (schedule.py:47 passes the "
-                    "schedule name to the placement's score table, so fifo + horus raises KeyError in the reference)");
+    if (!is_pack && opts->placement == RLGS_PLACE_HORUS)
+        return fail(RLGS_ERR_UNSUPPORTED, "the pack placement needs the horus or gandiva schedule (schedule.py:47 passes the schedule name "
+                    "to the placement's score table, so fifo + horus raises KeyError in the reference)");
+    if (is_pack && opts->placement != RLGS_PLACE_HORUS && opts->placement != RLGS_PLACE_YARN)
+        return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
     if (sched == RLGS_SCHED_HORUS && (opts->num_buffer < 0 || opts->num_buffer > 32)) return fail(RLGS_ERR_BAD_ARG, "num_buffer must be 0..32");
     const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
     if (is_dlas) {
@@ -389,7 +391,8 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
     // per-replica working set, 256-byte aligned pieces in this order
     const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J,
                          4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J,
-                         4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * PACK_CAL_W, 4 * J};
+                         4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * PACK_CAL_W, 4 * J,
+                         4 * N, 4 * N, 4 * W, 8 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J};
     size_t per = 0;
     for (size_t v : sz) per += align_up(v, 256);
     unsigned char *slab = nullptr;
@@ -409,6 +412,7 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
         D.imask = (uint32_t *)take(0); D.bmask = (uint32_t *)take(0); D.jflag = (int32_t *)take(0); D.pproc = (int32_t *)take(0);
         D.nstart = (int32_t *)take(0); D.qtick = (int32_t *)take(0); D.cbk = (int32_t *)take(0); D.snext = (int32_t *)take(0);
         D.shead = (int32_t *)take(0); D.sat = (int32_t *)take(0);
+        D.ybusy = (uint32_t *)take(0); D.ykey = (uint32_t *)take(0); D.yever = (uint32_t *)take(0); D.plog = (int2 *)take(0); D.pcnt = (int32_t *)take(0);
         D.cap_units = (int64_t)in->gpu_mem_cap_mib * unit; D.margin_units = 500 * unit;
         D.cap_mib = (double)in->gpu_mem_cap_mib; D.unit_mib = 1.0 / (double)unit;
     }
@@ -485,8 +489,11 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
             PackParams pp = s->pp; pp.tick_budget = budget;
-            if (pp.gandiva) pack_horus_kernel<true><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
-            else pack_horus_kernel<false><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first);
+#define RLGS_LAUNCH_PACK(G, Y) pack_horus_kernel<G, Y><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first)
+            const bool yarn = s->opts.placement == RLGS_PLACE_YARN;
+            if (pp.gandiva) { if (yarn) RLGS_LAUNCH_PACK(true, true); else RLGS_LAUNCH_PACK(true, false); }
+            else { if (yarn) RLGS_LAUNCH_PACK(false, true); else RLGS_LAUNCH_PACK(false, false); }
+#undef RLGS_LAUNCH_PACK
         } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         else

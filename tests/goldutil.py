@@ -34,7 +34,8 @@ def load(name):
     for k, v in list(flags.items()):
         if isinstance(v, str) and v.startswith('@'):
             flags[k] = os.path.join(ROOT, v[1:])
-    out = dict(meta=meta, flags=flags, job=None, cluster=None, schedule=case.get('schedule', 'fifo'), num_buffer=case.get('num_buffer', 5))
+    out = dict(meta=meta, flags=flags, job=None, cluster=None, schedule=case.get('schedule', 'fifo'), num_buffer=case.get('num_buffer', 5),
+               scheme=case.get('scheme', case.get('schedule', 'yarn') if case.get('schedule', 'fifo') != 'fifo' else 'yarn'))
     if os.path.exists(os.path.join(d, 'trace.csv')):
         out['trace'] = os.path.join(d, 'trace.csv')
         out['frame'] = None

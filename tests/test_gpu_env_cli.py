@@ -85,12 +85,12 @@ def test_env_step_by_step_matches_oracle_tape():
     env.close()
 
 
-@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec', 'horus_multi_node', 'horus_ties', 'gandiva_multi_node', 'gandiva_ties'])
+@pytest.mark.parametrize('name', ['kat6', 'multi_node', 'cluster_spec', 'horus_multi_node', 'horus_ties', 'gandiva_multi_node', 'gandiva_ties', 'horusyarn_probe100', 'gandivayarn_multi_node'])
 def test_run_sim_cli_writes_reference_outputs(name, tmp_path):
     g = goldutil.load(name)
     args = []
     if g['schedule'] != 'fifo':
-        args += ['--schedule', g['schedule'], '--scheme', g['schedule'], '--num_buffer', str(g['num_buffer'])]
+        args += ['--schedule', g['schedule'], '--scheme', g['scheme'], '--num_buffer', str(g['num_buffer'])]
     for k, v in g['flags'].items():
         args += ['--' + k, str(v)]
     trace = g['trace']

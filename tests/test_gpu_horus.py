@@ -26,10 +26,10 @@ CASES = {
 }
 
 
-def run_device(df, flags, k, seed=None, schedule='horus', **kw):
+def run_device(df, flags, k, seed=None, schedule='horus', scheme=None, **kw):
     cluster = rl.cluster_from_flags(flags)
     tr = rl.prepare_trace(df, cluster)
-    sim = rl.Simulator(cluster, schedule, schedule, n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, max_ticks=400000, **kw)
+    sim = rl.Simulator(cluster, schedule, scheme or schedule, n_replicas=2, rows=True, num_buffer=k, pack_seed=seed, max_ticks=400000, **kw)
     sim.load_trace(tr)
     sim.run()
     return sim, cluster, tr
@@ -94,7 +94,7 @@ def test_horus_matches_the_reference_golden(name):
     g = goldutil.load(name)
     cluster = rl.cluster_from_flags(g['flags'])
     tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
-    sim = rl.Simulator(cluster, g['schedule'], g['schedule'], n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
+    sim = rl.Simulator(cluster, g['schedule'], g['scheme'], n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
     sim.load_trace(tr)
     sim.run()
     for r in (0, 2):
@@ -106,4 +106,18 @@ def test_horus_matches_the_reference_golden(name):
         if g['job'] is not None:
             assert job == g['job'] and clu == g['cluster']
         assert goldutil.sha(job) == g['meta']['job_sha256'] and goldutil.sha(clu) == g['meta']['cluster_noutil_sha256']
+    sim.close()
+
+
+@pytest.mark.parametrize('schedule', ['horus', 'gandiva'])
+@pytest.mark.parametrize('name', ['probe100_1x4x8', 'gen300_3x2x4', 'gen2000_4x8x8_spread'])
+def test_pack_schedules_over_yarn_match_oracle(name, schedule):
+    """--schedule horus|gandiva --scheme yarn: no utilisation draw anywhere, traces keep their spread."""
+    frame, flags, k = CASES[name]
+    df = tracegen.frame_probe100() if name.startswith('probe') else (tracegen.frame_gen(300, 12, 60) if name.startswith('gen300') else frame())
+    sim, cluster, tr = run_device(df, flags, k, schedule=schedule, scheme='yarn', ticks_per_launch=(0 if name.startswith('probe') else 53))
+    otr = cpu_sim.prepare_trace(df)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, schedule, k, scheme='yarn')
+    for r in range(2):
+        check(sim, cluster, tr, o, otr, r)
     sim.close()

@@ -42,11 +42,8 @@ def test_plugin_registries_keep_the_reference_keys():
         algorithm.resolve('horus+', 'horus+')           # k-means queues: not on the device path
     with pytest.raises(NotImplementedError):
         algorithm.resolve('fifo', 'horus')              # KeyError 'fifo' in the reference (algorithm.py:58)
-    with pytest.raises(NotImplementedError):
-        algorithm.resolve('horus', 'yarn')
+    assert algorithm.resolve('horus', 'yarn')[1].device_id == _ffi.PLACE['yarn'] and algorithm.resolve('gandiva', 'yarn')[0].device_id == _ffi.SCHED['gandiva']
     assert algorithm.resolve('gandiva', 'gandiva')[0].device_id == _ffi.SCHED['gandiva']
-    with pytest.raises(NotImplementedError):
-        algorithm.resolve('gandiva', 'yarn')            # fifo + time slicing over the yarn fit: not on the device path
     with pytest.raises(KeyError):
         algorithm.resolve('lpjf', 'yarn')
     algorithm.scheduling_algorithms['mine'] = lambda *a, **k: (None, None, False)

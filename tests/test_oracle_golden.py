@@ -33,7 +33,7 @@ def test_oracle_matches_reference_big(name):
 def _run_pack(name):
     g = goldutil.load(name)
     tr = cpu_sim.prepare_trace(goldutil.trace_input(g))
-    res = cpu_sim.run_pack(cpu_sim.make_cluster(**g['flags']), tr, g['schedule'], g['num_buffer'])
+    res = cpu_sim.run_pack(cpu_sim.make_cluster(**g['flags']), tr, g['schedule'], g['num_buffer'], scheme=g['scheme'])
     return g, tr, res
 
 
