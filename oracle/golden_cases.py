@@ -174,3 +174,30 @@ CASES = {
     'gandivayarn_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='gandiva', scheme='yarn', big=True),
     'gandivayarn_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='gandiva', scheme='yarn', big=True),
 }
+
+
+def _pack_edges():
+    # zero and equal utilisations (CompareAbleByUtilization.__lt__ returns False for a falsy utilisation, base_factory.py:8-12),
+    # batches of simultaneous arrivals, a task wider than a node (always leaks, node.py:200-221), memory above the cap margin,
+    # used_gpus not divisible by gpu_per_container, long jobs that cross several time slices
+    rows = []
+    t = 0.0
+    for i in range(60):
+        g, gpc = [(1, 1), (2, 1), (2, 2), (4, 2), (3, 2), (8, 4), (8, 1), (6, 3), (4, 4), (12, 4)][i % 10]
+        ua = [0.0, 37.5, 37.5, 80.0, 12.25, 0.0, 55.0, 37.5, 99.0, 20.0][(i * 7) % 10]
+        rows.append(dict(normalized_time=t, minutes=float([3, 40, 7.5, 250, 12, 1, 90, 5, 420, 33][(i * 3) % 10]), used_gpus=float(g), gpu_per_container=gpc,
+                         gpu_utilization_avg=ua, gpu_utilization_max=ua, memory_avg=2e9,
+                         memory_max=int([3e9, 9e9, 15e9, 33.9e9, 5e9, 20e9, 1e9, 12e9, 7e9, 40e9][(i * 9) % 10])))
+        if i % 4 != 3:
+            t += [0.0, 12000.0, 30000.0][i % 3]
+    rows.append(dict(normalized_time=t + 4e6, minutes=2.0, used_gpus=1.0, gpu_per_container=1, gpu_utilization_avg=5.0, gpu_utilization_max=5.0))
+    return tg.frame_rows(rows)
+
+
+CASES.update({
+    'horus_edges': dict(frame=_pack_edges, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus', num_buffer=4),
+    'horus_edges_1node': dict(frame=_pack_edges, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8), schedule='horus', num_buffer=1),
+    'gandiva_edges': dict(frame=_pack_edges, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='gandiva'),
+    'horusyarn_edges': dict(frame=_pack_edges, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus', scheme='yarn', num_buffer=4),
+    'gandivayarn_edges': dict(frame=_pack_edges, flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4), schedule='gandiva', scheme='yarn'),
+})

@@ -121,3 +121,21 @@ def test_pack_schedules_over_yarn_match_oracle(name, schedule):
     for r in range(2):
         check(sim, cluster, tr, o, otr, r)
     sim.close()
+
+
+def test_pack_limits_are_reported():
+    """More than 32 tasks per job is outside the pack kernels' lane-per-task layout: refused at load time, not at run time."""
+    df = tracegen.frame_rows([dict(normalized_time=0, minutes=4, used_gpus=40.0, gpu_per_container=1)])
+    cluster = rl.Cluster(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8)
+    tr = rl.prepare_trace(df, cluster)
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=1)
+    with pytest.raises(_ffi.RlgsError) as e:
+        sim.load_trace(tr)
+    assert e.value.code == _ffi.ERR_UNSUPPORTED and '32' in str(e.value)
+    sim.close()
+    with pytest.raises(_ffi.RlgsError):
+        rl.Simulator(cluster, 'fifo', 'horus')          # KeyError 'fifo' in the reference's score table
+    sim = rl.Simulator(cluster, 'gandiva', 'yarn', n_replicas=1)
+    with pytest.raises(_ffi.RlgsError):
+        sim.run()                                        # no trace
+    sim.close()
