@@ -391,76 +391,109 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
 #ifdef PACK_PROFILE
     st.prof[11] += 1;
 #endif
-    // ---- score the nodes, keep the `cap` best in a heap (one pass per task: the reference re-scores per task)
-    int hlen = 0;
-    if (x.T == 1 && cap == 1) {
-        // a heap of one slot keeps, of the nodes with the lowest score, the one pushed last (a push with an equal or lower
-        // score displaces the resident): arg-min with ties to the higher node id, no sifting needed
-        pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, 0u, pj.util_avg);
-        PACK_T(2);
-        double bs = 1e300; int bn = -1;
-        for (int i = x.lane; i < c.N; i += 32) { const double sc = x.score[i]; if (sc >= 0.0 && sc <= bs) { bs = sc; bn = i; } }
+    // ---- score the nodes (pass 0); nothing can take a task, or a heap without slots: no trial, no side effect
+    pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, 0u, pj.util_avg);
+    PACK_T(2);
+    int n_fit = 0;
+    for (int i = x.lane; i < c.N; i += 32) n_fit += x.score[i] >= 0.0;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const double os = __shfl_xor_sync(RLGS_FULL, bs, o); const int on = __shfl_xor_sync(RLGS_FULL, bn, o);
-            if (on >= 0 && (bn < 0 || os < bs || (os == bs && on > bn))) { bs = os; bn = on; }
-        }
-        if (bn >= 0) { hlen = 1; if (x.lane == 0) { x.hscore[0] = bs; x.hnode[0] = bn; } }
-        PACK_T(3);
-    } else
-    for (int pass = 0; pass < x.T; ++pass) {
-        if (pass == 0 || P.rng_on) pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
-        PACK_T(2);
-        for (int base = 0; base < c.N; base += 32) {
-            const int i = base + x.lane;
-            const double sc = i < c.N ? x.score[i] : -1.0;
-            unsigned fb = __ballot_sync(RLGS_FULL, sc >= 0.0);
-            while (fb) {
-                const int src = __ffs(fb) - 1; fb &= fb - 1;
-                const double s1 = __shfl_sync(RLGS_FULL, sc, src);
-                if (x.lane == 0) pack_h_siftdown(x.hscore, x.hnode, hlen, s1, base + src);     // heappush (only lane 0 touches the heap arrays)
-                hlen += 1;
-                if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(x.hscore, x.hnode, hlen); }   // heappop: drop the worst
-            }
-        }
-        PACK_T(3);
-    }
-    if (hlen == 0) return 0;
-    // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array
-    if (x.lane == 0) for (int a = 1; a < hlen; ++a) {
-        const double vs = x.hscore[a]; const int vn = x.hnode[a];
-        int b = a - 1;
-        while (b >= 0 && x.hscore[b] > vs) { x.hscore[b + 1] = x.hscore[b]; x.hnode[b + 1] = x.hnode[b]; --b; }
-        x.hscore[b + 1] = vs; x.hnode[b + 1] = vn;
-    }
-    __syncwarp();
-    PACK_T(4);
-    // ---- a placement that is bound to fail and cannot leak: every trial walks every rack, maps the same tasks on every node
-    // with capacity and undoes them; all that stays is placed_jobs[job] on those nodes, popped from the home of the trial
-    // (algorithm.py:122-127), so after the last trial only that home lacks the key.  Same end state without the trials.
+    for (int o = 16; o; o >>= 1) n_fit += __shfl_xor_sync(RLGS_FULL, n_fit, o);
+    if (n_fit == 0 || cap <= 0) return 0;
+    // ---- is the placement bound to fail without leaking?  Then every trial walks every rack, maps the same tasks on every
+    // node with capacity and undoes them; all that stays is placed_jobs[job] on those nodes, popped from the home of each
+    // trial in turn (algorithm.py:122-127): afterwards only the home of the LAST trial lacks the key.  Excluded: a job with
+    // leaked entries (re-adding a task over its own leaked entry takes no slot, and undoing the trial removes that entry) and
+    // a job with +5 tasks (the skipped add_task calls would have reset them).
+    uint32_t capbits[4] = {0u, 0u, 0u, 0u};                            // bit b of word w: node (32 * (32 w + b) + lane) has capacity
+    bool doomed;
     {
         int tot = 0; bool leak_any = false;
-        for (int base = 0; base < c.N; base += 32) {
+        for (int base = 0, step = 0; base < c.N; base += 32, ++step) {
             const int i = base + x.lane;
             bool lk = false;
             const int cp = i < c.N ? pack_node_capacity(D, c, x, i, lk) : 0;
             tot += cp; leak_any |= lk;
-            if (i < c.N) x.score[i] = cp > 0 ? 1.0 : 0.0;              // the scores are spent: reuse the array as the node set
+            if (cp > 0) capbits[step >> 5] |= 1u << (step & 31);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(RLGS_FULL, tot, o);
         leak_any = __any_sync(RLGS_FULL, leak_any);
-        __syncwarp();
-        // (a job with leaked entries is excluded: re-adding a task over its own leaked entry takes no slot, and undoing the
-        // trial removes the leaked entry as well)
-        // (and a job with +5 tasks: the skipped add_task calls would have reset them)
-        if (tot < x.T && !leak_any && D.jflag[x.job] == 0 && x.bump == 0) {
-            for (int i = 0; i < c.N; ++i) if (x.score[i] > 0.0) pack_pj_set(D, st, i, x.job);
-            pack_pj_pop(D, st, x.hnode[hlen - 1], x.job);
-            PACK_T(5);
-            return 0;
-        }
+        doomed = tot < x.T && !leak_any && D.jflag[x.job] == 0 && x.bump == 0;
     }
+    int home_last = -1;
+    if (doomed && !P.rng_on && c.N <= 512) {
+        // Only the home of the last trial matters = the last element of the sorted heap.  Without draws every node is pushed T
+        // times with one score; the heap keeps the k = min(cap, T * n_fit) lowest entries, so its largest score is the score of the
+        // node whose copies cover rank k.  If no other node shares that score the last element is that node, whatever the order
+        // of the sifts; otherwise the heap is simulated below.
+        const int k = min(cap, x.T * n_fit);
+        int found = -1;
+        for (int i = x.lane; i < c.N; i += 32) {
+            const double si = x.score[i];
+            if (si < 0.0) continue;
+            int lt = 0, eq = 0;
+            for (int j = 0; j < c.N; ++j) { const double sj = x.score[j]; lt += (sj >= 0.0) & (sj < si); eq += sj == si; }
+            if (x.T * lt < k && k <= x.T * (lt + eq) && eq == 1) found = i;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) found = max(found, __shfl_xor_sync(RLGS_FULL, found, o));
+        home_last = found;
+#ifdef PACK_PROFILE
+        st.prof[4] += found >= 0;
+#endif
+    }
+    // ---- keep the `cap` best nodes in a heap (one pass per task: the reference re-scores per task)
+    int hlen = 0;
+    if (home_last < 0) {
+        if (x.T == 1 && cap == 1) {
+            // a heap of one slot keeps, of the nodes with the lowest score, the one pushed last (a push with an equal or lower
+            // score displaces the resident): arg-min with ties to the higher node id, no sifting needed
+            double bs = 1e300; int bn = -1;
+            for (int i = x.lane; i < c.N; i += 32) { const double sc = x.score[i]; if (sc >= 0.0 && sc <= bs) { bs = sc; bn = i; } }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double os = __shfl_xor_sync(RLGS_FULL, bs, o); const int on = __shfl_xor_sync(RLGS_FULL, bn, o);
+                if (on >= 0 && (bn < 0 || os < bs || (os == bs && on > bn))) { bs = os; bn = on; }
+            }
+            if (bn >= 0) { hlen = 1; if (x.lane == 0) { x.hscore[0] = bs; x.hnode[0] = bn; } }
+        } else
+        for (int pass = 0; pass < x.T; ++pass) {
+            if (pass > 0 && P.rng_on) pack_score_nodes<GANDIVA>(D, c, P, x, replica, (uint32_t)st.d, attempt, (uint32_t)pass, pj.util_avg);
+            for (int base = 0; base < c.N; base += 32) {
+                const int i = base + x.lane;
+                const double sc = i < c.N ? x.score[i] : -1.0;
+                unsigned fb = __ballot_sync(RLGS_FULL, sc >= 0.0);
+                while (fb) {
+                    const int src = __ffs(fb) - 1; fb &= fb - 1;
+                    const double s1 = __shfl_sync(RLGS_FULL, sc, src);
+                    if (x.lane == 0) pack_h_siftdown(x.hscore, x.hnode, hlen, s1, base + src);     // heappush (only lane 0 touches the heap arrays)
+                    hlen += 1;
+                    if (hlen > cap) { hlen -= 1; if (x.lane == 0) pack_h_pop(x.hscore, x.hnode, hlen); }   // heappop: drop the worst
+                }
+            }
+        }
+        PACK_T(3);
+        if (hlen == 0) return 0;
+        // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array
+        if (x.lane == 0) for (int a = 1; a < hlen; ++a) {
+            const double vs = x.hscore[a]; const int vn = x.hnode[a];
+            int b = a - 1;
+            while (b >= 0 && x.hscore[b] > vs) { x.hscore[b + 1] = x.hscore[b]; x.hnode[b + 1] = x.hnode[b]; --b; }
+            x.hscore[b + 1] = vs; x.hnode[b + 1] = vn;
+        }
+        __syncwarp();
+        if (doomed) home_last = x.hnode[hlen - 1];
+    }
+    if (doomed) {                                                      // same end state without the trials
+        for (int base = 0, step = 0; base < c.N; base += 32, ++step) {
+            unsigned sb = __ballot_sync(RLGS_FULL, (capbits[step >> 5] >> (step & 31)) & 1u);
+            while (sb) { const int node = base + __ffs(sb) - 1; sb &= sb - 1; pack_pj_set(D, st, node, x.job); }
+        }
+        pack_pj_pop(D, st, home_last, x.job);
+        PACK_T(5);
+        return 0;
+    }
+    PACK_T(4);
     // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
     int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
     for (int e = 0; e < hlen; ++e) {
