@@ -496,7 +496,11 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
     PACK_T(4);
     // ---- one trial placement per heap entry; lane t keeps the node of task t of the current / best plan
     int best_nn = RLGS_NEVER, best_map = -1, cur_map = -1;
-    for (int e = 0; e < hlen; ++e) {
+    // one task on one device and a single candidate: the trial takes the first fitting device of that node (its score says
+    // there is one), is undone, and the real placement repeats it; placed_jobs is set, popped and set again.  Skip the rehearsal.
+    const bool rehearsed = !(x.T == 1 && x.gpc == 1 && hlen == 1);
+    if (!rehearsed) { best_nn = 1; best_map = x.hnode[0]; }
+    for (int e = 0; rehearsed && e < hlen; ++e) {
         const int home = x.hnode[e];
         int cnt = 0;
         for (int t = 0; t < x.T; ++t) {
