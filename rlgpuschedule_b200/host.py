@@ -137,6 +137,9 @@ class Scheduler(object):
                 extra = dict(get_duration=trace.duration + 5.0 * (sim.job_plane(0, _ffi.PLANE_AUX) == 1),
                              jct=sim.job_plane(0, _ffi.PLANE_PREEMPT))
             self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt'], sim.durations(0) if net else None, extra))
+            if getattr(flags, 'columnar', False):
+                self.log_manager.write_columnar(sim.rows(0), cluster, trace, j, trace.mem_shift, get_duration=extra.get('get_duration'),
+                                                jct=extra.get('jct'), util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
         else:
             from . import _ffi
             j = sim.jobs(0)

@@ -179,6 +179,35 @@ class LogManager(object):
         with open(self.log_cluster, 'a+', newline='') as f:
             f.write(format_cluster_csv(rows, cluster, mem_shift, with_header=False, util_mode=util_mode, seed=seed))
 
+    def write_columnar(self, rows, cluster, trace, jobs, mem_shift, get_duration=None, jct=None, util_mode='mean', seed=None):
+        """cluster.parquet / job.parquet next to the CSVs: the same columns as typed arrays (with the
+        simulation on the device, rendering ~10^5 float rows as text dominates a run).  Float columns carry the same float64
+        values the CSV prints; avg_gpu_utilization is the float, not the reference's one-element-array repr."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        c = finish_rows(rows, cluster, mem_shift, util_mode, seed)
+        n = c['n']
+        busy = np.asarray(c['busy_gpus'])
+        mu = rows['util_mu_sum'].astype(np.float64) / 512.0 / cluster.num_gpus
+        util = mu if util_mode != 'sample' else np.array([float(u.strip('[]')) for u in c['util']])
+        cl = pa.table({'delta': np.arange(1, n + 1, dtype=np.int64), 'num_idle_nodes': np.asarray(c['idle_nodes'], np.int32),
+                       'num_busy_nodes': np.asarray(c['busy_nodes'], np.int32), 'num_busy_gpus': busy.astype(np.int32),
+                       'num_idle_gpus': np.asarray(c['idle_gpus'], np.int32), 'avg_gpu_utilization': util,
+                       'avg_gpu_memory_allocated': np.asarray(c['mem'], np.float64), 'avg_pending_time': np.asarray(c['avg_pending'], np.float64),
+                       'median_pending_time': np.asarray(c['median'], np.float64), 'max_pending_time': rows['max_pending'].astype(np.float64),
+                       'num_running_jobs': rows['running'].astype(np.int32), 'num_queuing_jobs': rows['queued'].astype(np.int32),
+                       'num_finish_jobs': rows['finished'].astype(np.int32)})
+        pq.write_table(cl, os.path.join(self.log_path, 'cluster.parquet'))
+        fo = np.asarray(jobs['finish_order'], dtype=np.int64)
+        st, en = np.asarray(jobs['start'])[fo], np.asarray(jobs['end'])[fo]
+        dur = trace.duration[fo]
+        act = dur if get_duration is None else np.asarray(get_duration)[fo]
+        jb = pa.table({'job_id': trace.label[fo].astype(np.int64), 'num_gpu': trace.used_gpus[fo], 'submit_time': trace.nt[fo].astype(np.int64),
+                       'start_time': st.astype(np.int64), 'end_time': en.astype(np.int64), 'original_duration': dur,
+                       'actual_duration': np.maximum(act, 0.0), 'jct': ((en - st) if jct is None else np.asarray(jct)[fo]).astype(np.int64),
+                       'preempt': np.asarray(jobs['preempt'])[fo].astype(np.int32)})
+        pq.write_table(jb, os.path.join(self.log_path, 'job.parquet'))
+
     def write_legacy(self, rows, cluster, trace, jobs, pending, resume, count_scheme):
         """cluster.csv / job.csv of the event-driven schedules (LOG.checkpoint log.py:137-258, LOG.job_complete
         log.py:316-330).  rows: _ffi.ROW_DTYPE with the legacy field mapping documented in include/rlgs.h."""

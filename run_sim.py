@@ -43,6 +43,7 @@ flags.DEFINE_string('queue_limit', '30,60,150', 'dlas-gpu: MLFQ demotion thresho
 flags.DEFINE_string('util_mode', 'sample', "avg_gpu_utilization column: 'sample' (seedable normal draw) or 'mean'")
 flags.DEFINE_integer('seed', None, 'seed of the utilisation draws: the avg_gpu_utilization column and the horus score (the reference draws unseeded)')
 flags.DEFINE_integer('device', 0, 'CUDA device ordinal')
+flags.DEFINE_boolean('columnar', False, 'also write cluster.parquet / job.parquet (typed columns, no float formatting)')
 flags.DEFINE_version('0.1')
 
 FLAGS = flags.FLAGS

@@ -131,3 +131,27 @@ def test_run_sim_cli_legacy_schedules(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', trace, '--schedule', 'horus+', '--scheme', 'horus+'],
                        cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode != 0 and 'not implemented by the device path' in r.stderr
+
+
+def test_run_sim_cli_columnar_output_matches_the_csv(tmp_path):
+    """--columnar: cluster.parquet / job.parquet carry the values the CSVs print (typed, no text formatting)."""
+    import pandas as pd
+    import pyarrow.parquet as pq
+    g = goldutil.load('multi_node')
+    args = []
+    for k, v in g['flags'].items():
+        args += ['--' + k, str(v)]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'run_sim.py'), '--trace_file', g['trace'], '--log_path', 'col', '--util_mode', 'mean',
+                        '--columnar', 'True'] + args, cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = tmp_path / 'log' / 'col'
+    out = out / sorted(os.listdir(out))[-1]
+    job = pq.read_table(out / 'job.parquet').to_pandas()
+    ref = pd.read_csv(out / 'job.csv')
+    for col in ('job_id', 'num_gpu', 'submit_time', 'start_time', 'end_time', 'original_duration', 'actual_duration', 'jct', 'preempt'):
+        assert np.array_equal(job[col].to_numpy().astype(np.float64), ref[col].to_numpy().astype(np.float64)), col
+    clu = pq.read_table(out / 'cluster.parquet').to_pandas()
+    refc = pd.read_csv(out / 'cluster.csv')
+    for col in ('delta', 'num_idle_nodes', 'num_busy_gpus', 'avg_gpu_memory_allocated', 'avg_pending_time', 'max_pending_time', 'num_finish_jobs'):
+        assert np.array_equal(clu[col].to_numpy().astype(np.float64), refc[col].to_numpy().astype(np.float64)), col
+    assert np.array_equal(np.isnan(clu['median_pending_time']), np.isnan(refc['median_pending_time']))
