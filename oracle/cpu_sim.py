@@ -73,7 +73,8 @@ def prepare_trace(trace, scale_factor=0.5):
                 gpc=np.ascontiguousarray(df['gpu_per_container'].to_numpy(dtype=np.int32)),
                 mem_mib=np.ascontiguousarray(df['memory_max'].to_numpy(dtype=np.float64) / 1024 / 1024),
                 util_avg=np.ascontiguousarray(df['gpu_utilization_avg'].to_numpy(dtype=np.float64)),
-                util_max=np.ascontiguousarray(df['gpu_utilization_max'].to_numpy(dtype=np.float64)))
+                util_max=np.ascontiguousarray(df['gpu_utilization_max'].to_numpy(dtype=np.float64)),
+                mem_avg_mib=np.ascontiguousarray(df['memory_avg'].to_numpy(dtype=np.float64) / 1024 / 1024))
 
 
 def _p(a, t):
@@ -119,7 +120,7 @@ def run_fifo_yarn(cluster, tr, rows_cap=None, netcost=None):
     return out
 
 
-def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, rows_cap=None, scheme=None):
+def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, rows_cap=None, scheme=None, num_queue=0, inject_seed=0):
     """Restated `--schedule horus|gandiva` with horus_placement (oracle_pack).  seed=None pins every utilisation draw
     to its mean (the reference's behaviour on traces with gpu_utilization_max == gpu_utilization_avg: PINNED); a seed
     enables the build-defined counter-based draw (UNPINNED)."""
@@ -138,7 +139,8 @@ def run_pack(cluster, tr, schedule='horus', num_buffer=5, seed=None, replica=0, 
                            C.c_int32(1 if schedule == 'gandiva' else 0), C.c_int32(1 if scheme == 'yarn' else 0), C.c_int32(num_buffer),
                            C.c_int32(0 if seed is None else 1), C.c_uint32(seed or 0), C.c_uint32(replica),
                            _p(fin, C.c_int32), _p(st, C.c_int32), _p(en, C.c_int32), C.byref(nfin), _p(dur, C.c_double),
-                           _p(jct, C.c_int32), _p(starts, C.c_int32), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
+                           _p(jct, C.c_int32), _p(starts, C.c_int32),
+                           C.c_int32(num_queue if schedule == 'horus+' else 0), _p(tr['mem_avg_mib'], C.c_double), C.c_uint32(inject_seed), rows.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(nticks), _p(counters, C.c_int64))
         if rc == -1:
             cap *= 4
             continue

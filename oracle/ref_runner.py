@@ -23,6 +23,7 @@ import logging, runpy, sys
 logging.disable(logging.CRITICAL)
 sys.path.insert(0, {ref!r})
 sys.argv = ['run_sim.py'] + {argv!r}
+{inject}
 try:
     runpy.run_path({ref!r} + '/run_sim.py', run_name='__main__')
 except SystemExit:
@@ -34,8 +35,40 @@ def available():
     return os.path.exists(os.path.join(REF, 'run_sim.py'))
 
 
-def run_reference(trace_csv, workdir=None, schedule='fifo', scheme='yarn', **flags):
-    """Returns dict(job_csv=str, cluster_csv=str, wall_s=float, out_dir=str)."""
+# Injected randomness for the k-means of horus+ (core/jobs/utils.py:39,60): the reference's code runs unmodified, but
+# numpy's module-level randint / choice are replaced by counter-based draws (call number, element) that oracle/cpu_sim.c
+# reproduces.  Everything else in np.random stays as it is.
+_INJECT = r'''
+import numpy as _np
+_SEED = {seed}
+_calls = [0]
+def _mix(z):
+    z &= 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+def _draw(call, elem, n):
+    h = _mix(((_SEED << 32) | (call & 0xFFFFFFFF)) + 0x9E3779B97F4A7C15)
+    h = _mix(h ^ elem)
+    return int((h >> 11) % n)
+def _randint(low, high=None, size=None, dtype=int):
+    assert high is None
+    c = _calls[0]; _calls[0] += 1
+    if size is None:
+        return _draw(c, 0, low)
+    return _np.array([_draw(c, i, low) for i in range(size)])
+def _choice(a, size=None, replace=True, p=None):
+    assert size is None and p is None
+    c = _calls[0]; _calls[0] += 1
+    return _draw(c, 0, a)
+_np.random.randint = _randint
+_np.random.choice = _choice
+'''
+
+
+def run_reference(trace_csv, workdir=None, schedule='fifo', scheme='yarn', inject_seed=None, **flags):
+    """Returns dict(job_csv=str, cluster_csv=str, wall_s=float, out_dir=str).  inject_seed: replace np.random.randint /
+    np.random.choice by the counter-based draws above (horus+ only)."""
     if not available():
         raise RuntimeError('reference not mounted at %s' % REF)
     workdir = workdir or tempfile.mkdtemp(prefix='rlgs_ref_')
@@ -43,7 +76,7 @@ def run_reference(trace_csv, workdir=None, schedule='fifo', scheme='yarn', **fla
             '--scheme', scheme, '--log_path', 'oracle']
     for k, v in flags.items():
         argv += ['--' + k, str(v)]
-    code = _DRIVER.format(ref=REF, argv=argv)
+    code = _DRIVER.format(ref=REF, argv=argv, inject=_INJECT.format(seed=int(inject_seed)) if inject_seed is not None else '')
     t0 = time.time()
     p = subprocess.run([sys.executable, '-c', code], cwd=workdir, stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True)

@@ -9,14 +9,14 @@ def zero_spread(df):
     df = df.copy(); df['gpu_utilization_max'] = df['gpu_utilization_avg']; return df
 
 
-def compare(df, flags, schedule, num_buffer=5, verbose=True, scheme=None):
+def compare(df, flags, schedule, num_buffer=5, verbose=True, scheme=None, num_queue=1, inject_seed=None):
     d = tempfile.mkdtemp(); p = os.path.join(d, 't.csv'); tracegen.write(df, p)
     t0 = time.time()
-    r = ref_runner.run_reference(p, schedule=schedule, scheme=scheme or schedule, num_buffer=num_buffer, **flags)
+    r = ref_runner.run_reference(p, schedule=schedule, scheme=scheme or schedule, num_buffer=num_buffer, num_queue=num_queue, inject_seed=inject_seed, **flags)
     tr = cpu_sim.prepare_trace(p)
     t1 = time.time()
     try:
-        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), tr, schedule, num_buffer, scheme=scheme)
+        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), tr, schedule, num_buffer, scheme=scheme, num_queue=num_queue, inject_seed=inject_seed or 0)
     except RuntimeError as e:
         print('oracle raised', e, '| ref rc', r['returncode'], r['stderr'][-300:]); return r['returncode'] != 0
     t2 = time.time()
