@@ -3,9 +3,9 @@
 (execute.py:5-55 there): every (placement, schedule, queues, look-ahead) combination is run `--repeats`
 times as its own child process and logs under log/thesis_fitted_<k>_nodes_p_s<N>_job_<trace>/<scheme>_<schedule>/.
 
-Default sweep = schedules this package runs on the GPU (horus, gandiva, fifo of the reference's list, plus sjf and
-dlas-gpu).  `--reference-sweep` replays the reference's own list (horus+ x3, horus, gandiva, yarn/fifo): horus+
-(k-means queues) is not implemented on the device path, so those children stop with a NotImplementedError.
+Default sweep = one run of every schedule family of the device path (the reference's horus+ / horus / gandiva / fifo plus
+sjf and dlas-gpu).  `--reference-sweep` replays the reference's own list (horus+ with 3, 4, 5 queues, horus, gandiva,
+yarn/fifo, each with look-ahead 15, 15, 15, 1, 1, 1).
 """
 import argparse
 import os
@@ -16,7 +16,7 @@ from collections import namedtuple
 Run = namedtuple('Run', 'scheme schedule num_queue num_buffer')
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-DEVICE_SWEEP = [Run('horus', 'horus', 1, 15), Run('horus', 'horus', 1, 1), Run('gandiva', 'gandiva', 1, 1), Run('yarn', 'fifo', 1, 1),
+DEVICE_SWEEP = [Run('horus+', 'horus+', 3, 15), Run('horus', 'horus', 1, 15), Run('horus', 'horus', 1, 1), Run('gandiva', 'gandiva', 1, 1), Run('yarn', 'fifo', 1, 1),
                 Run('yarn', 'sjf', 1, 1), Run('count', 'dlas-gpu', 4, 1)]
 REFERENCE_SWEEP = [Run(s, s, q, b) for s, q in (('horus+', 3), ('horus+', 4), ('horus+', 5), ('horus', 1), ('gandiva', 1))
                    for b in (15, 15, 15, 1, 1, 1)] + [Run('yarn', 'fifo', 1, b) for b in (15, 15, 15, 1, 1, 1)]

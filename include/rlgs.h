@@ -44,8 +44,11 @@ enum { RLGS_SCHED_FIFO = 0, RLGS_SCHED_SJF = 1, RLGS_SCHED_DLAS_GPU = 2,
        RLGS_SCHED_SHORTEST_GPU = 5, /* ... shortest remaining GPU-time first */
        RLGS_SCHED_HORUS = 6,        /* schedule_horus, core/scheduling/algorithm.py:204-240: utilisation-ordered heap queue
                                        (core/jobs/base_factory.py:1-12) + look-ahead window of opts.num_buffer jobs */
-       RLGS_SCHED_GANDIVA = 7       /* algorithm.py:292-298: schedule_fifo on a plain list + gandiva_score (horus.py:6-25) +
-                                       time_slice_check (algorithm.py:420-440): preempt every 100 processed ticks */ };
+       RLGS_SCHED_GANDIVA = 7,      /* algorithm.py:292-298: schedule_fifo on a plain list + gandiva_score (horus.py:6-25) +
+                                       time_slice_check (algorithm.py:420-440): preempt every 100 processed ticks */
+       RLGS_SCHED_HORUS_PLUS = 8    /* schedule_horus_plus, algorithm.py:242-290: opts.num_queue utilisation heaps refilled every tick by
+                                       a k-means of the queued jobs (core/jobs/utils.py:36-67), next job from the queue with the most
+                                       credit (job_queue_manager.py:103-127); the k-means draws are counter-based (opts.pack_seed) */ };
 /* --scheme (run_sim.py:27-37); yarn = core/scheduling/algorithm.py:28-32,301-417,
  * count = resource counting only (infra/cluster.py free_gpu accounting used by run_sim.py:808-823) */
 enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1,
@@ -79,7 +82,7 @@ typedef struct {
     int32_t n_streams;     /* replica groups, each on its own CUDA stream (kernel + result copies); 0 = auto */
     int32_t ticks_per_launch; /* 0 = run to completion in one launch; >0 = bounded launches (state is saved
                                  to / restored from HBM between launches) */
-    int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES */
+    int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES; horus+: number of job queues */
     int32_t enable_network_costs; /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
     int32_t fetch_jobs;    /* 1 = copy the per-job tables to the host inside rlgs_run as well */
     int32_t num_buffer;    /* horus: look-ahead window, --num_buffer (run_sim.py:76); 0 = the reference default 5 */
@@ -177,6 +180,10 @@ typedef struct {
     const int32_t *heap_cap;    /* floor(used_gpus): size of horus_placement's node heap (algorithm.py:64) */
     int32_t mem_shift;
     int32_t gpu_mem_cap_mib;    /* --gpu_memory_capacity * 1024 (infra/infrastructure.py:36) */
+    /* RLGS_SCHED_HORUS_PLUS only (k-means features, core/jobs/utils.py:4-22); NULL otherwise */
+    const double *util_max;     /* gpu_utilization_max */
+    const double *mem_avg_mib;  /* memory_avg in MiB */
+    const double *used_gpus;    /* used_gpus (float) */
 } rlgs_pack_inputs;
 int32_t rlgs_load_pack_inputs(rlgs_sim *sim, int32_t first_replica, int32_t n_replicas, const rlgs_pack_inputs *in, int32_t n);
 

@@ -201,3 +201,16 @@ CASES.update({
     'horusyarn_edges': dict(frame=_pack_edges, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus', scheme='yarn', num_buffer=4),
     'gandivayarn_edges': dict(frame=_pack_edges, flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4), schedule='gandiva', scheme='yarn'),
 })
+
+
+# --schedule horus+ (k-means queues): the reference is run with injected k-means draws (oracle/ref_runner.py _INJECT, seed below)
+CASES.update({
+    'horusplus_probe100_k3': dict(frame=_zs(tg.frame_probe100), flags=C148, schedule='horus+', num_queue=3, inject_seed=1),
+    'horusplus_racks_k2': dict(frame=_zs(tg.frame_probe100), flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=8), schedule='horus+', num_queue=2, inject_seed=5, num_buffer=15),
+    'horusplus_ties_k3': dict(frame=_zs(_ties), flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='horus+', num_queue=3, inject_seed=9),
+    'horusplus_edges_k3': dict(frame=_pack_edges, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='horus+', num_queue=3, inject_seed=4, num_buffer=4),
+    'horusplus_gpu_cap16_k5': dict(frame=_zs(lambda: tg.frame_gen(120, 7, 150)), flags=dict(num_switch=1, num_node_p_switch=8, num_gpu_p_node=8, gpu_memory_capacity=12), schedule='horus+', num_queue=5, inject_seed=7),
+    'horusplus_dense_k3': dict(frame=_zs(lambda: tg.frame_gen(300, 5, 30)), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus+', num_queue=3, inject_seed=1, num_buffer=15, big=True),
+    'horusplusyarn_probe100_k3': dict(frame=tg.frame_probe100, flags=C148, schedule='horus+', scheme='yarn', num_queue=3, inject_seed=2),
+    'horusplusyarn_dense_k4': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus+', scheme='yarn', num_queue=4, inject_seed=3, big=True),
+})

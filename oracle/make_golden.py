@@ -47,13 +47,15 @@ def make(name):
     sched = case.get('schedule', 'fifo')
     if sched != 'fifo':   # the pack placements are keyed by the schedule name (schedule.py:47)
         flags.update(schedule=sched, scheme=case.get('scheme', sched), num_buffer=case.get('num_buffer', 5))
+    if sched == 'horus+':   # k-means queues: the draws of np.random.randint / choice are injected (ref_runner._INJECT)
+        flags.update(num_queue=case['num_queue'], inject_seed=case['inject_seed'])
     res = ref_runner.run_reference(trace, workdir=work, **flags)
     job, clu = res['job_csv'], res['cluster_csv']
     if job is None or clu is None:
         raise RuntimeError('%s: reference failed: %s' % (name, res['stderr']))
     noutil = ref_runner.strip_util_column(clu)
     trace_bytes = open(trace, 'rb').read()
-    meta = dict(case=name, flags=case['flags'], schedule=sched, scheme=case.get('scheme', sched if sched != 'fifo' else 'yarn'), num_buffer=case.get('num_buffer', 5), trace_sha256=sha(trace_bytes),
+    meta = dict(case=name, flags=case['flags'], schedule=sched, scheme=case.get('scheme', sched if sched != 'fifo' else 'yarn'), num_buffer=case.get('num_buffer', 5), num_queue=case.get('num_queue', 1), inject_seed=case.get('inject_seed'), trace_sha256=sha(trace_bytes),
                 job_sha256=sha(job), cluster_noutil_sha256=sha(noutil),
                 n_job_rows=job.count('\r\n') - 1, n_ticks=clu.count('\r\n') - 1,
                 reference_wall_s=round(res['wall_s'], 2), reference_returncode=res['returncode'],

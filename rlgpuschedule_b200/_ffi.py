@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get('RLGS_LIB') or os.path.join(HERE, 'librlgs.so')   # RLGS_LIB: development override
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
-SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2, 'dlas': 3, 'shortest': 4, 'shortest-gpu': 5, 'horus': 6, 'gandiva': 7}
+SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2, 'dlas': 3, 'shortest': 4, 'shortest-gpu': 5, 'horus': 6, 'gandiva': 7, 'horus+': 8}
 PLACE = {'yarn': 0, 'count': 1, 'horus': 2, 'horus+': 2, 'gandiva': 2}   # the three pack names share horus_placement (algorithm.py:182-187)
 ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
 MAX_QUEUES = 8
@@ -36,7 +36,8 @@ class Opts(C.Structure):
 
 class PackInputs(C.Structure):
     _fields_ = [('util_avg', C.POINTER(C.c_double)), ('util_sd', C.POINTER(C.c_double)), ('task_mem', C.POINTER(C.c_int64)),
-                ('heap_cap', C.POINTER(C.c_int32)), ('mem_shift', C.c_int32), ('gpu_mem_cap_mib', C.c_int32)]
+                ('heap_cap', C.POINTER(C.c_int32)), ('mem_shift', C.c_int32), ('gpu_mem_cap_mib', C.c_int32),
+                ('util_max', C.POINTER(C.c_double)), ('mem_avg_mib', C.POINTER(C.c_double)), ('used_gpus', C.POINTER(C.c_double))]
 
 
 class NetcostInputs(C.Structure):

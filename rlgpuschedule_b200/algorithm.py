@@ -9,10 +9,10 @@
 
 The entries the hot path implements are DevicePolicy objects: Scheduler.start() hands their integer
 id to librlgs and the whole tick / event loop runs on the GPU.  `horus` (schedule_horus + horus_placement
-with horus_score) and `gandiva` (schedule_fifo + gandiva_score + the time-slice plugin) are among them; the
-reference's remaining key (horus+: k-means queues with an unseeded random init) is registered as
-HostOnlyPolicy so the key set is unchanged and selecting it fails loudly instead of silently running
-something else.
+with horus_score), `horus+` (k-means queues + credit pick) and `gandiva` (schedule_fifo + gandiva_score + the
+time-slice plugin) are among them, so every key of the reference's tables runs on the device.  HostOnlyPolicy
+remains for keys that have no device form (none at present): selecting one fails loudly instead of silently
+running something else.
 Users may register their own entries; only DevicePolicy entries can be executed by this package.
 """
 from . import _ffi
@@ -53,7 +53,7 @@ scheduling_algorithms = {
     'shortest': DevicePolicy('shortest', 'schedule', _ffi.SCHED['shortest'], 'run_sim.py:299-431 (dead code, restated)'),
     'shortest-gpu': DevicePolicy('shortest-gpu', 'schedule', _ffi.SCHED['shortest-gpu'], 'run_sim.py:299-431 with gputime (dead code, restated)'),
     'horus': DevicePolicy('horus', 'schedule', _ffi.SCHED['horus'], 'core/scheduling/algorithm.py:204-240'),
-    'horus+': HostOnlyPolicy('horus+', 'schedule', 'core/scheduling/algorithm.py:242-290'),
+    'horus+': DevicePolicy('horus+', 'schedule', _ffi.SCHED['horus+'], 'core/scheduling/algorithm.py:242-290 + core/jobs/utils.py:36-67 (k-means draws are counter-based)'),
     'gandiva': DevicePolicy('gandiva', 'schedule', _ffi.SCHED['gandiva'], 'core/scheduling/algorithm.py:292-298 (schedule_fifo) + time_slice_check :420-440'),
 }
 
@@ -73,7 +73,7 @@ plugin_algorithms = {
 
 score_fn = {
     'horus': DevicePolicy('horus', 'score', 0, 'core/scheduling/horus.py:28-56'),
-    'horus+': HostOnlyPolicy('horus+', 'score', 'core/scheduling/horus.py:28-56'),
+    'horus+': DevicePolicy('horus+', 'score', 0, 'core/scheduling/horus.py:28-56'),
     'gandiva': DevicePolicy('gandiva', 'score', 1, 'core/scheduling/horus.py:6-25'),
 }
 
@@ -89,7 +89,8 @@ def resolve(schedule, scheme):
                 p()  # raises NotImplementedError with the reference location
             raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
     packs = place.device_id == _ffi.PLACE['horus']
-    if (packs and schedule not in ('horus', 'gandiva')) or (schedule in ('horus', 'gandiva') and not packs and scheme != 'yarn'):
+    pack_schedules = ('horus', 'horus+', 'gandiva')
+    if (packs and schedule not in pack_schedules) or (schedule in pack_schedules and not packs and scheme != 'yarn'):
         # fifo + horus: KeyError 'fifo' in the reference's score table (algorithm.py:58)
         raise NotImplementedError('schedule %r with scheme %r is not implemented by the device path' % (schedule, scheme))
     post = plugin_algorithms.get(schedule, None)

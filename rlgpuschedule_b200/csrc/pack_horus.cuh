@@ -36,9 +36,16 @@ struct PackJob {              // per job of a trace, shared by the replicas that
     int32_t task_off;         // first entry of the job in tnode[]
 };
 
+#define PACK_MAX_Q 8
+struct PlusFeat {             // horus+ k-means features of a job (core/jobs/utils.py:4-22), float64 like the reference
+    double f[7];              // len(tasks), gpu_utilization_avg, gpu_per_worker, gpus, gpu_utilization_max, gpu_mem_avg, gpu_mem_max (MiB)
+    double tdist;             // transform_to_dist: their left-to-right sum
+};
+
 struct PackDesc {
     const rlgs_job *trace;
     const PackJob *pj;
+    const PlusFeat *feat;     // horus+ only
     int32_t *planes[6];       // start (of the last run), end, finish_order, 1 = get_duration() is duration + 5, ticks processed (jct), number of starts
     int32_t *units;           // [N] tasks charged to the node (cpu = 12u, mem = 60u)
     int32_t *ntk;             // [N] len(placed_tasks) << 16 | len(running_tasks)
@@ -66,6 +73,9 @@ struct PackDesc {
     uint32_t *ybusy, *ykey, *yever;   // [N], [N], [ceil(N/32)]
     int2 *plog;               // [sum of tasks] (node | tasks << 16, device mask) entries of job j at plog[task_off ..]
     int32_t *pcnt;            // [J] entries of the job's placement
+    // horus+: queue q is the heap (qkey, qjob) + q * J; the k-means works on kjobs / kassign / kold / ktmp
+    int32_t *kjobs, *kassign, *kold;  // [J]
+    double *ktmp;             // [J]
     int64_t cap_units, margin_units;  // gpu memory capacity and the 500 MiB margin in units
     double cap_mib, unit_mib; // capacity in MiB, 2^-shift
     int32_t J, W;
@@ -76,6 +86,8 @@ struct PackState {
     int32_t n_free_nodes, idle_nodes, busy_gpus, start_seq;
     int32_t lhead, ltail, mlo, mrank;
     int32_t done, status, max_q, max_r, r_pre, preempts;   // r_pre: running jobs before the post-tick plugin (schedule.py:195)
+    int32_t pqn[PACK_MAX_Q];  // horus+: length of each queue
+    uint32_t kcalls, pad1;    // horus+: np.random.randint / choice calls so far
     int64_t mem_sum, util_mu_sum, util_var_sum, sum_arr, sum_jct, sumQ, sumR, events;
 #ifdef PACK_PROFILE
     int64_t prof[12];   // cycles: 0 arrivals, 1 queue pops, 2 score, 3 heap, 4 sort, 5 trials, 6 real place, 7 re-push, 8 start, 9 finish, 10 row, 11 attempts
@@ -96,6 +108,8 @@ struct PackParams {
     int32_t nodes_per_rack, racks;
     int32_t tick_budget;
     int32_t gandiva;          // 1: --schedule gandiva = fifo queue + gandiva_score + time slicing (algorithm.py:292-298,420-444)
+    int32_t plus_k;           // horus+: number of queues (--num_queue), 0 otherwise
+    uint32_t plus_seed;       // horus+: seed of the k-means draws
     int64_t max_ticks;
 };
 #define PACK_QUANTA 100       // time_slice_check, algorithm.py:427
@@ -124,6 +138,18 @@ __device__ __forceinline__ void pack_q_siftdown(const PackDesc &D, int pos, doub
         D.qkey[pos] = pk; D.qjob[pos] = D.qjob[pp]; pos = pp;
     }
     D.qkey[pos] = key; D.qjob[pos] = job;
+}
+// the same two operations on queue `qi` of horus+ (arrays offset by qi * J)
+__device__ __forceinline__ void pack_qk_push(const PackDesc &D, int lane, int qi, int &n, double key, int job) {
+    PackDesc Q = D; Q.qkey = D.qkey + (size_t)qi * D.J; Q.qjob = D.qjob + (size_t)qi * D.J;
+    if (lane == 0) pack_q_siftdown(Q, n, key, job);
+    n += 1;
+    __syncwarp();
+}
+__device__ __forceinline__ void pack_q_pop(const PackDesc &D, int lane, int &q, double &key, int &job);
+__device__ __forceinline__ void pack_qk_pop(const PackDesc &D, int lane, int qi, int &n, double &key, int &job) {
+    PackDesc Q = D; Q.qkey = D.qkey + (size_t)qi * D.J; Q.qjob = D.qjob + (size_t)qi * D.J;
+    pack_q_pop(Q, lane, n, key, job);
 }
 __device__ __forceinline__ void pack_q_push(const PackDesc &D, int lane, int &q, double key, int job) {
     if (lane == 0) pack_q_siftdown(D, q, key, job);
@@ -191,7 +217,7 @@ struct PackCtx {              // registers shared by the placement helpers
     double *score;            // shared memory [N]: min_cost of each node, < 0 = node cannot take the task
     double *hscore; int32_t *hnode;   // shared memory [PACK_MAX_HEAP + 1]: horus_placement's nodes_stack
 };
-__host__ __device__ inline size_t pack_smem_bytes(int n_nodes) { return 8 * (size_t)((n_nodes + 1) & ~1) + 12 * (size_t)(PACK_MAX_HEAP + 1); }
+__host__ __device__ inline size_t pack_smem_bytes(int n_nodes) { return 8 * (size_t)((n_nodes + 1) & ~1) + 12 * (size_t)(PACK_MAX_HEAP + 1) + 8 * 8 * 8; }   // + horus+ centroid features [8][8]
 
 __device__ __forceinline__ void pack_idle_delta(PackState &st, bool was_idle, bool now_idle) { st.idle_nodes += (int)now_idle - (int)was_idle; }
 __device__ __forceinline__ bool pack_node_idle(const PackDesc &D, int i) { return D.ntk[i] == 0 && D.npj[i] == 0; }   // Node.is_idle (node.py:93-97)
@@ -616,6 +642,116 @@ __device__ __forceinline__ void pack_yarn_release(const PackDesc &D, const Clust
     __syncwarp();
 }
 
+// ---- horus+ (schedule_horus_plus, algorithm.py:242-290): k-means of the queued jobs into K utilisation heaps, credit-based pick
+__device__ __forceinline__ uint32_t plus_draw(uint32_t seed, uint32_t call, uint32_t elem, uint32_t n) {   // = _draw of oracle/ref_runner.py
+    uint64_t h = pack_mix64((((uint64_t)seed << 32) | call) + 0x9E3779B97F4A7C15ull);
+    h = pack_mix64(h ^ (uint64_t)elem);
+    return (uint32_t)((h >> 11) % n);
+}
+__device__ __forceinline__ double plus_job_dist(const PlusFeat &a, const double *b) {   // job_dist (utils.py:4-12), left to right
+    double s = fabs(a.f[0] - b[0]);
+    s += fabs(a.f[1] - b[1]); s += fabs(a.f[2] - b[2]); s += fabs(a.f[3] - b[3]); s += fabs(a.f[4] - b[4]); s += fabs(a.f[5] - b[5]); s += fabs(a.f[6] - b[6]);
+    return s;
+}
+__device__ __forceinline__ double plus_pairwise_leaf(const double *a, int n) {   // n <= 128
+    if (n < 8) { double res = 0.; for (int i = 0; i < n; ++i) res += a[i]; return res; }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) { r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3]; r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7]; }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+// numpy's DOUBLE_pairwise_sum (np.mean = (0 + this) / n): blocks of <= 128 summed with 8 accumulators, halves (the left one a multiple
+// of 8) combined as left + right.  The recursion is unrolled on an explicit stack: device threads have a small call stack.
+__device__ __forceinline__ double plus_pairwise_sum(const double *a, int n) {
+    const double *fa[24]; int fn[24], fs[24]; double fl[24];
+    int sp = 0; double ret = 0.0;
+    fa[0] = a; fn[0] = n; fs[0] = 0; sp = 1;
+    while (sp > 0) {
+        const int t = sp - 1;
+        if (fs[t] == 0) {
+            if (fn[t] <= 128) { ret = plus_pairwise_leaf(fa[t], fn[t]); sp -= 1; continue; }
+            int n2 = fn[t] / 2; n2 -= n2 % 8;
+            fs[t] = 1; fa[sp] = fa[t]; fn[sp] = n2; fs[sp] = 0; sp += 1;
+        } else if (fs[t] == 1) {
+            int n2 = fn[t] / 2; n2 -= n2 % 8;
+            fl[t] = ret; fs[t] = 2; fa[sp] = fa[t] + n2; fn[sp] = fn[t] - n2; fs[sp] = 0; sp += 1;
+        } else { ret = fl[t] + ret; sp -= 1; }
+    }
+    return ret;
+}
+// clusterize (utils.py:36-67) of kjobs[0..m): kassign[i] = queue.  cent_f = shared memory [K][8] scratch for the centroids' features.
+__device__ __forceinline__ void plus_clusterize(const PackDesc &D, const PackParams &P, PackState &st, int lane, int m, double *cent_f) {
+    const int K = P.plus_k;
+    int my_cent = -1;                                                  // lane c keeps the job of centroid c
+    { const uint32_t call = st.kcalls; st.kcalls += 1; if (lane < K) my_cent = D.kjobs[plus_draw(P.plus_seed, call, (uint32_t)lane, (uint32_t)m)]; }
+    for (int i = lane; i < m; i += 32) { D.kassign[i] = -1; D.kold[i] = -1; }
+    __syncwarp();
+    for (int iter = 0; iter < 1000; ++iter) {
+        bool diff = false;
+        for (int i = lane; i < m; i += 32) diff |= D.kassign[i] != D.kold[i];
+        if (!__any_sync(RLGS_FULL, diff) && iter != 0) break;
+        for (int i = lane; i < m; i += 32) D.kold[i] = D.kassign[i];
+        if (lane < K) { const PlusFeat cf = D.feat[my_cent]; for (int k = 0; k < 7; ++k) cent_f[lane * 8 + k] = cf.f[k]; }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {                           // np.argmin over the centroids: first minimum
+            const PlusFeat jf = D.feat[D.kjobs[i]];
+            int best = 0; double bd = plus_job_dist(jf, cent_f);
+            for (int c2 = 1; c2 < K; ++c2) { const double dd = plus_job_dist(jf, cent_f + c2 * 8); if (dd < bd) { bd = dd; best = c2; } }
+            D.kassign[i] = best;
+        }
+        __syncwarp();
+        for (int c2 = 0; c2 < K; ++c2) {
+            int cnt = 0;                                               // members in list order -> ktmp (their transform_to_dist)
+            for (int base = 0; base < m; base += 32) {
+                const int i = base + lane;
+                const bool mem = i < m && D.kassign[i] == c2;
+                const unsigned mb = __ballot_sync(RLGS_FULL, mem);
+                if (mem) D.ktmp[cnt + __popc(mb & ((1u << lane) - 1))] = D.feat[D.kjobs[i]].tdist;
+                cnt += __popc(mb);
+            }
+            __syncwarp();
+            int newc;
+            if (cnt > 0) {
+                double score = 0.0;
+                if (lane == 0) { const double mean = (0.0 + plus_pairwise_sum(D.ktmp, cnt)) / (double)cnt; score = (double)(long long)mean; }   // .astype(int)
+                score = __shfl_sync(RLGS_FULL, score, 0);
+                double bd = 99999999999.0; int bi = 0x7fffffff;        // get_closest: first strict minimum in list order
+                for (int i = lane; i < m; i += 32) if (D.kassign[i] == c2) { const double t = fabs(D.feat[D.kjobs[i]].tdist - score); if (t < bd) { bd = t; bi = i; } }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const double od = __shfl_xor_sync(RLGS_FULL, bd, o); const int oi = __shfl_xor_sync(RLGS_FULL, bi, o);
+                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                }
+                if (bi == 0x7fffffff) { st.status = RLGS_ERR_STATE; return; }
+                newc = D.kjobs[bi];
+            } else { newc = D.kjobs[plus_draw(P.plus_seed, st.kcalls, 0u, (uint32_t)m)]; st.kcalls += 1; }   // np.random.choice(len(jobs))
+            if (lane == c2) my_cent = newc;
+            __syncwarp();
+        }
+    }
+}
+// credit of queue qi at reference tick `ref` (job_queue_manager.py:115-127): median pending time x length
+__device__ __forceinline__ double plus_credit(const PackDesc &D, int lane, int qi, int n, int ref) {
+    if (n == 0) return 0.0;
+    const int32_t *qj = D.qjob + (size_t)qi * D.J;
+    const int r_lo = (n - 1) / 2, r_hi = n / 2;                        // order statistics of the arrival ticks
+    int a_lo = 0, a_hi = 0;
+    for (int i = lane; i < n; i += 32) {
+        const int ai = D.trace[qj[i]].arrival_tick;
+        int lt = 0, eq = 0;
+        for (int j = 0; j < n; ++j) { const int aj = D.trace[qj[j]].arrival_tick; lt += aj < ai; eq += aj == ai; }
+        if (lt <= r_lo && r_lo < lt + eq) a_lo = ai;
+        if (lt <= r_hi && r_hi < lt + eq) a_hi = ai;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a_lo = max(a_lo, __shfl_xor_sync(RLGS_FULL, a_lo, o)); a_hi = max(a_hi, __shfl_xor_sync(RLGS_FULL, a_hi, o)); }
+    const double med = ((double)(ref - a_lo) + (double)(ref - a_hi)) / 2.0;    // np.median: mean of the two middle values
+    const double mp = med > 0.0 ? med : 0.0;
+    return mp < 1.0 ? (double)n : mp * (double)n;
+}
+
 // removes `job` from a singly linked calendar bucket (lane 0)
 __device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, int bucket, int job) {
     int prev = -1, cur = head[bucket];
@@ -624,13 +760,14 @@ __device__ __forceinline__ void pack_chain_unlink(int32_t *head, int32_t *next, 
     if (prev < 0) head[bucket] = next[cur]; else next[prev] = next[cur];
 }
 
-template <bool GANDIVA, bool YARN>
+template <bool GANDIVA, bool YARN, bool PLUS>
 __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs, PackState *states, PackParams P, ClusterConst c,
                                                         RowStore rs, int64_t *returns) {
     extern __shared__ __align__(16) unsigned char pack_smem[];
     double *sm_score = reinterpret_cast<double *>(pack_smem);
     double *sm_hscore = sm_score + ((c.N + 1) & ~1);
     int32_t *sm_hnode = reinterpret_cast<int32_t *>(sm_hscore + PACK_MAX_HEAP + 1);
+    double *sm_cent = reinterpret_cast<double *>(sm_hnode + PACK_MAX_HEAP + 1);   // 8-byte aligned: (PACK_MAX_HEAP + 1) is even
     const int lane = lane_id();
     const PackDesc D = descs[blockIdx.x];
     PackState st = states[blockIdx.x];
@@ -664,12 +801,13 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
 
         // ---------------- arrivals (jobs_manager.py:228-241)
         if (!GANDIVA) {
-            // horus: heappush in trace order (job_queue_manager.py:147-152)
+            // horus: heappush in trace order (job_queue_manager.py:147-152); horus+: the queues are rebuilt below
+            const int c0 = st.cursor;
             while (st.cursor < J) {
                 const int job = st.cursor;
                 const int arr = D.trace[job].arrival_tick;
                 if (arr > d) break;
-                pack_q_push(D, lane, st.Q, D.pj[job].util_avg, job);
+                if (PLUS) st.Q += 1; else pack_q_push(D, lane, st.Q, D.pj[job].util_avg, job);
                 if (lane == 0) { D.lprev[job] = st.ltail; D.lnext[job] = -1; if (st.ltail >= 0) D.lnext[st.ltail] = job; }
                 if (st.ltail < 0) st.lhead = job;
                 st.ltail = job;
@@ -681,6 +819,27 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
                 st.cursor += 1;
                 if (st.Q > st.max_q) st.max_q = st.Q;
                 __syncwarp();
+            }
+            if (PLUS && st.Q > 0) {
+                // jobs_manager.insert (:115-140) runs every tick, also without arrivals: every queue is emptied in heappop order,
+                // queue after queue, the new jobs are appended, the list is clustered again (clusterize) and pushed back in order
+                int m = 0;
+                for (int q = 0; q < P.plus_k; ++q) {
+                    int n = st.pqn[q];
+                    while (n > 0) { double key = 0.0; int job = 0; pack_qk_pop(D, lane, q, n, key, job); if (lane == 0) D.kjobs[m] = job; m += 1; }
+                    st.pqn[q] = 0;
+                }
+                for (int i = c0 + lane; i < st.cursor; i += 32) D.kjobs[m + (i - c0)] = i;
+                m += st.cursor - c0;
+                __syncwarp();
+                plus_clusterize(D, P, st, lane, m, sm_cent);
+                if (st.status) { st.done = 1; break; }
+                for (int i = 0; i < m; ++i) {
+                    const int q = D.kassign[i], job = D.kjobs[i];
+                    int n = st.pqn[q];
+                    pack_qk_push(D, lane, q, n, D.pj[job].util_avg, job);
+                    st.pqn[q] = n;
+                }
             }
         } else {
             // gandiva: a plain list, queue.insert(i, job_i): the batch goes to the front in order (q1).  The queue is a stack
@@ -699,8 +858,24 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
         // ---------------- _schedule (schedule.py:40-60) -> schedule_horus (algorithm.py:204-240) | schedule_fifo (:189-202)
         if (st.Q > 0 && st.n_free_nodes >= 1) {
             const int k = GANDIVA ? 1 : min(max(P.num_buffer, 0), st.Q);
-            int my_job = -1; double my_key = 0.0;
-            if (!GANDIVA) for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
+            int my_job = -1, my_q = 0; double my_key = 0.0;
+            if (PLUS) {
+                // update_credits + np.argmax before every pop (algorithm.py:254-258); only the queue that lost a job changes
+                double credits[PACK_MAX_Q];
+                for (int q = 0; q < P.plus_k; ++q) credits[q] = plus_credit(D, lane, q, st.pqn[q], d);
+                for (int a = 0; a < k; ++a) {
+                    int qi = 0;
+                    for (int q = 1; q < P.plus_k; ++q) if (credits[q] > credits[qi]) qi = q;
+                    int n = st.pqn[qi];
+                    if (n == 0) { st.status = RLGS_ERR_UNSUPPORTED; break; }       // pop() returns None in the reference: AttributeError
+                    double key = 0.0; int job = 0;
+                    pack_qk_pop(D, lane, qi, n, key, job);
+                    st.pqn[qi] = n;
+                    if (lane == a) { my_job = job; my_key = key; my_q = qi; }
+                    credits[qi] = plus_credit(D, lane, qi, n, d);
+                }
+                if (st.status) { st.done = 1; break; }
+            } else if (!GANDIVA) for (int a = 0; a < k; ++a) { double key = 0.0; int job = 0; pack_q_pop(D, lane, st.Q, key, job); if (lane == a) { my_job = job; my_key = key; } }
             else my_job = D.qjob[st.Q - 1];                   // the head of the list stays queued unless it is placed
             __syncwarp();
             PACK_T(1);
@@ -730,8 +905,12 @@ __global__ void __launch_bounds__(32, 8) pack_horus_kernel(const PackDesc *descs
 #endif
             if (!GANDIVA) for (int a = 0; a < k; ++a) {     // jobs_manager.insert(look_ahead): heappush the rest in order
                 const int job = __shfl_sync(RLGS_FULL, my_job, a); const double key = __shfl_sync(RLGS_FULL, my_key, a);
-                if (a != pos) pack_q_push(D, lane, st.Q, key, job);
+                const int q = __shfl_sync(RLGS_FULL, my_q, a);
+                if (a == pos) continue;
+                if (PLUS) { int n = st.pqn[q]; pack_qk_push(D, lane, q, n, key, job); st.pqn[q] = n; }   // back into the queue it came from
+                else pack_q_push(D, lane, st.Q, key, job);
             }
+            if (PLUS && pos >= 0) st.Q -= 1;
             __syncwarp();
             PACK_T(7);
             if (pos >= 0) {                                   // add_to_running -> start_job (schedule.py:164-167, jobs_manager.py:189-207)

@@ -46,6 +46,7 @@ struct TraceBuf {
     double *net = nullptr;      // [3][cap_n] network-cost inputs
     double *dur_out = nullptr;  // [count][cap_n]
     PackJob *pack = nullptr;    // [n] horus placement inputs
+    PlusFeat *feat = nullptr;   // [n] horus+ k-means features
     int32_t n = 0, cap_n = 0;
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
@@ -128,18 +129,19 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     if (opts->n_replicas < 1) return fail(RLGS_ERR_BAD_ARG, "n_replicas must be >= 1");
     const int sched = opts->schedule;
     if (sched != RLGS_SCHED_FIFO && sched != RLGS_SCHED_SJF && sched != RLGS_SCHED_DLAS_GPU && sched != RLGS_SCHED_DLAS &&
-        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU && sched != RLGS_SCHED_HORUS && sched != RLGS_SCHED_GANDIVA)
+        sched != RLGS_SCHED_SHORTEST && sched != RLGS_SCHED_SHORTEST_GPU && sched != RLGS_SCHED_HORUS && sched != RLGS_SCHED_GANDIVA && sched != RLGS_SCHED_HORUS_PLUS)
         return fail(RLGS_ERR_UNSUPPORTED, "schedule id %d is not implemented on the device path", sched);
     const bool is_sjf_family = sched == RLGS_SCHED_SJF || sched == RLGS_SCHED_SHORTEST || sched == RLGS_SCHED_SHORTEST_GPU;
     if ((sched == RLGS_SCHED_FIFO || is_sjf_family) && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
-    const bool is_pack = sched == RLGS_SCHED_HORUS || sched == RLGS_SCHED_GANDIVA;
+    const bool is_pack = sched == RLGS_SCHED_HORUS || sched == RLGS_SCHED_GANDIVA || sched == RLGS_SCHED_HORUS_PLUS;
+    if (sched == RLGS_SCHED_HORUS_PLUS && (opts->num_queue < 1 || opts->num_queue > PACK_MAX_Q)) return fail(RLGS_ERR_BAD_ARG, "horus+: num_queue must be 1..%d", PACK_MAX_Q);
     if (!is_pack && opts->placement == RLGS_PLACE_HORUS)
         return fail(RLGS_ERR_UNSUPPORTED, "the pack placement needs the horus or gandiva schedule (schedule.py:47 passes the schedule name "
                     "to the placement's score table, so fifo + horus raises KeyError in the reference)");
     if (is_pack && opts->placement != RLGS_PLACE_HORUS && opts->placement != RLGS_PLACE_YARN)
         return fail(RLGS_ERR_UNSUPPORTED, "placement id %d is not implemented for schedule id %d", opts->placement, sched);
-    if (sched == RLGS_SCHED_HORUS && (opts->num_buffer < 0 || opts->num_buffer > 32)) return fail(RLGS_ERR_BAD_ARG, "num_buffer must be 0..32");
+    if (is_pack && (opts->num_buffer < 0 || opts->num_buffer > 32)) return fail(RLGS_ERR_BAD_ARG, "num_buffer must be 0..32");
     const bool is_dlas = sched == RLGS_SCHED_DLAS_GPU || sched == RLGS_SCHED_DLAS;
     if (is_dlas) {
         if (opts->num_queue < 1 || opts->num_queue > RLGS_MAX_QUEUES) return fail(RLGS_ERR_BAD_ARG, "num_queue must be 1..%d", RLGS_MAX_QUEUES);
@@ -162,6 +164,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     memset(&s->pp, 0, sizeof s->pp);
     s->pp.num_buffer = opts->num_buffer > 0 ? opts->num_buffer : 5;
     s->pp.rng_on = opts->pack_rng != 0; s->pp.seed = opts->pack_seed; s->pp.gandiva = sched == RLGS_SCHED_GANDIVA;
+    s->pp.plus_k = sched == RLGS_SCHED_HORUS_PLUS ? opts->num_queue : 0; s->pp.plus_seed = opts->pack_seed;
     s->pp.nodes_per_rack = spec->num_node_p_switch; s->pp.racks = spec->num_switch; s->pp.max_ticks = opts->max_ticks;
     s->cc.N = (int)N; s->cc.G = spec->num_gpu_p_node; s->cc.cpu_cap = spec->num_cpu_p_node; s->cc.mem_cap = spec->mem_p_node;
     s->cc.gmask = spec->num_gpu_p_node == 32 ? 0xffffffffu : ((1u << spec->num_gpu_p_node) - 1u);
@@ -223,7 +226,7 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); }
+    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); cudaFree(t.feat); }
     cudaFree(s->d_pdesc); cudaFree(s->d_pstate);
     if (s->h_pstate) cudaFreeHost(s->h_pstate);
     if (s->h_pinit) cudaFreeHost(s->h_pinit);
@@ -387,12 +390,29 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
     }
     CU(cudaMalloc(&tb->pack, sizeof(PackJob) * (size_t)n));
     CU(cudaMemcpy(tb->pack, pj.data(), sizeof(PackJob) * (size_t)n, cudaMemcpyHostToDevice));
+    const int K = s->pp.plus_k;
+    if (K > 0) {
+        if (!in->util_max || !in->mem_avg_mib || !in->used_gpus) return fail(RLGS_ERR_BAD_ARG, "horus+ needs util_max, mem_avg_mib and used_gpus (the k-means features of core/jobs/utils.py:4-22)");
+        std::vector<PlusFeat> ft((size_t)n);
+        const double unit_mib = 1.0 / (double)((int64_t)1 << in->mem_shift);
+        for (int i = 0; i < n; ++i) {
+            PlusFeat &f = ft[i];
+            f.f[0] = (double)jobs[i].tasks; f.f[1] = in->util_avg[i]; f.f[2] = (double)jobs[i].gpus_per_task; f.f[3] = in->used_gpus[i];
+            f.f[4] = in->util_max[i]; f.f[5] = in->mem_avg_mib[i]; f.f[6] = (double)in->task_mem[i] * unit_mib;
+            double t = f.f[0]; for (int k = 1; k < 7; ++k) t += f.f[k];   // transform_to_dist: left to right
+            f.tdist = t;
+        }
+        CU(cudaMalloc(&tb->feat, sizeof(PlusFeat) * (size_t)n));
+        CU(cudaMemcpy(tb->feat, ft.data(), sizeof(PlusFeat) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    const size_t KQ = (size_t)std::max(K, 1);
     const size_t N = (size_t)s->cc.N, Dv = (size_t)s->cc.D, J = (size_t)n, W = (N + 31) / 32;
     // per-replica working set, 256-byte aligned pieces in this order
-    const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J,
+    const size_t sz[] = {4 * N, 4 * N, 4 * N, 4 * Dv, 8 * Dv, 8 * PACK_DEV_SLOTS * Dv, 4 * J * W, 8 * J * KQ, 4 * J * KQ, 4 * J, 4 * J, 4 * J, 4 * J,
                          4 * PACK_CAL_W, 2 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J,
                          4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * J, 4 * PACK_CAL_W, 4 * J,
-                         4 * N, 4 * N, 4 * W, 8 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J};
+                         4 * N, 4 * N, 4 * W, 8 * (size_t)std::max<int64_t>(sum_tasks, 1), 4 * J,
+                         4 * J, 4 * J, 4 * J, 8 * J};
     size_t per = 0;
     for (size_t v : sz) per += align_up(v, 256);
     unsigned char *slab = nullptr;
@@ -413,6 +433,7 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
         D.nstart = (int32_t *)take(0); D.qtick = (int32_t *)take(0); D.cbk = (int32_t *)take(0); D.snext = (int32_t *)take(0);
         D.shead = (int32_t *)take(0); D.sat = (int32_t *)take(0);
         D.ybusy = (uint32_t *)take(0); D.ykey = (uint32_t *)take(0); D.yever = (uint32_t *)take(0); D.plog = (int2 *)take(0); D.pcnt = (int32_t *)take(0);
+        D.kjobs = (int32_t *)take(0); D.kassign = (int32_t *)take(0); D.kold = (int32_t *)take(0); D.ktmp = (double *)take(0); D.feat = tb->feat;
         D.cap_units = (int64_t)in->gpu_mem_cap_mib * unit; D.margin_units = 500 * unit;
         D.cap_mib = (double)in->gpu_mem_cap_mib; D.unit_mib = 1.0 / (double)unit;
     }
@@ -489,10 +510,11 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
             PackParams pp = s->pp; pp.tick_budget = budget;
-#define RLGS_LAUNCH_PACK(G, Y) pack_horus_kernel<G, Y><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first)
+#define RLGS_LAUNCH_PACK(G, Y, PL) pack_horus_kernel<G, Y, PL><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first)
             const bool yarn = s->opts.placement == RLGS_PLACE_YARN;
-            if (pp.gandiva) { if (yarn) RLGS_LAUNCH_PACK(true, true); else RLGS_LAUNCH_PACK(true, false); }
-            else { if (yarn) RLGS_LAUNCH_PACK(false, true); else RLGS_LAUNCH_PACK(false, false); }
+            if (pp.plus_k > 0) { if (yarn) RLGS_LAUNCH_PACK(false, true, true); else RLGS_LAUNCH_PACK(false, false, true); }
+            else if (pp.gandiva) { if (yarn) RLGS_LAUNCH_PACK(true, true, false); else RLGS_LAUNCH_PACK(true, false, false); }
+            else { if (yarn) RLGS_LAUNCH_PACK(false, true, false); else RLGS_LAUNCH_PACK(false, false, false); }
 #undef RLGS_LAUNCH_PACK
         } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
             dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);

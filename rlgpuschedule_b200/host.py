@@ -103,13 +103,18 @@ class Scheduler(object):
             limits = parse_queue_limit(getattr(flags, 'queue_limit', None))
             kw = dict(num_queue=len(limits) + 1, queue_limit=limits)
             scheme = 'count'   # dlas admits by GPU count (run_sim.py:808-823) whatever --scheme says
-        if self.schedule in ('horus', 'gandiva'):
+        if self.schedule in ('horus', 'horus+', 'gandiva'):
             # horus_score / gandiva_score draw device utilisations from an unseeded normal (infra/device.py:52); here the draw is
             # counter-based: --seed fixes it, --util_mode mean replaces every draw by its mean
             seed = getattr(flags, 'seed', None)
             if seed is None and getattr(flags, 'util_mode', 'sample') != 'mean':
                 seed = int.from_bytes(os.urandom(4), 'little')
             kw = dict(num_buffer=int(getattr(flags, 'num_buffer', 5)), pack_seed=seed)
+            if self.schedule == 'horus+':   # the k-means init is always drawn (core/jobs/utils.py:39): unseeded in the reference
+                if seed is None:
+                    seed = int.from_bytes(os.urandom(4), 'little')
+                kw.update(num_queue=int(getattr(flags, 'num_queue', 1)), pack_seed=seed,
+                          pack_rng=getattr(flags, 'util_mode', 'sample') != 'mean')
         net = bool(getattr(flags, 'enable_network_costs', False))
         if net and self.schedule != 'fifo':
             raise NotImplementedError('--enable_network_costs is implemented for the fifo tick loop only')
@@ -124,14 +129,14 @@ class Scheduler(object):
         sim.run()
         took = time.time() - t0
         summ = sim.summary(0)
-        legacy = self.schedule not in ('fifo', 'horus', 'gandiva')
+        legacy = self.schedule not in ('fifo', 'horus', 'horus+', 'gandiva')
         if not legacy:
             self.log_manager.write_cluster_rows(sim.rows(0), cluster, trace.mem_shift,
                                                 util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
             j = sim.jobs(0)
             logging.info('Total Time Taken in seconds: %d' % took)
             extra = {}
-            if self.schedule in ('horus', 'gandiva'):
+            if self.schedule in ('horus', 'horus+', 'gandiva'):
                 # Job.get_duration() = original + 5 once a task was de-interfered (jobs_manager.py:184-185); jct = Job.time_processed()
                 from . import _ffi
                 extra = dict(get_duration=trace.duration + 5.0 * (sim.job_plane(0, _ffi.PLANE_AUX) == 1),

@@ -78,6 +78,7 @@ class Trace:
     util_avg: np.ndarray = None      # gpu_utilization_avg / _max and memory_max in MiB: inputs of the pack placement
     util_max: np.ndarray = None
     mem_mib: np.ndarray = None
+    mem_avg_mib: np.ndarray = None   # memory_avg in MiB: a k-means feature of horus+ (core/jobs/utils.py:10)
 
     def pack_inputs(self):
         """Arrays of rlgs_pack_inputs (include/rlgs.h): what horus_score / Device.can_fit read from a Task
@@ -88,7 +89,10 @@ class Trace:
         return dict(util_avg=np.ascontiguousarray(self.util_avg, np.float64),
                     util_sd=np.ascontiguousarray((self.util_max - self.util_avg) / 2, np.float64),
                     task_mem=np.ascontiguousarray(mem.astype(np.int64)),
-                    heap_cap=np.ascontiguousarray(np.floor(self.used_gpus).astype(np.int32)))
+                    heap_cap=np.ascontiguousarray(np.floor(self.used_gpus).astype(np.int32)),
+                    util_max=np.ascontiguousarray(self.util_max, np.float64),
+                    mem_avg_mib=np.ascontiguousarray(self.mem_avg_mib, np.float64),
+                    used_gpus=np.ascontiguousarray(self.used_gpus, np.float64))
 
     def __len__(self):
         return len(self.records)
@@ -129,6 +133,7 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     used = df['used_gpus'].to_numpy(dtype=np.float64)
     gpc = df['gpu_per_container'].to_numpy()
     mem_mib = df['memory_max'].to_numpy(dtype=np.float64) / 1024 / 1024   # util.convert_bytes(.., "MiB")
+    mem_avg_mib = df['memory_avg'].to_numpy(dtype=np.float64) / 1024 / 1024
     ua = df['gpu_utilization_avg'].to_numpy(dtype=np.float64)
     um = df['gpu_utilization_max'].to_numpy(dtype=np.float64)
     if n and (np.any(gpc != np.floor(gpc)) or np.any(gpc < 1)):
@@ -174,4 +179,5 @@ def prepare_trace(trace, cluster, scale_factor=0.5):
     return Trace(label=df.index.to_numpy().astype(np.int64), nt=nt, duration=np.ascontiguousarray(duration), used_gpus=used,
                  records=np.ascontiguousarray(rec), mem_shift=shift, cap_mib=cap,
                  model_mb=np.ascontiguousarray(model_mb), iterations=np.ascontiguousarray(iters),
-                 util_avg=np.ascontiguousarray(ua), util_max=np.ascontiguousarray(um), mem_mib=np.ascontiguousarray(mem_mib))
+                 util_avg=np.ascontiguousarray(ua), util_max=np.ascontiguousarray(um), mem_mib=np.ascontiguousarray(mem_mib),
+                 mem_avg_mib=np.ascontiguousarray(mem_avg_mib))

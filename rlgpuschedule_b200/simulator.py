@@ -15,11 +15,12 @@ class Simulator(object):
     def __init__(self, cluster, schedule='fifo', scheme='yarn', n_replicas=1, rows=True, device=0, slot_cap=0,
                  n_streams=0, ticks_per_launch=0, rows_cap=0, fetch_jobs=False, num_queue=1, queue_limit=(),
                  max_ticks=0, enable_network_costs=False, bandwidth=1250, internode_latency=0.015, num_buffer=5,
-                 pack_seed=None):
+                 pack_seed=None, pack_rng=None):
         """rows: True / 'host' = rows copied to the pinned host store inside run(); 'device' = rows stay in
         HBM until asked for; False = no rows.  num_buffer: look-ahead window of the horus schedule (--num_buffer).
         pack_seed: None = utilisation draws of the horus score return their mean (the reference's behaviour on
-        zero-spread traces); an int seeds the build-defined counter-based draw."""
+        zero-spread traces); an int seeds the build-defined counter-based draw.  horus+: pack_seed also seeds the k-means draws
+        (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded."""
         if schedule not in _ffi.SCHED:
             raise NotImplementedError('schedule %r has no device implementation' % (schedule,))
         if scheme not in _ffi.PLACE:
@@ -31,7 +32,8 @@ class Simulator(object):
                         ticks_per_launch=ticks_per_launch, rows_cap=rows_cap, fetch_jobs=fetch_jobs,
                         num_queue=num_queue, queue_limit=tuple(queue_limit), max_ticks=max_ticks,
                         enable_network_costs=enable_network_costs, bandwidth=bandwidth,
-                        internode_latency=internode_latency, num_buffer=num_buffer, pack_seed=pack_seed)
+                        internode_latency=internode_latency, num_buffer=num_buffer, pack_seed=pack_seed,
+                        pack_rng=(pack_seed is not None) if pack_rng is None else bool(pack_rng))
         self._slot_cap = slot_cap
         self._traces = []   # (first, count, Trace)
         self._h = None
@@ -51,7 +53,7 @@ class Simulator(object):
         o.enable_network_costs = int(bool(k['enable_network_costs']))
         o.bandwidth = float(k['bandwidth']); o.internode_latency = float(k['internode_latency'])
         o.max_ticks = int(k['max_ticks'])
-        o.num_buffer = int(k['num_buffer']); o.pack_rng = int(k['pack_seed'] is not None); o.pack_seed = int(k['pack_seed'] or 0)
+        o.num_buffer = int(k['num_buffer']); o.pack_rng = int(k['pack_rng']); o.pack_seed = int(k['pack_seed'] or 0)
         spec = self.cluster.to_ffi()
         h = C.c_void_p()
         _ffi.check(L.rlgs_create(C.byref(spec), C.byref(o), C.byref(h)))
@@ -78,12 +80,13 @@ class Simulator(object):
                                      trace.iterations.ctypes.data_as(dp))
         _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
                                               C.byref(net) if net is not None else None))
-        if self._kw['schedule'] in ('horus', 'gandiva'):
+        if self._kw['schedule'] in ('horus', 'gandiva', 'horus+'):
             pi = trace.pack_inputs()
             dp = C.POINTER(C.c_double)
             inp = _ffi.PackInputs(pi['util_avg'].ctypes.data_as(dp), pi['util_sd'].ctypes.data_as(dp),
                                   pi['task_mem'].ctypes.data_as(C.POINTER(C.c_int64)), pi['heap_cap'].ctypes.data_as(C.POINTER(C.c_int32)),
-                                  trace.mem_shift, trace.cap_mib)
+                                  trace.mem_shift, trace.cap_mib, pi['util_max'].ctypes.data_as(dp), pi['mem_avg_mib'].ctypes.data_as(dp),
+                                  pi['used_gpus'].ctypes.data_as(dp))
             _ffi.check(_ffi.lib().rlgs_load_pack_inputs(self._h, first_replica, n_replicas, C.byref(inp), len(rec)))
         self._traces = [x for x in self._traces if (x[0], x[1]) != (first_replica, n_replicas)]
         self._traces.append((first_replica, n_replicas, trace))

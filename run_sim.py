@@ -20,8 +20,8 @@ from rlgpuschedule_b200.host import Infrastructure, JobQueueManager, JobsManager
 flags.DEFINE_string('trace_file', 'tf_job.csv', 'job trace file (*.csv) in the Philly-style schema')
 flags.DEFINE_string('log_path', 'result-' + time.strftime('%Y%m%d-%H-%M-%S', time.localtime()),
                     'simulation output folder under log/; default result-[time]')
-flags.DEFINE_string('scheme', 'yarn', 'job placement scheme: yarn | count | horus (= horus+ = gandiva, with --schedule horus | gandiva)')
-flags.DEFINE_string('schedule', 'fifo', 'job schedule: fifo | horus | gandiva | sjf | shortest | shortest-gpu | dlas | dlas-gpu (device); horus+ (not on the device path)')
+flags.DEFINE_string('scheme', 'yarn', 'job placement scheme: yarn | count | horus (= horus+ = gandiva, with --schedule horus | horus+ | gandiva)')
+flags.DEFINE_string('schedule', 'fifo', 'job schedule: fifo | horus | horus+ | gandiva | sjf | shortest | shortest-gpu | dlas | dlas-gpu (all on the device)')
 flags.DEFINE_boolean('pack', False, 'enable packing for gpu jobs (stored, not consulted by yarn)')
 flags.DEFINE_integer('num_switch', 1, 'cluster spec: number of switches')
 flags.DEFINE_integer('num_node_p_switch', 32, 'cluster spec: nodes under one switch')

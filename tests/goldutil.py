@@ -35,7 +35,8 @@ def load(name):
         if isinstance(v, str) and v.startswith('@'):
             flags[k] = os.path.join(ROOT, v[1:])
     out = dict(meta=meta, flags=flags, job=None, cluster=None, schedule=case.get('schedule', 'fifo'), num_buffer=case.get('num_buffer', 5),
-               scheme=case.get('scheme', case.get('schedule', 'yarn') if case.get('schedule', 'fifo') != 'fifo' else 'yarn'))
+               scheme=case.get('scheme', case.get('schedule', 'yarn') if case.get('schedule', 'fifo') != 'fifo' else 'yarn'),
+               num_queue=case.get('num_queue', 1), inject_seed=case.get('inject_seed', 0))
     if os.path.exists(os.path.join(d, 'trace.csv')):
         out['trace'] = os.path.join(d, 'trace.csv')
         out['frame'] = None

@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ffi.ClusterSpec) == 24
     assert C.sizeof(_ffi.Summary) == 6 * 8 + 8 * 4
     assert C.sizeof(_ffi.Opts) == 12 * 4 + 8 * 4 + 2 * 8 + 2 * 8 + 2 * 4
-    assert C.sizeof(_ffi.PackInputs) == 4 * 8 + 2 * 4
+    assert C.sizeof(_ffi.PackInputs) == 4 * 8 + 2 * 4 + 3 * 8
 
 
 def test_fails_loudly_without_gpu():
@@ -51,4 +51,4 @@ def test_bad_arguments_are_rejected_before_touching_the_device():
     assert L.rlgs_create(C.byref(spec), C.byref(o), C.byref(h)) == _ffi.ERR_BAD_ARG
     assert b'num_gpu_p_node' in L.rlgs_last_error()
     with pytest.raises(NotImplementedError):
-        rl.Simulator(rl.Cluster(), schedule='horus+')
+        rl.Simulator(rl.Cluster(), schedule='lpjf')

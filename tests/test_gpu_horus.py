@@ -88,13 +88,15 @@ def test_horus_bounded_launches_resume(schedule):
 
 
 @pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('big', 'horus') +
-                         goldutil.case_names('small', 'gandiva') + goldutil.case_names('big', 'gandiva'))
+                         goldutil.case_names('small', 'gandiva') + goldutil.case_names('big', 'gandiva') +
+                         goldutil.case_names('small', 'horus+') + goldutil.case_names('big', 'horus+'))
 def test_horus_matches_the_reference_golden(name):
     """Device outputs vs the files the UNMODIFIED reference wrote for `--schedule horus --scheme horus` (tests/golden)."""
     g = goldutil.load(name)
     cluster = rl.cluster_from_flags(g['flags'])
     tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
-    sim = rl.Simulator(cluster, g['schedule'], g['scheme'], n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000)
+    kw = dict(num_queue=g['num_queue'], pack_seed=g['inject_seed'], pack_rng=False) if g['schedule'] == 'horus+' else {}
+    sim = rl.Simulator(cluster, g['schedule'], g['scheme'], n_replicas=3, rows=True, num_buffer=g['num_buffer'], max_ticks=400000, **kw)
     sim.load_trace(tr)
     sim.run()
     for r in (0, 2):
@@ -138,4 +140,25 @@ def test_pack_limits_are_reported():
     sim = rl.Simulator(cluster, 'gandiva', 'yarn', n_replicas=1)
     with pytest.raises(_ffi.RlgsError):
         sim.run()                                        # no trace
+    sim.close()
+
+
+@pytest.mark.parametrize('scheme', ['horus+', 'yarn'])
+@pytest.mark.parametrize('name,kq,seed', [('probe100_1x4x8', 3, 1), ('probe100_2x2x8_k3', 2, 5), ('gen300_2x4x8', 4, 2), ('gen300_3x2x4', 5, 3),
+                                          ('gen2000_4x8x8_spread', 3, 7)])
+def test_horus_plus_matches_oracle(name, kq, seed, scheme):
+    """--schedule horus+: k-means queues + credit pick.  The oracle is pinned against the reference run with the same
+    injected k-means draws (oracle/ref_runner.py _INJECT, tests/golden/horusplus_*)."""
+    frame, flags, k = CASES[name]
+    df = frame()
+    cluster = rl.cluster_from_flags(flags)
+    tr = rl.prepare_trace(df, cluster)
+    sim = rl.Simulator(cluster, 'horus+', scheme, n_replicas=2, rows=True, num_buffer=k, num_queue=kq, pack_seed=seed, pack_rng=False,
+                       max_ticks=400000, ticks_per_launch=(0 if kq != 4 else 41))
+    sim.load_trace(tr)
+    sim.run()
+    otr = cpu_sim.prepare_trace(df)
+    o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus+', k, scheme=('yarn' if scheme == 'yarn' else None), num_queue=kq, inject_seed=seed)
+    for r in range(2):
+        check(sim, cluster, tr, o, otr, r)
     sim.close()

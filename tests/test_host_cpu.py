@@ -38,8 +38,7 @@ def test_plugin_registries_keep_the_reference_keys():
     assert s.device_id == _ffi.SCHED['fifo'] and p.device_id == _ffi.PLACE['yarn']
     assert algorithm.resolve('dlas-gpu', 'count')[0].device_id == 2 and algorithm.resolve('dlas', 'count')[0].device_id == 3
     assert algorithm.resolve('horus', 'gandiva')[0].device_id == _ffi.SCHED['horus']   # three names, one placement
-    with pytest.raises(NotImplementedError):
-        algorithm.resolve('horus+', 'horus+')           # k-means queues: not on the device path
+    assert algorithm.resolve('horus+', 'horus+')[0].device_id == _ffi.SCHED['horus+']
     with pytest.raises(NotImplementedError):
         algorithm.resolve('fifo', 'horus')              # KeyError 'fifo' in the reference (algorithm.py:58)
     assert algorithm.resolve('horus', 'yarn')[1].device_id == _ffi.PLACE['yarn'] and algorithm.resolve('gandiva', 'yarn')[0].device_id == _ffi.SCHED['gandiva']

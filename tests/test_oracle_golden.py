@@ -33,11 +33,12 @@ def test_oracle_matches_reference_big(name):
 def _run_pack(name):
     g = goldutil.load(name)
     tr = cpu_sim.prepare_trace(goldutil.trace_input(g))
-    res = cpu_sim.run_pack(cpu_sim.make_cluster(**g['flags']), tr, g['schedule'], g['num_buffer'], scheme=g['scheme'])
+    res = cpu_sim.run_pack(cpu_sim.make_cluster(**g['flags']), tr, g['schedule'], g['num_buffer'], scheme=g['scheme'],
+                           num_queue=g['num_queue'], inject_seed=g['inject_seed'])
     return g, tr, res
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('small', 'gandiva'))
+@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('small', 'gandiva') + goldutil.case_names('small', 'horus+'))
 def test_pack_oracle_matches_reference_small(name):
     g, tr, res = _run_pack(name)
     assert cpu_sim.format_job_csv(tr, res) == g['job']
@@ -45,7 +46,7 @@ def test_pack_oracle_matches_reference_small(name):
     assert res['n_ticks'] == g['meta']['n_ticks']
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus') + goldutil.case_names('big', 'gandiva'))
+@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus') + goldutil.case_names('big', 'gandiva') + goldutil.case_names('big', 'horus+'))
 def test_pack_oracle_matches_reference_big(name):
     g, tr, res = _run_pack(name)
     assert goldutil.sha(cpu_sim.format_job_csv(tr, res)) == g['meta']['job_sha256']
