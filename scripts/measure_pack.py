@@ -12,9 +12,10 @@ out = {}
 for name, n, seed, reps in (('probe2k', 2000, 1, (1, 1184)), ('probe10k', 10000, 2, (1, 1184))):
     df = synth.frame_gen(n, seed, n).copy(); df['gpu_utilization_max'] = df['gpu_utilization_avg']
     tr = rl.prepare_trace(df, C)
-    for sched, scheme in (('horus', 'horus'), ('gandiva', 'gandiva'), ('horus', 'yarn'), ('gandiva', 'yarn')):
+    for sched, scheme in (('horus', 'horus'), ('horus+', 'horus+'), ('gandiva', 'gandiva'), ('horus', 'yarn'), ('horus+', 'yarn'), ('gandiva', 'yarn')):
         for R in reps:
-            sim = rl.Simulator(C, sched, scheme, n_replicas=R, rows='device')
+            kw = dict(num_queue=3, num_buffer=15, pack_seed=1, pack_rng=False) if sched == 'horus+' else {}
+            sim = rl.Simulator(C, sched, scheme, n_replicas=R, rows='device', **kw)
             sim.load_trace(tr)
             sim.run(); sim.run()
             ms, nl = sim.kernel_ms(); s = sim.summary(0)
