@@ -7,7 +7,7 @@ from rlgpuschedule_b200 import synth
 
 C = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
 REF = {('horus', 'horus', 'probe2k'): 108.96, ('gandiva', 'gandiva', 'probe2k'): 137.85,
-       ('horus', 'yarn', 'probe2k'): 36.66, ('gandiva', 'yarn', 'probe2k'): 39.66}   # tests/golden/*/meta.json reference_wall_s (this container, 1 core)
+       ('horus', 'yarn', 'probe2k'): 36.66, ('gandiva', 'yarn', 'probe2k'): 39.66, ('horus+', 'horus+', 'probe2k'): 94.66}   # tests/golden/*/meta.json reference_wall_s (this container, 1 core)
 out = {}
 for name, n, seed, reps in (('probe2k', 2000, 1, (1, 1184)), ('probe10k', 10000, 2, (1, 1184))):
     df = synth.frame_gen(n, seed, n).copy(); df['gpu_utilization_max'] = df['gpu_utilization_avg']
