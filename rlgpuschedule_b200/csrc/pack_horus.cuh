@@ -90,7 +90,7 @@ struct PackState {
     uint32_t kcalls, pad1;    // horus+: np.random.randint / choice calls so far
     int64_t mem_sum, util_mu_sum, util_var_sum, sum_arr, sum_jct, sumQ, sumR, events;
 #ifdef PACK_PROFILE
-    int64_t prof[12];   // cycles: 0 arrivals, 1 queue pops, 2 score, 3 heap, 4 sort, 5 trials, 6 real place, 7 re-push, 8 start, 9 finish, 10 row, 11 attempts
+    int64_t prof[16];   // cycles: 0 arrivals, 1 queue pops, 2 score, 3 heap, 4 sort, 5 trials, 6 real place, 7 re-push, 8 start, 9 finish, 10 row, 11 attempts
 #endif
 };
 #ifdef PACK_PROFILE
@@ -498,6 +498,9 @@ __device__ __forceinline__ int pack_place(const PackDesc &D, const ClusterConst 
                 }
             }
         }
+#ifdef PACK_PROFILE
+        { long long _t1 = clock64(); if (doomed) { st.prof[12] += _t1 - _t0; st.prof[13] += 1; } else { st.prof[14] += 1; } }
+#endif
         PACK_T(3);
         if (hlen == 0) return 0;
         // ---- sorted(nodes_stack, key=min_score): stable insertion sort of the heap array

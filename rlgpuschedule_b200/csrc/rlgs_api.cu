@@ -713,8 +713,9 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
         out->events = z.events; out->n_jobs = s->h_pdesc[r].J; out->n_arrived = z.cursor; out->n_started = z.start_seq;
         out->n_finished = z.F; out->max_queued = z.max_q; out->max_running = z.max_r; out->status = z.status; out->done = z.done;
 #ifdef PACK_PROFILE
-        static const char *nm[12] = {"arrivals", "q_pop", "score", "heap", "sort", "trials", "real_place", "re_push", "start", "finish", "row", "attempts"};
-        for (int k = 0; k < 12; ++k) fprintf(stderr, "prof %-10s %lld\n", nm[k], (long long)z.prof[k]);
+        static const char *nm[16] = {"arrivals", "q_pop", "score", "heap", "sort", "trials", "real_place", "re_push", "start", "finish", "row", "attempts",
+                                     "heap_doomed", "n_doomed_sim", "n_other_sim", "-"};
+        for (int k = 0; k < 16; ++k) fprintf(stderr, "prof %-10s %lld\n", nm[k], (long long)z.prof[k]);
 #endif
     } else if (!s->legacy) {
         const RepState &z = s->h_state[r];
