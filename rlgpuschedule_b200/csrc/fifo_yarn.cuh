@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                 const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
                 const int cal_head = s.sv.bkt[cal];
+                __syncwarp();                                             // every lane has read the chain heads before lane 0 rewrites them
                 if (lane == 0) {
                     s.sv.a[sl] = make_int4(d + dur_ticks, st.start_seq, cal_head, job);
                     s.sv.bkt[cal] = sl;                                   // file under the end tick
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                     if (sl >= slot_cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
                     const int cal = (d + dur_ticks) & (RLGS_CAL_W - 1);
                     const int cal_head = s.sv.bkt[cal];
+                    __syncwarp();
                     if (lane == 0) {
                         s.sv.a[sl] = make_int4(d + dur_ticks, st.start_seq, cal_head, job);
                         s.sv.bkt[cal] = sl;                               // file under the end tick
@@ -401,6 +403,7 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
                 }
                 if (best < 0) break;
                 more = matches > 1;                                  // walk again only if another job finishes this tick
+                __syncwarp();                                        // the walk is over in every lane before lane 0 unlinks
                 if (lane == 0) { if (best_prev < 0) s.sv.bkt[bk] = best_next; else s.sv.a[best_prev].z = best_next; }
                 __syncwarp();
                 fifo_finish_slot(D, s, c, st, best, lane);

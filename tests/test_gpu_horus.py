@@ -144,7 +144,7 @@ def test_pack_limits_are_reported():
 
 
 @pytest.mark.parametrize('scheme', ['horus+', 'yarn'])
-@pytest.mark.parametrize('name,kq,seed', [('probe100_1x4x8', 3, 1), ('probe100_2x2x8_k3', 2, 5), ('gen300_2x4x8', 4, 2), ('gen300_3x2x4', 5, 3),
+@pytest.mark.parametrize('name,kq,seed', [('probe100_1x4x8', 3, 1), ('probe100_1x4x8', 1, 4), ('probe100_2x2x8_k3', 2, 5), ('gen300_2x4x8', 4, 2), ('gen300_3x2x4', 5, 3),
                                           ('gen2000_4x8x8_spread', 3, 7)])
 def test_horus_plus_matches_oracle(name, kq, seed, scheme):
     """--schedule horus+: k-means queues + credit pick.  The oracle is pinned against the reference run with the same
