@@ -47,6 +47,7 @@ struct TraceBuf {
     double *dur_out = nullptr;  // [count][cap_n]
     PackJob *pack = nullptr;    // [n] horus placement inputs
     PlusFeat *feat = nullptr;   // [n] horus+ k-means features
+    void *pack_slab = nullptr;  // per-replica working set of the pack kernels for this trace
     int32_t n = 0, cap_n = 0;
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
@@ -226,7 +227,7 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); cudaFree(t.feat); }
+    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); cudaFree(t.feat); cudaFree(t.pack_slab); }
     cudaFree(s->d_pdesc); cudaFree(s->d_pstate);
     if (s->h_pstate) cudaFreeHost(s->h_pstate);
     if (s->h_pinit) cudaFreeHost(s->h_pinit);
@@ -316,7 +317,14 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         CU(cudaMemcpy(tb.net + 2 * (size_t)n, net->iterations, 8 * (size_t)n, cudaMemcpyHostToDevice));
     }
     int tid = (int)s->traces.size();
-    s->traces.push_back(tb);
+    if (s->pack)   // a reload of the same replica range replaces the trace (and its working set) instead of piling up
+        for (size_t t = 0; t < s->traces.size(); ++t)
+            if (s->traces[t].first == first && s->traces[t].count == count) {
+                TraceBuf &old = s->traces[t];
+                cudaFree(old.dev); cudaFree(old.pack); cudaFree(old.feat); cudaFree(old.pack_slab);
+                tid = (int)t;
+            }
+    if (tid == (int)s->traces.size()) s->traces.push_back(tb); else s->traces[tid] = tb;
     unsigned char *slab = nullptr;
     if (s->pack) {
         for (int r = 0; r < count; ++r) { s->h_pdesc[first + r] = PackDesc{}; s->h_pdesc[first + r].trace = tb.dev; s->h_pdesc[first + r].J = n; s->h_ldesc[first + r].J = n; }
@@ -417,7 +425,7 @@ extern "C" int32_t rlgs_load_pack_inputs(rlgs_sim *s, int32_t first, int32_t cou
     for (size_t v : sz) per += align_up(v, 256);
     unsigned char *slab = nullptr;
     CU(cudaMalloc(&slab, per * (size_t)count));
-    s->slabs.push_back(slab);
+    tb->pack_slab = slab;
     const int64_t unit = (int64_t)1 << in->mem_shift;
     for (int r = 0; r < count; ++r) {
         unsigned char *p = slab + per * (size_t)r;

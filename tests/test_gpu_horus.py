@@ -162,3 +162,17 @@ def test_horus_plus_matches_oracle(name, kq, seed, scheme):
     for r in range(2):
         check(sim, cluster, tr, o, otr, r)
     sim.close()
+
+
+def test_pack_trace_reload_replaces_the_previous_one():
+    """load_trace on the same replica range twice (the e2e pattern): the second trace is the one that runs."""
+    frame, flags, k = CASES['probe100_2x2x8_k3']
+    cluster = rl.cluster_from_flags(flags)
+    sim = rl.Simulator(cluster, 'horus', 'horus', n_replicas=2, rows=True, num_buffer=k, max_ticks=400000)
+    for df in (zero_spread(tracegen.frame_gen(300, 12, 60)), frame()):
+        tr = rl.prepare_trace(df, cluster)
+        sim.load_trace(tr)
+        sim.run()
+        otr = cpu_sim.prepare_trace(df)
+        check(sim, cluster, tr, cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k), otr, 1)
+    sim.close()
