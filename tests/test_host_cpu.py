@@ -112,3 +112,18 @@ def test_ingest_rejects_what_the_reference_would_raise_on():
     df = tracegen.frame_rows([dict(memory_max=1e9 / 3)])
     with pytest.raises(ValueError):
         rl.prepare_trace(df, cluster)                    # not exactly summable in 53 bits
+
+
+def test_pack_inputs_follow_the_task_fields_the_scores_read():
+    """Trace.pack_inputs: utilisation mean / half spread, un-clamped task memory in the trace's dyadic unit, floor(used_gpus)."""
+    from rlgpuschedule_b200 import synth
+    df = synth.frame_rows([dict(used_gpus=4.0, gpu_per_container=2, gpu_utilization_avg=40.0, gpu_utilization_max=50.0, memory_max=5 * 2 ** 30, memory_avg=3 * 2 ** 30),
+                           dict(normalized_time=10000, used_gpus=3.0, gpu_per_container=2, gpu_utilization_avg=0.0, gpu_utilization_max=0.0, memory_max=40 * 10 ** 9, memory_avg=1e9)])
+    tr = rl.prepare_trace(df, rl.Cluster(num_gpu_p_node=8))
+    pi = tr.pack_inputs()
+    assert pi['util_sd'].tolist() == [5.0, 0.0] and pi['heap_cap'].tolist() == [4, 3]
+    unit = 2.0 ** tr.mem_shift
+    assert pi['task_mem'].tolist() == [int(5 * 1024 * unit), int(40e9 / 2 ** 20 * unit)]        # not clamped to the 32 GiB capacity
+    assert 40e9 / 2 ** 20 * unit == float(int(40e9 / 2 ** 20 * unit))                             # exact in the unit
+    assert tr.records['tasks'].tolist() == [2, 1] and pi['used_gpus'].tolist() == [4.0, 3.0]
+    assert np.allclose(pi['mem_avg_mib'], [3 * 1024, 1e9 / 2 ** 20])
