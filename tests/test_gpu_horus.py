@@ -176,3 +176,19 @@ def test_pack_trace_reload_replaces_the_previous_one():
         otr = cpu_sim.prepare_trace(df)
         check(sim, cluster, tr, cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus', k), otr, 1)
     sim.close()
+
+
+def test_horus_plus_with_seeded_utilisation_draws():
+    """horus+ on a trace with a utilisation spread: the k-means draws and the score's utilisation draws share opts.pack_seed."""
+    frame, flags, k = CASES['gen2000_4x8x8_spread']
+    df = frame()
+    cluster = rl.cluster_from_flags(flags)
+    tr = rl.prepare_trace(df, cluster)
+    sim = rl.Simulator(cluster, 'horus+', 'horus+', n_replicas=2, rows=True, num_buffer=k, num_queue=3, pack_seed=5, pack_rng=True, max_ticks=400000)
+    sim.load_trace(tr)
+    sim.run()
+    otr = cpu_sim.prepare_trace(df)
+    for r in range(2):
+        o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, 'horus+', k, seed=5, replica=r, num_queue=3, inject_seed=5)
+        check(sim, cluster, tr, o, otr, r)
+    sim.close()
