@@ -47,3 +47,41 @@ def test_oracle_equals_live_reference_on_random_cases():
             assert ref['job_csv'] is not None, (seed, ref['stderr'][-500:])
             assert job == ref['job_csv'], seed
             assert clu == ref_runner.strip_util_column(ref['cluster_csv']), seed
+
+
+# ---- the pack family: horus / horus+ / gandiva over the pack placement (zero utilisation spread: the reference's draws return
+# their mean) and over yarn (real spread); horus+ with its k-means draws injected (ref_runner._INJECT)
+PACK_COMBOS = [('horus', 'horus'), ('gandiva', 'gandiva'), ('horus+', 'horus+'), ('horus', 'yarn'), ('gandiva', 'yarn'), ('horus+', 'yarn')]
+
+
+def _run_pack(arg):
+    seed, (sched, scheme) = arg
+    df, flags = _case(seed)
+    if scheme != 'yarn':
+        df = df.copy(); df['gpu_utilization_max'] = df['gpu_utilization_avg']
+    rng = np.random.default_rng(seed + 7)
+    k = int(rng.integers(1, 8)); kq = int(rng.integers(1, 5)); inj = int(rng.integers(1, 1000))
+    work = tempfile.mkdtemp(prefix='rlgs_livepack_%d_' % seed)
+    trace = os.path.join(work, 't.csv')
+    synth.write(df, trace)
+    extra = dict(num_queue=kq, inject_seed=inj) if sched == 'horus+' else {}
+    ref = ref_runner.run_reference(trace, workdir=work, schedule=sched, scheme=scheme, num_buffer=k, **extra, **flags)
+    tr = cpu_sim.prepare_trace(trace)
+    try:
+        res = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), tr, sched, k, scheme=('yarn' if scheme == 'yarn' else None),
+                               num_queue=kq, inject_seed=inj)
+    except RuntimeError:
+        return seed, sched, scheme, ref, None, None     # the oracle says the reference raises on this input
+    return seed, sched, scheme, ref, cpu_sim.format_job_csv(tr, res), cpu_sim.format_cluster_csv(res)
+
+
+def test_pack_oracle_equals_live_reference_on_random_cases():
+    args = [(200 + 3 * i + j, combo) for i, combo in enumerate(PACK_COMBOS) for j in range(2)]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for seed, sched, scheme, ref, job, clu in ex.map(_run_pack, args):
+            if job is None:
+                assert ref['returncode'] != 0 or ref['job_csv'] is None or 'Error' in ref['stderr'], (seed, sched, scheme)
+                continue
+            assert ref['job_csv'] is not None, (seed, sched, scheme, ref['stderr'][-500:])
+            assert job == ref['job_csv'], (seed, sched, scheme)
+            assert clu == ref_runner.strip_util_column(ref['cluster_csv']), (seed, sched, scheme)
