@@ -43,3 +43,37 @@ def test_random_cases_all_schedules(block):
             assert np.array_equal(rows['median_lo'], o['rows']['time']) and np.array_equal(rows['busy_gpus'], o['rows']['busy_gpus']), (seed, sched)
             assert np.array_equal(rows['idle_nodes'], o['rows']['idle_nodes']) and np.array_equal(rows['queued'], o['rows']['pending']), (seed, sched)
             sim.close()
+
+
+PACK_COMBOS = [('horus', 'horus'), ('gandiva', 'gandiva'), ('horus+', 'horus+'), ('horus', 'yarn'), ('gandiva', 'yarn'), ('horus+', 'yarn')]
+
+
+@pytest.mark.parametrize('sched,scheme', PACK_COMBOS)
+def test_random_cases_pack_family(sched, scheme):
+    """The same generator as the live differential test of the oracle (tests/test_oracle_vs_live_reference.py): device vs oracle
+    on random traces / cluster shapes / look-ahead / queue counts, mean and seeded utilisation draws."""
+    for seed in range(300, 312):
+        df, flags = _case(seed)
+        rng = np.random.default_rng(seed + 7)
+        k = int(rng.integers(1, 8)); kq = int(rng.integers(1, 5)); inj = int(rng.integers(1, 1000))
+        draws = bool(seed % 3 == 0) and scheme != 'yarn'        # every third case: seeded utilisation draws on the real spread
+        if scheme != 'yarn' and not draws:
+            df = df.copy(); df['gpu_utilization_max'] = df['gpu_utilization_avg']
+        cluster = rl.cluster_from_flags(flags)
+        tr = rl.prepare_trace(df, cluster)
+        otr = cpu_sim.prepare_trace(df)
+        try:
+            o = cpu_sim.run_pack(cpu_sim.make_cluster(**flags), otr, sched, k, scheme=('yarn' if scheme == 'yarn' else None),
+                                 num_queue=kq, inject_seed=inj, seed=(inj if draws else None), replica=1)
+        except RuntimeError:
+            continue                                             # the reference would raise on this input
+        kw = dict(num_queue=kq) if sched == 'horus+' else {}
+        sim = rl.Simulator(cluster, sched, scheme, n_replicas=2, rows=True, num_buffer=k, pack_seed=inj, pack_rng=draws,
+                           max_ticks=400000, ticks_per_launch=int(seed % 4) * 29, **kw)
+        sim.load_trace(tr); sim.run()
+        j = sim.jobs(1)
+        dur = tr.duration + 5.0 * (sim.job_plane(1, _ffi.PLANE_AUX) == 1)
+        job = lm.format_job_csv(tr, j['finish_order'], j['start'], j['end'], j['preempt'], get_duration=dur, jct=sim.job_plane(1, _ffi.PLANE_PREEMPT))
+        assert job == cpu_sim.format_job_csv(otr, o), (seed, sched, scheme)
+        assert lm.format_cluster_csv(sim.rows(1), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o), (seed, sched, scheme)
+        sim.close()
