@@ -1,4 +1,7 @@
-"""Dev aid: per-phase cycle breakdown of the horus kernel (needs librlgs_prof.so built with -DPACK_PROFILE; RLGS_LIB points at it)."""
+"""Dev aid: per-phase cycle breakdown of the horus kernel.  Build the profiling variant first:
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared --fmad=false -DPACK_PROFILE \\
+         -o rlgpuschedule_b200/librlgs_prof.so rlgpuschedule_b200/csrc/rlgs_api.cu
+and run with RLGS_LIB=rlgpuschedule_b200/librlgs_prof.so (the counters are printed by rlgs_get_summary)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rlgpuschedule_b200 as rl
