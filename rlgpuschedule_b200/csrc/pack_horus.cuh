@@ -1,4 +1,5 @@
-// pack_horus.cuh — `--schedule horus` with horus_placement on the device, one warp per replica.
+// pack_horus.cuh — the schedules horus, horus+ and gandiva of the live reference on the device, one warp per replica, over the
+// packing placement (horus_placement) or the yarn fit.  pack_horus_kernel<GANDIVA, YARN, PLUS> is instantiated six times.
 //
 // Restates (reference paths):
 //   Scheduler.start tick loop            core/scheduling/schedule.py:178-216
@@ -11,6 +12,11 @@
 //   utilisation-ordered job queue        core/jobs/base_factory.py:1-12 + job_queue_manager.py:129-154 (stdlib heapq)
 //   interference bookkeeping             infra/node.py:71-91, core/jobs/jobs_manager.py:175-187 (+5 ticks once a flagged
 //                                        task is left alone on a device)
+//   gandiva                              schedule_fifo algorithm.py:189-202 on a plain list, gandiva_score horus.py:6-25,
+//                                        time_slice_check algorithm.py:420-444 -> JobsManager.preempt jobs_manager.py:150-173
+//   horus+                               schedule_horus_plus algorithm.py:242-290, clusterize core/jobs/utils.py:36-67,
+//                                        credits job_queue_manager.py:103-127, re-clustering insert jobs_manager.py:115-140
+//   --scheme yarn under these schedules  ms_yarn_placement algorithm.py:28-32 (yarn_place.cuh)
 //
 // Everything order-dependent in the reference (heapq sift order, stable sorts, dict insertion order, the order of
 // release calls) is kept, because ties are the common case (all idle nodes score the same).  Scalar phases (heap
