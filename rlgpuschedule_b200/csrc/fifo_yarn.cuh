@@ -28,7 +28,7 @@ struct SlotView {
 // Finish detection is a calendar: a started job is filed under its end tick modulo RLGS_CAL_W, so the
 // per-tick finish scan of the reference (jobs_manager.py:243-250, every running job) touches only
 // the bucket of the current tick.
-#define RLGS_CAL_W 128
+#define RLGS_CAL_W 256
 
 struct FifoSmem {
     NodeView nv;
@@ -239,11 +239,12 @@ __global__ void __launch_bounds__(32, RLGS_FIFO_MIN_BLOCKS) fifo_yarn_kernel(con
     h0.a = h0.b = make_int4(0, 0, 0, 0);
     if (st.Q > 0) h0 = load_rec(D.stack + st.head);
 
-    const int d_stop = st.d + tick_budget;
+    // the launch stops at its tick budget or at the safety limit max_ticks, whichever comes first (one compare per tick)
+    const int d_budget = st.d + tick_budget;
+    const int d_stop = (max_ticks > 0 && max_ticks < (long)d_budget) ? (int)max(max_ticks, (long)st.d) : d_budget;
     while (true) {
         if ((J - st.cursor) + st.R == 0) { st.done = 1; break; }   // schedule.py:185 (queue not consulted, q2)
-        if (st.d == d_stop) break;
-        if (max_ticks > 0 && st.d >= max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
+        if (st.d == d_stop) { if (max_ticks > 0 && st.d >= max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; } break; }
         const int d = st.d;
 
         // ---------------- arrivals: every job with arrival_tick <= d, pushed to the FRONT in order (q1)
