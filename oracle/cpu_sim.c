@@ -5,14 +5,19 @@
  * (bench.py cpu_baseline / --impl reference).  It is never linked into, imported by or called
  * from the product library (rlgpuschedule_b200/csrc, include/rlgs.h).
  *
- * It restates, function by function, the live tick-stepped simulator of matthewygf/RLGPUSchedule
- * for `--schedule fifo --scheme yarn`, keeping the reference's per-tick whole-state sweeps and all
- * quirks of SURVEY.md Appendix A.  Citations are path:line under /root/reference.
+ * It restates, function by function, the simulator of matthewygf/RLGPUSchedule, keeping the reference's
+ * per-tick whole-state sweeps and all quirks of SURVEY.md Appendix A.  Citations are path:line under
+ * /root/reference.  Sections and their parity status:
  *
- * Parity status: PINNED for fifo+yarn — tests/test_oracle_golden.py checks this file byte-for-byte
- * against job.csv / cluster.csv written by the unmodified reference (tests/golden, generated by
- * oracle/make_golden.py).  The sjf / dlas-gpu restatements live in oracle/cpu_legacy.c and are
- * "parity unpinned" (the reference code for them is dead and not runnable).
+ *   1. live tick loop, `--schedule fifo --scheme yarn` (oracle_env_yarn / oracle_fifo_yarn): PINNED — byte for byte
+ *      against job.csv / cluster.csv written by the unmodified reference (tests/golden, oracle/make_golden.py,
+ *      tests/test_oracle_golden.py) and on random traces run live (tests/test_oracle_vs_live_reference.py).
+ *      Its network-cost option and the window policies of the RL environment are build-defined: UNPINNED.
+ *   2. legacy event-driven schedules sjf / shortest / shortest-gpu / dlas / dlas-gpu (oracle_sjf_yarn, oracle_dlas):
+ *      PARITY UNPINNED — dead code in the reference, restated from its source only.
+ *   3. pack family, `--schedule horus | horus+ | gandiva` over horus_placement or yarn (oracle_pack): PINNED on traces
+ *      without utilisation spread (and on any trace over yarn); horus+ with its k-means draws injected into the
+ *      reference run.  The counter-based utilisation draw used when there is a spread is build-defined: UNPINNED.
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -shared -fPIC).
  */
