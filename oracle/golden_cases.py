@@ -215,3 +215,4 @@ CASES.update({
     'horusplusyarn_dense_k4': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8), schedule='horus+', scheme='yarn', num_queue=4, inject_seed=3, big=True),
 })
 CASES['horusplus_probe2k_k3'] = dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='horus+', num_queue=3, inject_seed=1, num_buffer=15, big=True)
+CASES['horus_probe10k'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)), flags=C4328, schedule='horus', big=True, huge=True)   # 72 min of reference time

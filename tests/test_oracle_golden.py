@@ -46,7 +46,8 @@ def test_pack_oracle_matches_reference_small(name):
     assert res['n_ticks'] == g['meta']['n_ticks']
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus') + goldutil.case_names('big', 'gandiva') + goldutil.case_names('big', 'horus+'))
+@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus') + goldutil.case_names('huge', 'horus') + goldutil.case_names('big', 'gandiva') +
+                         goldutil.case_names('big', 'horus+'))
 def test_pack_oracle_matches_reference_big(name):
     g, tr, res = _run_pack(name)
     assert goldutil.sha(cpu_sim.format_job_csv(tr, res)) == g['meta']['job_sha256']
