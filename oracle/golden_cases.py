@@ -216,3 +216,7 @@ CASES.update({
 })
 CASES['horusplus_probe2k_k3'] = dict(frame=_zs(lambda: tg.frame_gen(2000, 1, 2000)), flags=C4328, schedule='horus+', num_queue=3, inject_seed=1, num_buffer=15, big=True)
 CASES['horus_probe10k'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)), flags=C4328, schedule='horus', big=True, huge=True)   # 72 min of reference time
+CASES['gandiva_probe10k'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)), flags=C4328, schedule='gandiva', big=True, huge=True)
+CASES['horusyarn_probe10k'] = dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, schedule='horus', scheme='yarn', big=True, huge=True)
+CASES['gandivayarn_probe10k'] = dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, schedule='gandiva', scheme='yarn', big=True, huge=True)
+CASES['horusplus_probe10k_k3'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)), flags=C4328, schedule='horus+', num_queue=3, inject_seed=1, num_buffer=15, big=True, huge=True)

@@ -64,3 +64,8 @@ def trace_input(g):
     txt = buf.getvalue()
     assert sha(txt) == g['meta']['trace_sha256'], 'tracegen drifted from the fixture'
     return pd.read_csv(io.StringIO(txt))
+
+
+def pack_case_names(kinds=('small', 'big', 'huge')):
+    """Fixtures of the pack family (horus, horus+, gandiva; over the pack placement or yarn)."""
+    return [n for sched in ('horus', 'gandiva', 'horus+') for kind in kinds for n in case_names(kind, sched)]

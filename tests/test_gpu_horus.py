@@ -87,9 +87,7 @@ def test_horus_bounded_launches_resume(schedule):
     sim.close()
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('big', 'horus') + goldutil.case_names('huge', 'horus') +
-                         goldutil.case_names('small', 'gandiva') + goldutil.case_names('big', 'gandiva') +
-                         goldutil.case_names('small', 'horus+') + goldutil.case_names('big', 'horus+'))
+@pytest.mark.parametrize('name', goldutil.pack_case_names())
 def test_horus_matches_the_reference_golden(name):
     """Device outputs vs the files the UNMODIFIED reference wrote for `--schedule horus --scheme horus` (tests/golden)."""
     g = goldutil.load(name)

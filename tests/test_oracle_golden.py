@@ -38,7 +38,7 @@ def _run_pack(name):
     return g, tr, res
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('small', 'horus') + goldutil.case_names('small', 'gandiva') + goldutil.case_names('small', 'horus+'))
+@pytest.mark.parametrize('name', goldutil.pack_case_names(('small',)))
 def test_pack_oracle_matches_reference_small(name):
     g, tr, res = _run_pack(name)
     assert cpu_sim.format_job_csv(tr, res) == g['job']
@@ -46,8 +46,7 @@ def test_pack_oracle_matches_reference_small(name):
     assert res['n_ticks'] == g['meta']['n_ticks']
 
 
-@pytest.mark.parametrize('name', goldutil.case_names('big', 'horus') + goldutil.case_names('huge', 'horus') + goldutil.case_names('big', 'gandiva') +
-                         goldutil.case_names('big', 'horus+'))
+@pytest.mark.parametrize('name', goldutil.pack_case_names(('big', 'huge')))
 def test_pack_oracle_matches_reference_big(name):
     g, tr, res = _run_pack(name)
     assert goldutil.sha(cpu_sim.format_job_csv(tr, res)) == g['meta']['job_sha256']
