@@ -14,7 +14,14 @@
  *      tests/test_oracle_golden.py) and on random traces run live (tests/test_oracle_vs_live_reference.py).
  *      Its network-cost option and the window policies of the RL environment are build-defined: UNPINNED.
  *   2. legacy event-driven schedules sjf / shortest / shortest-gpu / dlas / dlas-gpu (oracle_sjf_yarn, oracle_dlas):
- *      PARITY UNPINNED — dead code in the reference, restated from its source only.
+ *      PINNED GIVEN SHIMS — the loops are dead code in the reference (undefined globals JOBS / CLUSTER / LOG / scheduler),
+ *      but oracle/ref_legacy_runner.py executes them UNMODIFIED (run_sim.py:162-287, :299-431, :664-947, with the
+ *      reference's own infra.cluster._Cluster and log._Log) after supplying the missing pieces at run time: the job
+ *      container JOBS (reconstructed; its semantics are listed in that file's header), scheduler.try_get_job_res = the live
+ *      ms_yarn_placement, and an empty stub for the missing module core.job.  This section matches the cluster.csv /
+ *      job.csv those runs wrote byte for byte on 26 fixtures (tests/golden/{sjf,shortest,shortestgpu,dlasgpu,dlas}_*,
+ *      up to the 10 000-job sjf trace = BASELINE config C2 and the 60 000-job dlas-gpu trace = C3).  What stays
+ *      build-defined: the trace -> (submit, duration, num_gpu) conversion in ticks and queue_limit = [30, 60, 150].
  *   3. pack family, `--schedule horus | horus+ | gandiva` over horus_placement or yarn (oracle_pack): PINNED on traces
  *      without utilisation spread (and on any trace over yarn); horus+ with its k-means draws injected into the
  *      reference run.  The counter-based utilisation draw used when there is a spread is build-defined: UNPINNED.
@@ -485,13 +492,14 @@ int64_t oracle_fifo_yarn_batch(const oracle_cluster *c, int32_t n, const double 
 }
 
 /* =============================================================================================
- * Legacy event-driven schedules: sjf and dlas-gpu.   PARITY UNPINNED.
+ * Legacy event-driven schedules: sjf family and dlas family.   PINNED GIVEN SHIMS (see the file header).
  *
- * The reference keeps these only as dead code (run_sim.py:162-287 smallest_first_sim_jobs and
- * run_sim.py:664-947 dlas_sim_jobs(gputime=True)); they depend on globals that are never defined
- * (JOBS, CLUSTER, LOG) and cannot be executed, so there are no reference outputs to pin against.
- * This is a line-by-line restatement of that code with the missing pieces reconstructed as
- * SURVEY.md Appendix B describes; the CUDA kernels are checked against it, nothing else is.
+ * The reference keeps these only as dead code (run_sim.py:162-287 smallest_first_sim_jobs, :299-431
+ * shortest_first_sim_jobs, :664-947 dlas_sim_jobs); they read globals that are never defined (JOBS, CLUSTER, LOG,
+ * scheduler).  oracle/ref_legacy_runner.py defines those at run time and calls the functions as they are;
+ * this restatement equals the files those runs wrote (tests/test_oracle_golden.py, 26 fixtures), including
+ * behaviour that only execution revealed: the 'end_jobs' list that run_sim.py:706-710 writes into the head
+ * start event survives a queue-jump event and completes jobs early (see oracle_dlas).
  *
  * Build-defined inputs: submit_time = ceil(normalized_time) ticks,
  * duration = max(1, ceil(minutes*0.5)) ticks, num_gpu = ceil(used_gpus); job_events = arrivals
@@ -500,7 +508,8 @@ int64_t oracle_fifo_yarn_batch(const oracle_cluster *c, int32_t n, const double 
  * Row per event = the legacy cluster.csv columns (log.py:137-258): time, idle_node, full_node,
  * busy_gpu, pending_job, running_job, completed_job (busy_node / idle_gpu derive from them).
  * For a placement scheme the reference leaves the node/gpu columns at 0 (the code computing them is
- * commented out, log.py:171-196); here they carry the values that commented code would produce.
+ * commented out, log.py:171-196); here they carry the values that commented code would produce, and the
+ * CSV formatters print 0 like the reference unless asked for them.
  * ========================================================================================== */
 
 typedef struct {
@@ -673,6 +682,7 @@ int oracle_dlas(const oracle_cluster *c, int32_t n, const double *nt, const doub
     }
     int32_t *runnable = (int32_t *)malloc(((size_t)n + 1) * 4), *end_jobs = (int32_t *)malloc(((size_t)n + 1) * 4);
     int32_t *tmp = (int32_t *)malloc(((size_t)n + 1) * 4);
+    int32_t *attached = (int32_t *)malloc(((size_t)n + 1) * 4); int n_att = -1;   /* 'end_jobs' key of the head start event, -1 = absent */
     int32_t **queues = (int32_t **)malloc(sizeof(int32_t *) * (size_t)num_queue); int32_t *qlen = (int32_t *)calloc((size_t)num_queue, 4);
     for (int q = 0; q < num_queue; ++q) queues[q] = (int32_t *)malloc(((size_t)n + 1) * 4);
     int rlen = 0, n_end = 0, end_time_next = INT32_MAX, cursor = 0, flen = 0, rc = 0, next_job_jump = INT32_MAX, free_gpu = total_gpu;
@@ -684,11 +694,20 @@ int oracle_dlas(const oracle_cluster *c, int32_t n, const double *nt, const doub
         int event_time, has_end = 0, has_start = 0;
         if (end_time < start_time) { event_time = end_time; has_end = 1; }             /* :699-701 */
         else if (end_time > start_time) { event_time = start_time; has_start = 1; }    /* :702-705 */
-        else { event_time = start_time; has_start = 1; has_end = 1; }                  /* :706-710 */
+        else {                                                                         /* :706-710 */
+            /* `event = start_event; event['end_jobs'] = end_events[0]['end_jobs']` writes the key into the dict that stays at
+               JOBS.job_events[0]: when the jump test below replaces the event, the head start event keeps this list, and it is
+               honoured when that start event is finally handled — even if the jobs in it were demoted / preempted meanwhile
+               (they are completed early, whatever their status).  Pinned by tests/golden/dlasgpu_*. */
+            event_time = start_time; has_start = 1; has_end = 1;
+            memcpy(attached, end_jobs, (size_t)n_end * 4); n_att = n_end;
+        }
         if (event_time > next_job_jump) { event_time = next_job_jump; has_end = has_start = 0; }  /* :715-717 */
-        if (has_end)                                                   /* :721-727 */
-            for (int k = 0; k < n_end; ++k) {
-                int e = end_jobs[k];
+        const int32_t *ending = end_jobs; int n_ending = has_end ? n_end : 0;
+        if (has_start) { ending = attached; n_ending = n_att > 0 ? n_att : 0; }        /* 'end_jobs' in start_event */
+        if (n_ending > 0)                                              /* :721-727 */
+            for (int k = 0; k < n_ending; ++k) {
+                int e = ending[k];
                 free_gpu += L[e].num_gpu; if (free_gpu > total_gpu) free_gpu = total_gpu;   /* cluster.py:1462-1468 */
                 L[e].status = L_END; L[e].end_time = event_time;
                 list_remove(runnable, &rlen, e);
@@ -701,6 +720,7 @@ int oracle_dlas(const oracle_cluster *c, int32_t n, const double *nt, const doub
                 j->status = L_PENDING; j->last_check = event_time; j->q_id = 0;
                 runnable[rlen++] = cursor; queues[0][qlen[0]++] = cursor; cursor++; ev_count++;
             }
+        if (has_start) n_att = -1;                                     /* :737 JOBS.job_events.pop(0): the next start event is a fresh dict */
         for (int k = 0; k < rlen; ++k) {                               /* :740-792 */
             int job = runnable[k]; ljob *j = &L[job];
             int d = event_time - j->last_check;
@@ -762,7 +782,7 @@ int oracle_dlas(const oracle_cluster *c, int32_t n, const double *nt, const doub
     *n_finished = flen; *n_events = nev;
     if (counters) { counters[0] = sweeps; counters[1] = ev_count; counters[2] = demotions; }
     for (int q = 0; q < num_queue; ++q) free(queues[q]);
-    free(queues); free(qlen); free(runnable); free(end_jobs); free(tmp); free(L);
+    free(queues); free(qlen); free(runnable); free(end_jobs); free(tmp); free(attached); free(L);
     return rc;
 }
 

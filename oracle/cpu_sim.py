@@ -240,13 +240,14 @@ def _run_legacy(fn_name, cluster, tr, extra_args, rows_cap=None):
 
 def run_sjf_yarn(cluster, tr, rows_cap=None, sort_mode=0):
     """Restated smallest_first_sim_jobs (run_sim.py:162-287; sort_mode 0) / shortest_first_sim_jobs
-    (run_sim.py:299-431; 1 = shortest, 2 = shortest-gpu) with the live yarn fit.  PARITY UNPINNED."""
+    (run_sim.py:299-431; 1 = shortest, 2 = shortest-gpu) with the live yarn fit.  Pinned against the reference's dead
+    code run unmodified under shim globals (oracle/ref_legacy_runner.py, tests/golden/sjf_*, shortest*_*)."""
     return _run_legacy('oracle_sjf_yarn', cluster, tr, [_p(tr['gpc'], C.c_int32), _p(tr['mem_mib'], C.c_double), C.c_int32(sort_mode)], rows_cap)
 
 
 def run_dlas_gpu(cluster, tr, queue_limit=(30, 60, 150), rows_cap=None, gputime=True):
     """Restated dlas_sim_jobs (run_sim.py:664-947), count-based admission; gputime=False is `--schedule dlas`.
-    PARITY UNPINNED."""
+    Pinned against the reference's dead code run unmodified under shim globals (tests/golden/dlasgpu_*, dlas_*)."""
     ql = np.asarray(queue_limit, np.int32)
     return _run_legacy('oracle_dlas', cluster, tr, [C.c_int32(int(gputime)), C.c_int32(len(ql) + 1), _p(ql, C.c_int32)], rows_cap)
 
@@ -267,6 +268,31 @@ def format_legacy_job_csv(tr, res, count_scheme):
                int(res['pending'][i]), int(res['preempt'][i])] + ([int(res['resume'][i])] if count_scheme else []) + [0]
         w.writerow(row)
     return buf.getvalue()
+
+
+def format_legacy_cluster_csv(res, cluster, count_scheme):
+    """cluster.csv in the legacy layout (/root/reference/log.py:43-45,137-258).  Under --scheme count the node / gpu columns
+    come from CLUSTER.free_gpu (log.py:233-238); under a placement scheme the reference's code for them is commented out
+    (log.py:171-189) and the columns stay 0."""
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    w.writerow(['time', 'idle_node', 'busy_node', 'full_node', 'idle_gpu', 'busy_gpu', 'pending_job', 'running_job', 'completed_job'])
+    N = cluster.num_switch * cluster.num_node_p_switch
+    D = N * cluster.num_gpu_p_node
+    for r in res['rows']:
+        if count_scheme:
+            w.writerow([int(r['time']), int(r['idle_nodes']), N - int(r['idle_nodes']), int(r['full_nodes']), D - int(r['busy_gpus']),
+                        int(r['busy_gpus']), int(r['pending']), int(r['running']), int(r['completed'])])
+        else:
+            w.writerow([int(r['time']), 0, 0, 0, 0, 0, int(r['pending']), int(r['running']), int(r['completed'])])
+    return buf.getvalue()
+
+
+def run_legacy(cluster, tr, schedule, queue_limit=(30, 60, 150)):
+    """Dispatch by --schedule name; returns (result, count_scheme)."""
+    if schedule in ('dlas-gpu', 'dlas'):
+        return run_dlas_gpu(cluster, tr, queue_limit, gputime=schedule == 'dlas-gpu'), True
+    return run_sjf_yarn(cluster, tr, sort_mode={'sjf': 0, 'shortest': 1, 'shortest-gpu': 2}[schedule]), False
 
 
 def run_env_yarn(cluster, tr, policy, window_k=5, seed=0, replica=0, actions=None, rows_cap=None):

@@ -220,3 +220,38 @@ CASES['gandiva_probe10k'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)
 CASES['horusyarn_probe10k'] = dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, schedule='horus', scheme='yarn', big=True, huge=True)
 CASES['gandivayarn_probe10k'] = dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, schedule='gandiva', scheme='yarn', big=True, huge=True)
 CASES['horusplus_probe10k_k3'] = dict(frame=_zs(lambda: tg.frame_gen(10000, 2, 10000)), flags=C4328, schedule='horus+', num_queue=3, inject_seed=1, num_buffer=15, big=True, huge=True)
+
+
+# ---- legacy event loops (dead code in the reference, executed unmodified by oracle/ref_legacy_runner.py under shim globals):
+# sjf / shortest / shortest-gpu over the live yarn fit, dlas-gpu / dlas with count-based admission.  `queue_limit` in GPU-ticks / ticks.
+LEGACY = ('sjf', 'shortest', 'shortest-gpu', 'dlas-gpu', 'dlas')
+_S248 = dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)
+_S164 = dict(num_switch=1, num_node_p_switch=6, num_gpu_p_node=4)
+CASES.update({
+    'sjf_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=_S248, schedule='sjf'),
+    'sjf_dense2': dict(frame=lambda: tg.frame_gen(500, 6, 60), flags=_S164, schedule='sjf', big=True),
+    'sjf_ties': dict(frame=_ties, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='sjf'),
+    'sjf_multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='sjf'),
+    'sjf_big_mem_leak': dict(frame=_big_mem, flags=dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=4, num_cpu_p_node=64, mem_p_node=256), schedule='sjf'),
+    'sjf_kat6': dict(frame=_kat6, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8), schedule='sjf'),
+    'sjf_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='sjf', big=True),
+    'sjf_loaded3k': dict(frame=lambda: tg.frame_gen(3000, 4, 500), flags=C4328, schedule='sjf', big=True, huge=True),
+    'sjf_probe10k': dict(frame=lambda: tg.frame_gen(10000, 2, 10000), flags=C4328, schedule='sjf', big=True, huge=True),   # BASELINE config C2
+    'shortest_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=_S248, schedule='shortest', big=True),
+    'shortest_light': dict(frame=lambda: tg.frame_gen(400, 8, 400), flags=_S248, schedule='shortest', big=True),
+    'shortest_multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='shortest'),
+    'shortestgpu_dense2': dict(frame=lambda: tg.frame_gen(500, 6, 60), flags=_S164, schedule='shortest-gpu', big=True),
+    'shortestgpu_ties': dict(frame=_ties, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='shortest-gpu'),
+    'dlasgpu_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=_S248, schedule='dlas-gpu', queue_limit=(30, 60, 150), big=True),
+    'dlasgpu_dense2_q2': dict(frame=lambda: tg.frame_gen(500, 6, 60), flags=_S164, schedule='dlas-gpu', queue_limit=(8,), big=True),
+    'dlasgpu_light_q6': dict(frame=lambda: tg.frame_gen(400, 8, 400), flags=_S248, schedule='dlas-gpu', queue_limit=(5, 9, 14, 20, 33), big=True),
+    'dlasgpu_ties': dict(frame=_ties, flags=dict(num_switch=1, num_node_p_switch=2, num_gpu_p_node=8), schedule='dlas-gpu', queue_limit=(30, 60, 150)),
+    'dlasgpu_multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='dlas-gpu', queue_limit=(30, 60, 150)),   # stale end_jobs on a start event (run_sim.py:706-717)
+    'dlasgpu_kat6': dict(frame=_kat6, flags=dict(num_switch=1, num_node_p_switch=1, num_gpu_p_node=8), schedule='dlas-gpu', queue_limit=(30, 60, 150)),
+    'dlasgpu_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='dlas-gpu', queue_limit=(30, 60, 150), big=True),
+    'dlasgpu_loaded3k': dict(frame=lambda: tg.frame_gen(3000, 4, 500), flags=C4328, schedule='dlas-gpu', queue_limit=(30, 60, 150), big=True, huge=True),
+    'dlasgpu_probe60k': dict(frame=lambda: tg.frame_gen(60000, 3, 60000), flags=C4328, schedule='dlas-gpu', queue_limit=(30, 60, 150), big=True, huge=True),   # BASELINE config C3
+    'dlas_dense': dict(frame=lambda: tg.frame_gen(300, 5, 30), flags=_S248, schedule='dlas', queue_limit=(30, 60, 150), big=True),
+    'dlas_multi_node': dict(frame=_multi_node, flags=dict(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4), schedule='dlas', queue_limit=(8, 12)),
+    'dlas_probe2k': dict(frame=lambda: tg.frame_gen(2000, 1, 2000), flags=C4328, schedule='dlas', queue_limit=(30, 60, 150), big=True),
+})

@@ -45,6 +45,8 @@ def make(name):
         if isinstance(v, str) and v.startswith('@'):
             flags[k] = os.path.join(ROOT, v[1:])
     sched = case.get('schedule', 'fifo')
+    if sched in golden_cases.LEGACY:
+        return make_legacy(name, case, out, work, trace, flags, big)
     if sched != 'fifo':   # the pack placements are keyed by the schedule name (schedule.py:47)
         flags.update(schedule=sched, scheme=case.get('scheme', sched), num_buffer=case.get('num_buffer', 5))
     if sched == 'horus+':   # k-means queues: the draws of np.random.randint / choice are injected (ref_runner._INJECT)
@@ -71,6 +73,32 @@ def make(name):
             f.write(noutil.encode())
     json.dump(meta, open(os.path.join(out, 'meta.json'), 'w'), indent=1, sort_keys=True)
     return name, meta['n_ticks'], meta['n_job_rows'], meta['reference_wall_s']
+
+
+def make_legacy(name, case, out, work, trace, flags, big):
+    """sjf / shortest / shortest-gpu / dlas-gpu / dlas: the reference's dead-code loops run unmodified under shim globals
+    (oracle/ref_legacy_runner.py); job.csv and cluster.csv are the files the reference's own log._Log wrote."""
+    import ref_legacy_runner
+    sched = case['schedule']
+    ql = tuple(case.get('queue_limit', ()))
+    res = ref_legacy_runner.run_legacy(trace, sched, workdir=work, queue_limit=ql or (30, 60, 150), **flags)
+    job, clu = res['job_csv'], res['cluster_csv']
+    trace_bytes = open(trace, 'rb').read()
+    meta = dict(case=name, flags=case['flags'], schedule=sched, scheme='count' if sched in ('dlas-gpu', 'dlas') else 'yarn', queue_limit=list(ql),
+                trace_sha256=sha(trace_bytes), job_sha256=sha(job), cluster_sha256=sha(clu), n_job_rows=job.count('\r\n') - 1,
+                n_events=clu.count('\r\n') - 1, reference_wall_s=round(res['wall_s'], 2),
+                generated_with='python %s; reference dead code run_sim.py run unmodified by oracle/ref_legacy_runner.py (shim JOBS / scheduler)' % sys.version.split()[0])
+    if not big:
+        open(os.path.join(out, 'trace.csv'), 'wb').write(trace_bytes)
+        open(os.path.join(out, 'job.csv'), 'w', newline='').write(job)
+        open(os.path.join(out, 'cluster.csv'), 'w', newline='').write(clu)
+    elif not case.get('huge', False):
+        with gzip.GzipFile(os.path.join(out, 'job.csv.gz'), 'wb', mtime=0) as f:
+            f.write(job.encode())
+        with gzip.GzipFile(os.path.join(out, 'cluster.csv.gz'), 'wb', mtime=0) as f:
+            f.write(clu.encode())
+    json.dump(meta, open(os.path.join(out, 'meta.json'), 'w'), indent=1, sort_keys=True)
+    return name, meta['n_events'], meta['n_job_rows'], meta['reference_wall_s']
 
 
 if __name__ == '__main__':

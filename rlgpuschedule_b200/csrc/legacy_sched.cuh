@@ -3,8 +3,10 @@
 //   sjf       restates smallest_first_sim_jobs   run_sim.py:162-287   (yarn placement = the live fit)
 //   dlas-gpu  restates dlas_sim_jobs(gputime=1)  run_sim.py:664-947   (admission by GPU count)
 //
-// Both are dead code in the reference (undefined globals JOBS/CLUSTER/LOG), so the only oracle is
-// oracle/cpu_sim.c's restatement: PARITY UNPINNED.
+// Both are dead code in the reference (undefined globals JOBS / CLUSTER / LOG / scheduler).  Parity is pinned
+// given shims: oracle/ref_legacy_runner.py runs those loops unmodified with the missing globals supplied at
+// run time, and the kernels reproduce the cluster.csv / job.csv of those runs byte for byte
+// (tests/golden/{sjf,shortest,shortestgpu,dlasgpu,dlas}_*, tests/test_gpu_legacy.py).
 //
 // Per event every runnable job is touched once (the "per-event advance" of the north star):
 // executed / pending time, demotion test, admission or re-placement, status flip, next-end and
@@ -127,8 +129,19 @@ __device__ __forceinline__ void flush_unfinished(const LegDesc &D, const Ent *bu
     }
 }
 
+// bit 24 of Ent::a.y: the job is in the 'end_jobs' list that run_sim.py:706-710 attached to the head start event.
+// `event = start_event; event['end_jobs'] = end_events[0]['end_jobs']` mutates the dict that stays at JOBS.job_events[0];
+// when the queue-jump test (:715-717) then replaces the event, the list survives and is honoured when that start event is
+// finally handled: its jobs complete there whatever their status (demoted / preempted meanwhile).  Pinned by the
+// dlasgpu_* fixtures (the reference's code run unmodified).
+#define L_ATTACHED (1 << 24)
+
 struct DlasEvent {
     int time, d, q, nq;
+    int end_ref;       // predicted end time that marks the natural end jobs: the event time, or next_end at a jump event
+    int is_jump;       // queue-jump event: nothing ends, no arrivals
+    int end_by_flag;   // start event with end_time > start_time: 'end_jobs' is whatever list is attached to it
+    int flag_op;       // 0 keep, 1 clear (the start event is popped), 2 set from the natural end test (list attached, event replaced by a jump)
     int free_gpu, n_run, n_pend;
     int lane_end, lane_jump;   // per-lane minima, reduced across the warp once per event
     int lane_flips;            // per-lane count of resumes + preemptions, reduced once per event
@@ -142,16 +155,19 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
                                            Ent *dst, Ent *dem_out, int t_prev, int lane) {
     bool ended = false, demote = false;
     if (valid && mode == 0) {
-        if (e.status() == L_RUNNING) {
-            // end_events hold the RUNNING jobs with the smallest predicted end (run_sim.py:908-922)
-            ended = t_prev + e.a.z - e.a.w == ev.time;
-            if (!ended) {
+        // end_events hold the RUNNING jobs with the smallest predicted end (run_sim.py:908-922)
+        const bool natural = e.status() == L_RUNNING && t_prev + e.a.z - e.a.w == ev.end_ref;
+        if (ev.flag_op == 2) e.a.y = natural ? (e.a.y | L_ATTACHED) : (e.a.y & ~L_ATTACHED);
+        ended = !ev.is_jump && (ev.end_by_flag ? (e.a.y & L_ATTACHED) != 0 : natural);
+        if (ev.flag_op == 1) e.a.y &= ~L_ATTACHED;
+        if (!ended) {                                                          // ended jobs left runnable_jobs before the sweep (:721-727)
+            if (e.status() == L_RUNNING) {
                 e.a.w += ev.d; e.b.x += ev.d;                                  // total_executed, executed (:741-744)
                 if (ev.q < ev.nq - 1 && (P.gputime ? (int64_t)e.b.x * e.gpus() : (int64_t)e.b.x) >= P.limit[ev.q]) demote = true;  // :747-759
+            } else {
+                e.b.y += ev.d;                                                 // pending_time (:765-767)
+                if (e.b.x > 0) e.b.w += ev.d;                                  // last_pending_time (:768-769)
             }
-        } else {
-            e.b.y += ev.d;                                                     // pending_time (:765-767)
-            if (e.b.x > 0) e.b.w += ev.d;                                      // last_pending_time (:768-769)
         }
     }
     // ---- ended jobs leave (run_sim.py:721-727)
@@ -223,7 +239,9 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
         if (rows_on && st.n_rows >= (int64_t)rs.n_chunks * RLGS_ROW_CHUNK) break;
         int event_time = min(next_arr, st.next_end);                                      // :684-713
         bool has_start = next_arr <= st.next_end;
-        if (event_time > st.next_jump) { event_time = st.next_jump; has_start = false; }  // :715-717
+        const bool attach = next_arr == st.next_end && next_arr != RLGS_NEVER;            // :706-710 start_event['end_jobs'] = ...
+        const bool is_jump = event_time > st.next_jump;
+        if (is_jump) { event_time = st.next_jump; has_start = false; }                    // :715-717
         if (P.max_time > 0 && event_time > P.max_time) { st.done = 1; st.status = RLGS_ERR_CAPACITY; break; }
         // new arrivals at this event (run_sim.py:730-737)
         int k_arr = 0;
@@ -241,6 +259,9 @@ __global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict_
         if (st.M + k_arr > D.cap) { st.status = RLGS_ERR_CAPACITY; st.done = 1; break; }
         DlasEvent ev;
         ev.time = event_time; ev.d = event_time - st.t_prev; ev.nq = P.nq;
+        ev.is_jump = is_jump; ev.end_ref = (is_jump && attach) ? st.next_end : event_time;
+        ev.end_by_flag = has_start && !attach;
+        ev.flag_op = has_start ? 1 : ((is_jump && attach) ? 2 : 0);
         ev.free_gpu = P.total_gpu; ev.n_run = ev.n_pend = 0; ev.lane_end = ev.lane_jump = RLGS_NEVER; ev.lane_flips = 0;
         ev.ne = 0; ev.events = 0; ev.demotions = 0; ev.nd = 0;
         const Ent *src = D.buf[st.cur];

@@ -48,6 +48,7 @@ struct TraceBuf {
     PackJob *pack = nullptr;    // [n] horus placement inputs
     PlusFeat *feat = nullptr;   // [n] horus+ k-means features
     void *pack_slab = nullptr;  // per-replica working set of the pack kernels for this trace
+    void *slab = nullptr;       // per-replica working set of the fifo / legacy kernels for this trace
     int32_t n = 0, cap_n = 0;
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
@@ -95,7 +96,6 @@ struct rlgs_sim {
     std::vector<PackDesc> h_pdesc;
     PackDesc *d_pdesc = nullptr;
     PackState *d_pstate = nullptr, *h_pstate = nullptr, *h_pinit = nullptr;
-    std::vector<void *> slabs;
     int slot_cap = 0;
     // chunk-major row store
     std::vector<rlgs_row *> d_chunks, h_chunks;
@@ -227,11 +227,10 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); cudaFree(t.feat); cudaFree(t.pack_slab); }
+    for (auto &t : s->traces) { cudaFree(t.dev); cudaFree(t.net); cudaFree(t.dur_out); cudaFree(t.pack); cudaFree(t.feat); cudaFree(t.pack_slab); cudaFree(t.slab); }
     cudaFree(s->d_pdesc); cudaFree(s->d_pstate);
     if (s->h_pstate) cudaFreeHost(s->h_pstate);
     if (s->h_pinit) cudaFreeHost(s->h_pinit);
-    for (void *p : s->slabs) cudaFree(p);
     for (auto p : s->d_chunks) cudaFree(p);
     for (auto p : s->h_chunks) if (p) cudaFreeHost(p);
     cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_ldesc); cudaFree(s->d_lstate); cudaFree(s->d_jobs);
@@ -288,7 +287,9 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     // the records (the e2e path: one host->device copy per step, no allocation)
     for (size_t t = 0; t < s->traces.size() && !s->pack; ++t) {
         TraceBuf &old = s->traces[t];
-        if (old.first == first && old.count == count && n <= old.cap_n && tb.log_cap <= old.cap_log) {
+        bool attached = old.dev != nullptr && old.first == first && old.count == count;
+        for (int r = 0; r < count && attached; ++r) attached = s->rep_trace[first + r] == (int)t;   // a later load may have re-pointed some of them
+        if (attached && n <= old.cap_n && tb.log_cap <= old.cap_log) {
             CU(cudaMemcpy(old.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice));
             if (s->opts.enable_network_costs) {
                 CU(cudaMemcpy(old.net, net->duration, 8 * (size_t)n, cudaMemcpyHostToDevice));
@@ -316,15 +317,21 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         CU(cudaMemcpy(tb.net + n, net->model_mb, 8 * (size_t)n, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(tb.net + 2 * (size_t)n, net->iterations, 8 * (size_t)n, cudaMemcpyHostToDevice));
     }
-    int tid = (int)s->traces.size();
-    if (s->pack)   // a reload of the same replica range replaces the trace (and its working set) instead of piling up
-        for (size_t t = 0; t < s->traces.size(); ++t)
-            if (s->traces[t].first == first && s->traces[t].count == count) {
-                TraceBuf &old = s->traces[t];
-                cudaFree(old.dev); cudaFree(old.pack); cudaFree(old.feat); cudaFree(old.pack_slab);
-                tid = (int)t;
-            }
-    if (tid == (int)s->traces.size()) s->traces.push_back(tb); else s->traces[tid] = tb;
+    // the replicas of this range leave their previous trace buffers; a buffer nobody points at any more is released
+    for (int r = 0; r < count; ++r) s->rep_trace[first + r] = -1;
+    int tid = -1;
+    for (size_t t = 0; t < s->traces.size(); ++t) {
+        TraceBuf &old = s->traces[t];
+        if (old.dev) {
+            bool used = false;
+            for (int r = 0; r < s->R && !used; ++r) used = s->rep_trace[r] == (int)t;
+            if (used) continue;
+            cudaFree(old.dev); cudaFree(old.net); cudaFree(old.dur_out); cudaFree(old.pack); cudaFree(old.feat); cudaFree(old.pack_slab); cudaFree(old.slab);
+            old = TraceBuf();
+        }
+        if (tid < 0) tid = (int)t;
+    }
+    if (tid < 0) { tid = (int)s->traces.size(); s->traces.push_back(tb); } else s->traces[tid] = tb;
     unsigned char *slab = nullptr;
     if (s->pack) {
         for (int r = 0; r < count; ++r) { s->h_pdesc[first + r] = PackDesc{}; s->h_pdesc[first + r].trace = tb.dev; s->h_pdesc[first + r].J = n; s->h_ldesc[first + r].J = n; }
@@ -370,7 +377,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
             D.place_scratch = reinterpret_cast<int2 *>(p);
         }
     }
-    s->slabs.push_back(slab);
+    s->traces[tid].slab = slab;
     for (int r = 0; r < count; ++r) s->rep_trace[first + r] = tid;
     s->ran = false;
     return RLGS_OK;

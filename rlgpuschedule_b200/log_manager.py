@@ -122,6 +122,48 @@ def format_job_csv(trace, finish_order, start, end, preempt=None, actual_duratio
     return buf.getvalue()
 
 
+def format_legacy_cluster_csv(rows, cluster, count_scheme, node_stats=False, with_header=True):
+    """cluster.csv of the event-driven schedules as the reference's log._Log.checkpoint writes it (log.py:137-258).
+    Under --scheme count the node / gpu columns come from CLUSTER.free_gpu (log.py:225-238).  Under a placement scheme the
+    reference's code for those columns is commented out (log.py:171-189) and it prints 0; node_stats=True prints what
+    that commented code would (the device keeps the numbers in the row)."""
+    N, Dv = cluster.num_nodes, cluster.num_gpus
+    idle = rows['idle_nodes']; full = rows['median_hi']; busy_g = rows['busy_gpus']
+    n = len(rows)
+    zero = [0] * n
+    if count_scheme:
+        cols = [idle.tolist(), full.tolist(), full.tolist(), (Dv - busy_g).tolist(), busy_g.tolist()]
+    elif node_stats:
+        cols = [idle.tolist(), (N - idle - full).tolist(), full.tolist(), (Dv - busy_g).tolist(), busy_g.tolist()]
+    else:
+        cols = [zero, zero, zero, zero, zero]
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    if with_header:
+        w.writerow(LEGACY_CLUSTER_HEADER)
+    w.writerows(zip(rows['median_lo'].tolist(), *cols, rows['queued'].tolist(), rows['running'].tolist(), rows['finished'].tolist()))
+    return buf.getvalue()
+
+
+def format_legacy_job_csv(trace, jobs, pending, resume, count_scheme, with_header=True):
+    """job.csv of the event-driven schedules as log._Log.job_complete writes it (log.py:86-88,316-330)."""
+    fo = np.asarray(jobs['finish_order'], dtype=np.int64)
+    sub = trace.records['arrival_tick'][fo].astype(np.int64)
+    st, en = jobs['start'][fo].astype(np.int64), jobs['end'][fo].astype(np.int64)
+    cols = [en.tolist(), [str(x) for x in trace.label[fo].tolist()], trace.records['gpus'][fo].tolist(), sub.tolist(),
+            st.tolist(), en.tolist(), (en - st).tolist(), (en - sub).tolist(), trace.records['dur_ticks'][fo].tolist(),
+            np.asarray(pending)[fo].tolist(), np.asarray(jobs['preempt'])[fo].tolist()]
+    if count_scheme:
+        cols.append(np.asarray(resume)[fo].tolist())
+    cols.append([0] * len(fo))
+    buf = io.StringIO(newline='')
+    w = csv.writer(buf)
+    if with_header:
+        w.writerow(LEGACY_JOB_HEADER_COUNT if count_scheme else LEGACY_JOB_HEADER)
+    w.writerows(zip(*cols))
+    return buf.getvalue()
+
+
 class LogManager(object):
     """Drop-in for the reference's LogManager: same constructor, init(), step_cluster(), jcts();
     plus bulk writers used by the device backend."""
@@ -208,27 +250,13 @@ class LogManager(object):
                        'preempt': np.asarray(jobs['preempt'])[fo].astype(np.int32)})
         pq.write_table(jb, os.path.join(self.log_path, 'job.parquet'))
 
-    def write_legacy(self, rows, cluster, trace, jobs, pending, resume, count_scheme):
+    def write_legacy(self, rows, cluster, trace, jobs, pending, resume, count_scheme, node_stats=False):
         """cluster.csv / job.csv of the event-driven schedules (LOG.checkpoint log.py:137-258, LOG.job_complete
         log.py:316-330).  rows: _ffi.ROW_DTYPE with the legacy field mapping documented in include/rlgs.h."""
-        N, Dv = cluster.num_nodes, cluster.num_gpus
-        idle = rows['idle_nodes']; full = rows['median_hi']; busy_g = rows['busy_gpus']
-        busy_n = (full if count_scheme else N - idle - full)
         with open(self.log_cluster, 'a+', newline='') as f:
-            csv.writer(f).writerows(zip(rows['median_lo'].tolist(), idle.tolist(), busy_n.tolist(), full.tolist(),
-                                        (Dv - busy_g).tolist(), busy_g.tolist(), rows['queued'].tolist(),
-                                        rows['running'].tolist(), rows['finished'].tolist()))
-        fo = np.asarray(jobs['finish_order'], dtype=np.int64)
-        sub = trace.records['arrival_tick'][fo].astype(np.int64)
-        st, en = jobs['start'][fo].astype(np.int64), jobs['end'][fo].astype(np.int64)
-        cols = [en.tolist(), [str(x) for x in trace.label[fo].tolist()], trace.records['gpus'][fo].tolist(), sub.tolist(),
-                st.tolist(), en.tolist(), (en - st).tolist(), (en - sub).tolist(), trace.records['dur_ticks'][fo].tolist(),
-                np.asarray(pending)[fo].tolist(), np.asarray(jobs['preempt'])[fo].tolist()]
-        if count_scheme:
-            cols.append(np.asarray(resume)[fo].tolist())
-        cols.append([0] * len(fo))
+            f.write(format_legacy_cluster_csv(rows, cluster, count_scheme, node_stats=node_stats, with_header=False))
         with open(self.log_job, 'a+', newline='') as f:
-            csv.writer(f).writerows(zip(*cols))
+            f.write(format_legacy_job_csv(trace, jobs, pending, resume, count_scheme, with_header=False))
 
     def jcts(self, finished_jobs):
         """finished_jobs: dict job_id -> object with the reference Job's attributes, or a tuple

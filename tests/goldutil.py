@@ -43,7 +43,8 @@ def load(name):
     else:
         out['trace'] = None
         out['frame'] = case['frame']()
-    for key, fn in (('job', 'job.csv'), ('cluster', 'cluster_noutil.csv')):
+    out['queue_limit'] = tuple(case.get('queue_limit', ()))
+    for key, fn in (('job', 'job.csv'), ('cluster', 'cluster_noutil.csv' if out['schedule'] not in golden_cases.LEGACY else 'cluster.csv')):
         p = os.path.join(d, fn)
         if os.path.exists(p):
             out[key] = open(p, newline='').read()
@@ -69,3 +70,8 @@ def trace_input(g):
 def pack_case_names(kinds=('small', 'big', 'huge')):
     """Fixtures of the pack family (horus, horus+, gandiva; over the pack placement or yarn)."""
     return [n for sched in ('horus', 'gandiva', 'horus+') for kind in kinds for n in case_names(kind, sched)]
+
+
+def legacy_case_names(kinds=('small', 'big', 'huge')):
+    """Fixtures of the legacy event loops (sjf family over yarn, dlas family with count admission)."""
+    return [n for sched in golden_cases.LEGACY for kind in kinds for n in case_names(kind, sched)]

@@ -1,14 +1,17 @@
-"""BASELINE.json's full-size configurations on the device, checked through size-independent properties
-(the oracle comparison at these sizes is covered for one replica by the golden hashes):
+"""BASELINE.json's full-size configurations on the device: one replica against the reference's own files (golden hashes) and
+the oracle, every other replica through size-independent properties:
 conservation of jobs per row, capacity never exceeded, end - start = runtime, rows consistent with
 the job table, identical replicas give identical results, sortedness of the finish order."""
 import numpy as np
 import pytest
 
+import cpu_sim
 import golden_cases
+import goldutil
 import tracegen
 import rlgpuschedule_b200 as rl
 from rlgpuschedule_b200 import _ffi
+from rlgpuschedule_b200 import log_manager as lm
 from rlgpuschedule_b200.env import Environment
 
 pytestmark = pytest.mark.gpu
@@ -59,21 +62,39 @@ def test_fifo_60k_trace_many_replicas_properties():
     sim.close()
 
 
-def test_dlas_gpu_60k_trace_properties():
-    """config C3: dlas-gpu, 4-queue MLFQ, 60k-job trace."""
-    tr = rl.prepare_trace(tracegen.frame_gen(60000, 3, 60000), C)
+def _legacy_csvs(sim, tr, r, count):
+    j = sim.jobs(r)
+    return (lm.format_legacy_job_csv(tr, j, sim.job_plane(r, _ffi.PLANE_AUX), sim.job_plane(r, _ffi.PLANE_RESUME), count),
+            lm.format_legacy_cluster_csv(sim.rows(r), C, count))
+
+
+def test_dlas_gpu_60k_trace_matches_reference_and_oracle():
+    """config C3: dlas-gpu, 4-queue MLFQ, 60k-job trace.  One replica is compared with the files the reference's dead-code
+    loop wrote (tests/golden/dlasgpu_probe60k, 212 s of reference time) and with the oracle; the others through properties."""
+    g = goldutil.load('dlasgpu_probe60k')
+    df = goldutil.trace_input(g)
+    tr = rl.prepare_trace(df, C)
     sim = rl.Simulator(C, 'dlas-gpu', 'count', n_replicas=64, rows='device', num_queue=4, queue_limit=(30, 60, 150))
     sim.load_trace(tr)
     sim.run()
+    job, clu = _legacy_csvs(sim, tr, 63, True)
+    assert goldutil.sha(job) == g['meta']['job_sha256'] and goldutil.sha(clu) == g['meta']['cluster_sha256']
+    ores = cpu_sim.run_dlas_gpu(cpu_sim.make_cluster(**golden_cases.C4328), cpu_sim.prepare_trace(df), (30, 60, 150))
+    j = sim.jobs(0)
+    assert np.array_equal(j['finish_order'], ores['finish_order']) and np.array_equal(j['end'], ores['end'])
+    assert np.array_equal(j['start'], ores['start']) and np.array_equal(j['preempt'], ores['preempt'])
+    assert np.array_equal(sim.job_plane(0, _ffi.PLANE_AUX), ores['pending'])
+    assert sim.summary(0)['events'] == ores['counters']['events'] and sim.summary(0)['n_ticks'] == ores['n_events']
     for r in (0, 63):
         j = sim.jobs(r); rows = sim.rows(r); rec = tr.records
         st, en = j['start'].astype(np.int64), j['end'].astype(np.int64)
         assert len(j['finish_order']) == 60000
         pend = sim.job_plane(r, _ffi.PLANE_AUX).astype(np.int64)
-        assert np.array_equal(en - rec['arrival_tick'], rec['dur_ticks'] + pend)  # JCT = executed + pending
-        assert (st >= rec['arrival_tick']).all() and (en - st >= rec['dur_ticks']).all()
         res, pre = sim.job_plane(r, _ffi.PLANE_RESUME), j['preempt']
-        assert np.array_equal(res, pre + 1)                                       # every finished job resumed once more than it was preempted
+        normal = res == pre + 1            # jobs completed through a stale 'end_jobs' list (run_sim.py:706-717) end while preempted
+        assert normal.mean() > 0.95 and ((res == pre) | normal).all()
+        assert np.array_equal((en - rec['arrival_tick'])[normal], (rec['dur_ticks'] + pend)[normal])  # JCT = executed + pending
+        assert (st >= rec['arrival_tick']).all()
         t = rows['median_lo']
         assert (np.diff(t) > 0).all()                                             # event times strictly increase
         assert (rows['busy_gpus'] <= C.num_gpus).all() and rows['finished'][-1] == 60000
@@ -83,16 +104,23 @@ def test_dlas_gpu_60k_trace_properties():
     sim.close()
 
 
-def test_sjf_10k_trace_properties():
-    """config C2: sjf + yarn, 10k-job trace."""
-    tr = rl.prepare_trace(tracegen.frame_gen(10000, 2, 10000), C)
+def test_sjf_10k_trace_matches_reference_and_oracle():
+    """config C2: sjf + yarn, 10k-job trace: byte-exact vs the reference's dead-code loop (tests/golden/sjf_probe10k) and the oracle."""
+    g = goldutil.load('sjf_probe10k')
+    df = goldutil.trace_input(g)
+    tr = rl.prepare_trace(df, C)
     sim = rl.Simulator(C, 'sjf', 'yarn', n_replicas=32, rows='device')
     sim.load_trace(tr)
     sim.run()
-    j = sim.jobs(5); rows = sim.rows(5); rec = tr.records
+    job, clu = _legacy_csvs(sim, tr, 5, False)
+    assert goldutil.sha(job) == g['meta']['job_sha256'] and goldutil.sha(clu) == g['meta']['cluster_sha256']
+    ores = cpu_sim.run_sjf_yarn(cpu_sim.make_cluster(**golden_cases.C4328), cpu_sim.prepare_trace(df))
+    j = sim.jobs(31); rows = sim.rows(31); rec = tr.records
+    assert np.array_equal(j['finish_order'], ores['finish_order']) and np.array_equal(j['end'], ores['end'])
+    assert np.array_equal(rows['idle_nodes'], ores['rows']['idle_nodes']) and np.array_equal(rows['busy_gpus'], ores['rows']['busy_gpus'])
     en = j['end'].astype(np.int64)
     assert len(j['finish_order']) == 10000 and (np.diff(en[j['finish_order']]) >= 0).all()
-    pend = sim.job_plane(5, _ffi.PLANE_AUX).astype(np.int64)
+    pend = sim.job_plane(31, _ffi.PLANE_AUX).astype(np.int64)
     assert np.array_equal(en - rec['arrival_tick'], rec['dur_ticks'] + pend)
     assert (np.diff(rows['median_lo']) > 0).all() and (rows['busy_gpus'] <= C.num_gpus).all()
     assert (rows['idle_nodes'] + rows['median_hi'] <= C.num_nodes).all()

@@ -1,8 +1,9 @@
-"""sjf and dlas-gpu on the device vs the CPU restatement of the reference's dead code
-(oracle/cpu_sim.c, oracle_sjf_yarn / oracle_dlas_gpu).  PARITY UNPINNED against the reference itself:
-those schedules are not runnable there (NotImplementedError at core/jobs/jobs_manager.py:62).
-Bit-exact bar on every integer output: per-job start / end / pending / preempt / resume, finish
-order, and every per-event row."""
+"""The legacy event loops (sjf / shortest / shortest-gpu over yarn, dlas-gpu / dlas with count admission) on the device.
+(1) against the fixtures tests/golden/{sjf,shortest,shortestgpu,dlasgpu,dlas}_*: cluster.csv / job.csv written by the
+reference's own log._Log while its dead-code loops (run_sim.py:162-287, :299-431, :664-947) ran UNMODIFIED under shim
+globals (oracle/ref_legacy_runner.py; the live simulator raises NotImplementedError for these schedules) - byte-exact;
+(2) against the CPU restatement oracle/cpu_sim.c (itself pinned on the same fixtures) on more traces - bit-exact on
+every integer output: per-job start / end / pending / preempt / resume, finish order, and every per-event row."""
 import numpy as np
 import pytest
 
@@ -12,6 +13,7 @@ import goldutil
 import tracegen
 import rlgpuschedule_b200 as rl
 from rlgpuschedule_b200 import _ffi
+from rlgpuschedule_b200 import log_manager as lm
 
 pytestmark = pytest.mark.gpu
 
@@ -98,3 +100,19 @@ def test_legacy_bounded_launches_resume_exactly():
         ores = cpu_sim.run_sjf_yarn(oc, ot) if sched == 'sjf' else cpu_sim.run_dlas_gpu(oc, ot, (30, 60, 150))
         compare(sim, tr, ores)
         sim.close()
+
+
+@pytest.mark.parametrize('name', goldutil.legacy_case_names(('small', 'big')))
+def test_legacy_device_matches_reference_files(name):
+    g = goldutil.load(name)
+    cluster = rl.cluster_from_flags(g['flags'])
+    tr = rl.prepare_trace(goldutil.trace_input(g), cluster)
+    count = g['schedule'] in ('dlas-gpu', 'dlas')
+    kw = dict(num_queue=len(g['queue_limit']) + 1, queue_limit=g['queue_limit']) if count else {}
+    sim = rl.Simulator(cluster, g['schedule'], 'count' if count else 'yarn', n_replicas=2, rows=True, **kw)
+    sim.load_trace(tr)
+    sim.run()
+    j = sim.jobs(1)
+    assert lm.format_legacy_job_csv(tr, j, sim.job_plane(1, _ffi.PLANE_AUX), sim.job_plane(1, _ffi.PLANE_RESUME), count) == g['job']
+    assert lm.format_legacy_cluster_csv(sim.rows(1), cluster, count) == g['cluster']
+    sim.close()
