@@ -1,48 +1,67 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the hot path (see DESIGN.md "Measurement").
+"""bench.py — benchmark of the hot path (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--replicas R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--workload NAME] [--replicas R] [--lpr L]
 
-Workload (BASELINE.json metric "simulated events/sec on 60k-job trace"): R independent replicas per
-GPU of the 60 000-job Philly-style trace (rlgpuschedule_b200/synth.py frame_gen(60000, seed, 60000); seed 3 is the
-trace whose reference output is pinned in tests/golden/probe60k) on the 4 switches x 32 nodes x 8 GPUs
-simulated cluster under fifo + yarn.  One "step" = every replica simulated to completion.
-An event = arrival | start | finish: 3 per finished job under non-preemptive fifo.
+Workloads (BASELINE.json configs; default fifo60k = the configuration the metric "simulated events/sec on 60k-job trace" is
+quoted on and the only one with a measured reference number on that trace):
+    fifo60k     fifo + yarn, 60 000-job trace gen(60000, seed, 60000), 4x32x8 simulated cluster        (C3-sized trace, live reference path)
+    dlas60k     dlas-gpu (4-queue MLFQ, limits 30/60/150 GPU-ticks), same trace, admission by GPU count    (C3)
+    sjf10k      sjf + yarn, 10 000-job trace gen(10000, seed, 10000)                                       (C2)
+    env512x10k  512 environment replicas per GPU of 10 000-job traces, random-window policy rolled out on the device  (C4; --gpus 8 = C5)
+One "step" = every replica of the GPU simulated to completion.  An event = arrival | start | finish | preemption | resume |
+queue jump; 3 per finished job under non-preemptive fifo.
 
-Prints ONE JSON line (rank 0).  `value` = events/s with traces resident in HBM (rows written to the
-device-resident row store); `e2e` = the same through the C ABI with host buffers: trace upload,
-simulation, rows + job tables copied back to the host, all inside the timed region.
-`--impl reference` times the reference's algorithm on the host cores (oracle/cpu_sim.c, the C port
-validated byte-for-byte against the real Python reference; the Python reference itself cannot
-travel to the GPU box).
+Prints ONE JSON line (rank 0).  `value` = events/s with traces resident in HBM (rows written to the device-resident row
+store); `e2e` = the same through the C ABI with host buffers: trace upload, simulation, rows + job tables copied back to the
+host, all inside the timed region.  `--impl reference` times the reference's algorithm on the host cores (oracle/cpu_sim.c, the
+C port validated byte-for-byte against the real Python reference) and, when the unmodified Python reference was staged under
+oracle/_ref/reference by __graft_entry__.build(), reports its own measured events/s beside it (`reference_python`).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_JOBS = 60000
 CLUSTER_FLAGS = dict(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
-N_TRACES = 8          # distinct traces per GPU, replicas are spread over them round-robin in blocks
 METRIC = 'simulated_events_per_sec'
 UNIT = 'events/s'
-WORKLOAD = 'fifo+yarn, 4x32x8 simulated cluster, 60k-job Philly-style trace (gen(60000, seed, 60000)), %d replicas/GPU over %d seeds'
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref', 'reference')
+
+WORKLOADS = {
+    'fifo60k': dict(schedule='fifo', scheme='yarn', n_jobs=60000, seed0=3, n_traces=16, replicas=9472, kw={},
+                    text='fifo+yarn, 4x32x8 simulated cluster, 60k-job Philly-style trace (gen(60000, seed, 60000))'),
+    'dlas60k': dict(schedule='dlas-gpu', scheme='count', n_jobs=60000, seed0=3, n_traces=8, replicas=2960,
+                    kw=dict(num_queue=4, queue_limit=(30, 60, 150)),
+                    text='dlas-gpu (4-queue MLFQ, limits 30/60/150 GPU-ticks), 4x32x8 simulated cluster, 60k-job trace (gen(60000, seed, 60000))'),
+    'sjf10k': dict(schedule='sjf', scheme='yarn', n_jobs=10000, seed0=2, n_traces=8, replicas=2960, kw={},
+                   text='sjf+yarn, 4x32x8 simulated cluster, 10k-job trace (gen(10000, seed, 10000))'),
+    'env512x10k': dict(schedule='fifo', scheme='yarn', n_jobs=10000, seed0=1000, n_traces=32, replicas=512, kw={}, env=True,
+                       text='RL environment rollouts (random pick inside a 5-job window, counter-based RNG), 4x32x8 simulated cluster, '
+                            '10k-job traces (gen(10000, 1000 + i, 10000))'),
+}
 
 
-def frames(rank):
+def frames(w, rank):
     from rlgpuschedule_b200 import synth
-    return [synth.frame_gen(N_JOBS, 3 + rank * N_TRACES + i, N_JOBS) for i in range(N_TRACES)]
+    return [synth.frame_gen(w['n_jobs'], w['seed0'] + rank * w['n_traces'] + i, w['n_jobs']) for i in range(w['n_traces'])]
 
 
-def algorithmic_bytes(summ, n_nodes, n_gpus):
-    """bytes_tick = 8Q + 12R + 12N + 8D + 64, summed over the ticks of one replica-run."""
-    return 8 * summ['sum_queued'] + 12 * summ['sum_running'] + summ['n_ticks'] * (12 * n_nodes + 8 * n_gpus + 64)
+def algorithmic_bytes(w, summ, n_nodes, n_gpus):
+    """SURVEY.md 8(d), per replica-run.  fifo: 8Q + 12R + 12N + 8D + 64 per tick; sjf: 28 + 16 B per runnable job per event
+    + 12N per event; dlas-gpu: 40 + 8 B per runnable job per event (sum_queued carries the swept runnable jobs there)."""
+    if w['schedule'] == 'fifo':
+        return 8 * summ['sum_queued'] + 12 * summ['sum_running'] + summ['n_ticks'] * (12 * n_nodes + 8 * n_gpus + 64)
+    if w['schedule'] == 'sjf':
+        return 44 * summ['sum_queued'] + 12 * n_nodes * summ['n_ticks']
+    return 48 * summ['sum_queued']
 
 
 class ClockSampler(threading.Thread):
@@ -84,22 +103,109 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(self.samples))
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle port on all host cores, a bounded sample of the same workload per step."""
+# ------------------------------------------------------------------------------------------------ CPU side (oracle/ is touched only here)
+def host_cores():
+    """Threads this process may actually use (cgroup / affinity aware), not the machine's core count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _cpu_sim():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import cpu_sim
+    cpu_sim.lib()
+    return cpu_sim
+
+
+def cpu_port_batch(cpu_sim, w, cl, traces, n_runs, threads):
+    """n_runs replica-runs of the workload on `threads` host threads with the C port; returns events."""
+    if w['schedule'] == 'fifo' and not w.get('env'):
+        per = [n_runs // len(traces) + (1 if i < n_runs % len(traces) else 0) for i in range(len(traces))]
+        return sum(cpu_sim.run_fifo_yarn_batch(cl, tr, n, threads, rows_cap=w['n_jobs'] + 16384) for tr, n in zip(traces, per) if n)
+    from concurrent.futures import ThreadPoolExecutor   # ctypes releases the GIL inside the C call
+
+    def one(i):
+        tr = traces[i % len(traces)]
+        if w.get('env'):
+            o = cpu_sim.run_env_yarn(cl, tr, 1, window_k=5, seed=1, replica=i, rows_cap=w['n_jobs'] + 16384)
+            return int((o['start'] >= 0).sum()) + int((o['end'] >= 0).sum()) + len(tr['nt'])
+        o, _ = cpu_sim.run_legacy(cl, tr, w['schedule'], w['kw'].get('queue_limit', (30, 60, 150)))
+        return o['counters']['events']
+    with ThreadPoolExecutor(threads) as ex:
+        return sum(ex.map(one, range(n_runs)))
+
+
+def reference_python_sample(w):
+    """The UNMODIFIED Python reference (staged by __graft_entry__.build() under oracle/_ref/reference) on this box's host:
+    one process, one core, a 2 000-job trace of the same generator (the 60k-job trace takes 709 s).  fifo: the live
+    simulator, `python run_sim.py`; sjf / dlas-gpu: the dead-code loops under the shim globals of oracle/ref_legacy_runner.py."""
+    if not os.path.exists(os.path.join(REF_DIR, 'run_sim.py')) or w.get('env'):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    os.environ['RLGS_REFERENCE_DIR'] = REF_DIR
+    from rlgpuschedule_b200 import synth
+    n = 2000
+    work = tempfile.mkdtemp(prefix='rlgs_benchref_')
+    fn = os.path.join(work, 'trace.csv')
+    synth.write(synth.frame_gen(n, 1, n), fn)
+    try:
+        if w['schedule'] == 'fifo':
+            import ref_runner
+            ref_runner.REF = REF_DIR
+            r = ref_runner.run_reference(fn, workdir=work, **CLUSTER_FLAGS)
+            jobs = r['job_csv'].count('\r\n') - 1
+            events = 3 * jobs
+        else:
+            import ref_legacy_runner
+            ref_legacy_runner.REF = REF_DIR
+            r = ref_legacy_runner.run_legacy(fn, w['schedule'], workdir=work, queue_limit=w['kw'].get('queue_limit', (30, 60, 150)), **CLUSTER_FLAGS)
+            cpu_sim = _cpu_sim()
+            o, _ = cpu_sim.run_legacy(cpu_sim.make_cluster(**CLUSTER_FLAGS), cpu_sim.prepare_trace(fn), w['schedule'], w['kw'].get('queue_limit', (30, 60, 150)))
+            jobs, events = r['job_csv'].count('\r\n') - 1, o['counters']['events']   # the port equals these runs byte for byte: its event count is theirs
+        return {'events_per_s': events / r['wall_s'], 'jobs_per_s': jobs / r['wall_s'], 'cores': 1, 'wall_s': round(r['wall_s'], 2),
+                'sample': 'unmodified Python reference, %s, one process on one core, gen(%d, 1, %d) trace on the 4x32x8 cluster, wall time incl. interpreter start' % (
+                    'python run_sim.py' if w['schedule'] == 'fifo' else 'dead-code loop under shim globals (oracle/ref_legacy_runner.py)', n, n)}
+    except Exception as e:   # the baseline is a report, not a gate
+        return {'error': str(e)[-300:]}
+
+
+def cpu_baseline_sample(w):
+    """Bounded cpu_baseline for the cuda arm's JSON line: a few seconds of the oracle port on every usable core."""
+    cpu_sim = _cpu_sim()
+    cores = host_cores()
+    cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
+    traces = [cpu_sim.prepare_trace(f) for f in frames(w, 0)[:2]]
+    cpu_port_batch(cpu_sim, w, cl, traces, cores, cores)
+    n_runs = (4 if w['n_jobs'] >= 60000 else 16) * cores
+    t0 = time.perf_counter()
+    ev = cpu_port_batch(cpu_sim, w, cl, traces, n_runs, cores)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    ev1 = cpu_port_batch(cpu_sim, w, cl, traces, 1, 1)
+    dt1 = time.perf_counter() - t1
+    out = {'value': ev / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+           'sample': '%d replica-runs of the workload\'s trace on %d host threads, %.1f s (oracle/cpu_sim.c, gcc -O2)' % (n_runs, cores, dt),
+           'single_core_value': ev1 / dt1}
+    rp = reference_python_sample(w)
+    if rp:
+        out['reference_python'] = rp
+    return out
+
+
+def run_reference(args, w, rank):
+    """CPU arm: the oracle port on all usable host cores, a bounded sample of the same workload per step."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))   # the only legs that touch oracle/: the CPU baseline
-    import cpu_sim
-    cores = os.cpu_count() or 1
+    cpu_sim = _cpu_sim()
+    cores = host_cores()
     cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
-    traces = [cpu_sim.prepare_trace(f) for f in frames(0)[:min(N_TRACES, 4)]]
-    cpu_sim.lib()
-    per_step = 2 * cores  # replica-runs per step: two per hardware thread (~0.25 s each)
-    k = [0]
+    traces = [cpu_sim.prepare_trace(f) for f in frames(w, 0)[:min(w['n_traces'], 4)]]
+    per_step = (2 if w['n_jobs'] >= 60000 else 8) * cores   # replica-runs per step
 
     def step():
-        k[0] += 1
-        return cpu_sim.run_fifo_yarn_batch(cl, traces[k[0] % len(traces)], per_step, cores, rows_cap=70000)
+        return cpu_port_batch(cpu_sim, w, cl, traces, per_step, cores)
 
     for _ in range(args.warmup):
         step()
@@ -109,36 +215,20 @@ def run_reference(args, rank, world):
         ev += step()
     dt = time.perf_counter() - t0
     val = ev / dt
-    sample = '%d replica-runs of the 60k-job trace per step on %d pthreads (oracle/cpu_sim.c, gcc -O2)' % (per_step, cores)
+    sample = '%d replica-runs of the workload per step on %d host threads (oracle/cpu_sim.c, gcc -O2)' % (per_step, cores)
+    cb = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    rp = reference_python_sample(w) if not args.no_python_reference else None
+    if rp:
+        cb['reference_python'] = rp
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD % (per_step, min(N_TRACES, 4)), 'note': 'CPU arm: bounded sample, host cores only'},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': '%s, %d replica-runs/step over %d seeds' % (w['text'], per_step, len(traces)), 'name': args.workload,
+                   'note': 'CPU arm: bounded sample, host cores only; kind "port" = the C restatement pinned byte-for-byte on the reference\'s outputs'},
+        'cpu_baseline': cb,
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
-
-
-def cpu_baseline_sample():
-    """Bounded cpu_baseline for the cuda arm's JSON line: a few seconds of the oracle on all cores."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import cpu_sim
-    cores = os.cpu_count() or 1
-    cl = cpu_sim.make_cluster(**CLUSTER_FLAGS)
-    tr = cpu_sim.prepare_trace(frames(0)[0])
-    cpu_sim.lib()
-    cpu_sim.run_fifo_yarn_batch(cl, tr, cores, cores, rows_cap=70000)
-    n_runs = 4 * cores
-    t0 = time.perf_counter()
-    ev = cpu_sim.run_fifo_yarn_batch(cl, tr, n_runs, cores, rows_cap=70000)
-    dt = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    ev1 = cpu_sim.run_fifo_yarn_batch(cl, tr, 1, 1, rows_cap=70000)
-    dt1 = time.perf_counter() - t1
-    return {'value': ev / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d replica-runs of the 60k-job trace on %d pthreads, %.1f s (oracle/cpu_sim.c, gcc -O2)' % (n_runs, cores, dt),
-            'single_core_value': ev1 / dt1}
 
 
 def bind_to_gpu_numa_node(index):
@@ -160,27 +250,41 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def load_profile(name):
+    """profiles/r02_bench_profile.json: numbers read off the committed ncu captures of the CURRENT kernels (scripts/summarize_ncu.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r02_bench_profile.json'))).get(name)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
-    ap.add_argument('--replicas', type=int, default=2960, help='replicas per GPU (default 20 resident warps x 148 SMs)')
+    ap.add_argument('--workload', default='fifo60k', choices=sorted(WORKLOADS))
+    ap.add_argument('--replicas', type=int, default=0, help='replicas per GPU (0 = the workload\'s default)')
+    ap.add_argument('--lpr', type=int, default=0, help='fifo tick loop: lanes of a warp per replica (0 = chosen by the library)')
+    ap.add_argument('--rows-format', default='wire16', choices=['wire16', 'wide'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-python-reference', action='store_true')
     args = ap.parse_args()
+    w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, w, rank)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
     import rlgpuschedule_b200 as rl
+    from rlgpuschedule_b200 import _ffi
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl cuda needs a CUDA device (no CPU fallback)')
     torch.cuda.set_device(local_rank)
@@ -195,29 +299,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    R = args.replicas
+    R = args.replicas or w['replicas']
+    NT = w['n_traces']
+    is_fifo = w['schedule'] == 'fifo'
+    is_env = bool(w.get('env'))
     cluster = rl.Cluster(**CLUSTER_FLAGS)
-    traces = [rl.prepare_trace(f, cluster) for f in frames(rank)]
-    bounds = [R * i // N_TRACES for i in range(N_TRACES + 1)]
+    traces = [rl.prepare_trace(f, cluster) for f in frames(w, rank)]
+    bounds = [R * i // NT for i in range(NT + 1)]
+    blocks = [(i, bounds[i], bounds[i + 1] - bounds[i]) for i in range(NT) if bounds[i + 1] > bounds[i]]
+    sim_kw = dict(w['kw'])
+    if is_fifo:
+        sim_kw.update(lanes_per_replica=args.lpr, rows_format=args.rows_format)
 
     def attach(sim):
-        for i, tr in enumerate(traces):
-            if bounds[i + 1] > bounds[i]:
-                sim.load_trace(tr, bounds[i], bounds[i + 1] - bounds[i])
+        for i, first, count in blocks:
+            sim.load_trace(traces[i], first, count)
+
+    class _Buf(object):
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<i8', 'data': (ptr, False), 'version': 3}
 
     # ---------------- device-resident arm: `value`
-    sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=R, rows='device', device=local_rank)
-    attach(sim)
-    ret_dev = None
-    if world > 1:
-        class _Buf(object):
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<i8', 'data': (ptr, False), 'version': 3}
-        ret_dev = torch.as_tensor(_Buf(sim.returns_device_ptr(), R), device='cuda')
-        gathered = torch.empty(world * R, dtype=torch.int64, device='cuda')
+    env = None
+    if is_env:
+        from rlgpuschedule_b200.env import Environment
+        env = Environment(cluster, [(traces[i], first, count) for i, first, count in blocks], n_replicas=R, window_k=5, device=local_rank, seed=1)
+        sim = env.sim
+    else:
+        sim = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='device', device=local_rank, **sim_kw)
+        attach(sim)
+    ret_dev = torch.as_tensor(_Buf(sim.returns_device_ptr(), R), device='cuda') if world > 1 else None
+    gathered = torch.empty(world * R, dtype=torch.int64, device='cuda') if world > 1 else None
+    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env_ms = [0.0]
 
     def step():
-        sim.run()
+        if is_env:
+            env.reset()
+            ev_k0.record()
+            env.rollout('random')
+            ev_k1.record()
+            env.sync()
+            env_ms[0] = ev_k0.elapsed_time(ev_k1)
+        else:
+            sim.run()
         if world > 1:  # the one collective of the path: episode returns of every replica of every GPU
             dist.all_gather_into_tensor(gathered, ret_dev)
 
@@ -231,18 +356,25 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-        ms, nl = sim.kernel_ms()
-        kernel_ms += ms
-        launches += nl
+        if is_env:
+            kernel_ms += env_ms[0]; launches += 2     # the zero-tick observation of reset() + the rollout
+        else:
+            ms, nl = sim.kernel_ms()
+            kernel_ms += ms; launches += nl
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.finish()
-    summ = [sim.summary(bounds[i]) for i in range(N_TRACES) if bounds[i + 1] > bounds[i]]
-    events_step = sum(s['events'] * (bounds[i + 1] - bounds[i]) for i, s in enumerate(summ))
-    jobs_step = sum(s['n_finished'] * (bounds[i + 1] - bounds[i]) for i, s in enumerate(summ))
-    ticks_step = sum(s['n_ticks'] * (bounds[i + 1] - bounds[i]) for i, s in enumerate(summ))
-    alg_bytes_step = sum(algorithmic_bytes(s, cluster.num_nodes, cluster.num_gpus) * (bounds[i + 1] - bounds[i]) for i, s in enumerate(summ))
-    hbm_stream_bytes_step = sum((s['n_jobs'] * (32 + 32 + 32 + 12 + 8) + s['n_ticks'] * 64) * (bounds[i + 1] - bounds[i]) for i, s in enumerate(summ))
+    summ = [sim.summary(first) for _, first, _ in blocks]
+    cnt = [c for _, _, c in blocks]
+    events_step = sum(s['events'] * c for s, c in zip(summ, cnt))
+    jobs_step = sum(s['n_finished'] * c for s, c in zip(summ, cnt))
+    ticks_step = sum(s['n_ticks'] * c for s, c in zip(summ, cnt))
+    if is_env:   # every replica draws its own picks: count them all
+        allsum = [sim.summary(r) for r in range(R)]
+        events_step, jobs_step, ticks_step = (sum(s[k] for s in allsum) for k in ('events', 'n_finished', 'n_ticks'))
+        summ, cnt = allsum, [1] * R
+    alg_bytes_step = sum(algorithmic_bytes(w, s, cluster.num_nodes, cluster.num_gpus) * c for s, c in zip(summ, cnt))
+    lpr_used = None
     t = torch.tensor([dt, kernel_ms / 1e3], dtype=torch.float64, device='cuda')
     tot = torch.tensor([events_step, jobs_step, ticks_step], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -254,18 +386,32 @@ def main():
     dt_max, kern_s = t.tolist()
     events_all, jobs_all, ticks_all = tot.tolist()
     value = events_all * args.steps / dt_max
-    sim.close()
+    jmax = max(len(tr.records) for tr in traces)
+    max_ticks = max(s['n_ticks'] for s in summ)
+    (env or sim).close()
 
     # ---------------- end-to-end arm through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        sim2 = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=R, rows='host', fetch_jobs=True, device=local_rank)
-        attach(sim2)
+        if is_env:
+            env2 = Environment(cluster, [(traces[i], first, count) for i, first, count in blocks], n_replicas=R, window_k=5, device=local_rank, seed=1)
 
-        def step2():
-            attach(sim2)          # host -> device: the step's input records
-            sim2.run()            # simulate; rows + job tables -> pinned host store, overlapped per stream
-            return int(sim2.summary(0)['n_finished'])
+            def step2():
+                for i, first, count in blocks:            # host -> device: the episode's traces
+                    env2.sim.load_trace(traces[i], first, count)
+                env2.reset()
+                env2.rollout('random')
+                return env2.returns()                      # device -> host: episode returns (sync + copy)
+            closer = env2
+        else:
+            sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=True, device=local_rank, **sim_kw)
+            attach(sim2)
+
+            def step2():
+                attach(sim2)          # host -> device: the step's input records
+                sim2.run()            # simulate; rows + job tables -> pinned host store, overlapped with compute
+                return int(sim2.summary(0)['n_finished'])
+            closer = sim2
         for _ in range(max(args.warmup, 3)):
             step2()
         barrier()
@@ -277,17 +423,19 @@ def main():
         t2 = torch.tensor([dt2], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        rows0 = sim2.rows_view(0)
-        j0 = sim2.jobs(0)
-        assert len(rows0) == summ[0]['n_ticks'] and int(rows0['finished'][-1]) == len(j0['finish_order'])
-        h2d = sum(len(tr.records) * 32 for tr in traces)
-        from rlgpuschedule_b200 import _ffi
-        n_chunks = -(-max(s_['n_ticks'] for s_ in summ) // _ffi.ROWS_PER_CHUNK)        # whole chunks travel (chunk-major row store)
-        jmax = max(len(tr.records) for tr in traces)
-        d2h = int(n_chunks * R * _ffi.ROWS_PER_CHUNK * 64 + 3 * 4 * R * jmax + R * 264)
+        h2d = sum(len(traces[i].records) * 32 for i, _, _ in blocks)
+        if is_env:
+            d2h = 8 * R + R * 264
+        else:
+            rows0 = sim2.rows(0)
+            j0 = sim2.jobs(0)
+            assert len(rows0) == summ[0]['n_ticks'] and int(rows0['finished'][-1]) == len(j0['finish_order'])
+            row_bytes = 16 if (is_fifo and args.rows_format == 'wire16') else 64
+            n_chunks = -(-max_ticks // _ffi.ROWS_PER_CHUNK)        # whole chunks travel (chunk-major row store)
+            d2h = int(n_chunks * R * _ffi.ROWS_PER_CHUNK * row_bytes + 3 * 4 * R * jmax + R * 264)
         e2e = {'value': events_all * args.steps / t2.item(), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'ms_per_step': 1e3 * t2.item() / args.steps}
-        sim2.close()
+        closer.close()
 
     if rank == 0:
         peaks = {}
@@ -295,39 +443,59 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        peak = float(peaks.get('hbm_gbs', 6650.0))
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
         per_launch_s = kern_s / args.steps
-        achieved = alg_bytes_step / per_launch_s / 1e9
-        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one step's kernel work, from the committed ncu capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_traffic.json')))
-            traffic = tj['traffic_bytes_per_launch'] * R / tj.get('replicas', 2368)   # rows + queue stack + job tables scale with the replica count
-        except Exception:
-            pass
+        alg_gbps = alg_bytes_step / per_launch_s / 1e9
+        prof = load_profile(args.workload) or {}
+        kernel_name = {'fifo': 'fifo_grp_kernel', 'sjf': 'sjf_yarn_kernel', 'dlas-gpu': 'dlas_gpu_kernel'}[w['schedule']]
+        # bytes per replica-tick (fifo) / per swept job (legacy) that the committed ncu capture of this kernel measured in DRAM
+        traffic = None
+        if prof.get('dram_bytes_per_unit') is not None:
+            units = ticks_step if is_fifo else sum(s['sum_queued'] * c for s, c in zip(summ, cnt))
+            traffic = prof['dram_bytes_per_unit'] * units
+        if is_fifo:
+            # the tick loop keeps the state SURVEY 8(d) counts in shared memory / registers: it is bound by instruction issue.
+            # achieved = warp instructions per replica-tick (ncu capture of THIS kernel) x replica-ticks/s measured now
+            sm_hz = 1e6 * float(clocks.get('sm_mhz') or 1965)
+            peak_issue = 148 * 4 * sm_hz / 1e9
+            ipt = prof.get('warp_inst_per_replica_tick')
+            ach = ipt * (ticks_step / per_launch_s) / 1e9 if ipt else None
+            roofline = {'bound': 'issue', 'achieved': ach, 'peak': peak_issue, 'unit': 'Gwarp-inst/s', 'frac': (ach / peak_issue) if ach else None,
+                        'traffic': traffic, 'warp_inst_per_replica_tick': ipt,
+                        'peak_source': '148 SMs x 4 schedulers x 1 warp-inst/clk at the SM clock sampled during the run',
+                        'profile': prof.get('source'),
+                        'algorithmic_equiv_GBps': alg_gbps, 'hbm_peak_GBps': hbm_peak,
+                        'dram_GBps': (traffic / per_launch_s / 1e9) if traffic else None,
+                        'dram_frac': (traffic / per_launch_s / 1e9 / hbm_peak) if traffic else None,
+                        'note': 'the per-tick state SURVEY 8(d) counts (8Q+12R+12N+8D+64 B) lives on chip, so algorithmic_equiv_GBps is not a bandwidth '
+                                'the kernel must sustain; ncu shows instruction issue as the limiter and DRAM at a few % of peak'}
+        else:
+            roofline = {'bound': 'hbm', 'achieved': alg_gbps, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': alg_gbps / hbm_peak, 'traffic': traffic,
+                        'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                        'profile': prof.get('source'),
+                        'note': 'achieved = SURVEY 8(d) algorithmic bytes of the per-event sweep (runnable entries streamed 32 at a time) / kernel time'}
+        roofline['launch'] = 'one step = %d launches of %s; bytes and time are per step' % (launches // max(args.steps, 1), kernel_name)
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': 1e3 * dt_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD % (R, N_TRACES), 'schedule': 'fifo', 'scheme': 'yarn', 'replicas_per_gpu': R,
-                       'jobs_per_replica': N_JOBS, 'l2': 'per-step working set (queue stacks + row store + job tables, %.1f GB/GPU) >> 126 MB L2; no explicit flush'
-                       % ((sum(len(tr.records) for tr in traces) / N_TRACES * 32 * R + ticks_step * 64) / 1e9),
-                       'parallelism': 'replicas: %d GPU x %d warps (1 warp = 1 replica)' % (world, R)},
+            'config': {'workload': '%s, %d replicas/GPU over %d seeds' % (w['text'], R, NT), 'name': args.workload, 'schedule': w['schedule'],
+                       'scheme': w['scheme'], 'replicas_per_gpu': R, 'jobs_per_replica': w['n_jobs'],
+                       'rows_format': (args.rows_format if is_fifo and not is_env else ('none' if is_env else 'wide')),
+                       'lanes_per_replica': (args.lpr or 'auto') if is_fifo else 32,
+                       'replica_note': 'replicas of one seed compute identical deterministic simulations (fifo / sjf / dlas draw nothing); the kernel '
+                                       'puts replicas a quarter of a launch apart into one warp, so the replicas sharing a warp follow different seeds',
+                       'l2': 'per-step working set (queue stacks + row store + job tables) >> 126 MB L2; no explicit flush',
+                       'parallelism': 'replicas: %d GPU x %d (share-nothing), one all-gather of returns' % (world, R)},
             'jobs_per_sec': jobs_all * args.steps / dt_max, 'ticks_per_sec': ticks_all * args.steps / dt_max,
             'gpu_launches': launches, 'kernel_ms_per_step': 1e3 * per_launch_s,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
-                         'launch': 'one step = %d concurrent launches of fifo_yarn_kernel<false> (one per replica group / CUDA stream); bytes and time are per step' % (launches // max(args.steps, 1)),
-                         'note': 'achieved = SURVEY 8(d) algorithmic bytes (8Q+12R+12N+8D+64 per tick) / kernel time; that state is held in '
-                                 'shared memory / registers, so it is not DRAM traffic. hbm_stream_GBps = bytes this layout must move through HBM '
-                                 '(records in, queue stack write+read, job tables, 64 B row per tick) / kernel time',
-                         'hbm_stream_GBps': hbm_stream_bytes_step / per_launch_s / 1e9},
-            'clocks': clocks,
+            'roofline': roofline, 'clocks': clocks,
         }
         if e2e:
             out['e2e'] = e2e
-        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only, on every host core
+        if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only, on every usable host core
             os.sched_setaffinity(0, all_cpus)
-            out['cpu_baseline'] = cpu_baseline_sample()
+            out['cpu_baseline'] = cpu_baseline_sample(w)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -12,7 +12,7 @@
  *    passed in are caller-owned and never retained after the call returns.
  *  - a handle is not thread-safe; distinct handles may be used from distinct host threads.
  *  - a "replica" is one independent simulation (one trace on one simulated cluster); replicas never
- *    communicate.  On the device one warp advances one replica.
+ *    communicate.  On the device a group of 8, 16 or 32 lanes of a warp advances one replica (opts.lanes_per_replica).
  *  - the library needs a CUDA device: there is no CPU fallback (rlgs_create fails with RLGS_ERR_CUDA).
  */
 #ifndef RLGS_H
@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RLGS_VERSION 100 /* 0.1.0 */
+#define RLGS_VERSION 200 /* 0.2.0: rlgs_opts gained rows_format / lanes_per_replica (appended), RLGS_ERR_SLOTS / RLGS_ERR_WIRE, rlgs_row16 */
 
 enum {
     RLGS_OK = 0,
@@ -33,7 +33,9 @@ enum {
     RLGS_ERR_OOM = -3,
     RLGS_ERR_UNSUPPORTED = -4, /* policy / option the device path does not implement */
     RLGS_ERR_CAPACITY = -5,    /* a fixed-size device table overflowed and could not be grown */
-    RLGS_ERR_STATE = -6        /* call order (e.g. run before load_trace) */
+    RLGS_ERR_STATE = -6,       /* call order (e.g. run before load_trace, env_step before env_reset) */
+    RLGS_ERR_SLOTS = -7,       /* more jobs ran concurrently than opts.slot_cap on-chip slots: recreate with a larger slot_cap */
+    RLGS_ERR_WIRE = -8         /* a value does not fit the 16-byte wire row (rlgs_row16): rerun with RLGS_ROWFMT_WIDE */
 };
 
 /* --schedule (run_sim.py:38-49); live fifo = core/scheduling/algorithm.py:189-202,
@@ -58,6 +60,12 @@ enum { RLGS_PLACE_YARN = 0, RLGS_PLACE_COUNT = 1,
  * copied to the handle's pinned host store inside rlgs_run (overlapped with compute, one stream per
  * replica group); DEVICE = rows stay in HBM until rlgs_read_rows / rlgs_rows_view asks for them. */
 enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1, RLGS_ROWS_DEVICE = 2 };
+
+/* rows_format: how a per-tick row is stored on the device and moved to the host (fifo tick loop; the other schedules always
+ * use RLGS_ROWFMT_WIDE).  WIDE = rlgs_row, 64 bytes, self-contained.  WIRE16 = rlgs_row16, 16 bytes: the per-tick state that is
+ * not an integral of the start / finish event stream; rlgs_read_rows expands it to rlgs_row on the host (two prefix sums over
+ * the per-job tables the run produced, see rlgs_row16).  Cuts the device->host traffic of a run by 2.7x. */
+enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1 };
 
 /* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
  * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
@@ -94,6 +102,9 @@ typedef struct {
     int32_t pack_rng;          /* horus: 0 = every utilisation draw of infra/device.py:52 returns its mean (the reference on
                                   traces with gpu_utilization_max == gpu_utilization_avg); 1 = build-defined counter-based draw */
     uint32_t pack_seed;        /* seed of that draw */
+    int32_t rows_format;       /* RLGS_ROWFMT_* (fifo tick loop only) */
+    int32_t lanes_per_replica; /* fifo tick loop: lanes of a warp that advance one replica: 8, 16 or 32 (a warp carries 4, 2 or 1
+                                  replicas); 0 = chosen from n_replicas so that the GPU is filled */
 } rlgs_opts;
 
 /*
@@ -141,6 +152,19 @@ typedef struct {
     int64_t util_mu_sum;  /* sum over busy devices of util_mu_q */
     int64_t util_var_sum; /* sum over busy devices of util_sd_q^2 */
 } rlgs_row;
+
+/* 16-byte wire row of the fifo tick loop (RLGS_ROWFMT_WIRE16), row i has delta = i + 1.  Bit fields, least significant first:
+ *   w[0]: idle_nodes:12 | finished:20          w[1]: queued:20 | max_pending[11:0]:12
+ *   w[2]: max_pending[23:12]:12 | median_lo[19:0]:20     w[3]: median_lo[23:20]:4 | median_hi:24 | 0:4
+ * Limits: nodes <= 4095, jobs < 2^20, ticks < 2^24 (else rlgs_run returns RLGS_ERR_WIRE / rlgs_create RLGS_ERR_UNSUPPORTED).
+ * The remaining rlgs_row fields are sums of per-job constants over the running (or queued) set, i.e. integrals of the
+ * event stream the run also returns (start_tick, end_tick, finish_order):
+ *   arrived(i) = #jobs with arrival_tick <= i;  running = arrived - queued - finished;  started = running + finished
+ *   X(i) = sum of x over the first started(i) jobs in start order - sum of x over the first finished(i) jobs in finish order
+ *          for x = devices, mem_term, util_mu_q * devices, util_sd_q^2 * devices      -> busy_gpus, mem_sum, util_mu_sum, util_var_sum
+ *   sum_pending = queued * (i + 1) - (sum of arrival_tick over the first arrived(i) jobs - same over the first started(i) in start order)
+ * rlgs_read_rows does this expansion (int64 prefix sums, exact). */
+typedef struct { uint32_t w[4]; } rlgs_row16;
 
 typedef struct {
     int64_t n_ticks;       /* rows produced (fifo: ticks; sjf/dlas: events) */
@@ -205,11 +229,14 @@ int32_t rlgs_read_jobs(rlgs_sim *sim, int32_t replica, int32_t *finish_order, in
 /* Replaces the per-tick LogManager.step_cluster rows (log_manager.py:118-135): copies rows
  * [first, first+count) of `replica` (rows_mode FULL). */
 int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row *out);
+/* The same rows in the 16-byte wire format (RLGS_ROWFMT_WIRE16 handles only), without the expansion. */
+int32_t rlgs_read_rows16(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16 *out);
 /* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
  * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
  * valid until the next rlgs_run / destroy. */
 #define RLGS_ROWS_PER_CHUNK 4096
-int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);
+int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);   /* RLGS_ROWFMT_WIDE */
+int32_t rlgs_rows16_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE16 */
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,
@@ -232,14 +259,19 @@ int32_t rlgs_read_durations(rlgs_sim *sim, int32_t replica, double *out);
  * fifo/yarn handle; the action picks which of the first `window_k` queued jobs gets the tick's placement
  * attempt (-1 = none).  policy 0 = queue head, 1 = random window (counter-based RNG keyed by seed, replica,
  * tick; n_ticks may be > 1 to roll whole episodes on the device), 2 = actions[] (n_ticks = 1).
- * obs [n_replicas][obs_dim]: free GPUs / free cpu / free mem per node, (gpus, tasks, dur_ticks, pending) of the
- * window jobs, then queued, running, finished, tick.  reward = -(queued + running) per tick.  All pointers
- * are DEVICE pointers; calls are asynchronous on the handle's stream until rlgs_env_sync.
+ * obs [n_replicas][obs_dim = 3 N + 5 window_k + 4]: free GPUs / free cpu / free mem per node, (gpus, tasks, dur_ticks, pending,
+ * trace index) of the window jobs (index -1 = empty place), then queued, running, finished, tick.  A handle created with
+ * RLGS_ROWS_DEVICE + RLGS_ROWFMT_WIDE + lanes_per_replica 32 also records one rlgs_row per stepped tick (rlgs_read_rows after
+ * rlgs_env_sync): what the host-callable scheduling plugins use.  reward = -(queued + running) per tick.  All pointers
+ * are DEVICE pointers; calls are asynchronous on the handle's stream until rlgs_env_sync.  rlgs_env_step before rlgs_env_reset
+ * (or after a new rlgs_load_trace) returns RLGS_ERR_STATE.
  */
 int32_t rlgs_env_obs_dim(rlgs_sim *sim, int32_t window_k, int32_t *dim);
 int32_t rlgs_env_reset(rlgs_sim *sim);
 int32_t rlgs_env_step(rlgs_sim *sim, const int32_t *actions, float *obs, float *reward, uint8_t *done,
                       int32_t policy, int32_t window_k, uint32_t seed, int32_t n_ticks);
+/* Writes the observation of the current state without advancing it (reward 0): the observation reset() hands out. */
+int32_t rlgs_env_observe(rlgs_sim *sim, float *obs, float *reward, uint8_t *done, int32_t window_k);
 int32_t rlgs_env_sync(rlgs_sim *sim);
 
 #ifdef __cplusplus

@@ -10,23 +10,33 @@
 The entries the hot path implements are DevicePolicy objects: Scheduler.start() hands their integer
 id to librlgs and the whole tick / event loop runs on the GPU.  `horus` (schedule_horus + horus_placement
 with horus_score), `horus+` (k-means queues + credit pick) and `gandiva` (schedule_fifo + gandiva_score + the
-time-slice plugin) are among them, so every key of the reference's tables runs on the device.  HostOnlyPolicy
-remains for keys that have no device form (none at present): selecting one fails loudly instead of silently
-running something else.
-Users may register their own entries; only DevicePolicy entries can be executed by this package.
+time-slice plugin) are among them, so every key of the reference's tables runs on the device.
+
+Users may register their own scheduling entries, plain callables with the reference's signature:
+
+    def mine(scheme, placement_algo, infrastructure, jobs_manager, delta, **kwargs): ... return nodes, job, success
+    algorithm.scheduling_algorithms['mine'] = mine            # then: run_sim.py --schedule mine --scheme yarn
+
+Scheduler.start() then keeps the tick loop on the device and calls `mine` once per tick with read-only views of the device
+state (rlgpuschedule_b200/plugin.py); the job it returns gets that tick's placement attempt.  The built-in 'fifo' and 'yarn'
+entries are callable over the same views (schedule_fifo and a dry run of ms_yarn_placement), so a plugin can compose them.
 """
 from . import _ffi
+from . import plugin
 
 
 class DevicePolicy(object):
     """A policy executed inside the CUDA kernels (rlgpuschedule_b200/csrc)."""
 
-    def __init__(self, name, kind, device_id, reference):
-        self.name, self.kind, self.device_id, self.reference = name, kind, device_id, reference
+    def __init__(self, name, kind, device_id, reference, host_fn=None):
+        self.name, self.kind, self.device_id, self.reference, self.host_fn = name, kind, device_id, reference, host_fn
 
     def __call__(self, *args, **kwargs):
-        raise RuntimeError('%s policy %r runs on the device as part of Scheduler.start(); it has no per-call '
-                           'host implementation' % (self.kind, self.name))
+        """Per-call form over the read-only views of plugin.py (what a user-registered scheduling callable composes with)."""
+        if self.host_fn is None:
+            raise RuntimeError('%s policy %r runs on the device as part of Scheduler.start(); it has no per-call '
+                               'host form' % (self.kind, self.name))
+        return self.host_fn(*args, **kwargs)
 
     def __repr__(self):
         return 'DevicePolicy(%s %r, id %d, restates %s)' % (self.kind, self.name, self.device_id, self.reference)
@@ -46,7 +56,7 @@ class HostOnlyPolicy(object):
 
 
 scheduling_algorithms = {
-    'fifo': DevicePolicy('fifo', 'schedule', _ffi.SCHED['fifo'], 'core/scheduling/algorithm.py:189-202'),
+    'fifo': DevicePolicy('fifo', 'schedule', _ffi.SCHED['fifo'], 'core/scheduling/algorithm.py:189-202', host_fn=plugin.schedule_fifo_host),
     'sjf': DevicePolicy('sjf', 'schedule', _ffi.SCHED['sjf'], 'run_sim.py:162-287 (dead code, restated)'),
     'dlas-gpu': DevicePolicy('dlas-gpu', 'schedule', _ffi.SCHED['dlas-gpu'], 'run_sim.py:664-947 (dead code, restated)'),
     'dlas': DevicePolicy('dlas', 'schedule', _ffi.SCHED['dlas'], 'run_sim.py:664-947 with gputime=False (dead code, restated)'),
@@ -58,7 +68,7 @@ scheduling_algorithms = {
 }
 
 placement_algorithms = {
-    'yarn': DevicePolicy('yarn', 'placement', _ffi.PLACE['yarn'], 'core/scheduling/algorithm.py:28-32,301-417'),
+    'yarn': DevicePolicy('yarn', 'placement', _ffi.PLACE['yarn'], 'core/scheduling/algorithm.py:28-32,301-417', host_fn=plugin.yarn_preview),
     'count': DevicePolicy('count', 'placement', _ffi.PLACE['count'], 'run_sim.py:808-823 (free_gpu counting)'),
     # one function under three names in the reference (algorithm.py:182-187); its score table is keyed by the SCHEDULE
     # name (schedule.py:47), so all three behave the same under --schedule horus
@@ -78,16 +88,25 @@ score_fn = {
 }
 
 
+def is_host_callable(entry):
+    """A user-registered scheduling entry: any callable that is not one of this package's policy objects."""
+    return callable(entry) and not isinstance(entry, (DevicePolicy, HostOnlyPolicy))
+
+
 def resolve(schedule, scheme):
     """(schedule name, scheme name) -> (DevicePolicy, DevicePolicy) or raises like the reference would
     (KeyError for unknown keys, NotImplementedError for host-only ones)."""
     sched = scheduling_algorithms[schedule]
     place = placement_algorithms[scheme]
+    if is_host_callable(sched):
+        if not (isinstance(place, DevicePolicy) and place.name == 'yarn'):
+            raise NotImplementedError('a user-registered scheduling callable runs over the device yarn placement (--scheme yarn)')
+        return sched, place
     for p in (sched, place):
         if not isinstance(p, DevicePolicy):
             if isinstance(p, HostOnlyPolicy):
                 p()  # raises NotImplementedError with the reference location
-            raise NotImplementedError('user-registered %r is a host callable; only DevicePolicy entries are executable here' % (p,))
+            raise NotImplementedError('user-registered placement %r: only scheduling entries may be host callables' % (p,))
     packs = place.device_id == _ffi.PLACE['horus']
     pack_schedules = ('horus', 'horus+', 'gandiva')
     if (packs and schedule not in pack_schedules) or (schedule in pack_schedules and not packs and scheme != 'yarn'):

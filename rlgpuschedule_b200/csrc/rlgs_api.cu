@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../../include/rlgs.h"
-#include "fifo_yarn.cuh"
+#include "fifo_grp.cuh"
 #include "legacy_sched.cuh"
 #include "pack_horus.cuh"
 
@@ -53,6 +53,7 @@ struct TraceBuf {
     int64_t log_cap = 0, cap_log = 0;
     int32_t max_arrival = 0;
     int first = 0, count = 0;   // replica range this trace is attached to
+    std::vector<rlgs_job> host; // host copy of the records: the expansion of the 16-byte wire rows needs the per-job constants
 };
 
 struct Group {            // a contiguous range of replicas driven through one CUDA stream
@@ -73,6 +74,13 @@ struct rlgs_sim {
     ClusterConst cc;
     LegParams lp;
     int R = 0, device = 0;
+    int lpr = 32;           // lanes of a warp per replica (fifo tick loop)
+    bool wire16 = false;    // rows are kept as rlgs_row16
+    size_t row_bytes = sizeof(rlgs_row);
+    bool env_ready = false; // rlgs_env_reset ran since the last rlgs_load_trace
+    int64_t env_ticks = 0;  // upper bound of the ticks simulated since rlgs_env_reset (sizes the row store while stepping)
+    int xp_replica = -1;    // replica whose prefix sums are cached below (expansion of wire rows)
+    std::vector<int64_t> xp[9];
     bool legacy = false;
     bool pack = false;      // horus schedule + horus placement (pack_horus.cuh)
     PackParams pp;
@@ -117,7 +125,7 @@ extern "C" int32_t rlgs_version(void) { return RLGS_VERSION; }
 extern "C" const char *rlgs_last_error(void) { return g_err; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static size_t chunk_bytes(const rlgs_sim *s) { return sizeof(rlgs_row) * (size_t)RLGS_ROW_CHUNK * (size_t)s->R; }
+static size_t chunk_bytes(const rlgs_sim *s) { return s->row_bytes * (size_t)RLGS_ROW_CHUNK * (size_t)s->R; }
 
 extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *opts, rlgs_sim **out) {
     if (!spec || !opts || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
@@ -151,6 +159,11 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     }
     if (opts->enable_network_costs && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "network costs are implemented for the fifo tick loop only");
     if (opts->enable_network_costs && !(opts->bandwidth > 0)) return fail(RLGS_ERR_BAD_ARG, "bandwidth must be > 0");
+    if (opts->rows_format != RLGS_ROWFMT_WIDE && opts->rows_format != RLGS_ROWFMT_WIRE16) return fail(RLGS_ERR_BAD_ARG, "rows_format must be RLGS_ROWFMT_WIDE or RLGS_ROWFMT_WIRE16");
+    if (opts->rows_format == RLGS_ROWFMT_WIRE16 && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "the 16-byte wire row belongs to the fifo tick loop");
+    if (opts->rows_format == RLGS_ROWFMT_WIRE16 && N > 4095) return fail(RLGS_ERR_UNSUPPORTED, "the 16-byte wire row holds at most 4095 nodes");
+    const int lpr_in = opts->lanes_per_replica;
+    if (lpr_in != 0 && lpr_in != 8 && lpr_in != 16 && lpr_in != 32) return fail(RLGS_ERR_BAD_ARG, "lanes_per_replica must be 0, 8, 16 or 32");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -180,6 +193,13 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->lp.total_gpu = s->cc.D; s->lp.num_node = s->cc.N; s->lp.gpus_per_node = s->cc.G; s->lp.max_time = opts->max_ticks;
     s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
     s->slot_cap = (s->slot_cap + 31) & ~31;
+    if (s->slot_cap > 65504) { delete s; return fail(RLGS_ERR_BAD_ARG, "slot_cap must be <= 65504"); }
+    s->wire16 = opts->rows_format == RLGS_ROWFMT_WIRE16;
+    s->row_bytes = s->wire16 ? sizeof(rlgs_row16) : sizeof(rlgs_row);
+    // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
+    // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
+    s->lpr = lpr_in ? lpr_in : (s->R >= 148 * 8 * 4 ? 8 : (s->R >= 148 * 8 * 2 ? 16 : 32));
+    while (s->lpr < 32 && (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr) > 227 * 1024) s->lpr *= 2;   // the warp's replicas must fit one SM
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
     s->h_ldesc.assign(s->R, LegDesc{});
@@ -266,6 +286,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     if (first < 0 || count < 1 || first + count > s->R) return fail(RLGS_ERR_BAD_ARG, "replica range [%d,%d) out of 0..%d", first, first + count, s->R);
     if (s->opts.enable_network_costs && (!net || !net->duration || !net->model_mb || !net->iterations))
         return fail(RLGS_ERR_BAD_ARG, "enable_network_costs needs duration / model_mb / iterations arrays");
+    if (s->wire16 && n >= (1 << 20)) return fail(RLGS_ERR_WIRE, "the 16-byte wire row counts at most 2^20 - 1 jobs: use RLGS_ROWFMT_WIDE");
     CU(cudaSetDevice(s->device));
     TraceBuf tb;
     tb.n = n;
@@ -298,6 +319,8 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
                 for (int r = 0; r < count; ++r) s->h_desc[first + r].dur_out = old.dur_out + (size_t)r * n;
             }
             old.n = n; old.log_cap = tb.log_cap; old.max_arrival = tb.max_arrival;
+            if (s->wire16) old.host.assign(jobs, jobs + n);
+            s->env_ready = false; s->xp_replica = -1;
             for (int r = 0; r < count; ++r) {
                 s->h_desc[first + r].J = n; s->h_desc[first + r].log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
                 s->h_ldesc[first + r].J = n;
@@ -307,6 +330,8 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         }
     }
     tb.cap_n = n; tb.cap_log = tb.log_cap;
+    if (s->wire16) tb.host.assign(jobs, jobs + n);
+    s->env_ready = false; s->xp_replica = -1;
     CU(cudaMalloc(&tb.dev, sizeof(rlgs_job) * (size_t)n));
     cudaError_t e = cudaMemcpy(tb.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(tb.dev); return fail(RLGS_ERR_CUDA, "trace upload: %s", cudaGetErrorString(e)); }
@@ -510,17 +535,50 @@ static NetCost netcost_of(const rlgs_sim *s) {
     return n;
 }
 
+// one instantiation of the fifo tick loop: LPR lanes per replica, env / rows / network-cost variants compiled apart
+template <int LPR, bool ENV, int ROWS, bool NET>
+static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, const RowStore &rs, const EnvIO &io, cudaStream_t st) {
+    constexpr int K = 32 / LPR;
+    const size_t smem = K * grp_smem_bytes(s->cc.N, s->slot_cap, LPR);
+    static size_t attr_set[64] = {0};   // per device: largest dynamic shared-memory size already allowed for this instantiation
+    const int dev = s->device & 63;
+    if (smem > attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(fifo_grp_kernel<LPR, ENV, ROWS, NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = smem;
+    }
+    fifo_grp_kernel<LPR, ENV, ROWS, NET><<<(count + K - 1) / K, 32, smem, st>>>(s->d_desc + first, s->d_state + first, count, s->cc, s->slot_cap, budget, rs,
+                                                                            s->d_returns + first, s->opts.max_ticks, io, netcost_of(s));
+    return cudaGetLastError();
+}
+
+// the environment with per-tick rows (host-callable scheduling plugins, rlgpuschedule_b200/plugin.py): one variant only
+static cudaError_t launch_env_rows(rlgs_sim *s, int first, int count, int budget, const RowStore &rs, const EnvIO &io, cudaStream_t st) {
+    if (s->lpr != 32 || s->wire16) return cudaErrorNotSupported;   // rlgs_env_reset refuses the combination before it gets here
+    return s->opts.enable_network_costs ? launch_grp<32, true, 1, true>(s, first, count, budget, rs, io, st)
+                                        : launch_grp<32, true, 1, false>(s, first, count, budget, rs, io, st);
+}
+
+// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16
+static cudaError_t launch_fifo(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
+    const bool net = s->opts.enable_network_costs != 0;
+#define RLGS_FIFO_VARIANTS(LPR)                                                                                                   \
+    if (env && rows == 0) return net ? launch_grp<LPR, true, 0, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, true, 0, false>(s, first, count, budget, rs, io, st); \
+    if (env) return launch_env_rows(s, first, count, budget, rs, io, st); \
+    if (rows == 0) return net ? launch_grp<LPR, false, 0, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 0, false>(s, first, count, budget, rs, io, st); \
+    if (rows == 1) return net ? launch_grp<LPR, false, 1, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 1, false>(s, first, count, budget, rs, io, st); \
+    return net ? launch_grp<LPR, false, 2, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 2, false>(s, first, count, budget, rs, io, st);
+    if (s->lpr == 8) { RLGS_FIFO_VARIANTS(8) }
+    if (s->lpr == 16) { RLGS_FIFO_VARIANTS(16) }
+    RLGS_FIFO_VARIANTS(32)
+#undef RLGS_FIFO_VARIANTS
+}
+
 static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cudaStream_t st) {
     RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
     if (!s->legacy) {
         EnvIO none; memset(&none, 0, sizeof none);
-        const size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
-        const NetCost nc = netcost_of(s);
-#define RLGS_LAUNCH_FIFO(ROWS, NET) fifo_yarn_kernel<false, ROWS, NET><<<count, 32, smem, st>>>(s->d_desc + first, s->d_state + first, s->cc, s->slot_cap, \
-                                        budget, rs, s->d_returns + first, s->opts.max_ticks, none, nc)
-        if (rows) { if (nc.enabled) RLGS_LAUNCH_FIFO(true, true); else RLGS_LAUNCH_FIFO(true, false); }
-        else { if (nc.enabled) RLGS_LAUNCH_FIFO(false, true); else RLGS_LAUNCH_FIFO(false, false); }
-#undef RLGS_LAUNCH_FIFO
+        launch_fifo(s, first, count, budget, rows ? (s->wire16 ? 2 : 1) : 0, false, none, rs, st);   // the caller reads cudaGetLastError
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
@@ -562,12 +620,8 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     const bool rows = mode != RLGS_ROWS_NONE, eager_rows = mode == RLGS_ROWS_FULL, eager_jobs = s->opts.fetch_jobs != 0;
     const int R = s->R;
     if (!s->legacy) {
-        size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
-        if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica (> 227 KB)", smem);
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(fifo_yarn_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr);
+        if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp (> 227 KB)", smem);
     } else if (!s->pack && s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
@@ -601,7 +655,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     }
     if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
     std::fill(s->h_chunk_valid.begin(), s->h_chunk_valid.end(), 0);
-    s->planes_on_host = 0; s->ran = false;
+    s->planes_on_host = 0; s->ran = false; s->xp_replica = -1;
 
     if (!s->legacy) {
         CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
@@ -663,18 +717,19 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
             total_ms += wave;
         }
         bool all_done = true, overflow = false, rows_full = false;
-        int bad = -1;
+        int bad = -1, bad_code = 0;
         for (int r = 0; r < R; ++r) {
             Progress p = progress_of(s, r);
-            if (p.status == RLGS_ERR_CAPACITY) { overflow = true; bad = r; }
+            if (p.status != RLGS_OK && !overflow) { overflow = true; bad = r; bad_code = p.status; }
             if (!p.done) { all_done = false; if (rows && p.rows >= (int64_t)s->d_chunks.size() * RLGS_ROW_CHUNK) rows_full = true; }
         }
         if (overflow) {
             cudaStreamSynchronize(s->copy_stream);
+            if (bad_code == RLGS_ERR_SLOTS) return fail(RLGS_ERR_SLOTS, "replica %d: running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", bad, s->slot_cap);
+            if (bad_code == RLGS_ERR_WIRE) return fail(RLGS_ERR_WIRE, "replica %d: a value no longer fits the 16-byte wire row: use RLGS_ROWFMT_WIDE", bad);
+            if (bad_code != RLGS_ERR_CAPACITY) return fail(bad_code, "replica %d stopped with status %d", bad, bad_code);
             if (s->opts.max_ticks > 0) return fail(RLGS_ERR_CAPACITY, "replica %d reached max_ticks", bad);
-            if (s->pack) return fail(RLGS_ERR_CAPACITY, "replica %d stopped on a capacity limit", bad);
-            if (!s->legacy) return fail(RLGS_ERR_CAPACITY, "running-job slot table overflow at slot_cap=%d: recreate with a larger opts.slot_cap", s->slot_cap);
-            return fail(RLGS_ERR_CAPACITY, "replica %d: runnable-entry table overflow", bad);
+            return fail(RLGS_ERR_CAPACITY, "replica %d stopped on a capacity limit (a device table is full)", bad);
         }
         if (all_done) break;
         if (pipelined) {   // the estimate was short: continue one chunk at a time
@@ -800,29 +855,122 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     return RLGS_OK;
 }
 
-extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
-    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
-    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
-    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
-    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
-    int64_t n = progress_of(s, r).rows;
-    if (first < 0 || count < 0 || first + count > n) return fail(RLGS_ERR_BAD_ARG, "row range [%lld,%lld) out of 0..%lld", (long long)first, (long long)(first + count), (long long)n);
-    CU(cudaSetDevice(s->device));
+// copies `count` rows starting at row `first` of replica r out of the chunk-major store (pinned mirror when valid, else the device)
+static int32_t copy_rows_raw(rlgs_sim *s, int r, int64_t first, int64_t count, unsigned char *out) {
+    const size_t rb = s->row_bytes;
     int64_t done = 0;
     while (done < count) {
         int64_t i = first + done;
         int k = (int)(i >> RLGS_ROW_CHUNK_LOG);
         int64_t off = i & (RLGS_ROW_CHUNK - 1), len = std::min<int64_t>(count - done, RLGS_ROW_CHUNK - off);
-        size_t pos = ((size_t)r << RLGS_ROW_CHUNK_LOG) + (size_t)off;
-        if (s->h_chunk_valid[k]) memcpy(out + done, s->h_chunks[k] + pos, sizeof(rlgs_row) * (size_t)len);
-        else CU(cudaMemcpy(out + done, s->d_chunks[k] + pos, sizeof(rlgs_row) * (size_t)len, cudaMemcpyDeviceToHost));
+        size_t pos = (((size_t)r << RLGS_ROW_CHUNK_LOG) + (size_t)off) * rb;
+        if (s->h_chunk_valid[k]) memcpy(out + done * rb, reinterpret_cast<unsigned char *>(s->h_chunks[k]) + pos, rb * (size_t)len);
+        else CU(cudaMemcpy(out + done * rb, reinterpret_cast<unsigned char *>(s->d_chunks[k]) + pos, rb * (size_t)len, cudaMemcpyDeviceToHost));
         done += len;
     }
     return RLGS_OK;
 }
 
-extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row **rows, int64_t *count) {
-    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+static int32_t rows_args_ok(rlgs_sim *s, int32_t r, int64_t first, int64_t count) {
+    if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
+    if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
+    if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
+    int64_t n = progress_of(s, r).rows;
+    if (first < 0 || count < 0 || first + count > n) return fail(RLGS_ERR_BAD_ARG, "row range [%lld,%lld) out of 0..%lld", (long long)first, (long long)(first + count), (long long)n);
+    return RLGS_OK;
+}
+
+// Prefix sums behind the expansion of rlgs_row16 (include/rlgs.h): per-job constants summed in start order, in finish order and
+// (arrival ticks) in trace order.  Cached for one replica at a time.
+static int32_t prepare_expansion(rlgs_sim *s, int r) {
+    if (s->xp_replica == r) return RLGS_OK;
+    int32_t rc = fetch_planes(s, 3);
+    if (rc) return rc;
+    const TraceBuf &tb = s->traces[s->rep_trace[r]];
+    const int J = tb.n;
+    if ((int)tb.host.size() != J) return fail(RLGS_ERR_STATE, "no host copy of the trace of replica %d", r);
+    const size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
+    const int32_t *st = s->h_jobs + off, *fo = s->h_jobs + 2 * plane + off;
+    const int F = s->h_state[r].F;
+    // start order: one job starts per tick (schedule.py:188-190), so start ticks are distinct; sort the started jobs by them
+    std::vector<std::pair<int32_t, int32_t>> so;
+    so.reserve((size_t)J);
+    for (int i = 0; i < J; ++i) if (st[i] >= 0) so.push_back(std::make_pair(st[i], i));
+    std::sort(so.begin(), so.end());
+    const size_t S = so.size();
+    // xp[0..3]: devices, mem_term, util_mu * devices, util_sd^2 * devices in start order; xp[4]: arrival ticks in start order;
+    // xp[5..8]: the first four in finish order.  Arrival ticks in trace order are summed on the fly (they are sorted).
+    for (int k = 0; k < 5; ++k) s->xp[k].assign(S + 1, 0);
+    for (int k = 5; k < 9; ++k) s->xp[k].assign((size_t)F + 1, 0);
+    auto consts = [&](int i, int64_t *v) {
+        const rlgs_job &j = tb.host[i];
+        const int64_t nd = (int64_t)j.tasks * j.gpus_per_task;
+        v[0] = nd; v[1] = j.mem_term; v[2] = (int64_t)j.util_mu_q * nd; v[3] = (int64_t)j.util_sd_q * j.util_sd_q * nd;
+    };
+    int64_t v[4];
+    for (size_t k = 0; k < S; ++k) {
+        consts(so[k].second, v);
+        for (int q = 0; q < 4; ++q) s->xp[q][k + 1] = s->xp[q][k] + v[q];
+        s->xp[4][k + 1] = s->xp[4][k] + tb.host[so[k].second].arrival_tick;
+    }
+    for (int k = 0; k < F; ++k) {
+        consts(fo[k], v);
+        for (int q = 0; q < 4; ++q) s->xp[5 + q][k + 1] = s->xp[5 + q][k] + v[q];
+    }
+    s->xp_replica = r;
+    return RLGS_OK;
+}
+
+extern "C" int32_t rlgs_read_rows16(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16 *out) {
+    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 64-byte rows (opts.rows_format)");
+    int32_t rc = rows_args_ok(s, r, first, count);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    return copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(out));
+}
+
+extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
+    if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    int32_t rc = rows_args_ok(s, r, first, count);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    if (!s->wire16) return copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(out));
+    // ---- expansion of the 16-byte wire rows (see rlgs_row16 in include/rlgs.h)
+    rc = prepare_expansion(s, r);
+    if (rc) return rc;
+    std::vector<rlgs_row16> w((size_t)count);
+    rc = copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(w.data()));
+    if (rc) return rc;
+    const TraceBuf &tb = s->traces[s->rep_trace[r]];
+    const int J = tb.n;
+    int64_t arrived = 0, sum_arr_all = 0;   // jobs with arrival_tick <= i and the sum of their arrival ticks
+    auto advance = [&](int64_t i) { while (arrived < J && tb.host[(size_t)arrived].arrival_tick <= i) { sum_arr_all += tb.host[(size_t)arrived].arrival_tick; ++arrived; } };
+    const int64_t S_max = (int64_t)s->xp[0].size() - 1, F_max = (int64_t)s->xp[5].size() - 1;
+    for (int64_t k = 0; k < count; ++k) {
+        const int64_t i = first + k;
+        advance(i);
+        const uint32_t *x = w[(size_t)k].w;
+        rlgs_row &o = out[k];
+        o.idle_nodes = (int32_t)(x[0] & 0xfffu);
+        o.finished = (int32_t)(x[0] >> 12);
+        o.queued = (int32_t)(x[1] & 0xfffffu);
+        o.max_pending = (int32_t)((x[1] >> 20) | ((x[2] & 0xfffu) << 12));
+        o.median_lo = (int32_t)((x[2] >> 12) | ((x[3] & 0xfu) << 20));
+        o.median_hi = (int32_t)((x[3] >> 4) & 0xffffffu);
+        const int64_t Fi = o.finished, Q = o.queued, Ri = arrived - Q - Fi, Si = Ri + Fi;
+        if (Ri < 0 || Si > S_max || Fi > F_max) return fail(RLGS_ERR_STATE, "row %lld of replica %d is inconsistent with the job tables", (long long)i, r);
+        o.running = (int32_t)Ri;
+        o.busy_gpus = (int32_t)(s->xp[0][(size_t)Si] - s->xp[5][(size_t)Fi]);
+        o.mem_sum = s->xp[1][(size_t)Si] - s->xp[6][(size_t)Fi];
+        o.util_mu_sum = s->xp[2][(size_t)Si] - s->xp[7][(size_t)Fi];
+        o.util_var_sum = s->xp[3][(size_t)Si] - s->xp[8][(size_t)Fi];
+        o.sum_pending = Q * (i + 1) - (sum_arr_all - s->xp[4][(size_t)Si]);
+    }
+    return RLGS_OK;
+}
+
+static int32_t rows_view_any(rlgs_sim *s, int32_t r, int32_t chunk, const void **rows, int64_t *count) {
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     if (s->opts.rows_mode == RLGS_ROWS_NONE) return fail(RLGS_ERR_STATE, "rows were not recorded (opts.rows_mode)");
@@ -834,9 +982,21 @@ extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const r
         CU(cudaMemcpy(s->h_chunks[chunk], s->d_chunks[chunk], chunk_bytes(s), cudaMemcpyDeviceToHost));
         s->h_chunk_valid[chunk] = 1;
     }
-    *rows = s->h_chunks[chunk] + ((size_t)r << RLGS_ROW_CHUNK_LOG);
+    *rows = reinterpret_cast<unsigned char *>(s->h_chunks[chunk]) + ((size_t)r << RLGS_ROW_CHUNK_LOG) * s->row_bytes;
     *count = std::min<int64_t>(RLGS_ROW_CHUNK, n - (int64_t)chunk * RLGS_ROW_CHUNK);
     return RLGS_OK;
+}
+
+extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 16-byte wire rows: use rlgs_rows16_view, or rlgs_read_rows for expanded rows");
+    return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
+}
+
+extern "C" int32_t rlgs_rows16_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row16 **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (!s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 64-byte rows (opts.rows_format)");
+    return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 
 extern "C" int32_t rlgs_returns(rlgs_sim *s, int64_t *out) {
@@ -860,7 +1020,7 @@ extern "C" int32_t rlgs_returns_device_ptr(rlgs_sim *s, void **dev_ptr) {
 extern "C" int32_t rlgs_env_obs_dim(rlgs_sim *s, int32_t window_k, int32_t *dim) {
     if (!s || !dim) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
-    *dim = 3 * s->cc.N + 4 * window_k + 4;
+    *dim = 3 * s->cc.N + 5 * window_k + 4;
     return RLGS_OK;
 }
 
@@ -870,10 +1030,16 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     CU(cudaSetDevice(s->device));
     int32_t rc = setup_job_arrays(s);
     if (rc) return rc;
-    size_t smem = fifo_smem_bytes(s->cc.N, s->slot_cap);
-    if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per replica", smem);
-    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(fifo_yarn_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr);
+    if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp", smem);
+    if (s->opts.rows_mode != RLGS_ROWS_NONE) {   // per-tick rows while stepping: 64-byte rows, one replica per warp
+        if (s->lpr != 32 || s->wire16) return fail(RLGS_ERR_UNSUPPORTED, "environment steps with rows need lanes_per_replica = 32 and RLGS_ROWFMT_WIDE");
+        if (s->opts.rows_mode != RLGS_ROWS_DEVICE) return fail(RLGS_ERR_UNSUPPORTED, "environment steps keep their rows on the device (RLGS_ROWS_DEVICE)");
+        rc = add_chunks(s, std::max<int>(1, (int)s->d_chunks.size()), false);
+        if (rc) return rc;
+        std::fill(s->h_chunk_valid.begin(), s->h_chunk_valid.end(), 0);
+    }
+    s->env_ticks = 0;
     cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     for (int r = 0; r < s->R; ++r) {
         RepState z; memset(&z, 0, sizeof z);
@@ -886,7 +1052,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * s->R, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, st));
     CU(cudaStreamSynchronize(st));   // h_init / h_desc may be rewritten by the caller's next call
-    s->planes_on_host = 0; s->ran = false;
+    s->planes_on_host = 0; s->ran = false; s->env_ready = true;
     return RLGS_OK;
 }
 
@@ -897,19 +1063,38 @@ extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs
     if (policy < 0 || policy > 2 || (policy == 2 && !actions)) return fail(RLGS_ERR_BAD_ARG, "policy must be 0, 1 or 2 (2 needs actions)");
     if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
     if (n_ticks < 1 || (policy == 2 && n_ticks != 1)) return fail(RLGS_ERR_BAD_ARG, "n_ticks must be >= 1 (exactly 1 with external actions)");
+    if (!s->env_ready) return fail(RLGS_ERR_STATE, "rlgs_env_step needs rlgs_env_reset after rlgs_load_trace");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     EnvIO io; io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.policy = policy; io.window_k = window_k;
-    io.seed = seed; io.obs_dim = 3 * s->cc.N + 4 * window_k + 4;
+    io.seed = seed; io.obs_dim = 3 * s->cc.N + 5 * window_k + 4;
     RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
-    const NetCost nc = netcost_of(s);
-    if (nc.enabled)
-        fifo_yarn_kernel<true, false, true><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
-                                                                                                   s->d_returns, s->opts.max_ticks, io, nc);
-    else
-        fifo_yarn_kernel<true, false, false><<<s->R, 32, fifo_smem_bytes(s->cc.N, s->slot_cap), st>>>(s->d_desc, s->d_state, s->cc, s->slot_cap, n_ticks, rs,
-                                                                                                    s->d_returns, s->opts.max_ticks, io, nc);
+    const bool rows = s->opts.rows_mode != RLGS_ROWS_NONE;
+    if (rows) {
+        // rows of the ticks this call may simulate: grow the store up to 16 chunks ahead; a launch stops where the store ends
+        int64_t upto = std::min<int64_t>(s->env_ticks + n_ticks, s->env_ticks + 16 * (int64_t)RLGS_ROW_CHUNK);
+        int need = (int)((upto + RLGS_ROW_CHUNK - 1) / RLGS_ROW_CHUNK);
+        if (need > (int)s->d_chunks.size()) { CU(cudaStreamSynchronize(st)); int32_t rc = add_chunks(s, need, false); if (rc) return rc; }
+        s->env_ticks = std::min<int64_t>(upto, (int64_t)s->d_chunks.size() * RLGS_ROW_CHUNK);
+        rs.chunks = s->d_chunk_ptrs; rs.n_chunks = (int)s->d_chunks.size();
+    }
+    CU(launch_fifo(s, 0, s->R, n_ticks, rows ? 1 : 0, true, io, rs, st));
     CU(cudaGetLastError());
+    return RLGS_OK;
+}
+
+// Observation of the current state without advancing it (a zero-tick launch of the same kernel): what reset() returns.
+extern "C" int32_t rlgs_env_observe(rlgs_sim *s, float *obs, float *reward, uint8_t *done, int32_t window_k) {
+    if (!s || !obs || !reward || !done) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
+    if (window_k < 1 || window_k > 32) return fail(RLGS_ERR_BAD_ARG, "window_k must be 1..32");
+    if (!s->env_ready) return fail(RLGS_ERR_STATE, "rlgs_env_observe needs rlgs_env_reset after rlgs_load_trace");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
+    EnvIO io; io.actions = nullptr; io.obs = obs; io.reward = reward; io.done = done; io.policy = 0; io.window_k = window_k;
+    io.seed = 0; io.obs_dim = 3 * s->cc.N + 5 * window_k + 4;
+    RowStore rs; rs.chunks = nullptr; rs.n_chunks = 0; rs.replica = 0;
+    CU(launch_fifo(s, 0, s->R, 0, 0, true, io, rs, st));
     return RLGS_OK;
 }
 
@@ -918,6 +1103,7 @@ extern "C" int32_t rlgs_env_step(rlgs_sim *s, const int32_t *actions, float *obs
 extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
     if (!s) return fail(RLGS_ERR_BAD_ARG, "null handle");
     if (s->legacy) return fail(RLGS_ERR_UNSUPPORTED, "the environment steps the fifo tick loop");
+    if (!s->env_ready) return fail(RLGS_ERR_STATE, "rlgs_env_sync needs rlgs_env_reset after rlgs_load_trace");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = s->use_user_stream ? (cudaStream_t)s->user_stream : s->stream;
     CU(cudaMemcpyAsync(s->h_state, s->d_state, sizeof(RepState) * s->R, cudaMemcpyDeviceToHost, st));

@@ -16,15 +16,17 @@ from .simulator import Simulator
 
 
 class Environment(object):
-    def __init__(self, cluster=None, traces=None, n_replicas=1, window_k=5, device=0, slot_cap=0, seed=0):
-        """traces: one Trace (shared by all replicas) or a list of (Trace, first_replica, count)."""
+    def __init__(self, cluster=None, traces=None, n_replicas=1, window_k=5, device=0, slot_cap=0, seed=0, rows=False):
+        """traces: one Trace (shared by all replicas) or a list of (Trace, first_replica, count).
+        rows=True also records one cluster.csv row per stepped tick (one replica per warp, 64-byte rows on the device)."""
         import torch
         self.torch = torch
         self.window_k = int(window_k)
         self.n_replicas = int(n_replicas)
         self.seed = int(seed)
         self.device = torch.device('cuda', device)
-        self.sim = Simulator(cluster, 'fifo', 'yarn', n_replicas=n_replicas, rows=False, device=device, slot_cap=slot_cap)
+        kw = dict(rows='device', rows_format='wide', lanes_per_replica=32) if rows else dict(rows=False)
+        self.sim = Simulator(cluster, 'fifo', 'yarn', n_replicas=n_replicas, device=device, slot_cap=slot_cap, **kw)
         if traces is not None:
             if isinstance(traces, (list, tuple)):
                 for tr, first, count in traces:
@@ -47,14 +49,8 @@ class Environment(object):
     def reset(self):
         self._bind_stream()
         _ffi.check(_ffi.lib().rlgs_env_reset(self.sim._h))
-        # a zero-tick observation: policy 2 with the no-op action would advance a tick, so observe the empty cluster
-        self.obs.zero_()
-        N = self.sim.cluster.num_nodes
-        self.obs[:, 0:N] = float(self.sim.cluster.num_gpu_p_node)
-        self.obs[:, N:2 * N] = float(self.sim.cluster.num_cpu_p_node)
-        self.obs[:, 2 * N:3 * N] = float(self.sim.cluster.mem_p_node)
-        self.reward.zero_()
-        self.done.zero_()
+        # the first observation is written by the kernel too (a zero-tick launch): the layout has one author
+        _ffi.check(_ffi.lib().rlgs_env_observe(self.sim._h, self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self.window_k))
         return self.obs
 
     def step(self, action):

@@ -97,6 +97,8 @@ class Scheduler(object):
         flags = self.infrastructure.flags
         t0 = time.time()
         sched, place = algorithm.resolve(self.schedule, self.placement)
+        if algorithm.is_host_callable(sched):
+            return self._start_host_plugin(sched, t0)
         scheme = self.placement
         kw = {}
         if self.schedule in ('dlas-gpu', 'dlas'):
@@ -154,4 +156,23 @@ class Scheduler(object):
         ms, launches = sim.kernel_ms()
         logging.info('device: %d rows, %d jobs finished, %d events, kernel %.3f ms in %d launches' % (
             summ['n_ticks'], summ['n_finished'], summ['events'], ms, launches))
+        return summ
+
+    def _start_host_plugin(self, fn, t0):
+        """A user-registered scheduling_algorithms entry (a Python callable with the reference's signature,
+        core/scheduling/schedule.py:45-47): the tick loop stays on the device, the callable picks the job of each tick."""
+        from . import plugin
+        flags = self.infrastructure.flags
+        cluster, trace = self.infrastructure.cluster, self.jobs_manager.trace
+        env, ticks, _tape = plugin.run_host_policy(fn, cluster, trace, flags, scheme=self.placement, k=int(getattr(flags, 'num_buffer', 5)),
+                                            device=getattr(flags, 'device', 0))
+        sim = env.sim
+        self.simulator = sim
+        self.log_manager.write_cluster_rows(sim.rows(0), cluster, trace.mem_shift,
+                                            util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
+        j = sim.jobs(0)
+        logging.info('Total Time Taken in seconds: %d' % (time.time() - t0))
+        self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt'], None, {}))
+        summ = sim.summary(0)
+        logging.info('device: %d ticks stepped for the host plugin %r, %d jobs finished' % (ticks, self.schedule, summ['n_finished']))
         return summ

@@ -15,16 +15,22 @@ class Simulator(object):
     def __init__(self, cluster, schedule='fifo', scheme='yarn', n_replicas=1, rows=True, device=0, slot_cap=0,
                  n_streams=0, ticks_per_launch=0, rows_cap=0, fetch_jobs=False, num_queue=1, queue_limit=(),
                  max_ticks=0, enable_network_costs=False, bandwidth=1250, internode_latency=0.015, num_buffer=5,
-                 pack_seed=None, pack_rng=None):
+                 pack_seed=None, pack_rng=None, rows_format=None, lanes_per_replica=0):
         """rows: True / 'host' = rows copied to the pinned host store inside run(); 'device' = rows stay in
         HBM until asked for; False = no rows.  num_buffer: look-ahead window of the horus schedule (--num_buffer).
         pack_seed: None = utilisation draws of the horus score return their mean (the reference's behaviour on
         zero-spread traces); an int seeds the build-defined counter-based draw.  horus+: pack_seed also seeds the k-means draws
-        (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded."""
+        (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded.
+        rows_format: 'wire16' (default for fifo) keeps 16-byte rows on the device / the wire and expands them in rows();
+        'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto."""
         if schedule not in _ffi.SCHED:
             raise NotImplementedError('schedule %r has no device implementation' % (schedule,))
         if scheme not in _ffi.PLACE:
             raise NotImplementedError('placement scheme %r has no device implementation' % (scheme,))
+        if rows_format is None:
+            rows_format = 'wire16' if (schedule == 'fifo' and cluster.num_nodes <= 4095) else 'wide'
+        if rows_format not in ('wire16', 'wide'):
+            raise ValueError('rows_format must be wire16 or wide')
         self.cluster = cluster
         self.n_replicas = n_replicas
         self.rows_mode = rows
@@ -33,7 +39,8 @@ class Simulator(object):
                         num_queue=num_queue, queue_limit=tuple(queue_limit), max_ticks=max_ticks,
                         enable_network_costs=enable_network_costs, bandwidth=bandwidth,
                         internode_latency=internode_latency, num_buffer=num_buffer, pack_seed=pack_seed,
-                        pack_rng=(pack_seed is not None) if pack_rng is None else bool(pack_rng))
+                        pack_rng=(pack_seed is not None) if pack_rng is None else bool(pack_rng),
+                        rows_format=rows_format, lanes_per_replica=int(lanes_per_replica))
         self._slot_cap = slot_cap
         self._traces = []   # (first, count, Trace)
         self._h = None
@@ -54,6 +61,8 @@ class Simulator(object):
         o.bandwidth = float(k['bandwidth']); o.internode_latency = float(k['internode_latency'])
         o.max_ticks = int(k['max_ticks'])
         o.num_buffer = int(k['num_buffer']); o.pack_rng = int(k['pack_rng']); o.pack_seed = int(k['pack_seed'] or 0)
+        o.rows_format = _ffi.ROWFMT_WIRE16 if k['rows_format'] == 'wire16' else _ffi.ROWFMT_WIDE
+        o.lanes_per_replica = k['lanes_per_replica']
         spec = self.cluster.to_ffi()
         h = C.c_void_p()
         _ffi.check(L.rlgs_create(C.byref(spec), C.byref(o), C.byref(h)))
@@ -78,8 +87,12 @@ class Simulator(object):
             dp = C.POINTER(C.c_double)
             net = _ffi.NetcostInputs(trace.duration.ctypes.data_as(dp), trace.model_mb.ctypes.data_as(dp),
                                      trace.iterations.ctypes.data_as(dp))
-        _ffi.check(_ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
-                                              C.byref(net) if net is not None else None))
+        rc = _ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
+                                        C.byref(net) if net is not None else None)
+        if rc == _ffi.ERR_WIRE and self._kw['rows_format'] == 'wire16':
+            self._rebuild(rows_format='wide')   # more jobs than the wire row can count: self-contained rows
+            return self.load_trace(trace, first_replica, n_replicas)
+        _ffi.check(rc)
         if self._kw['schedule'] in ('horus', 'gandiva', 'horus+'):
             pi = trace.pack_inputs()
             dp = C.POINTER(C.c_double)
@@ -97,22 +110,29 @@ class Simulator(object):
                 return t
         raise KeyError(replica)
 
+    def _rebuild(self, **changes):
+        traces = self._traces
+        self.close()
+        self._slot_cap = changes.pop('slot_cap', self._slot_cap)
+        self._kw.update(changes)
+        self._traces = []
+        self._create()
+        for f, c, t in traces:
+            self.load_trace(t, f, c)
+
     def run(self):
         L = _ffi.lib()
         while True:
             rc = L.rlgs_run(self._h)
-            if rc == _ffi.ERR_CAPACITY and b'slot table overflow' in L.rlgs_last_error():
+            if rc == _ffi.ERR_SLOTS:
                 # more jobs ran concurrently than on-chip slots: rebuild with a larger table
                 cap = max(64, 2 * (self._slot_cap or 128))
                 if cap > 2 * max(self.cluster.num_gpus, 32):
                     _ffi.check(rc)
-                traces = self._traces
-                self.close()
-                self._slot_cap = cap
-                self._traces = []
-                self._create()
-                for f, c, t in traces:
-                    self.load_trace(t, f, c)
+                self._rebuild(slot_cap=cap)
+                continue
+            if rc == _ffi.ERR_WIRE and self._kw['rows_format'] == 'wire16':
+                self._rebuild(rows_format='wide')   # a run longer than 2^24 ticks: self-contained rows
                 continue
             _ffi.check(rc)
             return self
@@ -140,7 +160,8 @@ class Simulator(object):
         return out
 
     def rows(self, replica=0):
-        """All rows of a replica as one numpy array (copied out of the chunk-major store)."""
+        """All rows of a replica as one numpy array (copied out of the chunk-major store; 'wire16' handles expand the
+        16-byte wire rows to full rows here, on the host, see rlgs_row16 in include/rlgs.h)."""
         n = self.summary(replica)['n_ticks']
         out = np.zeros(n, _ffi.ROW_DTYPE)
         if n:
@@ -150,11 +171,23 @@ class Simulator(object):
     rows_view = rows
 
     def rows_chunk_view(self, replica, chunk):
-        """Zero-copy numpy view of one 8192-row chunk of a replica in the pinned host mirror."""
+        """Zero-copy numpy view of one 4096-row chunk of a replica in the pinned host mirror: ROW_DTYPE for 'wide' handles,
+        ROW16_DTYPE (the packed wire rows, see rlgs_row16 in include/rlgs.h) for 'wire16' handles."""
         p, n = C.c_void_p(), C.c_int64(0)
-        _ffi.check(_ffi.lib().rlgs_rows_view(self._h, replica, chunk, C.byref(p), C.byref(n)))
-        buf = (C.c_char * (n.value * _ffi.ROW_DTYPE.itemsize)).from_address(p.value)
-        return np.frombuffer(buf, dtype=_ffi.ROW_DTYPE, count=n.value)
+        wire = self._kw['rows_format'] == 'wire16'
+        fn = _ffi.lib().rlgs_rows16_view if wire else _ffi.lib().rlgs_rows_view
+        dt = _ffi.ROW16_DTYPE if wire else _ffi.ROW_DTYPE
+        _ffi.check(fn(self._h, replica, chunk, C.byref(p), C.byref(n)))
+        buf = (C.c_char * (n.value * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n.value)
+
+    def rows16(self, replica=0):
+        """The packed 16-byte wire rows of a replica ('wire16' handles), unexpanded."""
+        n = self.summary(replica)['n_ticks']
+        out = np.zeros(n, _ffi.ROW16_DTYPE)
+        if n:
+            _ffi.check(_ffi.lib().rlgs_read_rows16(self._h, replica, 0, n, out.ctypes.data))
+        return out
 
     def durations(self, replica=0):
         """Per-job duration after network costs (enable_network_costs only)."""

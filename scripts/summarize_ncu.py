@@ -17,7 +17,9 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__average_warp_latency_per_inst_issued.ratio',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active']
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__thread_inst_executed.sum', 'smsp__inst_executed.sum',
+        'smsp__warps_eligible.avg.per_cycle_active', 'smsp__issue_inst0.avg.pct_of_peak_sustained_active', 'launch__shared_mem_per_block_dynamic']
 lines = ['# ' + desc, '', 'source report: `%s` (ncu --set full --clock-control none --import-source on)' % rep, '']
 for vals in rows[2:]:
     d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_header_symbols():
     assert declared == set(_ffi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _ffi.lib().rlgs_version() == 100
+    assert _ffi.lib().rlgs_version() == 200
 
 
 def test_struct_sizes_match_header():
@@ -30,7 +30,8 @@ def test_struct_sizes_match_header():
     assert _ffi.ROW_DTYPE.itemsize == 64
     assert C.sizeof(_ffi.ClusterSpec) == 24
     assert C.sizeof(_ffi.Summary) == 6 * 8 + 8 * 4
-    assert C.sizeof(_ffi.Opts) == 12 * 4 + 8 * 4 + 2 * 8 + 2 * 8 + 2 * 4
+    assert C.sizeof(_ffi.Opts) == 12 * 4 + 8 * 4 + 2 * 8 + 2 * 8 + 2 * 4 + 2 * 4
+    assert _ffi.ROW16_DTYPE.itemsize == 16
     assert C.sizeof(_ffi.PackInputs) == 4 * 8 + 2 * 4 + 3 * 8
 
 

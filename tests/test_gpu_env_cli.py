@@ -75,8 +75,8 @@ def test_env_step_by_step_matches_oracle_tape():
         s = env.sim.summary(r)
         assert s['n_ticks'] == T
         last = o['rows'][-1]
-        assert obs[r, 3 * N + 4 * K + 0] == last['queued'] and obs[r, 3 * N + 4 * K + 1] == last['running']
-        assert obs[r, 3 * N + 4 * K + 2] == last['finished'] and obs[r, 3 * N + 4 * K + 3] == T
+        assert obs[r, 3 * N + 5 * K + 0] == last['queued'] and obs[r, 3 * N + 5 * K + 1] == last['running']
+        assert obs[r, 3 * N + 5 * K + 2] == last['finished'] and obs[r, 3 * N + 5 * K + 3] == T
         assert obs[r, :N].sum() == last['idle_gpus']
         assert total_reward[r] == -float((o['rows']['queued'] + o['rows']['running']).sum())
         j = env.sim.jobs(r)
@@ -159,3 +159,46 @@ def test_run_sim_cli_columnar_output_matches_the_csv(tmp_path):
     for col in ('delta', 'num_idle_nodes', 'num_busy_gpus', 'avg_gpu_memory_allocated', 'avg_pending_time', 'max_pending_time', 'num_finish_jobs'):
         assert np.array_equal(clu[col].to_numpy().astype(np.float64), refc[col].to_numpy().astype(np.float64)), col
     assert np.array_equal(np.isnan(clu['median_pending_time']), np.isnan(refc['median_pending_time']))
+
+
+def test_user_registered_scheduling_callable_runs_against_device_views(tmp_path):
+    """The plugin surface of core/scheduling/schedule.py:45-47: a Python callable registered under a new --schedule key picks,
+    every tick, the smallest job inside the look-ahead window that the yarn dry run accepts.  The device executes the picks;
+    the result must equal the oracle's environment run on the same action tape, and the built-in 'fifo' entry called through
+    the same path must reproduce the fifo fixture."""
+    from rlgpuschedule_b200 import algorithm, plugin, log_manager as lm
+    df, cluster, tr, oc, otr = _setup(300, 5, 30)
+    seen = dict(calls=0, nodes=0)
+
+    def smallest_fit_first(scheme, placement_algo, infrastructure, jobs_manager, delta, **kwargs):
+        seen['calls'] += 1
+        assert delta == jobs_manager.delta and kwargs['k'] == 4
+        seen['nodes'] = len(infrastructure.nodes)
+        for job in sorted(jobs_manager.window(kwargs['k']), key=lambda j: (j.gpus, j.window_index)):
+            nodes, ok = placement_algo(infrastructure, job, scheme)
+            if ok:
+                return nodes, job, True
+        return None, None, False
+
+    algorithm.scheduling_algorithms['smallest-fit'] = smallest_fit_first
+    try:
+        sched, place = algorithm.resolve('smallest-fit', 'yarn')
+        assert sched is smallest_fit_first
+        env, ticks, tape = plugin.run_host_policy(sched, cluster, tr, None, scheme='yarn', k=4)
+    finally:
+        del algorithm.scheduling_algorithms['smallest-fit']
+    assert seen['calls'] > 100 and seen['nodes'] == cluster.num_nodes and (tape > 0).any()
+    o = cpu_sim.run_env_yarn(oc, otr, 2, window_k=4, actions=tape)
+    j = env.sim.jobs(0)
+    assert o['n_ticks'] == ticks == env.sim.summary(0)['n_ticks']
+    assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end']) and np.array_equal(j['finish_order'], o['finish_order'])
+    assert lm.format_cluster_csv(env.sim.rows(0), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+    assert len(j['finish_order']) == 300
+    env.close()
+    # the built-in entries are callable over the same views: fifo through the host path == fifo on the device
+    env, ticks, tape = plugin.run_host_policy(algorithm.scheduling_algorithms['fifo'], cluster, tr, None, scheme='yarn', k=5)
+    fifo = cpu_sim.run_fifo_yarn(oc, otr)
+    j = env.sim.jobs(0)
+    assert np.array_equal(j['end'], fifo['end']) and np.array_equal(j['finish_order'], fifo['finish_order'])
+    assert lm.format_cluster_csv(env.sim.rows(0), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(fifo)
+    env.close()

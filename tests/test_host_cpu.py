@@ -45,9 +45,10 @@ def test_plugin_registries_keep_the_reference_keys():
     assert algorithm.resolve('gandiva', 'gandiva')[0].device_id == _ffi.SCHED['gandiva']
     with pytest.raises(KeyError):
         algorithm.resolve('lpjf', 'yarn')
-    algorithm.scheduling_algorithms['mine'] = lambda *a, **k: (None, None, False)
+    algorithm.scheduling_algorithms['mine'] = lambda *a, **k: (None, None, False)   # a user-registered callable: executable over yarn
+    assert algorithm.resolve('mine', 'yarn')[0] is algorithm.scheduling_algorithms['mine']
     with pytest.raises(NotImplementedError):
-        algorithm.resolve('mine', 'yarn')
+        algorithm.resolve('mine', 'gandiva')
     del algorithm.scheduling_algorithms['mine']
 
 
@@ -127,3 +128,43 @@ def test_pack_inputs_follow_the_task_fields_the_scores_read():
     assert 40e9 / 2 ** 20 * unit == float(int(40e9 / 2 ** 20 * unit))                             # exact in the unit
     assert tr.records['tasks'].tolist() == [2, 1] and pi['used_gpus'].tolist() == [4.0, 3.0]
     assert np.allclose(pi['mem_avg_mib'], [3 * 1024, 1e9 / 2 ** 20])
+
+
+def test_plugin_views_and_host_forms_of_the_builtin_entries():
+    """The read-only views handed to a user-registered scheduling callable (rlgpuschedule_b200/plugin.py), built from an
+    observation vector laid out like the kernel writes it; no GPU involved."""
+    import numpy as np
+    import tracegen
+    import rlgpuschedule_b200 as rl
+    from rlgpuschedule_b200 import algorithm, plugin
+    cluster = rl.Cluster(num_switch=2, num_node_p_switch=2, num_gpu_p_node=4)
+    tr = rl.prepare_trace(tracegen.frame_gen(20, 3, 20), cluster)
+    N, K = 4, 3
+    obs = np.zeros(3 * N + 5 * K + 4, np.float32)
+    obs[0:N] = [0, 2, 4, 1]; obs[N:2 * N] = [128 - 48, 128 - 24, 128, 0]; obs[2 * N:3 * N] = [512 - 240, 512 - 120, 512, 0]
+    for i, (job, pend) in enumerate(((7, 3), (5, 9))):
+        rec = tr.records[job]
+        obs[3 * N + 5 * i: 3 * N + 5 * i + 5] = [rec['gpus'], rec['tasks'], rec['dur_ticks'], pend, job]
+    obs[3 * N + 5 * 2 + 4] = -1
+    obs[3 * N + 5 * K:] = [2, 3, 1, 17]
+    infra = plugin.InfrastructureView(cluster, None, obs)
+    jm = plugin.JobsManagerView(tr, obs, N, K)
+    assert list(infra.nodes) == ['1', '2', '3', '4'] and infra.nodes['3'].cpu_free() == 128 and infra.nodes['2'].rack_id == '0'
+    assert len(infra.nodes['2'].get_free_devices()) == 2 and not infra.nodes['4'].is_free() and infra.num_free_nodes() == 3
+    assert jm.delta == 17 and jm.queuing_jobs() == 2 and [j.trace_index for j in jm.window()] == [7, 5]
+    head = jm.get_next_job(17)
+    assert head.job_id == str(int(tr.label[7])) and head.pending_time == 3 and head.gpus == tr.used_gpus[7]
+    nodes, job, ok = algorithm.scheduling_algorithms['fifo']('yarn', algorithm.placement_algorithms['yarn'], infra, jm, 17, k=K)
+    need = int(np.ceil(head.gpus))
+    if need <= 4:
+        first = next(nid for nid, n in infra.nodes.items() if len(n.get_free_devices()) >= need and n.cpu_free() >= 12 * head.task_count and n.mem_free() >= 60 * head.task_count)
+        assert ok and job is head and list(nodes) == [first] and jm.popped is head
+    with pytest.raises(RuntimeError):
+        algorithm.scheduling_algorithms['horus']('horus', None, infra, jm, 17)
+    algorithm.scheduling_algorithms['user'] = lambda *a, **k: (None, None, False)
+    try:
+        assert algorithm.resolve('user', 'yarn')[0] is algorithm.scheduling_algorithms['user']
+        with pytest.raises(NotImplementedError):
+            algorithm.resolve('user', 'horus')
+    finally:
+        del algorithm.scheduling_algorithms['user']
