@@ -18,17 +18,18 @@
 // arrival, a start and a finish.
 //
 // On chip per replica (shared memory, 16-byte aligned pieces):
-//   key[N]    idle devices << 16 | min(cpu_free // 12, mem_free // 60) clamped to 0x7fff   (the two numbers every fit test needs)
-//   busy[N]   busy-device bitmask,  units[N]  tasks charged (placed + leaked, q8),  ever[N/32]  node ever used (q3)
+//   key[N]    idle devices << 16 | free task units = min(cpu_cap // 12, mem_cap // 60) - tasks charged (placed + leaked, q8):
+//             the two numbers every fit test needs; cpu_free and mem_free follow from the units (every task charges 12 / 60)
+//   busy[N]   busy-device bitmask (16-bit words when the node has <= 16 GPUs),  ever[N/32]  node ever used (q3)
 //   slot[S]   int4 {end tick | RLGS_NEVER, next slot in the calendar / free chain, node | tasks << 16 (or 0xffff | nnodes << 16),
 //                   device mask (or first placement-log entry)},  sjob[S] job index
-//   bkt[256]  calendar: head | tail << 16 of the chain of running jobs whose end tick == b (mod 256); a started job is appended
+//   bkt[128]  calendar: head | tail << 16 of the chain of running jobs whose end tick == b (mod 128); a started job is appended
 //             at the tail, so a chain is in start order and same-tick finishes come out in the running_jobs dict order
 // pending_time and time_processed are not stored: d - arrival and d - start.
 #pragma once
 #include "rlgs_device.cuh"
 
-#define RLGS_CAL_W 256
+#define RLGS_CAL_W 128
 #define RLGS_NONE16 0xffffu
 
 // ---- group of LPR lanes --------------------------------------------------------------------------------------------
@@ -68,8 +69,8 @@ struct Grp {
 // ---- shared-memory view of one replica -------------------------------------------------------------------------------
 struct GrpSm {
     uint32_t *key;    // [Npad] zero beyond N (a zero key never fits)
-    uint32_t *busy;   // [N]
-    int32_t *units;   // [N]
+    void *busy;       // [N] uint16_t when the node has <= 16 GPUs, else uint32_t
+    int busy16;
     uint32_t *ever;   // [ceil(N/32)]
     int4 *slot;       // [slot_cap]
     int32_t *sjob;    // [slot_cap]
@@ -78,19 +79,20 @@ struct GrpSm {
 
 __host__ __device__ inline int grp_npad(int N, int lpr) { int q = 4 * lpr; return (N + q - 1) / q * q; }
 
-__host__ __device__ inline size_t grp_smem_bytes(int N, int slot_cap, int lpr) {
-    size_t words = (size_t)grp_npad(N, lpr) + 2 * (size_t)N + (size_t)((N + 31) / 32);
+__host__ __device__ inline size_t grp_busy_words(int N, int G) { return G <= 16 ? ((size_t)N + 1) / 2 : (size_t)N; }
+
+__host__ __device__ inline size_t grp_smem_bytes(int N, int G, int slot_cap, int lpr) {
+    size_t words = (size_t)grp_npad(N, lpr) + grp_busy_words(N, G) + (size_t)((N + 31) / 32);
     words = (words + 3) & ~(size_t)3;
     words += 4 * (size_t)slot_cap + (size_t)slot_cap + RLGS_CAL_W;
     return ((words + 3) & ~(size_t)3) * 4;
 }
 
-__device__ __forceinline__ GrpSm grp_carve(unsigned char *base, int N, int slot_cap, int lpr) {
+__device__ __forceinline__ GrpSm grp_carve(unsigned char *base, int N, int G, int slot_cap, int lpr) {
     GrpSm s;
     uint32_t *w = reinterpret_cast<uint32_t *>(base);
     s.key = w; w += grp_npad(N, lpr);
-    s.busy = w; w += N;
-    s.units = reinterpret_cast<int32_t *>(w); w += N;
+    s.busy = w; s.busy16 = G <= 16; w += grp_busy_words(N, G);
     s.ever = w; w += (N + 31) / 32;
     while ((w - reinterpret_cast<uint32_t *>(base)) & 3) w += 1;
     s.slot = reinterpret_cast<int4 *>(w); w += 4 * slot_cap;
@@ -99,12 +101,22 @@ __device__ __forceinline__ GrpSm grp_carve(unsigned char *base, int N, int slot_
     return s;
 }
 
-// key = popc(idle devices) << 16 | min(cpu_free // 12, mem_free // 60) clamped to [0, 0x7fff]: both halves stay below 0x8000,
-// which lets one subtraction test "idle >= gpus and free units >= tasks" (see grp_fit4)
-__device__ __forceinline__ uint32_t grp_key(int units, uint32_t busy, const ClusterConst &c) {
-    int t = min(max(c.base_units - units, 0), 0x7fff);
-    return ((uint32_t)__popc(~busy & c.gmask) << 16) | (uint32_t)t;
+__device__ __forceinline__ uint32_t busy_ld(const GrpSm &s, int i) {
+    return s.busy16 ? (uint32_t)reinterpret_cast<const uint16_t *>(s.busy)[i] : reinterpret_cast<const uint32_t *>(s.busy)[i];
 }
+__device__ __forceinline__ void busy_st(const GrpSm &s, int i, uint32_t v) {
+    if (s.busy16) reinterpret_cast<uint16_t *>(s.busy)[i] = (uint16_t)v; else reinterpret_cast<uint32_t *>(s.busy)[i] = v;
+}
+
+// key = popc(idle devices) << 16 | free task units.  Free units = base_units - tasks charged, where base_units =
+// min(cpu_cap // 12, mem_cap // 60) <= 0x7fff (rlgs_create refuses larger nodes): a task is only ever charged to a node whose
+// key showed room for it (placement and the q8 leak alike), so the count never goes negative and nothing is clamped.  Both
+// halves stay below 0x8000, which lets one subtraction test "idle >= gpus and free units >= tasks" (see grp_fit4).
+__device__ __forceinline__ uint32_t grp_key(int free_units, uint32_t busy, const ClusterConst &c) {
+    return ((uint32_t)__popc(~busy & c.gmask) << 16) | (uint32_t)free_units;
+}
+// Node.is_free (node.py:59-60): cpu_free > 0 or mem_free > 0  <=>  tasks charged < free_limit  <=>  free units > base_units - free_limit
+__device__ __forceinline__ bool free_units_is_free(int free_units, const ClusterConst &c) { return free_units > c.free_floor; }
 
 // first of four consecutive node keys with idle devices >= need >> 16 and free units >= need & 0xffff, else -1
 // (algorithm.py:407-409: free devices >= gpus, cpu_free >= 12 T, mem_free >= 60 T).  (k | H) - need keeps bit 15 / bit 31
@@ -130,13 +142,13 @@ struct GrpPlace {
 // Charges k tasks of cpu / mem to `node` (all lanes of the group call with the same node): the q8 leak.
 template <int LPR>
 __device__ __forceinline__ void grp_charge(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, int node, int k, int &n_free_nodes) {
-    int u = s.units[node];
-    const uint32_t busy = s.busy[node];
-    const bool was = node_is_free(u, c);
-    u += k;
-    n_free_nodes += (int)node_is_free(u, c) - (int)was;
+    const uint32_t key = s.key[node];
+    int fu = (int)(key & 0xffffu);
+    const bool was = free_units_is_free(fu, c);
+    fu -= k;
+    n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
     G.sync();
-    s.units[node] = u; s.key[node] = grp_key(u, busy, c);
+    s.key[node] = (key & 0xffff0000u) | (uint32_t)fu;
 }
 
 // Tries to place job j under yarn (ms_yarn_placement, algorithm.py:28-32).  Every lane of the group calls; the result is
@@ -167,17 +179,17 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
             if (b) { const int l = __ffs(b) - 1; node = base + 4 * l + G.shfl(f, l); break; }
         }
         if (node < 0) return r;
-        int u = s.units[node];
-        const uint32_t busy = s.busy[node];
+        int fu = (int)(s.key[node] & 0xffffu);
+        const uint32_t busy = busy_ld(s, node);
         const uint32_t taken = lowest_bits(~busy & c.gmask, T * gpc);
-        const bool was = node_is_free(u, c);
-        u += T;
-        n_free_nodes += (int)node_is_free(u, c) - (int)was;
+        const bool was = free_units_is_free(fu, c);
+        fu -= T;
+        n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
         const uint32_t ew = s.ever[node >> 5], bit = 1u << (node & 31);
         if (!(ew & bit)) idle_nodes--;
         G.sync();                                   // every lane has read the old node state
-        s.units[node] = u; s.busy[node] = busy | taken; s.ever[node >> 5] = ew | bit;
-        s.key[node] = grp_key(u, busy | taken, c);
+        busy_st(s, node, busy | taken); s.ever[node >> 5] = ew | bit;
+        s.key[node] = grp_key(fu, busy | taken, c);
         if (G.gl == 0) place_log[log_pos] = make_int2(node | (T << 16), (int)taken);
         r.ok = 1; r.node = node; r.mask = taken; r.nnodes = 1;
         return r;
@@ -226,13 +238,14 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
         for (int q = 0; q < 4; ++q) {
             if (take[q] > 0) {
                 const int i = i0 + q;
-                int u = s.units[i];
-                const uint32_t busy = s.busy[i];
+                const uint32_t kq = q == 0 ? k.x : (q == 1 ? k.y : (q == 2 ? k.z : k.w));
+                int fu = (int)(kq & 0xffffu);
+                const uint32_t busy = busy_ld(s, i);
                 const uint32_t taken = lowest_bits(~busy & c.gmask, take[q] * gpc);
-                const bool was = node_is_free(u, c);
-                u += take[q];
-                dfree += (int)node_is_free(u, c) - (int)was;
-                s.units[i] = u; s.busy[i] = busy | taken; s.key[i] = grp_key(u, busy | taken, c);
+                const bool was = free_units_is_free(fu, c);
+                fu -= take[q];
+                dfree += (int)free_units_is_free(fu, c) - (int)was;
+                busy_st(s, i, busy | taken); s.key[i] = grp_key(fu, busy | taken, c);
                 const uint32_t bit = 1u << (i & 31);
                 if (!(atomicOr(&s.ever[i >> 5], bit) & bit)) didle += 1;   // several lanes share an `ever` word
                 place_log[pos++] = make_int2(i | (take[q] << 16), (int)taken);
@@ -251,13 +264,13 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
 // Node.release_allocated_resources (node.py:71-91) for a single-node job: every lane computes the same values and stores them.
 template <int LPR>
 __device__ __forceinline__ void grp_release_single(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, int node, int tasks, uint32_t mask, int &n_free_nodes) {
-    int u = s.units[node];
-    const bool was = node_is_free(u, c);
-    u -= tasks;
-    n_free_nodes += (int)node_is_free(u, c) - (int)was;
-    const uint32_t busy = s.busy[node] & ~mask;
+    int fu = (int)(s.key[node] & 0xffffu);
+    const bool was = free_units_is_free(fu, c);
+    fu += tasks;
+    n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
+    const uint32_t busy = busy_ld(s, node) & ~mask;
     G.sync();
-    s.units[node] = u; s.busy[node] = busy; s.key[node] = grp_key(u, busy, c);
+    busy_st(s, node, busy); s.key[node] = grp_key(fu, busy, c);
 }
 
 // ... and for a multi-node job: one placement-log entry per lane, distinct nodes
@@ -268,12 +281,12 @@ __device__ __forceinline__ int grp_release_multi(const Grp<LPR> &G, GrpSm s, con
     for (int b = G.gl; b < nn; b += LPR) {
         const int2 e = log[b];
         const int node = e.x & 0xffff, tasks = (e.x >> 16) & 0xffff;
-        int u = s.units[node];
-        const bool was = node_is_free(u, c);
-        u -= tasks;
-        dfree += (int)node_is_free(u, c) - (int)was;
-        const uint32_t busy = s.busy[node] & ~(uint32_t)e.y;
-        s.units[node] = u; s.busy[node] = busy; s.key[node] = grp_key(u, busy, c);
+        int fu = (int)(s.key[node] & 0xffffu);
+        const bool was = free_units_is_free(fu, c);
+        fu += tasks;
+        dfree += (int)free_units_is_free(fu, c) - (int)was;
+        const uint32_t busy = busy_ld(s, node) & ~(uint32_t)e.y;
+        busy_st(s, node, busy); s.key[node] = grp_key(fu, busy, c);
         ndev += __popc((uint32_t)e.y);
     }
     n_free_nodes += G.sum(dfree);
@@ -340,8 +353,8 @@ template <int LPR>
 __device__ __forceinline__ void grp_state_io(const Grp<LPR> &G, const RepDesc &D, GrpSm s, const ClusterConst &c, int slot_cap, RepState &st, bool save) {
     const int N = c.N;
     for (int i = G.gl; i < N; i += LPR) {
-        if (save) { D.node_save[i] = s.units[i]; D.node_save[N + i] = (int32_t)s.busy[i]; }
-        else { s.units[i] = D.node_save[i]; s.busy[i] = (uint32_t)D.node_save[N + i]; }
+        if (save) { D.node_save[i] = c.base_units - (int)(s.key[i] & 0xffffu); D.node_save[N + i] = (int32_t)busy_ld(s, i); }   // tasks charged, busy mask
+        else busy_st(s, i, (uint32_t)D.node_save[N + i]);
     }
     for (int i = G.gl; i < (N + 31) / 32; i += LPR) {
         if (save) D.node_save[2 * N + i] = (int32_t)s.ever[i]; else s.ever[i] = (uint32_t)D.node_save[2 * N + i];
@@ -354,7 +367,7 @@ __device__ __forceinline__ void grp_state_io(const Grp<LPR> &G, const RepDesc &D
     G.sync();
     if (!save) {
         const int Npad = grp_npad(N, LPR);
-        for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < N ? grp_key(s.units[i], s.busy[i], c) : 0u;
+        for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < N ? grp_key(c.base_units - D.node_save[i], busy_ld(s, i), c) : 0u;
         for (int i = G.gl; i < RLGS_CAL_W; i += LPR) s.bkt[i] = RLGS_NONE16 | (RLGS_NONE16 << 16);
         G.sync();
         int free_head = -1;
@@ -391,6 +404,15 @@ __device__ __forceinline__ int4 pack_row16(int idle_nodes, int finished, int que
 #ifndef RLGS_GRP_MIN_BLOCKS
 #define RLGS_GRP_MIN_BLOCKS 16
 #endif
+
+// ---- the tick loop, in LOCKSTEP over the groups of a warp --------------------------------------------------------------
+// Control flow is warp-uniform: a phase runs when ANY group of the warp needs it (__any_sync over the full warp) and every
+// lane guards its effects with its own group's predicate.  All hot-path collectives therefore use the full-warp mask with
+// width-LPR segments, every warp instruction serves all 32 / LPR replicas, and nothing depends on where divergent groups
+// would reconverge (measured with per-group masks and free control flow: 9.4 active threads per instruction at LPR = 8,
+// i.e. the groups simply took turns).  Rare paths — a job wider than a node, the q8 leak, an arrival batch longer than the
+// register ring, the environment's queue.pop(pick) — stay group-local inside per-group branches.
+#define RLGS_FULLMASK 0xffffffffu
 // ROWS: 0 = no rows, 1 = 64-byte rlgs_row per tick, 2 = 16-byte rlgs_row16 per tick
 template <int LPR, bool ENV, int ROWS, bool NET>
 __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states, int n_rep,
@@ -398,235 +420,308 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                                                                            int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env, NetCost net) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Grp<LPR> G;
+    constexpr unsigned GBITS = LPR == 32 ? 0xffffffffu : ((1u << (LPR & 31)) - 1u);
+#define GBALLOT(p) ((__ballot_sync(RLGS_FULLMASK, (p)) >> G.shift) & GBITS)
+#define GSHFL(v, src) __shfl_sync(RLGS_FULLMASK, (v), (src), LPR)
     // the groups of a warp take replicas a quarter (half) of the launch apart: traces are attached to contiguous replica
-    // ranges, so the replicas sharing a warp usually follow different traces and the measured divergence is the real one
-    const int rep = G.g * (int)gridDim.x + (int)blockIdx.x;
-    if (rep >= n_rep) return;                     // groups only ever synchronise with themselves
+    // ranges, so the replicas sharing a warp usually follow different traces
+    const int rep_raw = G.g * (int)gridDim.x + (int)blockIdx.x;
+    const bool valid = rep_raw < n_rep;
+    const int rep = valid ? rep_raw : 0;          // lanes of an empty group keep executing (collectives are warp-wide) but touch nothing
     const RepDesc D = descs[rep];
     RepState st = states[rep];
-    if (st.done || st.status != RLGS_OK) {
-        if (ENV && G.gl == 0) { env.reward[rep] = 0.f; env.done[rep] = 1; }
-        return;
-    }
-    const GrpSm s = grp_carve(smem_raw + (size_t)G.g * grp_smem_bytes(c.N, slot_cap, LPR), c.N, slot_cap, LPR);
+    bool act = valid && !st.done && st.status == RLGS_OK;   // this group's replica still ticks in this launch
+    const bool resident = act;                              // ... and its state has to be written back at the end
     const bool writer = G.gl == 0;
+    if (ENV && valid && !act && writer) { env.reward[rep] = 0.f; env.done[rep] = 1; }
+    const GrpSm s = grp_carve(smem_raw + (size_t)G.g * grp_smem_bytes(c.N, c.G, slot_cap, LPR), c.N, c.G, slot_cap, LPR);
     float reward_acc = 0.f;
     constexpr int ROW_BYTES = ROWS == 2 ? 16 : 64;
     unsigned char *row_cur = nullptr;   // next row of this replica inside the current chunk
     if (ROWS && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)   // the launch stops when the allocated chunks are full
         tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
-    if (st.d == 0) {   // first launch of a run: empty cluster, no running jobs
-        const uint32_t empty_key = grp_key(0, 0u, c);
-        const int Npad = grp_npad(c.N, LPR);
-        for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < c.N ? empty_key : 0u;
-        for (int i = G.gl; i < c.N; i += LPR) { s.units[i] = 0; s.busy[i] = 0u; }
-        for (int i = G.gl; i < (c.N + 31) / 32; i += LPR) s.ever[i] = 0u;
-        for (int i = G.gl; i < RLGS_CAL_W; i += LPR) s.bkt[i] = RLGS_NONE16 | (RLGS_NONE16 << 16);
-        G.sync();
-    } else {
-        grp_state_io(G, D, s, c, slot_cap, st, false);
+    const int Npad = grp_npad(c.N, LPR);
+    if (act) {
+        if (st.d == 0) {   // first launch of a run: empty cluster, no running jobs
+            const uint32_t empty_key = grp_key(c.base_units, 0u, c);
+            for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < c.N ? empty_key : 0u;
+            for (int i = G.gl; i < c.N; i += LPR) busy_st(s, i, 0u);
+            for (int i = G.gl; i < (c.N + 31) / 32; i += LPR) s.ever[i] = 0u;
+            for (int i = G.gl; i < RLGS_CAL_W; i += LPR) s.bkt[i] = RLGS_NONE16 | (RLGS_NONE16 << 16);
+        } else {
+            grp_state_io(G, D, s, c, slot_cap, st, false);
+        }
     }
+    __syncwarp();
     const int J = D.J;
 
     // register ring over the trace: lane l of the group holds job ring_base + l (one coalesced read per LPR arrivals)
     int ring_base = st.cursor - (st.cursor % LPR);
     JobRec ring;
-    {
-        const int idx = ring_base + G.gl;
-        if (idx < J) ring = load_rec(D.trace + idx); else { ring.a = make_int4(RLGS_NEVER, 0, 0, 0); ring.b = make_int4(0, 0, 0, 0); }
-    }
+    ring.a = make_int4(RLGS_NEVER, 0, 0, 0); ring.b = make_int4(0, 0, 0, 0);
+    if (act && ring_base + G.gl < J) ring = load_rec(D.trace + ring_base + G.gl);
+    int ring_next = RLGS_NEVER;   // arrival tick of the first job behind the ring: tells whether a batch that fills the ring ends there
+    if (act && ring_base + LPR < J) ring_next = D.trace[ring_base + LPR].arrival_tick;
     JobRec h0;   // the queue front lives in registers; after a pop the next record is fetched while the tick finishes
     h0.a = h0.b = make_int4(0, 0, 0, 0);
-    if (st.Q > 0) h0 = load_rec(D.stack + st.head);
+    if (act && st.Q > 0) h0 = load_rec(D.stack + st.head);
 
     // the launch stops at its tick budget or at the safety limit max_ticks, whichever comes first (one compare per tick)
     const int d_budget = st.d + tick_budget;
     const int d_stop = (max_ticks > 0 && max_ticks < (long)d_budget) ? (int)max(max_ticks, (long)st.d) : d_budget;
     while (true) {
-        if ((J - st.cursor) + st.R == 0) { st.done = 1; break; }   // schedule.py:185 (queue not consulted, q2)
-        if (st.d == d_stop) { if (max_ticks > 0 && st.d >= max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; } break; }
+        if (act) {
+            if ((J - st.cursor) + st.R == 0) { st.done = 1; act = false; }   // schedule.py:185 (queue not consulted, q2)
+            else if (st.d == d_stop) { if (max_ticks > 0 && st.d >= max_ticks) { st.done = 1; st.status = RLGS_ERR_CAPACITY; } act = false; }
+        }
+        if (!__any_sync(RLGS_FULLMASK, act)) break;
         const int d = st.d;
 
         // ---------------- arrivals: every job with arrival_tick <= d, pushed to the FRONT in order (q1)
-        if (st.cursor < J) {
+        {
             const int idx = ring_base + G.gl;
-            const bool arr = idx >= st.cursor && ring.arrival() <= d;   // entries beyond J carry RLGS_NEVER
-            const unsigned ab = G.ballot(arr);
-            if (ab) {
+            const bool arr = act && idx >= st.cursor && ring.arrival() <= d;   // entries beyond J carry RLGS_NEVER
+            const unsigned ab = GBALLOT(arr);
+            if (__any_sync(RLGS_FULLMASK, ab != 0u)) {
                 int k = __popc(ab);
-                const bool ring_covers_batch = (st.cursor + k < ring_base + LPR) || (ring_base + LPR >= J);
-                if (ring_covers_batch) {
-                    const int first = st.cursor - ring_base;
-                    if (arr) store_rec(D.stack + (st.head - k) + (idx - st.cursor), ring);
-                    h0 = G.shfl_rec(ring, first);
-                } else {
-                    // the batch runs past the ring: count it from global memory, then copy the records
-                    int pos = ring_base + LPR;
-                    while (pos < J) {
-                        const int i2 = pos + G.gl;
-                        const int c2 = __popc(G.ballot(i2 < J && D.trace[i2].arrival_tick <= d));
-                        k += c2;
-                        if (c2 < LPR) break;
-                        pos += LPR;
+                const bool covered = (st.cursor + k < ring_base + LPR) || ring_next > d;
+                const int first = (st.cursor - ring_base) & (LPR - 1);
+                JobRec n0;
+                n0.a.x = GSHFL(ring.a.x, first); n0.a.y = GSHFL(ring.a.y, first); n0.a.z = GSHFL(ring.a.z, first); n0.a.w = GSHFL(ring.a.w, first);
+                n0.b.x = GSHFL(ring.b.x, first); n0.b.y = GSHFL(ring.b.y, first); n0.b.z = GSHFL(ring.b.z, first); n0.b.w = GSHFL(ring.b.w, first);
+                if (ab) {
+                    if (covered) {
+                        if (arr) store_rec(D.stack + (st.head - k) + (idx - st.cursor), ring);
+                    } else {
+                        // the batch runs past the ring (rare): count it from global memory, then copy the records; group-local
+                        int pos = ring_base + LPR;
+                        while (pos < J) {
+                            const int i2 = pos + G.gl;
+                            const int c2 = __popc(G.ballot(i2 < J && D.trace[i2].arrival_tick <= d));
+                            k += c2;
+                            if (c2 < LPR) break;
+                            pos += LPR;
+                        }
+                        for (int b = G.gl; b < k; b += LPR) store_rec(D.stack + (st.head - k) + b, load_rec(D.trace + st.cursor + b));
                     }
-                    for (int b = G.gl; b < k; b += LPR) store_rec(D.stack + (st.head - k) + b, load_rec(D.trace + st.cursor + b));
-                    h0 = load_rec(D.trace + st.cursor);
+                    h0 = n0;   // the first arrived job = trace[cursor], which the ring holds in lane `first`
+                    if (st.Q == 0) st.bottom_arr = d;
+                    st.head -= k; st.Q += k; st.cursor += k;
+                    if (ROWS == 1) st.sum_arr += (int64_t)k * d;
+                    st.head_blocked = 0;
+                    if (st.Q > st.max_q) st.max_q = st.Q;
+                    if (st.cursor >= ring_base + LPR) {
+                        ring_base = st.cursor - (st.cursor % LPR);
+                        const int i3 = ring_base + G.gl;
+                        if (i3 < J) ring = load_rec(D.trace + i3); else ring.a = make_int4(RLGS_NEVER, 0, 0, 0);
+                        ring_next = ring_base + LPR < J ? D.trace[ring_base + LPR].arrival_tick : RLGS_NEVER;
+                    }
                 }
-                if (st.Q == 0) st.bottom_arr = d;
-                st.head -= k; st.Q += k; st.cursor += k;
-                if (ROWS == 1) st.sum_arr += (int64_t)k * d;
-                st.head_blocked = 0;
-                if (st.Q > st.max_q) st.max_q = st.Q;
-                if (st.cursor >= ring_base + LPR) {
-                    ring_base = st.cursor - (st.cursor % LPR);
-                    const int i3 = ring_base + G.gl;
-                    if (i3 < J) ring = load_rec(D.trace + i3); else ring.a = make_int4(RLGS_NEVER, 0, 0, 0);
-                }
-                G.sync();   // the stack records are visible to the whole group (median loads, env window)
+                __syncwarp();   // the stack records are visible to the whole group (median loads, env window, next head)
             }
         }
 
         // ---------------- one scheduling attempt (schedule.py:188-190): the queue head, or the policy's pick inside the window
         int pick = 0;
         bool attempt;
-        if (!ENV) attempt = st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked;
+        if (!ENV) attempt = act && st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked;
         else {
             const int win = min(st.Q, env.window_k);
             if (env.policy == 1 && win > 0) pick = (int)(rlgs_hash3(env.seed, (uint32_t)(rs.replica + rep), (uint32_t)d) % (uint32_t)win);
-            else if (env.policy == 2) pick = env.actions[rep];
-            attempt = st.Q > 0 && pick >= 0 && pick < win && st.n_free_nodes >= 1;
+            else if (env.policy == 2 && valid) pick = env.actions[rep];
+            attempt = act && st.Q > 0 && pick >= 0 && pick < win && st.n_free_nodes >= 1;
         }
-        if (attempt) {
+        if (__any_sync(RLGS_FULLMASK, attempt)) {
             JobRec hx = h0;
-            if (ENV && pick > 0) hx = load_rec(D.stack + st.head + pick);
-            const GrpPlace pr = grp_place(G, s, c, hx, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
-            if (pr.ok) {
+            if (ENV && attempt && pick > 0) hx = load_rec(D.stack + st.head + pick);
+            const int T = hx.tasks(), gpc = hx.gpc(), need_g = hx.gpus();
+            const bool one_node = attempt && need_g <= c.G;
+            GrpPlace pr; pr.ok = 0; pr.node = -1; pr.mask = 0; pr.nnodes = 0;
+            // ---- try_single_node_alloc_ms (algorithm.py:396-417): first node in id order with enough idle devices, cpu and mem
+            {
+                const uint32_t need = ((uint32_t)need_g << 16) | (uint32_t)T;
+                bool searching = one_node && hx.fits();
+                int node = -1;
+                for (int base = 0; base < Npad && __any_sync(RLGS_FULLMASK, searching); base += 4 * LPR) {
+                    const uint4 k4 = *reinterpret_cast<const uint4 *>(s.key + base + 4 * G.gl);
+                    const int f = searching ? grp_fit4(k4, need) : -1;
+                    const unsigned b = GBALLOT(f >= 0);
+                    const int l = b ? __ffs(b) - 1 : 0;
+                    const int fl = GSHFL(f, l);
+                    if (searching && b) { node = base + 4 * l + fl; searching = false; }
+                }
+                const bool hit = node >= 0;
+                if (__any_sync(RLGS_FULLMASK, hit)) {
+                    const int ni = hit ? node : 0;
+                    int fu = (int)(s.key[ni] & 0xffffu);
+                    const uint32_t busy = busy_ld(s, ni);
+                    const uint32_t ew = s.ever[ni >> 5], bit = 1u << (ni & 31);
+                    const uint32_t taken = lowest_bits(~busy & c.gmask, hit ? T * gpc : 0);
+                    __syncwarp();                               // every lane has read the old node state
+                    if (hit) {
+                        const bool was = free_units_is_free(fu, c);
+                        fu -= T;
+                        st.n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
+                        if (!(ew & bit)) st.idle_nodes--;
+                        busy_st(s, ni, busy | taken); s.ever[ni >> 5] = ew | bit;
+                        s.key[ni] = grp_key(fu, busy | taken, c);
+                        if (writer) D.place_log[st.log_len] = make_int2(ni | (T << 16), (int)taken);
+                        pr.ok = 1; pr.node = ni; pr.mask = taken; pr.nnodes = 1;
+                    }
+                }
+            }
+            // ---- rare, group-local: the q8 leak of a task no device accepts, and jobs wider than a node (algorithm.py:301-393)
+            if (attempt && (!one_node || !hx.fits()))
+                pr = grp_place(G, s, c, hx, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
+            bool ok = pr.ok != 0;
+            if (__any_sync(RLGS_FULLMASK, ok)) {
                 const int job = hx.index();
-                const int dur_ticks = NET ? netcost_dur_ticks(D, net, job, hx.tasks(), pr.nnodes, writer) : hx.dur();
-                int sl = st.free_hint;                                    // pop the free-slot chain, else a fresh slot
-                if (sl >= 0) { const int nx = s.slot[sl].y; st.free_hint = nx == (int)RLGS_NONE16 ? -1 : nx; } else sl = st.hw++;
-                if (sl >= slot_cap) { st.status = RLGS_ERR_SLOTS; st.done = 1; break; }
+                int dur_ticks = hx.dur();
+                if (NET && ok) dur_ticks = netcost_dur_ticks(D, net, job, T, pr.nnodes, writer);
+                int sl = st.free_hint, free_next = -1;                    // pop the free-slot chain, else a fresh slot
+                if (ok) {
+                    if (sl >= 0) { const int nx = s.slot[sl].y; free_next = nx == (int)RLGS_NONE16 ? -1 : nx; }
+                    else sl = st.hw;
+                    if (sl >= slot_cap) { st.status = RLGS_ERR_SLOTS; st.done = 1; act = false; ok = false; }
+                }
                 const int end = d + dur_ticks, cal = end & (RLGS_CAL_W - 1);
                 const uint32_t hb = s.bkt[cal];
                 const uint32_t tail = hb >> 16;
-                G.sync();                                                 // every lane has read the chain state
-                s.slot[sl] = make_int4(end, (int)RLGS_NONE16, pr.node >= 0 ? (pr.node | (hx.tasks() << 16)) : (int)(0xffffu | ((uint32_t)pr.nnodes << 16)),
-                                       pr.node >= 0 ? (int)pr.mask : st.log_len);
-                s.sjob[sl] = job;
-                if (tail == RLGS_NONE16) s.bkt[cal] = (uint32_t)sl | ((uint32_t)sl << 16);   // append: chains stay in start order
-                else { s.slot[tail].y = sl; s.bkt[cal] = (hb & 0xffffu) | ((uint32_t)sl << 16); }
-                if (writer) { D.start_tick[job] = d; D.place_off[job] = st.log_len; }
-                st.log_len += pr.nnodes;
-                st.start_seq += 1;
-                if (ROWS == 1) {
-                    const int ndev = hx.tasks() * hx.gpc();
-                    st.busy_gpus += ndev;
-                    st.mem_sum += hx.mem_term();
-                    const int64_t mu = hx.util() & 0xffff, sd = hx.util() >> 16;
-                    st.util_mu_sum += mu * ndev;
-                    st.util_var_sum += sd * sd * ndev;
-                    st.sum_arr -= hx.arrival();
-                }
-                st.sum_jct += (int64_t)(end - hx.arrival());   // the end is fixed at start (no preemption under fifo)
-                if (ENV && pick > 0) {
-                    // queue.pop(pick): entries in front of it move one place towards the back of the stack
-                    JobRec mv; const bool m = G.gl < pick;
-                    for (int b0 = 0; b0 < pick; b0 += LPR) {   // window_k <= 32 may exceed the group width
-                        const int i = pick - 1 - b0 - G.gl;    // from the back so that a chunk never overwrites an unread entry
-                        const bool mm = i >= 0;
-                        if (mm) mv = load_rec(D.stack + st.head + i);
-                        G.sync();
-                        if (mm) store_rec(D.stack + st.head + i + 1, mv);
-                        G.sync();
+                __syncwarp();                                             // every lane has read the chain state
+                if (ok) {
+                    if (st.free_hint >= 0) st.free_hint = free_next; else st.hw += 1;
+                    s.slot[sl] = make_int4(end, (int)RLGS_NONE16, pr.node >= 0 ? (pr.node | (T << 16)) : (int)(0xffffu | ((uint32_t)pr.nnodes << 16)),
+                                           pr.node >= 0 ? (int)pr.mask : st.log_len);
+                    s.sjob[sl] = job;
+                    if (tail == RLGS_NONE16) s.bkt[cal] = (uint32_t)sl | ((uint32_t)sl << 16);   // append: chains stay in start order
+                    else { s.slot[tail].y = sl; s.bkt[cal] = (hb & 0xffffu) | ((uint32_t)sl << 16); }
+                    if (writer) { D.start_tick[job] = d; D.place_off[job] = st.log_len; }
+                    st.log_len += pr.nnodes;
+                    st.start_seq += 1;
+                    if (ROWS == 1) {
+                        const int ndev = T * gpc;
+                        st.busy_gpus += ndev;
+                        st.mem_sum += hx.mem_term();
+                        const int64_t mu = hx.util() & 0xffff, sd = hx.util() >> 16;
+                        st.util_mu_sum += mu * ndev;
+                        st.util_var_sum += sd * sd * ndev;
+                        st.sum_arr -= hx.arrival();
                     }
-                    (void)m;
+                    st.sum_jct += (int64_t)(end - hx.arrival());   // the end is fixed at start (no preemption under fifo)
+                    if (ENV && pick > 0) {
+                        // queue.pop(pick): entries in front of it move one place towards the back of the stack (group-local)
+                        for (int b0 = 0; b0 < pick; b0 += LPR) {   // window_k <= 32 may exceed the group width
+                            const int i = pick - 1 - b0 - G.gl;    // from the back so that a chunk never overwrites an unread entry
+                            JobRec mv;
+                            if (i >= 0) mv = load_rec(D.stack + st.head + i);
+                            G.sync();
+                            if (i >= 0) store_rec(D.stack + st.head + i + 1, mv);
+                            G.sync();
+                        }
+                    }
+                    st.R += 1; st.Q -= 1; st.head += 1;
+                    if (st.R > st.max_r) st.max_r = st.R;
+                    if (st.Q > 0) {
+                        h0 = load_rec(D.stack + st.head);   // consumed by the next tick's attempt
+                        if (ENV) st.bottom_arr = D.stack[st.head + st.Q - 1].arrival_tick;
+                    }
                 }
-                st.R += 1; st.Q -= 1; st.head += 1;
-                if (st.R > st.max_r) st.max_r = st.R;
-                if (st.Q > 0) {
-                    h0 = load_rec(D.stack + st.head);   // consumed by the next tick's attempt
-                    if (ENV) st.bottom_arr = D.stack[st.head + st.Q - 1].arrival_tick;
-                }
-            } else if (!ENV && hx.fits()) {
-                st.head_blocked = 1;   // a failed attempt has no side effect: skip retries until a release
             }
+            if (!ENV && attempt && !pr.ok && hx.fits()) st.head_blocked = 1;   // a failed attempt has no side effect: skip retries until a release
         }
 
         // median loads are issued early; they are consumed when the row is written
         int med_lo_arr = 0, med_hi_arr = 0;
-        if (ROWS && st.Q > 0) {
+        if (ROWS && act && st.Q > 0) {
             med_lo_arr = D.stack[st.head + (st.Q - 1) / 2].arrival_tick;
             med_hi_arr = D.stack[st.head + st.Q / 2].arrival_tick;
         }
 
         // ---------------- delta_time += 1; step; release the jobs whose end tick is now, in start order (schedule.py:141-162)
-        st.d = d + 1;
+        if (act) st.d = d + 1;
         {
             const int bk = st.d & (RLGS_CAL_W - 1);
             const uint32_t hb = s.bkt[bk];
             uint32_t head = hb & 0xffffu, tail = hb >> 16;
-            int sl = (int)head, prev = (int)RLGS_NONE16;
+            int sl = act ? (int)head : (int)RLGS_NONE16, prev = (int)RLGS_NONE16;
             bool changed = false;
-            while (sl != (int)RLGS_NONE16) {
-                const int4 e = s.slot[sl];                          // one 16-byte load per hop: end, next, placement
+            while (__any_sync(RLGS_FULLMASK, sl != (int)RLGS_NONE16)) {
+                const bool v = sl != (int)RLGS_NONE16;
+                const int4 e = s.slot[v ? sl : 0];                  // one 16-byte load per hop: end, next, placement
                 const int nx = e.y;
-                if (e.x == st.d) {
-                    const int job = s.sjob[sl];
+                const bool match = v && e.x == st.d;
+                if (__any_sync(RLGS_FULLMASK, match)) {
                     const uint32_t place = (uint32_t)e.z, mask = (uint32_t)e.w;
-                    int ndev;
-                    if ((place & 0xffffu) != 0xffffu) {
-                        grp_release_single(G, s, c, (int)(place & 0xffffu), (int)(place >> 16), mask, st.n_free_nodes);   // syncs before it writes
+                    const bool m1 = match && (place & 0xffffu) != 0xffffu;   // single-node job (the hot case)
+                    const int ni = m1 ? (int)(place & 0xffffu) : 0;
+                    int fu = (int)(s.key[ni] & 0xffffu);
+                    const uint32_t busy = busy_ld(s, ni) & ~mask;
+                    const int job = s.sjob[v ? sl : 0];
+                    __syncwarp();                                   // every lane has read the slot, the job and the old node state
+                    int ndev = 0;
+                    if (m1) {                                       // Node.release_allocated_resources (node.py:71-91)
+                        const bool was = free_units_is_free(fu, c);
+                        fu += (int)(place >> 16);
+                        st.n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
+                        busy_st(s, ni, busy); s.key[ni] = grp_key(fu, busy, c);
                         ndev = __popc(mask);
-                    } else {
-                        ndev = grp_release_multi(G, s, c, D.place_log + (int)mask, (int)(place >> 16), st.n_free_nodes);
+                    } else if (match) {
+                        ndev = grp_release_multi(G, s, c, D.place_log + (int)mask, (int)(place >> 16), st.n_free_nodes);   // group-local, rare
                     }
-                    // unlink from the calendar chain, push on the free-slot chain (all lanes store the same words)
-                    if (prev == (int)RLGS_NONE16) head = (uint32_t)nx; else s.slot[prev].y = nx;
-                    if (nx == (int)RLGS_NONE16) tail = (uint32_t)prev;
-                    changed = true;
-                    s.slot[sl] = make_int4(RLGS_NEVER, st.free_hint < 0 ? (int)RLGS_NONE16 : st.free_hint, 0, 0);
-                    st.free_hint = sl;
-                    if (ROWS == 1) {
-                        const JobRec jr = load_rec(D.trace + job);   // the row sums need the job's constants again
-                        st.busy_gpus -= ndev;
-                        st.mem_sum -= jr.mem_term();
-                        const int64_t mu = jr.util() & 0xffff, sd = jr.util() >> 16;
-                        st.util_mu_sum -= mu * ndev;
-                        st.util_var_sum -= sd * sd * ndev;
+                    if (match) {
+                        // unlink from the calendar chain, push on the free-slot chain (all lanes of the group store the same words)
+                        if (prev == (int)RLGS_NONE16) head = (uint32_t)nx; else s.slot[prev].y = nx;
+                        if (nx == (int)RLGS_NONE16) tail = (uint32_t)prev;
+                        changed = true;
+                        s.slot[sl] = make_int4(RLGS_NEVER, st.free_hint < 0 ? (int)RLGS_NONE16 : st.free_hint, 0, 0);
+                        st.free_hint = sl;
+                        if (ROWS == 1) {
+                            const JobRec jr = load_rec(D.trace + job);   // the row sums need the job's constants again
+                            st.busy_gpus -= ndev;
+                            st.mem_sum -= jr.mem_term();
+                            const int64_t mu = jr.util() & 0xffff, sd = jr.util() >> 16;
+                            st.util_mu_sum -= mu * ndev;
+                            st.util_var_sum -= sd * sd * ndev;
+                        }
+                        if (writer) { D.end_tick[job] = st.d; D.finish_order[st.F] = job; }
+                        st.F += 1; st.R -= 1;
+                        st.head_blocked = 0;   // resources were freed: the queue head may fit now
                     }
-                    if (writer) { D.end_tick[job] = st.d; D.finish_order[st.F] = job; }
-                    st.F += 1; st.R -= 1;
-                    st.head_blocked = 0;   // resources were freed: the queue head may fit now
-                } else prev = sl;
-                sl = nx;
+                }
+                if (v) { if (!match) prev = sl; sl = nx; }
             }
             if (changed) s.bkt[bk] = head | (tail << 16);
         }
 
         // ---------------- stats row (schedule.py:204-205)
-        st.sumQ += st.Q; st.sumR += st.R;
-        if (ENV) reward_acc -= (float)(st.Q + st.R);
-        if (ROWS) {
-            if (((st.d - 1) & (RLGS_ROW_CHUNK - 1)) == 0 || row_cur == nullptr) {
-                const int64_t i = st.d - 1;
-                row_cur = reinterpret_cast<unsigned char *>(rs.chunks[i >> RLGS_ROW_CHUNK_LOG]) +
-                          (((size_t)(rs.replica + rep) << RLGS_ROW_CHUNK_LOG) + (size_t)(i & (RLGS_ROW_CHUNK - 1))) * ROW_BYTES;
+        if (act) {
+            st.sumQ += st.Q; st.sumR += st.R;
+            if (ENV) reward_acc -= (float)(st.Q + st.R);
+            if (ROWS) {
+                if (((st.d - 1) & (RLGS_ROW_CHUNK - 1)) == 0 || row_cur == nullptr) {
+                    const int64_t i = st.d - 1;
+                    row_cur = reinterpret_cast<unsigned char *>(rs.chunks[i >> RLGS_ROW_CHUNK_LOG]) +
+                              (((size_t)(rs.replica + rep) << RLGS_ROW_CHUNK_LOG) + (size_t)(i & (RLGS_ROW_CHUNK - 1))) * ROW_BYTES;
+                }
+                const int maxp = st.Q > 0 ? st.d - st.bottom_arr : 0, mlo = st.Q > 0 ? st.d - med_lo_arr : 0, mhi = st.Q > 0 ? st.d - med_hi_arr : 0;
+                if (ROWS == 2) {
+                    if (writer) *reinterpret_cast<int4 *>(row_cur) = pack_row16(st.idle_nodes, st.F, st.Q, maxp, mlo, mhi);
+                } else if (writer) {
+                    const int64_t sp = (int64_t)st.Q * st.d - st.sum_arr;
+                    int4 *o = reinterpret_cast<int4 *>(row_cur);
+                    o[0] = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
+                    o[1] = make_int4(st.F, mlo, mhi, maxp);
+                    o[2] = make_int4((int)(uint32_t)sp, (int)(sp >> 32), (int)(uint32_t)st.mem_sum, (int)(st.mem_sum >> 32));
+                    o[3] = make_int4((int)(uint32_t)st.util_mu_sum, (int)(st.util_mu_sum >> 32), (int)(uint32_t)st.util_var_sum,
+                                     (int)(st.util_var_sum >> 32));
+                }
+                row_cur += ROW_BYTES;
             }
-            const int maxp = st.Q > 0 ? st.d - st.bottom_arr : 0, mlo = st.Q > 0 ? st.d - med_lo_arr : 0, mhi = st.Q > 0 ? st.d - med_hi_arr : 0;
-            if (ROWS == 2) {
-                if (writer) *reinterpret_cast<int4 *>(row_cur) = pack_row16(st.idle_nodes, st.F, st.Q, maxp, mlo, mhi);
-            } else if (writer) {
-                const int64_t sp = (int64_t)st.Q * st.d - st.sum_arr;
-                int4 *o = reinterpret_cast<int4 *>(row_cur);
-                o[0] = make_int4(st.idle_nodes, st.busy_gpus, st.R, st.Q);
-                o[1] = make_int4(st.F, mlo, mhi, maxp);
-                o[2] = make_int4((int)(uint32_t)sp, (int)(sp >> 32), (int)(uint32_t)st.mem_sum, (int)(st.mem_sum >> 32));
-                o[3] = make_int4((int)(uint32_t)st.util_mu_sum, (int)(st.util_mu_sum >> 32), (int)(uint32_t)st.util_var_sum,
-                                 (int)(st.util_var_sum >> 32));
-            }
-            row_cur += ROW_BYTES;
         }
     }
+#undef GBALLOT
+#undef GSHFL
+    if (!resident) return;                        // the remaining code is per group (group-local synchronisation only)
     if (ROWS == 2 && st.d >= (1 << 24)) { st.status = RLGS_ERR_WIRE; st.done = 1; }   // pending times no longer fit the 24-bit wire fields
 
     st.events = (int64_t)st.cursor + st.start_seq + st.F;   // arrivals + starts + finishes
@@ -635,9 +730,11 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
         // observation: per node free GPUs / cpu / mem, the look-ahead window, queue statistics
         float *o = env.obs + (size_t)rep * env.obs_dim;
         for (int i = G.gl; i < c.N; i += LPR) {
-            o[i] = (float)__popc(~s.busy[i] & c.gmask);
-            o[c.N + i] = (float)(c.cpu_cap - RLGS_CPUS_PER_TASK * s.units[i]);
-            o[2 * c.N + i] = (float)(c.mem_cap - RLGS_MEM_PER_TASK * s.units[i]);
+            const uint32_t key = s.key[i];
+            const int units = c.base_units - (int)(key & 0xffffu);   // tasks charged to the node: cpu_used = 12 u, mem_used = 60 u
+            o[i] = (float)(key >> 16);
+            o[c.N + i] = (float)(c.cpu_cap - RLGS_CPUS_PER_TASK * units);
+            o[2 * c.N + i] = (float)(c.mem_cap - RLGS_MEM_PER_TASK * units);
         }
         for (int i = G.gl; i < env.window_k; i += LPR) {
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);

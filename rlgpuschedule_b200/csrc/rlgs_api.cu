@@ -185,6 +185,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->cc.D = s->cc.N * s->cc.G;
     s->cc.base_units = std::max(0, std::min(s->cc.cpu_cap > 0 ? s->cc.cpu_cap / RLGS_CPUS_PER_TASK : 0, s->cc.mem_cap > 0 ? s->cc.mem_cap / RLGS_MEM_PER_TASK : 0));
     s->cc.free_limit = std::max(rlgs_ceil_div_pos(s->cc.cpu_cap, RLGS_CPUS_PER_TASK), rlgs_ceil_div_pos(s->cc.mem_cap, RLGS_MEM_PER_TASK));
+    s->cc.free_floor = s->cc.base_units - s->cc.free_limit;
+    if (sched == RLGS_SCHED_FIFO && s->cc.base_units > 0x7fff) { delete s; return fail(RLGS_ERR_UNSUPPORTED, "a node takes at most 32767 tasks (num_cpu_p_node / 12, mem_p_node / 60)"); }
     memset(&s->lp, 0, sizeof s->lp);
     s->lp.nq = is_dlas ? opts->num_queue : 1;
     s->lp.gputime = sched == RLGS_SCHED_DLAS_GPU;
@@ -199,7 +201,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
     // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
     s->lpr = lpr_in ? lpr_in : (s->R >= 148 * 8 * 4 ? 8 : (s->R >= 148 * 8 * 2 ? 16 : 32));
-    while (s->lpr < 32 && (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr) > 227 * 1024) s->lpr *= 2;   // the warp's replicas must fit one SM
+    while (s->lpr < 32 && (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr) > 227 * 1024) s->lpr *= 2;   // the warp's replicas must fit one SM
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
     s->h_ldesc.assign(s->R, LegDesc{});
@@ -539,7 +541,7 @@ static NetCost netcost_of(const rlgs_sim *s) {
 template <int LPR, bool ENV, int ROWS, bool NET>
 static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, const RowStore &rs, const EnvIO &io, cudaStream_t st) {
     constexpr int K = 32 / LPR;
-    const size_t smem = K * grp_smem_bytes(s->cc.N, s->slot_cap, LPR);
+    const size_t smem = K * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, LPR);
     static size_t attr_set[64] = {0};   // per device: largest dynamic shared-memory size already allowed for this instantiation
     const int dev = s->device & 63;
     if (smem > attr_set[dev]) {
@@ -620,7 +622,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     const bool rows = mode != RLGS_ROWS_NONE, eager_rows = mode == RLGS_ROWS_FULL, eager_jobs = s->opts.fetch_jobs != 0;
     const int R = s->R;
     if (!s->legacy) {
-        size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr);
+        size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr);
         if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp (> 227 KB)", smem);
     } else if (!s->pack && s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
         CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
@@ -1030,7 +1032,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     CU(cudaSetDevice(s->device));
     int32_t rc = setup_job_arrays(s);
     if (rc) return rc;
-    size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->slot_cap, s->lpr);
+    size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr);
     if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp", smem);
     if (s->opts.rows_mode != RLGS_ROWS_NONE) {   // per-tick rows while stepping: 64-byte rows, one replica per warp
         if (s->lpr != 32 || s->wire16) return fail(RLGS_ERR_UNSUPPORTED, "environment steps with rows need lanes_per_replica = 32 and RLGS_ROWFMT_WIDE");

@@ -66,6 +66,7 @@ struct ClusterConst {
     int32_t free_limit;    // a node is "free" (cpu_free > 0 or mem_free > 0, node.py:59) while its charged units < this
     uint32_t gmask;        // G low bits set
     int32_t D;             // N*G
+    int32_t free_floor;    // base_units - free_limit: a node is "free" while its free task units exceed this (fifo_grp.cuh)
 };
 
 // chunk-major row store shared by all kernels: row i of replica r lives in chunk i / RLGS_ROW_CHUNK

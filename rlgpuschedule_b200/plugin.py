@@ -125,7 +125,20 @@ class JobsManagerView(object):
         self._queued, self._running, self._finished, self.delta = int(t[0]), int(t[1]), int(t[2]), int(t[3])
         w = obs[base: base + 5 * window_k].reshape(window_k, 5)
         n = min(self._queued, window_k)
-        self._window = [JobView(trace, w[i, 4], i, w[i, 0], w[i, 1], w[i, 2], w[i, 3]) for i in range(n)]
+        seen = [JobView(trace, w[i, 4], i, w[i, 0], w[i, 1], w[i, 2], w[i, 3]) for i in range(n)]
+        # The observation was written at the end of the previous tick; the reference calls the scheduling callable after
+        # this tick's arrivals joined the FRONT of the queue (schedule.py:187-190, q1), and the kernel applies the returned
+        # index after pushing them too.  Those jobs are known from the trace: every not yet arrived job with arrival_tick <= delta.
+        rec = trace.records
+        arrived = self._queued + self._running + self._finished
+        hi = arrived
+        while hi < len(rec) and rec['arrival_tick'][hi] <= self.delta:
+            hi += 1
+        fresh = [JobView(trace, i, 0, rec['gpus'][i], rec['tasks'][i], rec['dur_ticks'][i], 0) for i in range(arrived, min(hi, arrived + window_k))]
+        self._queued += hi - arrived
+        self._window = (fresh + seen)[:window_k]
+        for i, j in enumerate(self._window):
+            j.window_index = i
         self.popped = None
 
     def window(self, k=None):

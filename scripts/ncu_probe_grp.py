@@ -14,7 +14,7 @@ n, lpr, R, fmt, nt = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.a
 cluster = rl.Cluster(num_switch=4, num_node_p_switch=32, num_gpu_p_node=8)
 traces = [rl.prepare_trace(synth.frame_gen(n, 3 + i, n), cluster) for i in range(nt)]
 kw = dict(rows=False) if fmt == '0' else dict(rows='device', rows_format=fmt)
-sim = rl.Simulator(cluster, n_replicas=R, lanes_per_replica=lpr, n_streams=1, **kw)
+sim = rl.Simulator(cluster, n_replicas=R, lanes_per_replica=lpr, n_streams=1, rows_cap=n + 8192, **kw)   # one launch per run
 for i in range(nt):
     lo, hi = R * i // nt, R * (i + 1) // nt
     if hi > lo:

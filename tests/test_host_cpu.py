@@ -146,7 +146,9 @@ def test_plugin_views_and_host_forms_of_the_builtin_entries():
         rec = tr.records[job]
         obs[3 * N + 5 * i: 3 * N + 5 * i + 5] = [rec['gpus'], rec['tasks'], rec['dur_ticks'], pend, job]
     obs[3 * N + 5 * 2 + 4] = -1
-    obs[3 * N + 5 * K:] = [2, 3, 1, 17]
+    arrived = int((tr.records['arrival_tick'] <= 17).sum())          # jobs the trace has delivered by tick 17
+    assert arrived >= 7
+    obs[3 * N + 5 * K:] = [2, 3, arrived - 5, 17]
     infra = plugin.InfrastructureView(cluster, None, obs)
     jm = plugin.JobsManagerView(tr, obs, N, K)
     assert list(infra.nodes) == ['1', '2', '3', '4'] and infra.nodes['3'].cpu_free() == 128 and infra.nodes['2'].rack_id == '0'
@@ -159,6 +161,11 @@ def test_plugin_views_and_host_forms_of_the_builtin_entries():
     if need <= 4:
         first = next(nid for nid, n in infra.nodes.items() if len(n.get_free_devices()) >= need and n.cpu_free() >= 12 * head.task_count and n.mem_free() >= 60 * head.task_count)
         assert ok and job is head and list(nodes) == [first] and jm.popped is head
+    # jobs that arrive at this tick join the FRONT of the window before the callable runs (schedule.py:187-190, q1)
+    obs2 = obs.copy(); obs2[3 * N + 5 * K + 2] -= 2
+    jm2 = plugin.JobsManagerView(tr, obs2, N, K)
+    assert jm2.queuing_jobs() == 4 and [j.trace_index for j in jm2.window()] == [arrived - 2, arrived - 1, 7]
+    assert [j.window_index for j in jm2.window()] == [0, 1, 2] and jm2.window()[0].pending_time == 0
     with pytest.raises(RuntimeError):
         algorithm.scheduling_algorithms['horus']('horus', None, infra, jm, 17)
     algorithm.scheduling_algorithms['user'] = lambda *a, **k: (None, None, False)
