@@ -36,7 +36,7 @@ UNIT = 'events/s'
 REF_DIR = os.path.join(ROOT, 'oracle', '_ref', 'reference')
 
 WORKLOADS = {
-    'fifo60k': dict(schedule='fifo', scheme='yarn', n_jobs=60000, seed0=3, n_traces=16, replicas=9472, kw={},
+    'fifo60k': dict(schedule='fifo', scheme='yarn', n_jobs=60000, seed0=3, n_traces=16, replicas=8880, kw={},
                     text='fifo+yarn, 4x32x8 simulated cluster, 60k-job Philly-style trace (gen(60000, seed, 60000))'),
     'dlas60k': dict(schedule='dlas-gpu', scheme='count', n_jobs=60000, seed0=3, n_traces=8, replicas=2960,
                     kw=dict(num_queue=4, queue_limit=(30, 60, 150)),

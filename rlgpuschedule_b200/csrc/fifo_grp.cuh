@@ -18,9 +18,8 @@
 // arrival, a start and a finish.
 //
 // On chip per replica (shared memory, 16-byte aligned pieces):
-//   key[N]    idle devices << 16 | free task units = min(cpu_cap // 12, mem_cap // 60) - tasks charged (placed + leaked, q8):
-//             the two numbers every fit test needs; cpu_free and mem_free follow from the units (every task charges 12 / 60)
-//   busy[N]   busy-device bitmask (16-bit words when the node has <= 16 GPUs),  ever[N/32]  node ever used (q3)
+//   key[N]    one word per node: idle devices, busy-device mask and free task units (see NodeC below)
+//   ever[N/32] node ever used (q3)
 //   slot[S]   int4 {end tick | RLGS_NEVER, next slot in the calendar / free chain, node | tasks << 16 (or 0xffff | nnodes << 16),
 //                   device mask (or first placement-log entry)},  sjob[S] job index
 //   bkt[128]  calendar: head | tail << 16 of the chain of running jobs whose end tick == b (mod 128); a started job is appended
@@ -29,7 +28,9 @@
 #pragma once
 #include "rlgs_device.cuh"
 
+#ifndef RLGS_CAL_W
 #define RLGS_CAL_W 128
+#endif
 #define RLGS_NONE16 0xffffu
 
 // ---- group of LPR lanes --------------------------------------------------------------------------------------------
@@ -67,10 +68,17 @@ struct Grp {
 };
 
 // ---- shared-memory view of one replica -------------------------------------------------------------------------------
+// Node word ("key"), the only per-node state the tick touches on its hot path.  Two layouts, chosen at compile time:
+//   PK  (nodes with <= 8 GPUs, the reference's default):  idle devices << 25 | busy-device mask << 16 | free task units
+//   !PK (9 .. 32 GPUs per node):                          idle devices << 16 | free task units,  busy mask in its own array
+// Free task units = min(cpu_cap // 12, mem_cap // 60) - tasks charged (placed + leaked, q8) <= 0x7fff (rlgs_create refuses larger
+// nodes).  A task is only ever charged to a node whose key showed room for it (placement and the q8 leak alike), so the count
+// never goes negative and nothing is clamped; cpu_free and mem_free follow from it (every task charges exactly 12 / 60).
+// In both layouts bit 15 and bit 31 are clear and the high half compares like the idle count, which lets ONE subtraction test
+// "idle >= gpus and free units >= tasks" for a node (grp_fit4).
 struct GrpSm {
     uint32_t *key;    // [Npad] zero beyond N (a zero key never fits)
-    void *busy;       // [N] uint16_t when the node has <= 16 GPUs, else uint32_t
-    int busy16;
+    uint32_t *busy;   // [N] (!PK only)
     uint32_t *ever;   // [ceil(N/32)]
     int4 *slot;       // [slot_cap]
     int32_t *sjob;    // [slot_cap]
@@ -78,11 +86,10 @@ struct GrpSm {
 };
 
 __host__ __device__ inline int grp_npad(int N, int lpr) { int q = 4 * lpr; return (N + q - 1) / q * q; }
-
-__host__ __device__ inline size_t grp_busy_words(int N, int G) { return G <= 16 ? ((size_t)N + 1) / 2 : (size_t)N; }
+__host__ __device__ inline bool grp_packed(int G) { return G <= 8; }
 
 __host__ __device__ inline size_t grp_smem_bytes(int N, int G, int slot_cap, int lpr) {
-    size_t words = (size_t)grp_npad(N, lpr) + grp_busy_words(N, G) + (size_t)((N + 31) / 32);
+    size_t words = (size_t)grp_npad(N, lpr) + (grp_packed(G) ? 0 : (size_t)N) + (size_t)((N + 31) / 32);
     words = (words + 3) & ~(size_t)3;
     words += 4 * (size_t)slot_cap + (size_t)slot_cap + RLGS_CAL_W;
     return ((words + 3) & ~(size_t)3) * 4;
@@ -92,7 +99,7 @@ __device__ __forceinline__ GrpSm grp_carve(unsigned char *base, int N, int G, in
     GrpSm s;
     uint32_t *w = reinterpret_cast<uint32_t *>(base);
     s.key = w; w += grp_npad(N, lpr);
-    s.busy = w; s.busy16 = G <= 16; w += grp_busy_words(N, G);
+    s.busy = w; if (!grp_packed(G)) w += N;
     s.ever = w; w += (N + 31) / 32;
     while ((w - reinterpret_cast<uint32_t *>(base)) & 3) w += 1;
     s.slot = reinterpret_cast<int4 *>(w); w += 4 * slot_cap;
@@ -101,24 +108,27 @@ __device__ __forceinline__ GrpSm grp_carve(unsigned char *base, int N, int G, in
     return s;
 }
 
-__device__ __forceinline__ uint32_t busy_ld(const GrpSm &s, int i) {
-    return s.busy16 ? (uint32_t)reinterpret_cast<const uint16_t *>(s.busy)[i] : reinterpret_cast<const uint32_t *>(s.busy)[i];
-}
-__device__ __forceinline__ void busy_st(const GrpSm &s, int i, uint32_t v) {
-    if (s.busy16) reinterpret_cast<uint16_t *>(s.busy)[i] = (uint16_t)v; else reinterpret_cast<uint32_t *>(s.busy)[i] = v;
-}
+template <bool PK>
+struct NodeC {
+    static constexpr int IDLE_SHIFT = PK ? 25 : 16;
+    __device__ static __forceinline__ uint32_t need_word(int gpus, int tasks) { return ((uint32_t)gpus << IDLE_SHIFT) | (uint32_t)tasks; }
+    __device__ static __forceinline__ int idle(uint32_t k) { return (int)(k >> IDLE_SHIFT); }
+    __device__ static __forceinline__ int free_units(uint32_t k) { return (int)(k & 0xffffu); }
+    __device__ static __forceinline__ uint32_t busy(const GrpSm &s, int i, uint32_t k) { return PK ? ((k >> 16) & 0x1ffu) : s.busy[i]; }
+    __device__ static __forceinline__ uint32_t make(int fu, uint32_t busy, const ClusterConst &c) {
+        const uint32_t idle = (uint32_t)__popc(~busy & c.gmask);
+        return PK ? ((idle << 25) | (busy << 16) | (uint32_t)fu) : ((idle << 16) | (uint32_t)fu);
+    }
+    __device__ static __forceinline__ void store(const GrpSm &s, int i, int fu, uint32_t busy, const ClusterConst &c) {
+        if (!PK) s.busy[i] = busy;
+        s.key[i] = make(fu, busy, c);
+    }
+    __device__ static __forceinline__ int cap(uint32_t k, int gpc) {   // Node.can_fit_num_task (node.py:109-127): tasks this node can take
+        return min(idle(k) / gpc, free_units(k));
+    }
+};
 
-// key = popc(idle devices) << 16 | free task units.  Free units = base_units - tasks charged, where base_units =
-// min(cpu_cap // 12, mem_cap // 60) <= 0x7fff (rlgs_create refuses larger nodes): a task is only ever charged to a node whose
-// key showed room for it (placement and the q8 leak alike), so the count never goes negative and nothing is clamped.  Both
-// halves stay below 0x8000, which lets one subtraction test "idle >= gpus and free units >= tasks" (see grp_fit4).
-__device__ __forceinline__ uint32_t grp_key(int free_units, uint32_t busy, const ClusterConst &c) {
-    return ((uint32_t)__popc(~busy & c.gmask) << 16) | (uint32_t)free_units;
-}
-// Node.is_free (node.py:59-60): cpu_free > 0 or mem_free > 0  <=>  tasks charged < free_limit  <=>  free units > base_units - free_limit
-__device__ __forceinline__ bool free_units_is_free(int free_units, const ClusterConst &c) { return free_units > c.free_floor; }
-
-// first of four consecutive node keys with idle devices >= need >> 16 and free units >= need & 0xffff, else -1
+// first of four consecutive node keys with idle devices >= gpus and free units >= tasks (need = NodeC::need_word), else -1
 // (algorithm.py:407-409: free devices >= gpus, cpu_free >= 12 T, mem_free >= 60 T).  (k | H) - need keeps bit 15 / bit 31
 // exactly when the low / high half did not borrow.
 __device__ __forceinline__ int grp_fit4(uint4 k, uint32_t need) {
@@ -128,10 +138,6 @@ __device__ __forceinline__ int grp_fit4(uint4 k, uint32_t need) {
     return o0 ? 0 : (o1 ? 1 : (o2 ? 2 : (o3 ? 3 : -1)));
 }
 
-__device__ __forceinline__ int grp_cap(uint32_t k, int gpc) {   // Node.can_fit_num_task (node.py:109-127): tasks this node can take
-    return min((int)(k >> 16) / gpc, (int)(k & 0xffff));
-}
-
 struct GrpPlace {
     int ok;          // 1 placed, 0 not placed
     int node;        // single-node: node index; multi-node: -1
@@ -139,72 +145,49 @@ struct GrpPlace {
     int nnodes;      // entries appended to the placement log
 };
 
+// The reference gates a scheduling attempt on num_free_nodes() >= 1 (schedule.py:40-44; a node is free while cpu_free > 0 or
+// mem_free > 0).  The gate cannot change an outcome: when it is closed every node has used up cpu and mem, so every free-unit
+// count is 0 and any attempt fails without a side effect (the q8 leak needs free units too).  The tick loop therefore does not
+// keep that count.
+
 // Charges k tasks of cpu / mem to `node` (all lanes of the group call with the same node): the q8 leak.
 template <int LPR>
-__device__ __forceinline__ void grp_charge(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, int node, int k, int &n_free_nodes) {
+__device__ __forceinline__ void grp_charge(const Grp<LPR> &G, GrpSm s, int node, int k) {
     const uint32_t key = s.key[node];
-    int fu = (int)(key & 0xffffu);
-    const bool was = free_units_is_free(fu, c);
-    fu -= k;
-    n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
     G.sync();
-    s.key[node] = (key & 0xffff0000u) | (uint32_t)fu;
+    s.key[node] = key - (uint32_t)k;      // free units live in the low half and k never exceeds them
 }
 
-// Tries to place job j under yarn (ms_yarn_placement, algorithm.py:28-32).  Every lane of the group calls; the result is
-// group-uniform.  On success node state is updated and the placement appended to place_log[log_pos ...].
-template <int LPR>
-__device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, const JobRec &j, int2 *place_log,
-                                              int log_pos, int &n_free_nodes, int &idle_nodes) {
+// The rare, group-local placements (ms_yarn_placement, algorithm.py:28-32): the q8 leak of a task no device accepts and
+// try_cross_node_alloc_ms for jobs wider than a node.  Every lane of the group calls; the result is group-uniform.
+template <int LPR, bool PK>
+__device__ __forceinline__ GrpPlace grp_place_rare(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, const JobRec &j, int2 *place_log,
+                                                   int log_pos, int &idle_nodes) {
+    typedef NodeC<PK> NC;
     GrpPlace r; r.ok = 0; r.node = -1; r.mask = 0; r.nnodes = 0;
     const int T = j.tasks(), gpc = j.gpc(), need_g = j.gpus();
     const bool fits = j.fits();
     const int Npad = grp_npad(c.N, LPR);
     if (need_g <= c.G) {
-        // ---- try_single_node_alloc_ms (algorithm.py:396-417): first node in id order with enough idle devices, cpu and mem
-        const uint32_t need = ((uint32_t)need_g << 16) | (uint32_t)T;
-        if (!fits) {
-            // no device accepts the task (device.py:67-77): every candidate node charges T tasks of cpu / mem and keeps them (q8)
-            for (int i = 0; i < c.N; ++i) {
-                const uint32_t k = s.key[i];
-                if ((int)(k >> 16) >= need_g && (int)(k & 0xffff) >= T) grp_charge(G, s, c, i, T, n_free_nodes);
-            }
-            return r;
+        // no device accepts the task (device.py:67-77): every candidate node of try_single_node_alloc_ms charges T tasks of
+        // cpu / mem and keeps them (q8)
+        for (int i = 0; i < c.N; ++i) {
+            const uint32_t k = s.key[i];
+            if (NC::idle(k) >= need_g && NC::free_units(k) >= T) grp_charge(G, s, i, T);
         }
-        int node = -1;
-        for (int base = 0; base < Npad; base += 4 * LPR) {
-            const uint4 k = *reinterpret_cast<const uint4 *>(s.key + base + 4 * G.gl);
-            const int f = grp_fit4(k, need);
-            const unsigned b = G.ballot(f >= 0);
-            if (b) { const int l = __ffs(b) - 1; node = base + 4 * l + G.shfl(f, l); break; }
-        }
-        if (node < 0) return r;
-        int fu = (int)(s.key[node] & 0xffffu);
-        const uint32_t busy = busy_ld(s, node);
-        const uint32_t taken = lowest_bits(~busy & c.gmask, T * gpc);
-        const bool was = free_units_is_free(fu, c);
-        fu -= T;
-        n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
-        const uint32_t ew = s.ever[node >> 5], bit = 1u << (node & 31);
-        if (!(ew & bit)) idle_nodes--;
-        G.sync();                                   // every lane has read the old node state
-        busy_st(s, node, busy | taken); s.ever[node >> 5] = ew | bit;
-        s.key[node] = grp_key(fu, busy | taken, c);
-        if (G.gl == 0) place_log[log_pos] = make_int2(node | (T << 16), (int)taken);
-        r.ok = 1; r.node = node; r.mask = taken; r.nnodes = 1;
         return r;
     }
     // ---- try_cross_node_alloc_ms (algorithm.py:301-393): walk the nodes in id order, each takes min(capacity, remaining) tasks;
     //      the fit+1 attempt of q11 has no side effect
     if (!fits) {   // the first task attempt on every node with capacity >= 1 leaks one task of cpu / mem (q8)
         for (int i = 0; i < c.N; ++i)
-            if (grp_cap(s.key[i], gpc) >= 1) grp_charge(G, s, c, i, 1, n_free_nodes);
+            if (NC::cap(s.key[i], gpc) >= 1) grp_charge(G, s, i, 1);
         return r;
     }
     int remaining = T, nodes_assigned = 0;
     for (int base = 0; base < Npad && remaining > 0; base += 4 * LPR) {
         const uint4 k = *reinterpret_cast<const uint4 *>(s.key + base + 4 * G.gl);
-        const int c0 = grp_cap(k.x, gpc), c1 = grp_cap(k.y, gpc), c2 = grp_cap(k.z, gpc), c3 = grp_cap(k.w, gpc);
+        const int c0 = NC::cap(k.x, gpc), c1 = NC::cap(k.y, gpc), c2 = NC::cap(k.z, gpc), c3 = NC::cap(k.w, gpc);
         const int sum4 = c0 + c1 + c2 + c3;
         const int incl = G.incl_scan(sum4);
         const int tot = G.shfl(incl, LPR - 1);
@@ -224,7 +207,7 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
     for (int base = 0; base < Npad && remaining > 0; base += 4 * LPR) {
         const int i0 = base + 4 * G.gl;
         const uint4 k = *reinterpret_cast<const uint4 *>(s.key + i0);
-        const int cap[4] = {grp_cap(k.x, gpc), grp_cap(k.y, gpc), grp_cap(k.z, gpc), grp_cap(k.w, gpc)};
+        const int cap[4] = {NC::cap(k.x, gpc), NC::cap(k.y, gpc), NC::cap(k.z, gpc), NC::cap(k.w, gpc)};
         const int sum4 = cap[0] + cap[1] + cap[2] + cap[3];
         const int incl = G.incl_scan(sum4);
         const int tot = G.shfl(incl, LPR - 1);
@@ -233,25 +216,20 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
 #pragma unroll
         for (int q = 0; q < 4; ++q) { take[q] = max(0, min(cap[q], remaining - before)); before += cap[q]; cnt += take[q] > 0; }
         const int cincl = G.incl_scan(cnt);
-        int pos = log_pos + written + cincl - cnt, dfree = 0, didle = 0;
+        int pos = log_pos + written + cincl - cnt, didle = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (take[q] > 0) {
                 const int i = i0 + q;
                 const uint32_t kq = q == 0 ? k.x : (q == 1 ? k.y : (q == 2 ? k.z : k.w));
-                int fu = (int)(kq & 0xffffu);
-                const uint32_t busy = busy_ld(s, i);
+                const uint32_t busy = NC::busy(s, i, kq);
                 const uint32_t taken = lowest_bits(~busy & c.gmask, take[q] * gpc);
-                const bool was = free_units_is_free(fu, c);
-                fu -= take[q];
-                dfree += (int)free_units_is_free(fu, c) - (int)was;
-                busy_st(s, i, busy | taken); s.key[i] = grp_key(fu, busy | taken, c);
+                NC::store(s, i, NC::free_units(kq) - take[q], busy | taken, c);
                 const uint32_t bit = 1u << (i & 31);
                 if (!(atomicOr(&s.ever[i >> 5], bit) & bit)) didle += 1;   // several lanes share an `ever` word
                 place_log[pos++] = make_int2(i | (take[q] << 16), (int)taken);
             }
         }
-        n_free_nodes += G.sum(dfree);
         idle_nodes -= G.sum(didle);
         written += G.shfl(cincl, LPR - 1);
         remaining -= min(remaining, tot);
@@ -261,35 +239,19 @@ __device__ __forceinline__ GrpPlace grp_place(const Grp<LPR> &G, GrpSm s, const 
     return r;
 }
 
-// Node.release_allocated_resources (node.py:71-91) for a single-node job: every lane computes the same values and stores them.
-template <int LPR>
-__device__ __forceinline__ void grp_release_single(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, int node, int tasks, uint32_t mask, int &n_free_nodes) {
-    int fu = (int)(s.key[node] & 0xffffu);
-    const bool was = free_units_is_free(fu, c);
-    fu += tasks;
-    n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
-    const uint32_t busy = busy_ld(s, node) & ~mask;
-    G.sync();
-    busy_st(s, node, busy); s.key[node] = grp_key(fu, busy, c);
-}
-
-// ... and for a multi-node job: one placement-log entry per lane, distinct nodes
-template <int LPR>
-__device__ __forceinline__ int grp_release_multi(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, const int2 *log, int nn, int &n_free_nodes) {
-    int ndev = 0, dfree = 0;
+// Node.release_allocated_resources (node.py:71-91) for a multi-node job: one placement-log entry per lane, distinct nodes
+template <int LPR, bool PK>
+__device__ __forceinline__ int grp_release_multi(const Grp<LPR> &G, GrpSm s, const ClusterConst &c, const int2 *log, int nn) {
+    typedef NodeC<PK> NC;
+    int ndev = 0;
     G.sync();
     for (int b = G.gl; b < nn; b += LPR) {
         const int2 e = log[b];
         const int node = e.x & 0xffff, tasks = (e.x >> 16) & 0xffff;
-        int fu = (int)(s.key[node] & 0xffffu);
-        const bool was = free_units_is_free(fu, c);
-        fu += tasks;
-        dfree += (int)free_units_is_free(fu, c) - (int)was;
-        const uint32_t busy = busy_ld(s, node) & ~(uint32_t)e.y;
-        busy_st(s, node, busy); s.key[node] = grp_key(fu, busy, c);
+        const uint32_t k = s.key[node];
+        NC::store(s, node, NC::free_units(k) + tasks, NC::busy(s, node, k) & ~(uint32_t)e.y, c);
         ndev += __popc((uint32_t)e.y);
     }
-    n_free_nodes += G.sum(dfree);
     ndev = G.sum(ndev);
     G.sync();
     return ndev;
@@ -349,13 +311,15 @@ __device__ __forceinline__ int netcost_dur_ticks(const RepDesc &D, const NetCost
 
 // Saves / restores the shared-memory state of a replica (bounded launches and env steps).  The node keys, the calendar and
 // the free-slot chain are derived data: they are rebuilt on restore (calendar chains in start order, from start_tick[job]).
-template <int LPR>
+template <int LPR, bool PK>
 __device__ __forceinline__ void grp_state_io(const Grp<LPR> &G, const RepDesc &D, GrpSm s, const ClusterConst &c, int slot_cap, RepState &st, bool save) {
+    typedef NodeC<PK> NC;
     const int N = c.N;
-    for (int i = G.gl; i < N; i += LPR) {
-        if (save) { D.node_save[i] = c.base_units - (int)(s.key[i] & 0xffffu); D.node_save[N + i] = (int32_t)busy_ld(s, i); }   // tasks charged, busy mask
-        else busy_st(s, i, (uint32_t)D.node_save[N + i]);
-    }
+    if (save)
+        for (int i = G.gl; i < N; i += LPR) {
+            const uint32_t k = s.key[i];
+            D.node_save[i] = c.base_units - NC::free_units(k); D.node_save[N + i] = (int32_t)NC::busy(s, i, k);   // tasks charged, busy mask
+        }
     for (int i = G.gl; i < (N + 31) / 32; i += LPR) {
         if (save) D.node_save[2 * N + i] = (int32_t)s.ever[i]; else s.ever[i] = (uint32_t)D.node_save[2 * N + i];
     }
@@ -367,7 +331,9 @@ __device__ __forceinline__ void grp_state_io(const Grp<LPR> &G, const RepDesc &D
     G.sync();
     if (!save) {
         const int Npad = grp_npad(N, LPR);
-        for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < N ? grp_key(c.base_units - D.node_save[i], busy_ld(s, i), c) : 0u;
+        for (int i = G.gl; i < Npad; i += LPR) {
+            if (i < N) NC::store(s, i, c.base_units - D.node_save[i], (uint32_t)D.node_save[N + i], c); else s.key[i] = 0u;
+        }
         for (int i = G.gl; i < RLGS_CAL_W; i += LPR) s.bkt[i] = RLGS_NONE16 | (RLGS_NONE16 << 16);
         G.sync();
         int free_head = -1;
@@ -401,6 +367,14 @@ __device__ __forceinline__ int4 pack_row16(int idle_nodes, int finished, int que
     return make_int4((int)w0, (int)w1, (int)w2, (int)w3);
 }
 
+// address of row i of replica `rep` in the chunk-major row store; called once per 4096 rows, kept out of line so that the tick
+// pays one decrement + branch for it
+template <int ROW_BYTES>
+__device__ __noinline__ unsigned char *row_address(const RowStore &rs, int rep, int64_t i) {
+    return reinterpret_cast<unsigned char *>(rs.chunks[i >> RLGS_ROW_CHUNK_LOG]) +
+           (((size_t)(rs.replica + rep) << RLGS_ROW_CHUNK_LOG) + (size_t)(i & (RLGS_ROW_CHUNK - 1))) * ROW_BYTES;
+}
+
 #ifndef RLGS_GRP_MIN_BLOCKS
 #define RLGS_GRP_MIN_BLOCKS 16
 #endif
@@ -414,11 +388,12 @@ __device__ __forceinline__ int4 pack_row16(int idle_nodes, int finished, int que
 // register ring, the environment's queue.pop(pick) — stay group-local inside per-group branches.
 #define RLGS_FULLMASK 0xffffffffu
 // ROWS: 0 = no rows, 1 = 64-byte rlgs_row per tick, 2 = 16-byte rlgs_row16 per tick
-template <int LPR, bool ENV, int ROWS, bool NET>
+template <int LPR, bool PK, bool ENV, int ROWS, bool NET>
 __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states, int n_rep,
                                                                            ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
                                                                            int64_t *__restrict__ returns, int64_t max_ticks, EnvIO env, NetCost net) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef NodeC<PK> NC;
     const Grp<LPR> G;
     constexpr unsigned GBITS = LPR == 32 ? 0xffffffffu : ((1u << (LPR & 31)) - 1u);
 #define GBALLOT(p) ((__ballot_sync(RLGS_FULLMASK, (p)) >> G.shift) & GBITS)
@@ -438,18 +413,19 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
     float reward_acc = 0.f;
     constexpr int ROW_BYTES = ROWS == 2 ? 16 : 64;
     unsigned char *row_cur = nullptr;   // next row of this replica inside the current chunk
+    int rows_left = 0;                  // rows that still fit the chunk behind row_cur
     if (ROWS && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)   // the launch stops when the allocated chunks are full
         tick_budget = (int)max((int64_t)0, (int64_t)rs.n_chunks * RLGS_ROW_CHUNK - st.d);
     const int Npad = grp_npad(c.N, LPR);
     if (act) {
         if (st.d == 0) {   // first launch of a run: empty cluster, no running jobs
-            const uint32_t empty_key = grp_key(c.base_units, 0u, c);
-            for (int i = G.gl; i < Npad; i += LPR) s.key[i] = i < c.N ? empty_key : 0u;
-            for (int i = G.gl; i < c.N; i += LPR) busy_st(s, i, 0u);
+            for (int i = G.gl; i < Npad; i += LPR) {
+                if (i < c.N) NC::store(s, i, c.base_units, 0u, c); else s.key[i] = 0u;
+            }
             for (int i = G.gl; i < (c.N + 31) / 32; i += LPR) s.ever[i] = 0u;
             for (int i = G.gl; i < RLGS_CAL_W; i += LPR) s.bkt[i] = RLGS_NONE16 | (RLGS_NONE16 << 16);
         } else {
-            grp_state_io(G, D, s, c, slot_cap, st, false);
+            grp_state_io<LPR, PK>(G, D, s, c, slot_cap, st, false);
         }
     }
     __syncwarp();
@@ -524,12 +500,12 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
         // ---------------- one scheduling attempt (schedule.py:188-190): the queue head, or the policy's pick inside the window
         int pick = 0;
         bool attempt;
-        if (!ENV) attempt = act && st.Q > 0 && st.n_free_nodes >= 1 && !st.head_blocked;
+        if (!ENV) attempt = act && st.Q > 0 && !st.head_blocked;
         else {
             const int win = min(st.Q, env.window_k);
             if (env.policy == 1 && win > 0) pick = (int)(rlgs_hash3(env.seed, (uint32_t)(rs.replica + rep), (uint32_t)d) % (uint32_t)win);
             else if (env.policy == 2 && valid) pick = env.actions[rep];
-            attempt = act && st.Q > 0 && pick >= 0 && pick < win && st.n_free_nodes >= 1;
+            attempt = act && st.Q > 0 && pick >= 0 && pick < win;
         }
         if (__any_sync(RLGS_FULLMASK, attempt)) {
             JobRec hx = h0;
@@ -539,7 +515,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             GrpPlace pr; pr.ok = 0; pr.node = -1; pr.mask = 0; pr.nnodes = 0;
             // ---- try_single_node_alloc_ms (algorithm.py:396-417): first node in id order with enough idle devices, cpu and mem
             {
-                const uint32_t need = ((uint32_t)need_g << 16) | (uint32_t)T;
+                const uint32_t need = NC::need_word(need_g, T);
                 bool searching = one_node && hx.fits();
                 int node = -1;
                 for (int base = 0; base < Npad && __any_sync(RLGS_FULLMASK, searching); base += 4 * LPR) {
@@ -553,18 +529,14 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                 const bool hit = node >= 0;
                 if (__any_sync(RLGS_FULLMASK, hit)) {
                     const int ni = hit ? node : 0;
-                    int fu = (int)(s.key[ni] & 0xffffu);
-                    const uint32_t busy = busy_ld(s, ni);
+                    const uint32_t kn = s.key[ni];
+                    const uint32_t busy = NC::busy(s, ni, kn);
                     const uint32_t ew = s.ever[ni >> 5], bit = 1u << (ni & 31);
                     const uint32_t taken = lowest_bits(~busy & c.gmask, hit ? T * gpc : 0);
                     __syncwarp();                               // every lane has read the old node state
                     if (hit) {
-                        const bool was = free_units_is_free(fu, c);
-                        fu -= T;
-                        st.n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
-                        if (!(ew & bit)) st.idle_nodes--;
-                        busy_st(s, ni, busy | taken); s.ever[ni >> 5] = ew | bit;
-                        s.key[ni] = grp_key(fu, busy | taken, c);
+                        if (!(ew & bit)) { st.idle_nodes--; s.ever[ni >> 5] = ew | bit; }
+                        NC::store(s, ni, NC::free_units(kn) - T, busy | taken, c);
                         if (writer) D.place_log[st.log_len] = make_int2(ni | (T << 16), (int)taken);
                         pr.ok = 1; pr.node = ni; pr.mask = taken; pr.nnodes = 1;
                     }
@@ -572,7 +544,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             }
             // ---- rare, group-local: the q8 leak of a task no device accepts, and jobs wider than a node (algorithm.py:301-393)
             if (attempt && (!one_node || !hx.fits()))
-                pr = grp_place(G, s, c, hx, D.place_log, st.log_len, st.n_free_nodes, st.idle_nodes);
+                pr = grp_place_rare<LPR, PK>(G, s, c, hx, D.place_log, st.log_len, st.idle_nodes);
             bool ok = pr.ok != 0;
             if (__any_sync(RLGS_FULLMASK, ok)) {
                 const int job = hx.index();
@@ -654,19 +626,16 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                     const uint32_t place = (uint32_t)e.z, mask = (uint32_t)e.w;
                     const bool m1 = match && (place & 0xffffu) != 0xffffu;   // single-node job (the hot case)
                     const int ni = m1 ? (int)(place & 0xffffu) : 0;
-                    int fu = (int)(s.key[ni] & 0xffffu);
-                    const uint32_t busy = busy_ld(s, ni) & ~mask;
+                    const uint32_t kn = s.key[ni];
+                    const uint32_t busy = NC::busy(s, ni, kn) & ~mask;
                     const int job = s.sjob[v ? sl : 0];
                     __syncwarp();                                   // every lane has read the slot, the job and the old node state
                     int ndev = 0;
                     if (m1) {                                       // Node.release_allocated_resources (node.py:71-91)
-                        const bool was = free_units_is_free(fu, c);
-                        fu += (int)(place >> 16);
-                        st.n_free_nodes += (int)free_units_is_free(fu, c) - (int)was;
-                        busy_st(s, ni, busy); s.key[ni] = grp_key(fu, busy, c);
+                        NC::store(s, ni, NC::free_units(kn) + (int)(place >> 16), busy, c);
                         ndev = __popc(mask);
                     } else if (match) {
-                        ndev = grp_release_multi(G, s, c, D.place_log + (int)mask, (int)(place >> 16), st.n_free_nodes);   // group-local, rare
+                        ndev = grp_release_multi<LPR, PK>(G, s, c, D.place_log + (int)mask, (int)(place >> 16));   // group-local, rare
                     }
                     if (match) {
                         // unlink from the calendar chain, push on the free-slot chain (all lanes of the group store the same words)
@@ -698,10 +667,9 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             st.sumQ += st.Q; st.sumR += st.R;
             if (ENV) reward_acc -= (float)(st.Q + st.R);
             if (ROWS) {
-                if (((st.d - 1) & (RLGS_ROW_CHUNK - 1)) == 0 || row_cur == nullptr) {
-                    const int64_t i = st.d - 1;
-                    row_cur = reinterpret_cast<unsigned char *>(rs.chunks[i >> RLGS_ROW_CHUNK_LOG]) +
-                              (((size_t)(rs.replica + rep) << RLGS_ROW_CHUNK_LOG) + (size_t)(i & (RLGS_ROW_CHUNK - 1))) * ROW_BYTES;
+                if (--rows_left < 0) {   // first row of the launch or of a chunk
+                    row_cur = row_address<ROW_BYTES>(rs, rep, st.d - 1);
+                    rows_left = RLGS_ROW_CHUNK - 1 - ((st.d - 1) & (RLGS_ROW_CHUNK - 1));
                 }
                 const int maxp = st.Q > 0 ? st.d - st.bottom_arr : 0, mlo = st.Q > 0 ? st.d - med_lo_arr : 0, mhi = st.Q > 0 ? st.d - med_hi_arr : 0;
                 if (ROWS == 2) {
@@ -731,8 +699,8 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
         float *o = env.obs + (size_t)rep * env.obs_dim;
         for (int i = G.gl; i < c.N; i += LPR) {
             const uint32_t key = s.key[i];
-            const int units = c.base_units - (int)(key & 0xffffu);   // tasks charged to the node: cpu_used = 12 u, mem_used = 60 u
-            o[i] = (float)(key >> 16);
+            const int units = c.base_units - NC::free_units(key);   // tasks charged to the node: cpu_used = 12 u, mem_used = 60 u
+            o[i] = (float)NC::idle(key);
             o[c.N + i] = (float)(c.cpu_cap - RLGS_CPUS_PER_TASK * units);
             o[2 * c.N + i] = (float)(c.mem_cap - RLGS_MEM_PER_TASK * units);
         }
@@ -750,7 +718,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             env.done[rep] = (uint8_t)(st.done != 0);
         }
     }
-    grp_state_io(G, D, s, c, slot_cap, st, true);
+    grp_state_io<LPR, PK>(G, D, s, c, slot_cap, st, true);
     if (writer) {
         states[rep] = st;
         if (st.done) returns[rep] = -st.sum_jct;   // episode return, read by the all-gather

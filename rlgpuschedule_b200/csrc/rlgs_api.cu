@@ -201,6 +201,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
     // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
     s->lpr = lpr_in ? lpr_in : (s->R >= 148 * 8 * 4 ? 8 : (s->R >= 148 * 8 * 2 ? 16 : 32));
+    if (opts->enable_network_costs) s->lpr = 32;   // the float64 network-cost variant is compiled for one replica per warp
     while (s->lpr < 32 && (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr) > 227 * 1024) s->lpr *= 2;   // the warp's replicas must fit one SM
     s->rep_trace.assign(s->R, -1);
     s->h_desc.assign(s->R, RepDesc{});
@@ -537,43 +538,46 @@ static NetCost netcost_of(const rlgs_sim *s) {
     return n;
 }
 
-// one instantiation of the fifo tick loop: LPR lanes per replica, env / rows / network-cost variants compiled apart
-template <int LPR, bool ENV, int ROWS, bool NET>
+// one instantiation of the fifo tick loop: LPR lanes per replica, packed / split node words, env / rows / network-cost variants
+template <int LPR, bool PK, bool ENV, int ROWS, bool NET>
 static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, const RowStore &rs, const EnvIO &io, cudaStream_t st) {
     constexpr int K = 32 / LPR;
     const size_t smem = K * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, LPR);
     static size_t attr_set[64] = {0};   // per device: largest dynamic shared-memory size already allowed for this instantiation
     const int dev = s->device & 63;
     if (smem > attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(fifo_grp_kernel<LPR, ENV, ROWS, NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fifo_grp_kernel<LPR, PK, ENV, ROWS, NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set[dev] = smem;
     }
-    fifo_grp_kernel<LPR, ENV, ROWS, NET><<<(count + K - 1) / K, 32, smem, st>>>(s->d_desc + first, s->d_state + first, count, s->cc, s->slot_cap, budget, rs,
-                                                                            s->d_returns + first, s->opts.max_ticks, io, netcost_of(s));
+    fifo_grp_kernel<LPR, PK, ENV, ROWS, NET><<<(count + K - 1) / K, 32, smem, st>>>(s->d_desc + first, s->d_state + first, count, s->cc, s->slot_cap, budget, rs,
+                                                                                s->d_returns + first, s->opts.max_ticks, io, netcost_of(s));
     return cudaGetLastError();
 }
 
-// the environment with per-tick rows (host-callable scheduling plugins, rlgpuschedule_b200/plugin.py): one variant only
-static cudaError_t launch_env_rows(rlgs_sim *s, int first, int count, int budget, const RowStore &rs, const EnvIO &io, cudaStream_t st) {
-    if (s->lpr != 32 || s->wire16) return cudaErrorNotSupported;   // rlgs_env_reset refuses the combination before it gets here
-    return s->opts.enable_network_costs ? launch_grp<32, true, 1, true>(s, first, count, budget, rs, io, st)
-                                        : launch_grp<32, true, 1, false>(s, first, count, budget, rs, io, st);
+// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16.  The network-cost and env-with-rows variants exist for one replica per warp only
+// (rlgs_create pins lanes_per_replica to 32 for them).
+template <int LPR, bool PK>
+static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
+    if (s->opts.enable_network_costs != 0) {
+        if (LPR != 32) return cudaErrorNotSupported;
+        if (env) return rows ? launch_grp<32, PK, true, 1, true>(s, first, count, budget, rs, io, st) : launch_grp<32, PK, true, 0, true>(s, first, count, budget, rs, io, st);
+        if (rows == 0) return launch_grp<32, PK, false, 0, true>(s, first, count, budget, rs, io, st);
+        if (rows == 1) return launch_grp<32, PK, false, 1, true>(s, first, count, budget, rs, io, st);
+        return launch_grp<32, PK, false, 2, true>(s, first, count, budget, rs, io, st);
+    }
+    if (env && rows) return LPR == 32 && !s->wire16 ? launch_grp<32, PK, true, 1, false>(s, first, count, budget, rs, io, st) : cudaErrorNotSupported;
+    if (env) return launch_grp<LPR, PK, true, 0, false>(s, first, count, budget, rs, io, st);
+    if (rows == 0) return launch_grp<LPR, PK, false, 0, false>(s, first, count, budget, rs, io, st);
+    if (rows == 1) return launch_grp<LPR, PK, false, 1, false>(s, first, count, budget, rs, io, st);
+    return launch_grp<LPR, PK, false, 2, false>(s, first, count, budget, rs, io, st);
 }
 
-// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16
 static cudaError_t launch_fifo(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
-    const bool net = s->opts.enable_network_costs != 0;
-#define RLGS_FIFO_VARIANTS(LPR)                                                                                                   \
-    if (env && rows == 0) return net ? launch_grp<LPR, true, 0, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, true, 0, false>(s, first, count, budget, rs, io, st); \
-    if (env) return launch_env_rows(s, first, count, budget, rs, io, st); \
-    if (rows == 0) return net ? launch_grp<LPR, false, 0, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 0, false>(s, first, count, budget, rs, io, st); \
-    if (rows == 1) return net ? launch_grp<LPR, false, 1, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 1, false>(s, first, count, budget, rs, io, st); \
-    return net ? launch_grp<LPR, false, 2, true>(s, first, count, budget, rs, io, st) : launch_grp<LPR, false, 2, false>(s, first, count, budget, rs, io, st);
-    if (s->lpr == 8) { RLGS_FIFO_VARIANTS(8) }
-    if (s->lpr == 16) { RLGS_FIFO_VARIANTS(16) }
-    RLGS_FIFO_VARIANTS(32)
-#undef RLGS_FIFO_VARIANTS
+    const bool pk = grp_packed(s->cc.G);
+    if (s->lpr == 8) return pk ? launch_fifo_lp<8, true>(s, first, count, budget, rows, env, io, rs, st) : launch_fifo_lp<8, false>(s, first, count, budget, rows, env, io, rs, st);
+    if (s->lpr == 16) return pk ? launch_fifo_lp<16, true>(s, first, count, budget, rows, env, io, rs, st) : launch_fifo_lp<16, false>(s, first, count, budget, rows, env, io, rs, st);
+    return pk ? launch_fifo_lp<32, true>(s, first, count, budget, rows, env, io, rs, st) : launch_fifo_lp<32, false>(s, first, count, budget, rows, env, io, rs, st);
 }
 
 static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cudaStream_t st) {
