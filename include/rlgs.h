@@ -64,8 +64,9 @@ enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1, RLGS_ROWS_DEVICE = 2 };
 /* rows_format: how a per-tick row is stored on the device and moved to the host (fifo tick loop; the other schedules always
  * use RLGS_ROWFMT_WIDE).  WIDE = rlgs_row, 64 bytes, self-contained.  WIRE16 = rlgs_row16, 16 bytes: the per-tick state that is
  * not an integral of the start / finish event stream; rlgs_read_rows expands it to rlgs_row on the host (two prefix sums over
- * the per-job tables the run produced, see rlgs_row16).  Cuts the device->host traffic of a run by 2.7x. */
-enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1 };
+ * the per-job tables the run produced, see rlgs_row16).  WIRE12 = rlgs_row12, 12 bytes: the counts leave too (they are cumulative
+ * counts of the same tables).  With opts.fetch_jobs = 2 a 60k-job run crosses PCIe as 1.24 MB instead of 4.76 MB. */
+enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1, RLGS_ROWFMT_WIRE12 = 2 };
 
 /* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
  * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
@@ -92,7 +93,9 @@ typedef struct {
                                  to / restored from HBM between launches) */
     int32_t num_queue;     /* dlas-gpu: number of MLFQ queues (README.md:57-62), 1..RLGS_MAX_QUEUES; horus+: number of job queues */
     int32_t enable_network_costs; /* --enable_network_costs (run_sim.py:54); network_service.py:3-39 */
-    int32_t fetch_jobs;    /* 1 = copy the per-job tables to the host inside rlgs_run as well */
+    int32_t fetch_jobs;    /* 1 = copy the per-job tables (start, end, finish_order) to the host inside rlgs_run as well; 2 = end and
+                              finish_order only: under fifo without network costs a finished job started at end - dur_ticks, which is
+                              what rlgs_read_jobs / the row expansion then use (the start plane stays on the device, fetched if ever needed) */
     int32_t num_buffer;    /* horus: look-ahead window, --num_buffer (run_sim.py:76); 0 = the reference default 5 */
     int32_t queue_limit[RLGS_MAX_QUEUES]; /* dlas-gpu demotion thresholds in GPU-ticks */
     double bandwidth;          /* --bandwidth MB/s (run_sim.py:59) */
@@ -166,6 +169,12 @@ typedef struct {
  * rlgs_read_rows does this expansion (int64 prefix sums, exact). */
 typedef struct { uint32_t w[4]; } rlgs_row16;
 
+/* 12-byte wire row (RLGS_ROWFMT_WIRE12): the per-tick quantities that are not functions of the event tables.
+ *   w[0]: max_pending:24 | idle_nodes[7:0]:8      w[1]: median_lo:24 | idle_nodes[11:8]:4 | 0:4      w[2]: median_hi:24 | 0:8
+ * finished(i) = #jobs with end_tick <= i + 1, started(i) = #jobs with start_tick <= i, queued = arrived(i) - started(i); the
+ * rest as for rlgs_row16.  Same limits. */
+typedef struct { uint32_t w[3]; } rlgs_row12;
+
 typedef struct {
     int64_t n_ticks;       /* rows produced (fifo: ticks; sjf/dlas: events) */
     int64_t makespan;      /* last simulated time */
@@ -229,14 +238,16 @@ int32_t rlgs_read_jobs(rlgs_sim *sim, int32_t replica, int32_t *finish_order, in
 /* Replaces the per-tick LogManager.step_cluster rows (log_manager.py:118-135): copies rows
  * [first, first+count) of `replica` (rows_mode FULL). */
 int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row *out);
-/* The same rows in the 16-byte wire format (RLGS_ROWFMT_WIRE16 handles only), without the expansion. */
+/* The same rows in the handle's wire format (RLGS_ROWFMT_WIRE16 -> rlgs_row16, RLGS_ROWFMT_WIRE12 -> rlgs_row12), without the expansion. */
 int32_t rlgs_read_rows16(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16 *out);
+int32_t rlgs_read_rows12(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row12 *out);
 /* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
  * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
  * valid until the next rlgs_run / destroy. */
 #define RLGS_ROWS_PER_CHUNK 4096
 int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);   /* RLGS_ROWFMT_WIDE */
 int32_t rlgs_rows16_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE16 */
+int32_t rlgs_rows12_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row12 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE12 */
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,

@@ -75,12 +75,14 @@ struct rlgs_sim {
     LegParams lp;
     int R = 0, device = 0;
     int lpr = 32;           // lanes of a warp per replica (fifo tick loop)
-    bool wire16 = false;    // rows are kept as rlgs_row16
+    int wire = 0;           // 0 = rows are kept as rlgs_row, 1 = rlgs_row16, 2 = rlgs_row12 (RLGS_ROWFMT_*)
+    int planes_mask = 0;    // bit k: job plane k is on the host (h_jobs)
     size_t row_bytes = sizeof(rlgs_row);
     bool env_ready = false; // rlgs_env_reset ran since the last rlgs_load_trace
     int64_t env_ticks = 0;  // upper bound of the ticks simulated since rlgs_env_reset (sizes the row store while stepping)
     int xp_replica = -1;    // replica whose prefix sums are cached below (expansion of wire rows)
     std::vector<int64_t> xp[9];
+    std::vector<int32_t> xp_start;   // start ticks of the started jobs, ascending
     bool legacy = false;
     bool pack = false;      // horus schedule + horus placement (pack_horus.cuh)
     PackParams pp;
@@ -112,7 +114,7 @@ struct rlgs_sim {
     // job planes [N_PLANES][R][Jmax]
     int32_t *d_jobs = nullptr, *h_jobs = nullptr;
     size_t jobs_bytes = 0;
-    int planes_on_host = 0;
+    bool env_used = false;  // job tables were produced by environment steps (picks inside the window: start = end - dur still holds)
     int32_t Jmax = 0;
     int64_t *d_returns = nullptr, *h_returns = nullptr;
     bool ran = false;
@@ -159,9 +161,11 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     }
     if (opts->enable_network_costs && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "network costs are implemented for the fifo tick loop only");
     if (opts->enable_network_costs && !(opts->bandwidth > 0)) return fail(RLGS_ERR_BAD_ARG, "bandwidth must be > 0");
-    if (opts->rows_format != RLGS_ROWFMT_WIDE && opts->rows_format != RLGS_ROWFMT_WIRE16) return fail(RLGS_ERR_BAD_ARG, "rows_format must be RLGS_ROWFMT_WIDE or RLGS_ROWFMT_WIRE16");
-    if (opts->rows_format == RLGS_ROWFMT_WIRE16 && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "the 16-byte wire row belongs to the fifo tick loop");
-    if (opts->rows_format == RLGS_ROWFMT_WIRE16 && N > 4095) return fail(RLGS_ERR_UNSUPPORTED, "the 16-byte wire row holds at most 4095 nodes");
+    if (opts->rows_format < RLGS_ROWFMT_WIDE || opts->rows_format > RLGS_ROWFMT_WIRE12) return fail(RLGS_ERR_BAD_ARG, "rows_format must be one of RLGS_ROWFMT_*");
+    if (opts->rows_format != RLGS_ROWFMT_WIDE && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "the wire rows belong to the fifo tick loop");
+    if (opts->rows_format != RLGS_ROWFMT_WIDE && N > 4095) return fail(RLGS_ERR_UNSUPPORTED, "a wire row holds at most 4095 nodes");
+    if (opts->fetch_jobs < 0 || opts->fetch_jobs > 2) return fail(RLGS_ERR_BAD_ARG, "fetch_jobs must be 0, 1 or 2");
+    if (opts->fetch_jobs == 2 && (sched != RLGS_SCHED_FIFO || opts->enable_network_costs)) return fail(RLGS_ERR_UNSUPPORTED, "fetch_jobs = 2 needs the fifo tick loop without network costs (start = end - dur_ticks)");
     const int lpr_in = opts->lanes_per_replica;
     if (lpr_in != 0 && lpr_in != 8 && lpr_in != 16 && lpr_in != 32) return fail(RLGS_ERR_BAD_ARG, "lanes_per_replica must be 0, 8, 16 or 32");
     int ndev = 0;
@@ -196,8 +200,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->slot_cap = opts->slot_cap > 0 ? opts->slot_cap : std::min(128, std::max(32, s->cc.D));
     s->slot_cap = (s->slot_cap + 31) & ~31;
     if (s->slot_cap > 65504) { delete s; return fail(RLGS_ERR_BAD_ARG, "slot_cap must be <= 65504"); }
-    s->wire16 = opts->rows_format == RLGS_ROWFMT_WIRE16;
-    s->row_bytes = s->wire16 ? sizeof(rlgs_row16) : sizeof(rlgs_row);
+    s->wire = opts->rows_format;
+    s->row_bytes = s->wire == RLGS_ROWFMT_WIRE16 ? sizeof(rlgs_row16) : (s->wire == RLGS_ROWFMT_WIRE12 ? sizeof(rlgs_row12) : sizeof(rlgs_row));
     // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
     // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
     s->lpr = lpr_in ? lpr_in : (s->R >= 148 * 8 * 4 ? 8 : (s->R >= 148 * 8 * 2 ? 16 : 32));
@@ -289,7 +293,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
     if (first < 0 || count < 1 || first + count > s->R) return fail(RLGS_ERR_BAD_ARG, "replica range [%d,%d) out of 0..%d", first, first + count, s->R);
     if (s->opts.enable_network_costs && (!net || !net->duration || !net->model_mb || !net->iterations))
         return fail(RLGS_ERR_BAD_ARG, "enable_network_costs needs duration / model_mb / iterations arrays");
-    if (s->wire16 && n >= (1 << 20)) return fail(RLGS_ERR_WIRE, "the 16-byte wire row counts at most 2^20 - 1 jobs: use RLGS_ROWFMT_WIDE");
+    if (s->wire && n >= (1 << 20)) return fail(RLGS_ERR_WIRE, "a wire row counts at most 2^20 - 1 jobs: use RLGS_ROWFMT_WIDE");
     CU(cudaSetDevice(s->device));
     TraceBuf tb;
     tb.n = n;
@@ -322,7 +326,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
                 for (int r = 0; r < count; ++r) s->h_desc[first + r].dur_out = old.dur_out + (size_t)r * n;
             }
             old.n = n; old.log_cap = tb.log_cap; old.max_arrival = tb.max_arrival;
-            if (s->wire16) old.host.assign(jobs, jobs + n);
+            if (s->wire || s->opts.fetch_jobs == 2) old.host.assign(jobs, jobs + n);
             s->env_ready = false; s->xp_replica = -1;
             for (int r = 0; r < count; ++r) {
                 s->h_desc[first + r].J = n; s->h_desc[first + r].log_cap = (int32_t)std::min<int64_t>(tb.log_cap, 0x7fffffff);
@@ -333,7 +337,7 @@ extern "C" int32_t rlgs_load_trace(rlgs_sim *s, int32_t first, int32_t count, co
         }
     }
     tb.cap_n = n; tb.cap_log = tb.log_cap;
-    if (s->wire16) tb.host.assign(jobs, jobs + n);
+    if (s->wire || s->opts.fetch_jobs == 2) tb.host.assign(jobs, jobs + n);
     s->env_ready = false; s->xp_replica = -1;
     CU(cudaMalloc(&tb.dev, sizeof(rlgs_job) * (size_t)n));
     cudaError_t e = cudaMemcpy(tb.dev, jobs, sizeof(rlgs_job) * (size_t)n, cudaMemcpyHostToDevice);
@@ -555,7 +559,7 @@ static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, con
     return cudaGetLastError();
 }
 
-// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16.  The network-cost and env-with-rows variants exist for one replica per warp only
+// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16, 3 = rlgs_row12.  The network-cost and env-with-rows variants exist for one replica per warp only
 // (rlgs_create pins lanes_per_replica to 32 for them).
 template <int LPR, bool PK>
 static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
@@ -564,13 +568,15 @@ static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget,
         if (env) return rows ? launch_grp<32, PK, true, 1, true>(s, first, count, budget, rs, io, st) : launch_grp<32, PK, true, 0, true>(s, first, count, budget, rs, io, st);
         if (rows == 0) return launch_grp<32, PK, false, 0, true>(s, first, count, budget, rs, io, st);
         if (rows == 1) return launch_grp<32, PK, false, 1, true>(s, first, count, budget, rs, io, st);
-        return launch_grp<32, PK, false, 2, true>(s, first, count, budget, rs, io, st);
+        if (rows == 2) return launch_grp<32, PK, false, 2, true>(s, first, count, budget, rs, io, st);
+        return launch_grp<32, PK, false, 3, true>(s, first, count, budget, rs, io, st);
     }
-    if (env && rows) return LPR == 32 && !s->wire16 ? launch_grp<32, PK, true, 1, false>(s, first, count, budget, rs, io, st) : cudaErrorNotSupported;
+    if (env && rows) return LPR == 32 && !s->wire ? launch_grp<32, PK, true, 1, false>(s, first, count, budget, rs, io, st) : cudaErrorNotSupported;
     if (env) return launch_grp<LPR, PK, true, 0, false>(s, first, count, budget, rs, io, st);
     if (rows == 0) return launch_grp<LPR, PK, false, 0, false>(s, first, count, budget, rs, io, st);
     if (rows == 1) return launch_grp<LPR, PK, false, 1, false>(s, first, count, budget, rs, io, st);
-    return launch_grp<LPR, PK, false, 2, false>(s, first, count, budget, rs, io, st);
+    if (rows == 2) return launch_grp<LPR, PK, false, 2, false>(s, first, count, budget, rs, io, st);
+    return launch_grp<LPR, PK, false, 3, false>(s, first, count, budget, rs, io, st);
 }
 
 static cudaError_t launch_fifo(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
@@ -584,7 +590,7 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
     RowStore rs; rs.chunks = rows ? s->d_chunk_ptrs : nullptr; rs.n_chunks = (int)s->d_chunks.size(); rs.replica = first;
     if (!s->legacy) {
         EnvIO none; memset(&none, 0, sizeof none);
-        launch_fifo(s, first, count, budget, rows ? (s->wire16 ? 2 : 1) : 0, false, none, rs, st);   // the caller reads cudaGetLastError
+        launch_fifo(s, first, count, budget, rows ? 1 + s->wire : 0, false, none, rs, st);   // the caller reads cudaGetLastError
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
         if (s->pack) {
@@ -661,7 +667,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     }
     if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
     std::fill(s->h_chunk_valid.begin(), s->h_chunk_valid.end(), 0);
-    s->planes_on_host = 0; s->ran = false; s->xp_replica = -1;
+    s->planes_mask = 0; s->ran = false; s->xp_replica = -1;
 
     if (!s->legacy) {
         CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
@@ -755,8 +761,13 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
     }
     if (eager_jobs) {
         size_t plane = (size_t)R * (size_t)s->Jmax;
-        CU(cudaMemcpyAsync(s->h_jobs, s->d_jobs, sizeof(int32_t) * 3 * plane, cudaMemcpyDeviceToHost, s->copy_stream));  // start, end, finish_order
-        s->planes_on_host = 3;
+        if (s->opts.fetch_jobs == 2) {   // end, finish_order: a finished fifo job started at end - dur_ticks
+            CU(cudaMemcpyAsync(s->h_jobs + plane, s->d_jobs + plane, sizeof(int32_t) * 2 * plane, cudaMemcpyDeviceToHost, s->copy_stream));
+            s->planes_mask = 6;
+        } else {
+            CU(cudaMemcpyAsync(s->h_jobs, s->d_jobs, sizeof(int32_t) * 3 * plane, cudaMemcpyDeviceToHost, s->copy_stream));  // start, end, finish_order
+            s->planes_mask = 7;
+        }
     }
     CU(cudaStreamSynchronize(s->copy_stream));
     s->last_ms = total_ms; s->last_launches = launches;
@@ -807,13 +818,32 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
     return RLGS_OK;
 }
 
+// Makes job planes [0, upto) available in h_jobs.  The start plane of a fifo handle that fetched only end + finish_order is
+// derived (start = end - dur_ticks) when every started job of every replica has finished; otherwise it is copied like the rest.
 static int32_t fetch_planes(rlgs_sim *s, int upto) {
-    if (s->planes_on_host >= upto) return RLGS_OK;
+    const int want = (1 << upto) - 1;
+    if ((s->planes_mask & want) == want) return RLGS_OK;
     if (!s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
-    size_t plane = (size_t)s->R * (size_t)s->Jmax;
-    CU(cudaMemcpy(s->h_jobs + s->planes_on_host * plane, s->d_jobs + s->planes_on_host * plane,
-                  sizeof(int32_t) * (size_t)(upto - s->planes_on_host) * plane, cudaMemcpyDeviceToHost));
-    s->planes_on_host = upto;
+    const size_t plane = (size_t)s->R * (size_t)s->Jmax;
+    if (!(s->planes_mask & 1) && (s->planes_mask & 2) && !s->legacy && !s->opts.enable_network_costs) {
+        bool derivable = true;
+        for (int r = 0; r < s->R && derivable; ++r)
+            derivable = s->h_state[r].R == 0 && (int)s->traces[s->rep_trace[r]].host.size() == s->h_desc[r].J;
+        if (derivable) {
+            for (int r = 0; r < s->R; ++r) {
+                const std::vector<rlgs_job> &jobs = s->traces[s->rep_trace[r]].host;
+                int32_t *st = s->h_jobs + (size_t)r * s->Jmax;
+                const int32_t *en = s->h_jobs + plane + (size_t)r * s->Jmax;
+                for (int i = 0; i < (int)jobs.size(); ++i) st[i] = en[i] >= 0 ? en[i] - jobs[i].dur_ticks : -1;
+            }
+            s->planes_mask |= 1;
+        }
+    }
+    for (int k = 0; k < upto; ++k)
+        if (!(s->planes_mask & (1 << k))) {
+            CU(cudaMemcpy(s->h_jobs + k * plane, s->d_jobs + k * plane, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost));
+            s->planes_mask |= 1 << k;
+        }
     return RLGS_OK;
 }
 
@@ -904,6 +934,8 @@ static int32_t prepare_expansion(rlgs_sim *s, int r) {
     for (int i = 0; i < J; ++i) if (st[i] >= 0) so.push_back(std::make_pair(st[i], i));
     std::sort(so.begin(), so.end());
     const size_t S = so.size();
+    s->xp_start.resize(S);
+    for (size_t k = 0; k < S; ++k) s->xp_start[k] = so[k].first;
     // xp[0..3]: devices, mem_term, util_mu * devices, util_sd^2 * devices in start order; xp[4]: arrival ticks in start order;
     // xp[5..8]: the first four in finish order.  Arrival ticks in trace order are summed on the fly (they are sorted).
     for (int k = 0; k < 5; ++k) s->xp[k].assign(S + 1, 0);
@@ -927,43 +959,63 @@ static int32_t prepare_expansion(rlgs_sim *s, int r) {
     return RLGS_OK;
 }
 
-extern "C" int32_t rlgs_read_rows16(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16 *out) {
+static int32_t read_wire_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, void *out, int wire) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
-    if (!s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 64-byte rows (opts.rows_format)");
+    if (s->wire != wire) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format = %d)", s->wire);
     int32_t rc = rows_args_ok(s, r, first, count);
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
     return copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(out));
 }
+extern "C" int32_t rlgs_read_rows16(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE16); }
+extern "C" int32_t rlgs_read_rows12(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row12 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE12); }
 
 extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
     int32_t rc = rows_args_ok(s, r, first, count);
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
-    if (!s->wire16) return copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(out));
-    // ---- expansion of the 16-byte wire rows (see rlgs_row16 in include/rlgs.h)
+    if (!s->wire) return copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(out));
+    // ---- expansion of the wire rows (see rlgs_row16 / rlgs_row12 in include/rlgs.h)
     rc = prepare_expansion(s, r);
     if (rc) return rc;
-    std::vector<rlgs_row16> w((size_t)count);
-    rc = copy_rows_raw(s, r, first, count, reinterpret_cast<unsigned char *>(w.data()));
+    std::vector<unsigned char> w((size_t)count * s->row_bytes);
+    rc = copy_rows_raw(s, r, first, count, w.data());
     if (rc) return rc;
     const TraceBuf &tb = s->traces[s->rep_trace[r]];
     const int J = tb.n;
+    const size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
+    const int32_t *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off;
     int64_t arrived = 0, sum_arr_all = 0;   // jobs with arrival_tick <= i and the sum of their arrival ticks
-    auto advance = [&](int64_t i) { while (arrived < J && tb.host[(size_t)arrived].arrival_tick <= i) { sum_arr_all += tb.host[(size_t)arrived].arrival_tick; ++arrived; } };
+    int64_t n_fin = 0, n_sta = 0;           // rlgs_row12: jobs with end_tick <= i + 1 (finish order is sorted by end tick), with start_tick <= i
     const int64_t S_max = (int64_t)s->xp[0].size() - 1, F_max = (int64_t)s->xp[5].size() - 1;
+    auto advance = [&](int64_t i) {
+        while (arrived < J && tb.host[(size_t)arrived].arrival_tick <= i) { sum_arr_all += tb.host[(size_t)arrived].arrival_tick; ++arrived; }
+        while (n_fin < F_max && en[fo[n_fin]] <= i + 1) ++n_fin;
+        while (n_sta < S_max && s->xp_start[(size_t)n_sta] <= i) ++n_sta;
+    };
+    if (s->wire == RLGS_ROWFMT_WIRE12 && first > 0) advance(first - 1);   // the cumulative counts are positional: catch up with the rows before `first`
     for (int64_t k = 0; k < count; ++k) {
         const int64_t i = first + k;
         advance(i);
-        const uint32_t *x = w[(size_t)k].w;
         rlgs_row &o = out[k];
-        o.idle_nodes = (int32_t)(x[0] & 0xfffu);
-        o.finished = (int32_t)(x[0] >> 12);
-        o.queued = (int32_t)(x[1] & 0xfffffu);
-        o.max_pending = (int32_t)((x[1] >> 20) | ((x[2] & 0xfffu) << 12));
-        o.median_lo = (int32_t)((x[2] >> 12) | ((x[3] & 0xfu) << 20));
-        o.median_hi = (int32_t)((x[3] >> 4) & 0xffffffu);
+        if (s->wire == RLGS_ROWFMT_WIRE16) {
+            const uint32_t *x = reinterpret_cast<const rlgs_row16 *>(w.data())[k].w;
+            o.idle_nodes = (int32_t)(x[0] & 0xfffu);
+            o.finished = (int32_t)(x[0] >> 12);
+            o.queued = (int32_t)(x[1] & 0xfffffu);
+            o.max_pending = (int32_t)((x[1] >> 20) | ((x[2] & 0xfffu) << 12));
+            o.median_lo = (int32_t)((x[2] >> 12) | ((x[3] & 0xfu) << 20));
+            o.median_hi = (int32_t)((x[3] >> 4) & 0xffffffu);
+        } else {
+            const uint32_t *x = reinterpret_cast<const rlgs_row12 *>(w.data())[k].w;
+            o.max_pending = (int32_t)(x[0] & 0xffffffu);
+            o.median_lo = (int32_t)(x[1] & 0xffffffu);
+            o.median_hi = (int32_t)(x[2] & 0xffffffu);
+            o.idle_nodes = (int32_t)((x[0] >> 24) | (((x[1] >> 24) & 0xfu) << 8));
+            o.finished = (int32_t)n_fin;
+            o.queued = (int32_t)(arrived - n_sta);
+        }
         const int64_t Fi = o.finished, Q = o.queued, Ri = arrived - Q - Fi, Si = Ri + Fi;
         if (Ri < 0 || Si > S_max || Fi > F_max) return fail(RLGS_ERR_STATE, "row %lld of replica %d is inconsistent with the job tables", (long long)i, r);
         o.running = (int32_t)Ri;
@@ -995,13 +1047,19 @@ static int32_t rows_view_any(rlgs_sim *s, int32_t r, int32_t chunk, const void *
 
 extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row **rows, int64_t *count) {
     if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
-    if (s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 16-byte wire rows: use rlgs_rows16_view, or rlgs_read_rows for expanded rows");
+    if (s->wire) return fail(RLGS_ERR_STATE, "the handle keeps wire rows: use rlgs_rows16_view / rlgs_rows12_view, or rlgs_read_rows for expanded rows");
     return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 
 extern "C" int32_t rlgs_rows16_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row16 **rows, int64_t *count) {
     if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
-    if (!s->wire16) return fail(RLGS_ERR_STATE, "the handle keeps 64-byte rows (opts.rows_format)");
+    if (s->wire != RLGS_ROWFMT_WIRE16) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
+    return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
+}
+
+extern "C" int32_t rlgs_rows12_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row12 **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->wire != RLGS_ROWFMT_WIRE12) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
     return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 
@@ -1039,7 +1097,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr);
     if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp", smem);
     if (s->opts.rows_mode != RLGS_ROWS_NONE) {   // per-tick rows while stepping: 64-byte rows, one replica per warp
-        if (s->lpr != 32 || s->wire16) return fail(RLGS_ERR_UNSUPPORTED, "environment steps with rows need lanes_per_replica = 32 and RLGS_ROWFMT_WIDE");
+        if (s->lpr != 32 || s->wire) return fail(RLGS_ERR_UNSUPPORTED, "environment steps with rows need lanes_per_replica = 32 and RLGS_ROWFMT_WIDE");
         if (s->opts.rows_mode != RLGS_ROWS_DEVICE) return fail(RLGS_ERR_UNSUPPORTED, "environment steps keep their rows on the device (RLGS_ROWS_DEVICE)");
         rc = add_chunks(s, std::max<int>(1, (int)s->d_chunks.size()), false);
         if (rc) return rc;
@@ -1058,7 +1116,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * s->R, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, st));
     CU(cudaStreamSynchronize(st));   // h_init / h_desc may be rewritten by the caller's next call
-    s->planes_on_host = 0; s->ran = false; s->env_ready = true;
+    s->planes_mask = 0; s->ran = false; s->env_ready = true;
     return RLGS_OK;
 }
 
@@ -1118,7 +1176,7 @@ extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
         s->h_returns[r] = -s->h_state[r].sum_jct;
         if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
     }
-    s->planes_on_host = 0; s->ran = true;
+    s->planes_mask = 0; s->ran = true;
     return RLGS_OK;
 }
 

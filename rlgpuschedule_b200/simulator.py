@@ -21,16 +21,18 @@ class Simulator(object):
         pack_seed: None = utilisation draws of the horus score return their mean (the reference's behaviour on
         zero-spread traces); an int seeds the build-defined counter-based draw.  horus+: pack_seed also seeds the k-means draws
         (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded.
-        rows_format: 'wire16' (default for fifo) keeps 16-byte rows on the device / the wire and expands them in rows();
-        'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto."""
+        rows_format: 'wire12' (default for fifo) / 'wire16' keep 12- / 16-byte rows on the device and on the wire and expand them
+        in rows(); 'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto.
+        fetch_jobs: True = start / end / finish_order tables copied to the host inside run(); 'end' = end and finish_order only
+        (fifo without network costs: a finished job started at end - dur_ticks)."""
         if schedule not in _ffi.SCHED:
             raise NotImplementedError('schedule %r has no device implementation' % (schedule,))
         if scheme not in _ffi.PLACE:
             raise NotImplementedError('placement scheme %r has no device implementation' % (scheme,))
         if rows_format is None:
-            rows_format = 'wire16' if (schedule == 'fifo' and cluster.num_nodes <= 4095) else 'wide'
-        if rows_format not in ('wire16', 'wide'):
-            raise ValueError('rows_format must be wire16 or wide')
+            rows_format = 'wire12' if (schedule == 'fifo' and cluster.num_nodes <= 4095) else 'wide'
+        if rows_format not in _ffi.ROWFMT:
+            raise ValueError('rows_format must be one of %s' % sorted(_ffi.ROWFMT))
         self.cluster = cluster
         self.n_replicas = n_replicas
         self.rows_mode = rows
@@ -54,14 +56,14 @@ class Simulator(object):
         o.schedule = _ffi.SCHED[k['schedule']]; o.placement = _ffi.PLACE[k['scheme']]
         o.rows_mode = (_ffi.ROWS_DEVICE if k['rows'] == 'device' else _ffi.ROWS_FULL) if k['rows'] else _ffi.ROWS_NONE
         o.slot_cap = self._slot_cap; o.n_streams = k['n_streams']; o.ticks_per_launch = k['ticks_per_launch']
-        o.rows_cap = k['rows_cap']; o.fetch_jobs = int(bool(k['fetch_jobs'])); o.num_queue = k['num_queue']
+        o.rows_cap = k['rows_cap']; o.fetch_jobs = 2 if k['fetch_jobs'] == 'end' else int(bool(k['fetch_jobs'])); o.num_queue = k['num_queue']
         for i, v in enumerate(k['queue_limit'][:_ffi.MAX_QUEUES]):
             o.queue_limit[i] = int(v)
         o.enable_network_costs = int(bool(k['enable_network_costs']))
         o.bandwidth = float(k['bandwidth']); o.internode_latency = float(k['internode_latency'])
         o.max_ticks = int(k['max_ticks'])
         o.num_buffer = int(k['num_buffer']); o.pack_rng = int(k['pack_rng']); o.pack_seed = int(k['pack_seed'] or 0)
-        o.rows_format = _ffi.ROWFMT_WIRE16 if k['rows_format'] == 'wire16' else _ffi.ROWFMT_WIDE
+        o.rows_format = _ffi.ROWFMT[k['rows_format']]
         o.lanes_per_replica = k['lanes_per_replica']
         spec = self.cluster.to_ffi()
         h = C.c_void_p()
@@ -89,7 +91,7 @@ class Simulator(object):
                                      trace.iterations.ctypes.data_as(dp))
         rc = _ffi.lib().rlgs_load_trace(self._h, first_replica, n_replicas, rec.ctypes.data, len(rec),
                                         C.byref(net) if net is not None else None)
-        if rc == _ffi.ERR_WIRE and self._kw['rows_format'] == 'wire16':
+        if rc == _ffi.ERR_WIRE and self._kw['rows_format'] != 'wide':
             self._rebuild(rows_format='wide')   # more jobs than the wire row can count: self-contained rows
             return self.load_trace(trace, first_replica, n_replicas)
         _ffi.check(rc)
@@ -131,7 +133,7 @@ class Simulator(object):
                     _ffi.check(rc)
                 self._rebuild(slot_cap=cap)
                 continue
-            if rc == _ffi.ERR_WIRE and self._kw['rows_format'] == 'wire16':
+            if rc == _ffi.ERR_WIRE and self._kw['rows_format'] != 'wide':
                 self._rebuild(rows_format='wide')   # a run longer than 2^24 ticks: self-contained rows
                 continue
             _ffi.check(rc)
@@ -172,22 +174,26 @@ class Simulator(object):
 
     def rows_chunk_view(self, replica, chunk):
         """Zero-copy numpy view of one 4096-row chunk of a replica in the pinned host mirror: ROW_DTYPE for 'wide' handles,
-        ROW16_DTYPE (the packed wire rows, see rlgs_row16 in include/rlgs.h) for 'wire16' handles."""
+        ROW16_DTYPE / ROW12_DTYPE (the packed wire rows, see include/rlgs.h) for 'wire16' / 'wire12' handles."""
         p, n = C.c_void_p(), C.c_int64(0)
-        wire = self._kw['rows_format'] == 'wire16'
-        fn = _ffi.lib().rlgs_rows16_view if wire else _ffi.lib().rlgs_rows_view
-        dt = _ffi.ROW16_DTYPE if wire else _ffi.ROW_DTYPE
+        L = _ffi.lib()
+        fn, dt = {'wide': (L.rlgs_rows_view, _ffi.ROW_DTYPE), 'wire16': (L.rlgs_rows16_view, _ffi.ROW16_DTYPE),
+                  'wire12': (L.rlgs_rows12_view, _ffi.ROW12_DTYPE)}[self._kw['rows_format']]
         _ffi.check(fn(self._h, replica, chunk, C.byref(p), C.byref(n)))
         buf = (C.c_char * (n.value * dt.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=dt, count=n.value)
 
-    def rows16(self, replica=0):
-        """The packed 16-byte wire rows of a replica ('wire16' handles), unexpanded."""
+    def rows_wire(self, replica=0):
+        """The packed wire rows of a replica ('wire16' / 'wire12' handles), unexpanded."""
         n = self.summary(replica)['n_ticks']
-        out = np.zeros(n, _ffi.ROW16_DTYPE)
+        L = _ffi.lib()
+        fn, dt = {'wire16': (L.rlgs_read_rows16, _ffi.ROW16_DTYPE), 'wire12': (L.rlgs_read_rows12, _ffi.ROW12_DTYPE)}[self._kw['rows_format']]
+        out = np.zeros(n, dt)
         if n:
-            _ffi.check(_ffi.lib().rlgs_read_rows16(self._h, replica, 0, n, out.ctypes.data))
+            _ffi.check(fn(self._h, replica, 0, n, out.ctypes.data))
         return out
+
+    rows16 = rows_wire
 
     def durations(self, replica=0):
         """Per-job duration after network costs (enable_network_costs only)."""

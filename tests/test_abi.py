@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_ffi.ClusterSpec) == 24
     assert C.sizeof(_ffi.Summary) == 6 * 8 + 8 * 4
     assert C.sizeof(_ffi.Opts) == 12 * 4 + 8 * 4 + 2 * 8 + 2 * 8 + 2 * 4 + 2 * 4
-    assert _ffi.ROW16_DTYPE.itemsize == 16
+    assert _ffi.ROW16_DTYPE.itemsize == 16 and _ffi.ROW12_DTYPE.itemsize == 12
     assert C.sizeof(_ffi.PackInputs) == 4 * 8 + 2 * 4 + 3 * 8
 
 

@@ -14,7 +14,7 @@ from rlgpuschedule_b200 import _ffi, log_manager as lm
 pytestmark = pytest.mark.gpu
 
 LPRS = (8, 16, 32)
-FORMATS = ('wire16', 'wide')
+FORMATS = ('wire12', 'wire16', 'wide')
 
 
 def _csvs(sim, cluster, tr, r):
@@ -78,13 +78,20 @@ def test_wire_rows_expand_to_the_wide_rows(lpr):
         sim.run()
         rows[fmt] = sim.rows(3)
         if fmt == 'wire16':
-            w = sim.rows16(3)['w']
+            w = sim.rows_wire(3)['w']
             assert np.array_equal(w[:, 0] & 0xfff, rows[fmt]['idle_nodes']) and np.array_equal(w[:, 0] >> 12, rows[fmt]['finished'])
             assert np.array_equal(sim.rows_chunk_view(3, 0)['w'], w[:4096])
+        if fmt == 'wire12':
+            w = sim.rows_wire(3)['w']
+            assert w.shape[1] == 3 and np.array_equal(w[:, 0] & 0xffffff, rows[fmt]['max_pending']) and np.array_equal(w[:, 2], rows[fmt]['median_hi'])
+            part = np.zeros(50, _ffi.ROW_DTYPE)          # a sub-range: the cumulative counts must not depend on where reading starts
+            _ffi.check(_ffi.lib().rlgs_read_rows(sim._h, 3, 100, 50, part.ctypes.data))
+            assert np.array_equal(part, rows[fmt][100:150])
         sim.close()
-    assert rows['wide'].dtype == rows['wire16'].dtype == _ffi.ROW_DTYPE
+    assert rows['wide'].dtype == rows['wire16'].dtype == rows['wire12'].dtype == _ffi.ROW_DTYPE
     for f in _ffi.ROW_DTYPE.names:
         assert np.array_equal(rows['wide'][f], rows['wire16'][f]), f
+        assert np.array_equal(rows['wide'][f], rows['wire12'][f]), f
     assert rows['wide']['busy_gpus'].max() > 0 and rows['wide']['sum_pending'].max() > 0 and rows['wide']['util_var_sum'].max() > 0
 
 
@@ -143,4 +150,23 @@ def test_slot_overflow_has_its_own_status_code():
     assert _ffi.lib().rlgs_run(sim._h) == _ffi.ERR_SLOTS                        # also with max_ticks set (round-1 advisor finding)
     sim.run()                                                                   # the wrapper regrows the table from the code
     assert sim.summary(0)['max_running'] > 32
+    sim.close()
+
+
+@pytest.mark.parametrize('fmt', FORMATS)
+def test_end_only_job_tables_derive_the_start_ticks(fmt):
+    """fetch_jobs='end' moves end ticks and the finish order to the host inside run(); a finished fifo job started at
+    end - dur_ticks, which jobs() and the row expansion then use.  Must equal the three-table path and the oracle."""
+    flags = dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)
+    cluster = rl.cluster_from_flags(flags)
+    df = tracegen.frame_gen(500, 13, 70)
+    tr = rl.prepare_trace(df, cluster)
+    o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df))
+    sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=5, rows=True, rows_format=fmt, fetch_jobs='end')
+    sim.load_trace(tr)
+    sim.run()
+    for r in (0, 4):
+        j = sim.jobs(r)
+        assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end']) and np.array_equal(j['finish_order'], o['finish_order'])
+        assert lm.format_cluster_csv(sim.rows(r), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
     sim.close()
