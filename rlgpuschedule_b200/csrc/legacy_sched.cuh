@@ -502,10 +502,79 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
         }
         // ---- pass in priority order: (fused: drop ended jobs, sweep,) re-place, flip, minima
         const int M0 = st.M;
+        // Unit jobs (one GPU, one task, a device accepts it) lead the sjf order, and on the emptied cluster the first-fit of a run
+        // of them is known in closed form: the r-th one lands on node r / c_node, device r % c_node, c_node = min(GPUs, task units)
+        // per node.  While nothing else has been placed yet, a whole chunk of them is handled lane-parallel (one entry per lane
+        // instead of one entry per warp step); the node arrays are materialised from the count before the first ordinary
+        // placement and before the row statistics.
+        const int c_node = min(c.G, c.base_units), unit_cap = c_node * c.N;
+        bool pure = fused;          // every entry placed so far in this event was a unit job
+        int unit_count = 0;         // unit jobs placed so far
+        auto materialise = [&]() {
+            for (int i = lane; i < c.N; i += 32) {
+                const int placed = min(max(unit_count - i * c_node, 0), c_node);
+                nv.units[i] = placed; nv.busy[i] = placed >= 32 ? 0xffffffffu : ((1u << placed) - 1u); nv.key[i] = node_key(placed, nv.busy[i], c);
+            }
+            int nf = 0;
+            for (int b2 = 0; b2 < c.N; b2 += 32) {
+                const int i = b2 + lane;
+                nf += __popc(__ballot_sync(RLGS_FULL, i < c.N && node_is_free(min(max(unit_count - i * c_node, 0), c_node), c)));
+            }
+            n_free_nodes = nf;
+            __syncwarp();
+        };
         for (int b = 0; b < M0; b += 32) {
             const int cnt = min(32, M0 - b);
             Ent mine; mine.a = mine.b = make_int4(0, 0, 0, 0);
             if (lane < cnt) mine = load_ent(src + b + lane);
+            if (pure) {
+                const bool unit = lane >= cnt || (mine.b.x == (1 | (1 << 16)) && (mine.b.w & 0xffff) == 1 && (mine.b.w >> 31));
+                if (__all_sync(RLGS_FULL, unit)) {
+                    // ---- a chunk of unit jobs, one entry per lane (same effects as the ordinary loop below, in the same order)
+                    const bool valid = lane < cnt;
+                    Ent e = mine;
+                    const int job = e.job();
+                    const bool ended = valid && e.status() == L_RUNNING && st.t_prev + e.a.z - e.a.w == event_time;     // :198-204
+                    const unsigned eb = __ballot_sync(RLGS_FULL, ended);
+                    if (ended) {
+                        D.planes[1][job] = event_time; D.planes[3][job] = e.b.y;
+                        D.planes[4][job] = e.b.z & 0xffff; D.planes[5][job] = (e.b.z >> 16) & 0xffff;
+                        D.planes[2][st.F + __popc(eb & ((1u << lane) - 1))] = job;
+                    }
+                    int64_t jct = ended ? event_time - D.trace[job].arrival_tick : 0;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) jct += __shfl_xor_sync(RLGS_FULL, jct, o);
+                    st.sum_jct += jct; st.F += __popc(eb); n_events += __popc(eb);
+                    const bool stay = valid && !ended;
+                    if (stay) {
+                        if (e.a.y & (1 << 23)) e.a.y &= ~(1 << 23);                                              // last_check_time == event_time
+                        else if (e.status() == L_RUNNING) e.a.w += d; else e.b.y += d;                           // :216-230
+                    }
+                    const unsigned sb = __ballot_sync(RLGS_FULL, stay);
+                    const bool ok = stay && unit_count + __popc(sb & ((1u << lane) - 1)) < unit_cap;               // :246 first fit in closed form
+                    unit_count += __popc(__ballot_sync(RLGS_FULL, ok));
+                    bool flipped = false;
+                    if (ok) {
+                        if (!e.started()) { e.set_started(); D.planes[0][job] = event_time; }                     // :251-252
+                        if (e.status() == L_PENDING) { e.set_status(L_RUNNING); e.b.z += 1 << 16; flipped = true; }   // :265-267
+                    } else if (stay && e.status() == L_RUNNING) {
+                        e.set_status(L_PENDING); e.b.z = (e.b.z & ~0xffff) | ((e.b.z + 1) & 0xffff); flipped = true;  // :262-264
+                    }
+                    n_events += __popc(__ballot_sync(RLGS_FULL, flipped));
+                    const bool running = stay && e.status() == L_RUNNING;
+                    n_run += __popc(__ballot_sync(RLGS_FULL, running)); n_pend += __popc(__ballot_sync(RLGS_FULL, stay && !running));
+                    int le = running ? event_time + e.a.z - e.a.w : RLGS_NEVER;                                   // :270-284
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) le = min(le, __shfl_xor_sync(RLGS_FULL, le, o));
+                    new_end = min(new_end, le);
+                    if (stay) store_ent(buf + w_out + __popc(sb & ((1u << lane) - 1)), e);
+                    w_out += __popc(sb);
+                    __syncwarp();
+                    continue;
+                }
+                materialise();      // the first chunk with another kind of job: continue on real node state
+                pure = false;
+            }
             bool keep = false;
             for (int k = 0; k < cnt; ++k) {
                 Ent e; e.a = shfl_int4(mine.a, k); e.b = shfl_int4(mine.b, k);
@@ -542,6 +611,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
             w_out += __popc(kb);
             __syncwarp();
         }
+        if (pure && unit_count > 0) materialise();   // the row statistics below read the node arrays
         st.sweep_jobs += w_out;  // runnable jobs swept at this event (after ends left and arrivals joined)
         st.M = w_out;
         if (st.M > st.max_m) st.max_m = st.M;
