@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
         // of them is known in closed form: the r-th one lands on node r / c_node, device r % c_node, c_node = min(GPUs, task units)
         // per node.  While nothing else has been placed yet, a whole chunk of them is handled lane-parallel (one entry per lane
         // instead of one entry per warp step); the node arrays are materialised from the count before the first ordinary
-        // placement and before the row statistics.
+        // placement and before the row statistics.  A chunk that starts with unit jobs and continues with others is split.
         const int c_node = min(c.G, c.base_units), unit_cap = c_node * c.N;
         bool pure = fused;          // every entry placed so far in this event was a unit job
         int unit_count = 0;         // unit jobs placed so far
@@ -527,11 +527,14 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
             const int cnt = min(32, M0 - b);
             Ent mine; mine.a = mine.b = make_int4(0, 0, 0, 0);
             if (lane < cnt) mine = load_ent(src + b + lane);
+            int k0 = 0;                 // entries of this chunk already handled by the lane-parallel path
             if (pure) {
-                const bool unit = lane >= cnt || (mine.b.x == (1 | (1 << 16)) && (mine.b.w & 0xffff) == 1 && (mine.b.w >> 31));
-                if (__all_sync(RLGS_FULL, unit)) {
-                    // ---- a chunk of unit jobs, one entry per lane (same effects as the ordinary loop below, in the same order)
-                    const bool valid = lane < cnt;
+                const bool unit = lane < cnt && mine.b.x == (1 | (1 << 16)) && (mine.b.w & 0xffff) == 1 && (mine.b.w >> 31);
+                const unsigned nb = ~__ballot_sync(RLGS_FULL, unit);
+                const int up = nb ? __ffs(nb) - 1 : 32;     // leading unit jobs of the chunk
+                if (up > 0) {
+                    // ---- a run of unit jobs, one entry per lane (same effects as the ordinary loop below, in the same order)
+                    const bool valid = lane < up;
                     Ent e = mine;
                     const int job = e.job();
                     const bool ended = valid && e.status() == L_RUNNING && st.t_prev + e.a.z - e.a.w == event_time;     // :198-204
@@ -570,13 +573,14 @@ __global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict_
                     if (stay) store_ent(buf + w_out + __popc(sb & ((1u << lane) - 1)), e);
                     w_out += __popc(sb);
                     __syncwarp();
-                    continue;
+                    if (up >= cnt) continue;
+                    k0 = up;
                 }
-                materialise();      // the first chunk with another kind of job: continue on real node state
+                materialise();      // another kind of job follows: continue on real node state
                 pure = false;
             }
             bool keep = false;
-            for (int k = 0; k < cnt; ++k) {
+            for (int k = k0; k < cnt; ++k) {
                 Ent e; e.a = shfl_int4(mine.a, k); e.b = shfl_int4(mine.b, k);
                 const int job = e.job();
                 int status = e.status();

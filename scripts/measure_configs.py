@@ -1,4 +1,4 @@
-"""Measures BASELINE.json's five configurations on one GPU and writes profiles/r01_configs.json.
+"""Measures BASELINE.json's five configurations on one GPU and writes profiles/r02_configs.json.
 (C5's 8-GPU layout is exercised by bench.py under torchrun; here its per-GPU share of 512 replicas is run.)"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,7 +26,7 @@ out['C1 fifo+yarn 1x4x8 100 jobs, 1 replica'] = dict(wall_ms=w * 1e3, kernel_ms=
 sim.close()
 # C2 sjf + yarn 10k
 tr = rl.prepare_trace(tracegen.frame_gen(10000, 2, 10000), C4)
-for R in (1, 2960):
+for R in (1, 2368):
     sim = rl.Simulator(C4, 'sjf', 'yarn', n_replicas=R, rows='device'); sim.load_trace(tr)
     w = timed(sim.run, 2); s = sim.summary(0); ms, _ = sim.kernel_ms()
     out['C2 sjf+yarn 4x32x8 10k jobs, %d replica(s)' % R] = dict(wall_ms=w * 1e3, kernel_ms=ms, event_rows=s['n_ticks'], events=s['events'], events_per_s=s['events'] * R / w,
@@ -59,5 +59,10 @@ for _ in range(2000): env.step(a)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 out['C4 env step API (external actions, 1 launch per tick) 512 replicas'] = dict(us_per_step=dt / 2000 * 1e6, env_steps_per_s=512 * 2000 / dt)
 env.close()
-json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'r01_configs.json'), 'w'), indent=1)
+# C4 with enough environment replicas to fill the GPU (4 per warp)
+env = Environment(C4, tr10, n_replicas=8880, window_k=5, seed=1)
+w = timed(lambda: (env.reset(), env.rollout('random'), env.sync())); s = env.sim.summary(0)
+out['env rollout (random window policy on device) 8880 replicas x 10k jobs'] = dict(wall_ms=w * 1e3, ticks=s['n_ticks'], env_steps_per_s=8880 * s['n_ticks'] / w, events_per_s=8880 * s['events'] / w)
+env.close()
+json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'r02_configs.json'), 'w'), indent=1)
 print(json.dumps(out, indent=1))
