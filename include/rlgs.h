@@ -65,8 +65,13 @@ enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1, RLGS_ROWS_DEVICE = 2 };
  * use RLGS_ROWFMT_WIDE).  WIDE = rlgs_row, 64 bytes, self-contained.  WIRE16 = rlgs_row16, 16 bytes: the per-tick state that is
  * not an integral of the start / finish event stream; rlgs_read_rows expands it to rlgs_row on the host (two prefix sums over
  * the per-job tables the run produced, see rlgs_row16).  WIRE12 = rlgs_row12, 12 bytes: the counts leave too (they are cumulative
- * counts of the same tables).  With opts.fetch_jobs = 2 a 60k-job run crosses PCIe as 1.24 MB instead of 4.76 MB. */
-enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1, RLGS_ROWFMT_WIRE12 = 2 };
+ * counts of the same tables).  With opts.fetch_jobs = 2 a 60k-job run crosses PCIe as 1.24 MB instead of 4.76 MB.
+ * EVENT16 = rlgs_row16e, 16 bytes: the 12-byte row plus the tick's start event (at most one job starts per tick,
+ * schedule.py:188-190).  The row stream then IS the event log: without network costs a job ends dur_ticks after it started and
+ * jobs finish in (end tick, start tick) order, so rlgs_read_jobs / rlgs_read_rows rebuild the per-job tables from the rows of the
+ * replica when they were not copied (opts.fetch_jobs = 0), and a run crosses PCIe as 16 bytes per tick, all of it while the
+ * simulation is still running. */
+enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1, RLGS_ROWFMT_WIRE12 = 2, RLGS_ROWFMT_EVENT16 = 3 };
 
 /* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
  * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
@@ -175,6 +180,13 @@ typedef struct { uint32_t w[4]; } rlgs_row16;
  * rest as for rlgs_row16.  Same limits. */
 typedef struct { uint32_t w[3]; } rlgs_row12;
 
+/* 16-byte event row (RLGS_ROWFMT_EVENT16): w[0..2] as rlgs_row12, w[3] = 1 + trace index of the job that started at this
+ * tick (row i: start_tick = i), 0 = none.  Derived on the host when the tables were not copied (fifo without network costs):
+ * end_tick = start_tick + dur_ticks, finish_order = the started jobs sorted by (end_tick, start_tick) — the order in which
+ * release_finished_jobs walks running_jobs (schedule.py:141-162).  The device keeps its own tables (rlgs_opts.fetch_jobs = 1 copies
+ * them; tests compare both). */
+typedef struct { uint32_t w[4]; } rlgs_row16e;
+
 typedef struct {
     int64_t n_ticks;       /* rows produced (fifo: ticks; sjf/dlas: events) */
     int64_t makespan;      /* last simulated time */
@@ -241,6 +253,7 @@ int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t co
 /* The same rows in the handle's wire format (RLGS_ROWFMT_WIRE16 -> rlgs_row16, RLGS_ROWFMT_WIRE12 -> rlgs_row12), without the expansion. */
 int32_t rlgs_read_rows16(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16 *out);
 int32_t rlgs_read_rows12(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row12 *out);
+int32_t rlgs_read_rows16e(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16e *out);
 /* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
  * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
  * valid until the next rlgs_run / destroy. */
@@ -248,6 +261,7 @@ int32_t rlgs_read_rows12(rlgs_sim *sim, int32_t replica, int64_t first, int64_t 
 int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row **rows, int64_t *count);   /* RLGS_ROWFMT_WIDE */
 int32_t rlgs_rows16_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE16 */
 int32_t rlgs_rows12_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row12 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE12 */
+int32_t rlgs_rows16e_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16e **rows, int64_t *count); /* RLGS_ROWFMT_EVENT16 */
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,

@@ -387,7 +387,8 @@ __device__ __noinline__ unsigned char *row_address(const RowStore &rs, int rep, 
 // i.e. the groups simply took turns).  Rare paths — a job wider than a node, the q8 leak, an arrival batch longer than the
 // register ring, the environment's queue.pop(pick) — stay group-local inside per-group branches.
 #define RLGS_FULLMASK 0xffffffffu
-// ROWS: 0 = no rows, 1 = 64-byte rlgs_row per tick, 2 = 16-byte rlgs_row16 per tick, 3 = 12-byte rlgs_row12 per tick
+// ROWS: 0 = no rows, 1 = 64-byte rlgs_row per tick, 2 = 16-byte rlgs_row16 per tick, 3 = 12-byte rlgs_row12 per tick,
+//       4 = 16-byte rlgs_row16e per tick (row12 + the tick's start event)
 template <int LPR, bool PK, bool ENV, int ROWS, bool NET>
 __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const RepDesc *__restrict__ descs, RepState *__restrict__ states, int n_rep,
                                                                            ClusterConst c, int slot_cap, int tick_budget, RowStore rs,
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
     if (ENV && valid && !act && writer) { env.reward[rep] = 0.f; env.done[rep] = 1; }
     const GrpSm s = grp_carve(smem_raw + (size_t)G.g * grp_smem_bytes(c.N, c.G, slot_cap, LPR), c.N, c.G, slot_cap, LPR);
     float reward_acc = 0.f;
-    constexpr int ROW_BYTES = ROWS == 2 ? 16 : (ROWS == 3 ? 12 : 64);
+    constexpr int ROW_BYTES = (ROWS == 2 || ROWS == 4) ? 16 : (ROWS == 3 ? 12 : 64);
     unsigned char *row_cur = nullptr;   // next row of this replica inside the current chunk
     int rows_left = 0;                  // rows that still fit the chunk behind row_cur
     if (ROWS && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)   // the launch stops when the allocated chunks are full
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
 
         // ---------------- one scheduling attempt (schedule.py:188-190): the queue head, or the policy's pick inside the window
         int pick = 0;
+        int started = 0;   // 1 + the job started at this tick (rlgs_row16e)
         bool attempt;
         if (!ENV) attempt = act && st.Q > 0 && !st.head_blocked;
         else {
@@ -570,6 +572,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                     if (writer) { D.start_tick[job] = d; D.place_off[job] = st.log_len; }
                     st.log_len += pr.nnodes;
                     st.start_seq += 1;
+                    started = job + 1;
                     if (ROWS == 1) {
                         const int ndev = T * gpc;
                         st.busy_gpus += ndev;
@@ -674,10 +677,10 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                 const int maxp = st.Q > 0 ? st.d - st.bottom_arr : 0, mlo = st.Q > 0 ? st.d - med_lo_arr : 0, mhi = st.Q > 0 ? st.d - med_hi_arr : 0;
                 if (ROWS == 2) {
                     if (writer) *reinterpret_cast<int4 *>(row_cur) = pack_row16(st.idle_nodes, st.F, st.Q, maxp, mlo, mhi);
-                } else if (ROWS == 3) {   // rlgs_row12: lanes 0..2 of the group store one word each
+                } else if (ROWS == 3 || ROWS == 4) {   // rlgs_row12 / rlgs_row16e: lanes 0..2 (0..3) of the group store one word each
                     const uint32_t idle = (uint32_t)st.idle_nodes;
-                    const uint32_t wv = G.gl == 0 ? ((uint32_t)maxp | (idle << 24)) : (G.gl == 1 ? ((uint32_t)mlo | ((idle >> 8) << 24)) : (uint32_t)mhi);
-                    if (G.gl < 3) reinterpret_cast<uint32_t *>(row_cur)[G.gl] = wv;
+                    const uint32_t wv = G.gl == 0 ? ((uint32_t)maxp | (idle << 24)) : (G.gl == 1 ? ((uint32_t)mlo | ((idle >> 8) << 24)) : (G.gl == 2 ? (uint32_t)mhi : (uint32_t)started));
+                    if (G.gl < (ROWS == 4 ? 4 : 3)) reinterpret_cast<uint32_t *>(row_cur)[G.gl] = wv;
                 } else if (writer) {
                     const int64_t sp = (int64_t)st.Q * st.d - st.sum_arr;
                     int4 *o = reinterpret_cast<int4 *>(row_cur);

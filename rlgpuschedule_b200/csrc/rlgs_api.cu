@@ -75,7 +75,8 @@ struct rlgs_sim {
     LegParams lp;
     int R = 0, device = 0;
     int lpr = 32;           // lanes of a warp per replica (fifo tick loop)
-    int wire = 0;           // 0 = rows are kept as rlgs_row, 1 = rlgs_row16, 2 = rlgs_row12 (RLGS_ROWFMT_*)
+    int wire = 0;           // 0 = rows are kept as rlgs_row, 1 = rlgs_row16, 2 = rlgs_row12, 3 = rlgs_row16e (RLGS_ROWFMT_*)
+    std::vector<char> derived;   // per replica: job planes 0..2 in h_jobs were rebuilt from the event rows
     int planes_mask = 0;    // bit k: job plane k is on the host (h_jobs)
     size_t row_bytes = sizeof(rlgs_row);
     bool env_ready = false; // rlgs_env_reset ran since the last rlgs_load_trace
@@ -113,6 +114,7 @@ struct rlgs_sim {
     rlgs_row **d_chunk_ptrs = nullptr;
     // job planes [N_PLANES][R][Jmax]
     int32_t *d_jobs = nullptr, *h_jobs = nullptr;
+    bool h_jobs_pinned = false;   // pinned when rlgs_run copies tables itself (opts.fetch_jobs); pageable (lazily committed) when only read on demand
     size_t jobs_bytes = 0;
     bool env_used = false;  // job tables were produced by environment steps (picks inside the window: start = end - dur still holds)
     int32_t Jmax = 0;
@@ -123,10 +125,26 @@ struct rlgs_sim {
     int64_t rows_hint = 0;   // rows of the longest replica in the previous run: sizes the speculative pipeline
 };
 
+static void free_host_jobs(rlgs_sim *s) {
+    if (!s->h_jobs) return;
+    if (s->h_jobs_pinned) cudaFreeHost(s->h_jobs); else free(s->h_jobs);
+    s->h_jobs = nullptr;
+}
+static int32_t alloc_host_jobs(rlgs_sim *s, bool pinned) {
+    if (s->h_jobs && (s->h_jobs_pinned || !pinned)) return RLGS_OK;
+    free_host_jobs(s);
+    if (pinned) { CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes)); }
+    else { s->h_jobs = static_cast<int32_t *>(calloc(s->jobs_bytes, 1)); if (!s->h_jobs) return fail(RLGS_ERR_OOM, "host allocation of the job tables failed"); }
+    s->h_jobs_pinned = pinned;
+    return RLGS_OK;
+}
+
 extern "C" int32_t rlgs_version(void) { return RLGS_VERSION; }
 extern "C" const char *rlgs_last_error(void) { return g_err; }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static void free_host_jobs(rlgs_sim *s);
+static int32_t alloc_host_jobs(rlgs_sim *s, bool pinned);
 static size_t chunk_bytes(const rlgs_sim *s) { return s->row_bytes * (size_t)RLGS_ROW_CHUNK * (size_t)s->R; }
 
 extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *opts, rlgs_sim **out) {
@@ -161,7 +179,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     }
     if (opts->enable_network_costs && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "network costs are implemented for the fifo tick loop only");
     if (opts->enable_network_costs && !(opts->bandwidth > 0)) return fail(RLGS_ERR_BAD_ARG, "bandwidth must be > 0");
-    if (opts->rows_format < RLGS_ROWFMT_WIDE || opts->rows_format > RLGS_ROWFMT_WIRE12) return fail(RLGS_ERR_BAD_ARG, "rows_format must be one of RLGS_ROWFMT_*");
+    if (opts->rows_format < RLGS_ROWFMT_WIDE || opts->rows_format > RLGS_ROWFMT_EVENT16) return fail(RLGS_ERR_BAD_ARG, "rows_format must be one of RLGS_ROWFMT_*");
     if (opts->rows_format != RLGS_ROWFMT_WIDE && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "the wire rows belong to the fifo tick loop");
     if (opts->rows_format != RLGS_ROWFMT_WIDE && N > 4095) return fail(RLGS_ERR_UNSUPPORTED, "a wire row holds at most 4095 nodes");
     if (opts->fetch_jobs < 0 || opts->fetch_jobs > 2) return fail(RLGS_ERR_BAD_ARG, "fetch_jobs must be 0, 1 or 2");
@@ -201,7 +219,8 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->slot_cap = (s->slot_cap + 31) & ~31;
     if (s->slot_cap > 65504) { delete s; return fail(RLGS_ERR_BAD_ARG, "slot_cap must be <= 65504"); }
     s->wire = opts->rows_format;
-    s->row_bytes = s->wire == RLGS_ROWFMT_WIRE16 ? sizeof(rlgs_row16) : (s->wire == RLGS_ROWFMT_WIRE12 ? sizeof(rlgs_row12) : sizeof(rlgs_row));
+    s->row_bytes = s->wire == RLGS_ROWFMT_WIRE16 ? sizeof(rlgs_row16) : (s->wire == RLGS_ROWFMT_WIRE12 ? sizeof(rlgs_row12) : (s->wire == RLGS_ROWFMT_EVENT16 ? sizeof(rlgs_row16e) : sizeof(rlgs_row)));
+    s->derived.assign(s->R, 0);
     // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
     // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
     s->lpr = lpr_in ? lpr_in : (s->R >= 148 * 8 * 4 ? 8 : (s->R >= 148 * 8 * 2 ? 16 : 32));
@@ -262,7 +281,7 @@ extern "C" void rlgs_destroy(rlgs_sim *s) {
     for (auto p : s->h_chunks) if (p) cudaFreeHost(p);
     cudaFree(s->d_desc); cudaFree(s->d_state); cudaFree(s->d_ldesc); cudaFree(s->d_lstate); cudaFree(s->d_jobs);
     cudaFree(s->d_returns); cudaFree(s->d_chunk_ptrs);
-    if (s->h_jobs) cudaFreeHost(s->h_jobs);
+    free_host_jobs(s);
     if (s->h_returns) cudaFreeHost(s->h_returns);
     if (s->h_state) cudaFreeHost(s->h_state);
     if (s->h_init) cudaFreeHost(s->h_init);
@@ -497,7 +516,7 @@ static int32_t setup_job_arrays(rlgs_sim *s) {
     }
     if (Jmax != s->Jmax || !s->d_jobs) {
         cudaFree(s->d_jobs); s->d_jobs = nullptr;
-        if (s->h_jobs) { cudaFreeHost(s->h_jobs); s->h_jobs = nullptr; }
+        free_host_jobs(s);
         s->Jmax = Jmax;
         s->jobs_bytes = sizeof(int32_t) * N_PLANES * (size_t)s->R * (size_t)Jmax;
         CU(cudaMalloc(&s->d_jobs, s->jobs_bytes));
@@ -559,7 +578,7 @@ static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, con
     return cudaGetLastError();
 }
 
-// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16, 3 = rlgs_row12.  The network-cost and env-with-rows variants exist for one replica per warp only
+// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16, 3 = rlgs_row12, 4 = rlgs_row16e.  The network-cost and env-with-rows variants exist for one replica per warp only
 // (rlgs_create pins lanes_per_replica to 32 for them).
 template <int LPR, bool PK>
 static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
@@ -569,14 +588,16 @@ static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget,
         if (rows == 0) return launch_grp<32, PK, false, 0, true>(s, first, count, budget, rs, io, st);
         if (rows == 1) return launch_grp<32, PK, false, 1, true>(s, first, count, budget, rs, io, st);
         if (rows == 2) return launch_grp<32, PK, false, 2, true>(s, first, count, budget, rs, io, st);
-        return launch_grp<32, PK, false, 3, true>(s, first, count, budget, rs, io, st);
+        if (rows == 3) return launch_grp<32, PK, false, 3, true>(s, first, count, budget, rs, io, st);
+        return launch_grp<32, PK, false, 4, true>(s, first, count, budget, rs, io, st);
     }
     if (env && rows) return LPR == 32 && !s->wire ? launch_grp<32, PK, true, 1, false>(s, first, count, budget, rs, io, st) : cudaErrorNotSupported;
     if (env) return launch_grp<LPR, PK, true, 0, false>(s, first, count, budget, rs, io, st);
     if (rows == 0) return launch_grp<LPR, PK, false, 0, false>(s, first, count, budget, rs, io, st);
     if (rows == 1) return launch_grp<LPR, PK, false, 1, false>(s, first, count, budget, rs, io, st);
     if (rows == 2) return launch_grp<LPR, PK, false, 2, false>(s, first, count, budget, rs, io, st);
-    return launch_grp<LPR, PK, false, 3, false>(s, first, count, budget, rs, io, st);
+    if (rows == 3) return launch_grp<LPR, PK, false, 3, false>(s, first, count, budget, rs, io, st);
+    return launch_grp<LPR, PK, false, 4, false>(s, first, count, budget, rs, io, st);
 }
 
 static cudaError_t launch_fifo(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
@@ -665,9 +686,9 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         rc = add_chunks(s, std::max(target_chunks, (int)s->d_chunks.size()), eager_rows);
         if (rc) return rc;
     }
-    if (eager_jobs && !s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
+    if (eager_jobs) { rc = alloc_host_jobs(s, true); if (rc) return rc; }
     std::fill(s->h_chunk_valid.begin(), s->h_chunk_valid.end(), 0);
-    s->planes_mask = 0; s->ran = false; s->xp_replica = -1;
+    s->planes_mask = 0; std::fill(s->derived.begin(), s->derived.end(), 0); s->ran = false; s->xp_replica = -1;
 
     if (!s->legacy) {
         CU(cudaMemcpyAsync(s->d_state, s->h_init, sizeof(RepState) * R, cudaMemcpyHostToDevice, main_st));
@@ -823,7 +844,7 @@ extern "C" int32_t rlgs_get_summary(rlgs_sim *s, int32_t r, rlgs_summary *out) {
 static int32_t fetch_planes(rlgs_sim *s, int upto) {
     const int want = (1 << upto) - 1;
     if ((s->planes_mask & want) == want) return RLGS_OK;
-    if (!s->h_jobs) CU(cudaMallocHost(&s->h_jobs, s->jobs_bytes));
+    { int32_t rc_a = alloc_host_jobs(s, false); if (rc_a) return rc_a; }
     const size_t plane = (size_t)s->R * (size_t)s->Jmax;
     if (!(s->planes_mask & 1) && (s->planes_mask & 2) && !s->legacy && !s->opts.enable_network_costs) {
         bool derivable = true;
@@ -847,13 +868,49 @@ static int32_t fetch_planes(rlgs_sim *s, int upto) {
     return RLGS_OK;
 }
 
+static int32_t copy_rows_raw(rlgs_sim *s, int r, int64_t first, int64_t count, unsigned char *out);
+
+// Job planes 0..2 (start, end, finish_order) of replica r in h_jobs: copied from the device, or rebuilt from the replica's event
+// rows (RLGS_ROWFMT_EVENT16, no network costs): start_tick = the row that names the job, end_tick = start_tick + dur_ticks when
+// the run got that far, finish order = (end tick, start tick), the order release_finished_jobs walks running_jobs (schedule.py:141-162).
+static int32_t ensure_tables(rlgs_sim *s, int r) {
+    if ((s->planes_mask & 7) == 7 || s->derived[r]) return RLGS_OK;
+    const bool can_derive = s->wire == RLGS_ROWFMT_EVENT16 && !s->legacy && !s->opts.enable_network_costs && s->opts.rows_mode != RLGS_ROWS_NONE &&
+                            (int)s->traces[s->rep_trace[r]].host.size() == s->h_desc[r].J;
+    if (!can_derive) return fetch_planes(s, 3);
+    { int32_t rc_a = alloc_host_jobs(s, false); if (rc_a) return rc_a; }
+    const std::vector<rlgs_job> &jobs = s->traces[s->rep_trace[r]].host;
+    const int J = (int)jobs.size();
+    const int64_t n = s->h_state[r].d;
+    std::vector<rlgs_row16e> w((size_t)std::max<int64_t>(n, 1));
+    if (n > 0) { int32_t rc = copy_rows_raw(s, r, 0, n, reinterpret_cast<unsigned char *>(w.data())); if (rc) return rc; }
+    const size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
+    int32_t *st = s->h_jobs + off, *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off;
+    for (int i = 0; i < J; ++i) { st[i] = -1; en[i] = -1; fo[i] = -1; }
+    std::vector<std::pair<int64_t, int32_t>> fin;   // (end << 32 | start, job)
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t j1 = w[(size_t)i].w[3];
+        if (!j1) continue;
+        if ((int64_t)j1 > J) return fail(RLGS_ERR_STATE, "row %lld of replica %d names job %u of %d", (long long)i, r, j1 - 1, J);
+        const int j = (int)j1 - 1;
+        st[j] = (int32_t)i;
+        const int64_t e = i + jobs[(size_t)j].dur_ticks;
+        if (e <= n) { en[j] = (int32_t)e; fin.push_back(std::make_pair((e << 32) | i, j)); }
+    }
+    std::sort(fin.begin(), fin.end());
+    if ((int)fin.size() != s->h_state[r].F) return fail(RLGS_ERR_STATE, "replica %d: %zu finished jobs in the event rows, %d on the device", r, fin.size(), s->h_state[r].F);
+    for (size_t k = 0; k < fin.size(); ++k) fo[k] = fin[k].second;
+    s->derived[r] = 1;
+    return RLGS_OK;
+}
+
 extern "C" int32_t rlgs_read_job_plane(rlgs_sim *s, int32_t r, int32_t plane_id, int32_t *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R || plane_id < 0 || plane_id >= N_PLANES) return fail(RLGS_ERR_BAD_ARG, "replica / plane out of range");
     if (!s->legacy && plane_id > RLGS_PLANE_AUX) return fail(RLGS_ERR_BAD_ARG, "plane %d is only recorded by the preemptive schedules", plane_id);
     CU(cudaSetDevice(s->device));
-    int32_t rc = fetch_planes(s, plane_id + 1 <= 3 ? 3 : N_PLANES);
+    int32_t rc = plane_id < 3 ? ensure_tables(s, r) : fetch_planes(s, N_PLANES);
     if (rc) return rc;
     size_t plane = (size_t)s->R * (size_t)s->Jmax;
     int J = s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J;
@@ -867,7 +924,7 @@ extern "C" int32_t rlgs_read_jobs(rlgs_sim *s, int32_t r, int32_t *finish_order,
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");
     if (r < 0 || r >= s->R) return fail(RLGS_ERR_BAD_ARG, "replica %d out of range", r);
     CU(cudaSetDevice(s->device));
-    int32_t rc = fetch_planes(s, (first_node || (preempt && s->legacy)) ? N_PLANES : 3);   // pack is a legacy-layout family
+    int32_t rc = (first_node || (preempt && s->legacy)) ? fetch_planes(s, N_PLANES) : ensure_tables(s, r);   // pack is a legacy-layout family
     if (rc) return rc;
     size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
     int J = s->legacy ? s->h_ldesc[r].J : s->h_desc[r].J;
@@ -920,7 +977,7 @@ static int32_t rows_args_ok(rlgs_sim *s, int32_t r, int64_t first, int64_t count
 // (arrival ticks) in trace order.  Cached for one replica at a time.
 static int32_t prepare_expansion(rlgs_sim *s, int r) {
     if (s->xp_replica == r) return RLGS_OK;
-    int32_t rc = fetch_planes(s, 3);
+    int32_t rc = ensure_tables(s, r);
     if (rc) return rc;
     const TraceBuf &tb = s->traces[s->rep_trace[r]];
     const int J = tb.n;
@@ -969,6 +1026,7 @@ static int32_t read_wire_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t cou
 }
 extern "C" int32_t rlgs_read_rows16(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE16); }
 extern "C" int32_t rlgs_read_rows12(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row12 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE12); }
+extern "C" int32_t rlgs_read_rows16e(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16e *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_EVENT16); }
 
 extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
@@ -994,7 +1052,7 @@ extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t
         while (n_fin < F_max && en[fo[n_fin]] <= i + 1) ++n_fin;
         while (n_sta < S_max && s->xp_start[(size_t)n_sta] <= i) ++n_sta;
     };
-    if (s->wire == RLGS_ROWFMT_WIRE12 && first > 0) advance(first - 1);   // the cumulative counts are positional: catch up with the rows before `first`
+    if (s->wire >= RLGS_ROWFMT_WIRE12 && first > 0) advance(first - 1);   // the cumulative counts are positional: catch up with the rows before `first`
     for (int64_t k = 0; k < count; ++k) {
         const int64_t i = first + k;
         advance(i);
@@ -1008,7 +1066,7 @@ extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t
             o.median_lo = (int32_t)((x[2] >> 12) | ((x[3] & 0xfu) << 20));
             o.median_hi = (int32_t)((x[3] >> 4) & 0xffffffu);
         } else {
-            const uint32_t *x = reinterpret_cast<const rlgs_row12 *>(w.data())[k].w;
+            const uint32_t *x = reinterpret_cast<const uint32_t *>(w.data() + (size_t)k * s->row_bytes);   // rlgs_row12 / rlgs_row16e share w[0..2]
             o.max_pending = (int32_t)(x[0] & 0xffffffu);
             o.median_lo = (int32_t)(x[1] & 0xffffffu);
             o.median_hi = (int32_t)(x[2] & 0xffffffu);
@@ -1054,6 +1112,12 @@ extern "C" int32_t rlgs_rows_view(rlgs_sim *s, int32_t r, int32_t chunk, const r
 extern "C" int32_t rlgs_rows16_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row16 **rows, int64_t *count) {
     if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (s->wire != RLGS_ROWFMT_WIRE16) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
+    return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
+}
+
+extern "C" int32_t rlgs_rows16e_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row16e **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->wire != RLGS_ROWFMT_EVENT16) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
     return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 
@@ -1116,7 +1180,7 @@ extern "C" int32_t rlgs_env_reset(rlgs_sim *s) {
     CU(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), sizeof(RepDesc) * s->R, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(s->d_jobs, 0xff, s->jobs_bytes, st));
     CU(cudaStreamSynchronize(st));   // h_init / h_desc may be rewritten by the caller's next call
-    s->planes_mask = 0; s->ran = false; s->env_ready = true;
+    s->planes_mask = 0; std::fill(s->derived.begin(), s->derived.end(), 0); s->ran = false; s->env_ready = true;
     return RLGS_OK;
 }
 
@@ -1176,7 +1240,7 @@ extern "C" int32_t rlgs_env_sync(rlgs_sim *s) {
         s->h_returns[r] = -s->h_state[r].sum_jct;
         if (s->h_state[r].status != RLGS_OK) return fail(s->h_state[r].status, "replica %d stopped with status %d at tick %d", r, s->h_state[r].status, s->h_state[r].d);
     }
-    s->planes_mask = 0; s->ran = true;
+    s->planes_mask = 0; std::fill(s->derived.begin(), s->derived.end(), 0); s->ran = true;
     return RLGS_OK;
 }
 

@@ -21,8 +21,9 @@ class Simulator(object):
         pack_seed: None = utilisation draws of the horus score return their mean (the reference's behaviour on
         zero-spread traces); an int seeds the build-defined counter-based draw.  horus+: pack_seed also seeds the k-means draws
         (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded.
-        rows_format: 'wire12' (default for fifo) / 'wire16' keep 12- / 16-byte rows on the device and on the wire and expand them
-        in rows(); 'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto.
+        rows_format: 'event16' (default for fifo without network costs: 12-byte row + the tick's start event, from which the job
+        tables are rebuilt on the host when they were not copied) / 'wire12' / 'wire16' keep compact rows on the device and on the
+        wire and expand them in rows(); 'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto.
         fetch_jobs: True = start / end / finish_order tables copied to the host inside run(); 'end' = end and finish_order only
         (fifo without network costs: a finished job started at end - dur_ticks)."""
         if schedule not in _ffi.SCHED:
@@ -30,7 +31,9 @@ class Simulator(object):
         if scheme not in _ffi.PLACE:
             raise NotImplementedError('placement scheme %r has no device implementation' % (scheme,))
         if rows_format is None:
-            rows_format = 'wire12' if (schedule == 'fifo' and cluster.num_nodes <= 4095) else 'wide'
+            rows_format = 'wide'
+            if schedule == 'fifo' and cluster.num_nodes <= 4095:
+                rows_format = 'wire12' if enable_network_costs else 'event16'
         if rows_format not in _ffi.ROWFMT:
             raise ValueError('rows_format must be one of %s' % sorted(_ffi.ROWFMT))
         self.cluster = cluster
@@ -178,7 +181,7 @@ class Simulator(object):
         p, n = C.c_void_p(), C.c_int64(0)
         L = _ffi.lib()
         fn, dt = {'wide': (L.rlgs_rows_view, _ffi.ROW_DTYPE), 'wire16': (L.rlgs_rows16_view, _ffi.ROW16_DTYPE),
-                  'wire12': (L.rlgs_rows12_view, _ffi.ROW12_DTYPE)}[self._kw['rows_format']]
+                  'wire12': (L.rlgs_rows12_view, _ffi.ROW12_DTYPE), 'event16': (L.rlgs_rows16e_view, _ffi.ROW16_DTYPE)}[self._kw['rows_format']]
         _ffi.check(fn(self._h, replica, chunk, C.byref(p), C.byref(n)))
         buf = (C.c_char * (n.value * dt.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=dt, count=n.value)
@@ -187,7 +190,8 @@ class Simulator(object):
         """The packed wire rows of a replica ('wire16' / 'wire12' handles), unexpanded."""
         n = self.summary(replica)['n_ticks']
         L = _ffi.lib()
-        fn, dt = {'wire16': (L.rlgs_read_rows16, _ffi.ROW16_DTYPE), 'wire12': (L.rlgs_read_rows12, _ffi.ROW12_DTYPE)}[self._kw['rows_format']]
+        fn, dt = {'wire16': (L.rlgs_read_rows16, _ffi.ROW16_DTYPE), 'wire12': (L.rlgs_read_rows12, _ffi.ROW12_DTYPE),
+                  'event16': (L.rlgs_read_rows16e, _ffi.ROW16_DTYPE)}[self._kw['rows_format']]
         out = np.zeros(n, dt)
         if n:
             _ffi.check(fn(self._h, replica, 0, n, out.ctypes.data))

@@ -14,7 +14,7 @@ from rlgpuschedule_b200 import _ffi, log_manager as lm
 pytestmark = pytest.mark.gpu
 
 LPRS = (8, 16, 32)
-FORMATS = ('wire12', 'wire16', 'wide')
+FORMATS = ('event16', 'wire12', 'wire16', 'wide')
 
 
 def _csvs(sim, cluster, tr, r):
@@ -88,10 +88,10 @@ def test_wire_rows_expand_to_the_wide_rows(lpr):
             _ffi.check(_ffi.lib().rlgs_read_rows(sim._h, 3, 100, 50, part.ctypes.data))
             assert np.array_equal(part, rows[fmt][100:150])
         sim.close()
-    assert rows['wide'].dtype == rows['wire16'].dtype == rows['wire12'].dtype == _ffi.ROW_DTYPE
+    assert rows['wide'].dtype == rows['wire16'].dtype == rows['wire12'].dtype == rows['event16'].dtype == _ffi.ROW_DTYPE
     for f in _ffi.ROW_DTYPE.names:
-        assert np.array_equal(rows['wide'][f], rows['wire16'][f]), f
-        assert np.array_equal(rows['wide'][f], rows['wire12'][f]), f
+        for fmt in ('wire16', 'wire12', 'event16'):
+            assert np.array_equal(rows['wide'][f], rows[fmt][f]), (fmt, f)
     assert rows['wide']['busy_gpus'].max() > 0 and rows['wide']['sum_pending'].max() > 0 and rows['wide']['util_var_sum'].max() > 0
 
 
@@ -170,3 +170,33 @@ def test_end_only_job_tables_derive_the_start_ticks(fmt):
         assert np.array_equal(j['start'], o['start']) and np.array_equal(j['end'], o['end']) and np.array_equal(j['finish_order'], o['finish_order'])
         assert lm.format_cluster_csv(sim.rows(r), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
     sim.close()
+
+
+@pytest.mark.parametrize('lpr', LPRS)
+def test_event_rows_rebuild_the_job_tables(lpr):
+    """RLGS_ROWFMT_EVENT16: every row names the job that started at its tick, so the row stream is the event log.  The tables
+    rebuilt from it on the host (start, end = start + dur_ticks, finish order = (end, start)) must equal the tables the device
+    wrote itself, on traces with many same-tick finishes and jobs that never start, and the wire word must name the right job."""
+    flags = dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=8)
+    cluster = rl.cluster_from_flags(flags)
+    df = tracegen.frame_gen(700, 21, 60)
+    df.loc[df.index[::7], 'minutes'] = 6.0                      # many equal durations: several jobs finish at the same tick
+    df.loc[df.index[5], 'used_gpus'] = 64.0; df.loc[df.index[5], 'gpu_per_container'] = 8   # wider than the cluster: never starts
+    tr = rl.prepare_trace(df, cluster)
+    o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df))
+    tables = {}
+    for fetch in (False, True):
+        sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=5, rows=True, lanes_per_replica=lpr, rows_format='event16', fetch_jobs=fetch)
+        sim.load_trace(tr)
+        sim.run()
+        tables[fetch] = sim.jobs(4)
+        if not fetch:
+            w = sim.rows_wire(4)['w'][:, 3]
+            ticks = np.nonzero(w)[0]
+            assert np.array_equal(o['start'][w[ticks] - 1], ticks) and len(ticks) == (o['start'] >= 0).sum()
+            assert lm.format_cluster_csv(sim.rows(4), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+        sim.close()
+    for k in ('start', 'end', 'finish_order', 'preempt'):
+        assert np.array_equal(tables[False][k], tables[True][k]), k
+    assert np.array_equal(tables[False]['finish_order'], o['finish_order']) and np.array_equal(tables[False]['end'], o['end'])
+    assert (np.diff(o['end'][o['finish_order']]) == 0).sum() > 20 and (o['start'] < 0).any()
