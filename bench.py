@@ -335,11 +335,10 @@ def main():
 
     def step():
         if is_env:
-            env.reset()
             ev_k0.record()
-            env.rollout('random')
+            env.run_episodes('random')       # reset + device rollout of every episode + sync (regrows the slot table if a policy needs it)
             ev_k1.record()
-            env.sync()
+            torch.cuda.synchronize()
             env_ms[0] = ev_k0.elapsed_time(ev_k1)
         else:
             sim.run()
@@ -399,9 +398,8 @@ def main():
             def step2():
                 for i, first, count in blocks:            # host -> device: the episode's traces
                     env2.sim.load_trace(traces[i], first, count)
-                env2.reset()
-                env2.rollout('random')
-                return env2.returns()                      # device -> host: episode returns (sync + copy)
+                env2.run_episodes('random')
+                return env2.sim.returns()                  # device -> host: episode returns
             closer = env2
         else:
             sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=(False if args.rows_format == 'event16' else 'end') if is_fifo else True, device=local_rank, **sim_kw)

@@ -73,8 +73,28 @@ class Environment(object):
         return self.obs, self.reward, self.done, {}
 
     def sync(self):
-        _ffi.check(_ffi.lib().rlgs_env_sync(self.sim._h))
+        rc = _ffi.lib().rlgs_env_sync(self.sim._h)
+        if rc == _ffi.ERR_SLOTS:
+            raise _ffi.RlgsError(rc, _ffi.lib().rlgs_last_error().decode(errors='replace') +
+                                 ' - more jobs ran at once than on-chip slots: create the Environment with a larger slot_cap, or use run_episodes()')
+        _ffi.check(rc)
         return self
+
+    def run_episodes(self, policy='random'):
+        """reset() + rollout(policy) to the end of every episode + sync().  A policy that packs more jobs at once than the on-chip
+        slot table holds (RLGS_ERR_SLOTS) restarts the batch with a table twice as large, like Simulator.run() does."""
+        while True:
+            self.reset()
+            self.rollout(policy)
+            rc = _ffi.lib().rlgs_env_sync(self.sim._h)
+            if rc == _ffi.ERR_SLOTS:
+                cap = max(64, 2 * (self.sim._slot_cap or 128))
+                if cap > 2 * max(self.sim.cluster.num_gpus, 32):
+                    _ffi.check(rc)
+                self.sim._rebuild(slot_cap=cap)
+                continue
+            _ffi.check(rc)
+            return self
 
     def returns(self):
         """Episode returns so far, -(sum of job completion times) per replica (host numpy int64)."""
