@@ -267,7 +267,7 @@ def main():
     ap.add_argument('--workload', default='fifo60k', choices=sorted(WORKLOADS))
     ap.add_argument('--replicas', type=int, default=0, help='replicas per GPU (0 = the workload\'s default)')
     ap.add_argument('--lpr', type=int, default=0, help='fifo tick loop: lanes of a warp per replica (0 = chosen by the library)')
-    ap.add_argument('--rows-format', default='event16', choices=['event16', 'wire12', 'wire16', 'wide'])
+    ap.add_argument('--rows-format', default='event4', choices=['event4', 'event16', 'wire12', 'wire16', 'wide'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-python-reference', action='store_true')
@@ -402,7 +402,7 @@ def main():
                 return env2.sim.returns()                  # device -> host: episode returns
             closer = env2
         else:
-            sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=(False if args.rows_format == 'event16' else 'end') if is_fifo else True, device=local_rank, **sim_kw)
+            sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=(False if args.rows_format.startswith('event') else 'end') if is_fifo else True, device=local_rank, **sim_kw)
             attach(sim2)
 
             def step2():
@@ -428,8 +428,8 @@ def main():
             rows0 = sim2.rows(0)
             j0 = sim2.jobs(0)
             assert len(rows0) == summ[0]['n_ticks'] and int(rows0['finished'][-1]) == len(j0['finish_order'])
-            row_bytes = {'event16': 16, 'wire12': 12, 'wire16': 16, 'wide': 64}[args.rows_format] if is_fifo else 64
-            n_planes = (0 if args.rows_format == 'event16' else 2) if is_fifo else 3
+            row_bytes = {'event4': 4, 'event16': 16, 'wire12': 12, 'wire16': 16, 'wide': 64}[args.rows_format] if is_fifo else 64
+            n_planes = (0 if args.rows_format.startswith('event') else 2) if is_fifo else 3
             n_chunks = -(-max_ticks // _ffi.ROWS_PER_CHUNK)        # whole chunks travel (chunk-major row store)
             d2h = int(n_chunks * R * _ffi.ROWS_PER_CHUNK * row_bytes + n_planes * 4 * R * jmax + R * 264)   # rows + job tables + replica states
         e2e = {'value': events_all * args.steps / t2.item(), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -481,7 +481,11 @@ def main():
             'config': {'workload': '%s, %d replicas/GPU over %d seeds' % (w['text'], R, NT), 'name': args.workload, 'schedule': w['schedule'],
                        'scheme': w['scheme'], 'replicas_per_gpu': R, 'jobs_per_replica': w['n_jobs'],
                        'rows_format': (args.rows_format if is_fifo and not is_env else ('none' if is_env else 'wide')),
-                       'e2e_result': (('16-byte event rows: the per-tick statistics + the job started at the tick; start / end / finish-order tables are rebuilt from '
+                       'e2e_result': (('4-byte event rows (idle nodes | the queue head started | queue length): the event log of every replica; rlgs_read_jobs / '
+                                       'rlgs_read_rows replay the queue on the host to rebuild start / end / finish-order and the per-tick statistics of a replica '
+                                       'when asked for (tests compare them with the device-written tables and the 64-byte rows); --rows-format wide|wire16|wire12|event16 '
+                                       'move progressively fewer derived bytes' if args.rows_format == 'event4' else
+                                       '16-byte event rows: the per-tick statistics + the job started at the tick; start / end / finish-order tables are rebuilt from '
                                        'them on the host when asked for (end = start + dur_ticks, finish order = (end, start))' if args.rows_format == 'event16' else
                                        'per-tick rows in the wire format + end_tick and finish_order per job (fifo: start = end - dur_ticks, derived on the host)')
                                       if is_fifo and not is_env else ('episode returns' if is_env else 'per-event rows + start / end / finish_order per job')),

@@ -70,8 +70,13 @@ enum { RLGS_ROWS_NONE = 0, RLGS_ROWS_FULL = 1, RLGS_ROWS_DEVICE = 2 };
  * schedule.py:188-190).  The row stream then IS the event log: without network costs a job ends dur_ticks after it started and
  * jobs finish in (end tick, start tick) order, so rlgs_read_jobs / rlgs_read_rows rebuild the per-job tables from the rows of the
  * replica when they were not copied (opts.fetch_jobs = 0), and a run crosses PCIe as 16 bytes per tick, all of it while the
- * simulation is still running. */
-enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1, RLGS_ROWFMT_WIRE12 = 2, RLGS_ROWFMT_EVENT16 = 3 };
+ * simulation is still running.
+ * EVENT4 = rlgs_row4e, 4 bytes: the event log alone — idle_nodes, "the queue head started at this tick" and a check field.
+ * Under fifo the job that starts is always the queue head and the queue is a function of the trace and of the earlier start
+ * events, so a replay of the queue on the host (one push per arrival, one pop per start event, O(ticks + jobs)) names every
+ * started job and yields the pending-time statistics of every tick (they are arrival ticks at fixed positions of the queue);
+ * the tables and the remaining row fields then follow as for EVENT16.  Fifo without network costs only. */
+enum { RLGS_ROWFMT_WIDE = 0, RLGS_ROWFMT_WIRE16 = 1, RLGS_ROWFMT_WIRE12 = 2, RLGS_ROWFMT_EVENT16 = 3, RLGS_ROWFMT_EVENT4 = 4 };
 
 /* Cluster spec: flags --num_switch .. --mem_p_node (run_sim.py:50-82) or cluster_spec.csv
  * (infra/infrastructure.py:78-105).  Replaces Infrastructure._init_nodes (infrastructure.py:45-69). */
@@ -187,6 +192,18 @@ typedef struct { uint32_t w[3]; } rlgs_row12;
  * them; tests compare both). */
 typedef struct { uint32_t w[4]; } rlgs_row16e;
 
+/* 4-byte event row (RLGS_ROWFMT_EVENT4), row i has delta = i + 1:
+ *   w: idle_nodes:12 | started:1 | queued[18:0]:19
+ * started = 1 when the scheduling attempt of tick i started the queue head (schedule.py:188-190).  The host replays the queue
+ * exactly as the tick loop keeps it (jobs_manager.py:228-241: the jobs arriving at a tick go to the FRONT of the queue in trace
+ * order; the attempt takes the front): the front at a row with started = 1 is the job whose start_tick is i.  After the tick's
+ * pushes and pop the queue holds Q jobs, front first; with delta = i + 1
+ *   max_pending = delta - arrival tick of the back of the queue (the tick at which the queue last became non-empty)
+ *   median_lo / median_hi = delta - arrival tick of the jobs at positions (Q - 1) / 2 and Q / 2 from the front
+ * (the queue is sorted by arrival tick, newest first, so these are np.median's two middle elements, jobs_manager.py:87).
+ * queued[18:0] must equal the low bits of the replayed Q at every row (else RLGS_ERR_STATE).  Tables and sums as for rlgs_row16e. */
+typedef struct { uint32_t w; } rlgs_row4e;
+
 typedef struct {
     int64_t n_ticks;       /* rows produced (fifo: ticks; sjf/dlas: events) */
     int64_t makespan;      /* last simulated time */
@@ -254,6 +271,7 @@ int32_t rlgs_read_rows(rlgs_sim *sim, int32_t replica, int64_t first, int64_t co
 int32_t rlgs_read_rows16(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16 *out);
 int32_t rlgs_read_rows12(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row12 *out);
 int32_t rlgs_read_rows16e(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row16e *out);
+int32_t rlgs_read_rows4e(rlgs_sim *sim, int32_t replica, int64_t first, int64_t count, rlgs_row4e *out);
 /* Zero-copy variant: rows [chunk*RLGS_ROWS_PER_CHUNK, ...) of `replica` inside the handle's pinned host
  * mirror (the store is chunk-major so that a whole chunk of every replica moves in one contiguous copy);
  * valid until the next rlgs_run / destroy. */
@@ -262,6 +280,7 @@ int32_t rlgs_rows_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs
 int32_t rlgs_rows16_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE16 */
 int32_t rlgs_rows12_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row12 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE12 */
 int32_t rlgs_rows16e_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16e **rows, int64_t *count); /* RLGS_ROWFMT_EVENT16 */
+int32_t rlgs_rows4e_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row4e **rows, int64_t *count);   /* RLGS_ROWFMT_EVENT4 */
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,

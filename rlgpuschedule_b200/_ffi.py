@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get('RLGS_LIB') or os.path.join(HERE, 'librlgs.so')   # RLGS_LIB: development override
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE, ERR_SLOTS, ERR_WIRE = 0, -1, -2, -3, -4, -5, -6, -7, -8
-ROWFMT_WIDE, ROWFMT_WIRE16, ROWFMT_WIRE12, ROWFMT_EVENT16 = 0, 1, 2, 3
-ROWFMT = {'wide': 0, 'wire16': 1, 'wire12': 2, 'event16': 3}
+ROWFMT_WIDE, ROWFMT_WIRE16, ROWFMT_WIRE12, ROWFMT_EVENT16, ROWFMT_EVENT4 = 0, 1, 2, 3, 4
+ROWFMT = {'wide': 0, 'wire16': 1, 'wire12': 2, 'event16': 3, 'event4': 4}
 SCHED = {'fifo': 0, 'sjf': 1, 'dlas-gpu': 2, 'dlas': 3, 'shortest': 4, 'shortest-gpu': 5, 'horus': 6, 'gandiva': 7, 'horus+': 8}
 PLACE = {'yarn': 0, 'count': 1, 'horus': 2, 'horus+': 2, 'gandiva': 2}   # the three pack names share horus_placement (algorithm.py:182-187)
 ROWS_NONE, ROWS_FULL, ROWS_DEVICE = 0, 1, 2
@@ -64,11 +64,12 @@ ROW_DTYPE = np.dtype([('idle_nodes', '<i4'), ('busy_gpus', '<i4'), ('running', '
                       ('sum_pending', '<i8'), ('mem_sum', '<i8'), ('util_mu_sum', '<i8'), ('util_var_sum', '<i8')])
 ROW16_DTYPE = np.dtype([('w', '<u4', (4,))])
 ROW12_DTYPE = np.dtype([('w', '<u4', (3,))])
-assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64 and ROW16_DTYPE.itemsize == 16 and ROW12_DTYPE.itemsize == 12
+ROW4_DTYPE = np.dtype([('w', '<u4')])
+assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64 and ROW16_DTYPE.itemsize == 16 and ROW12_DTYPE.itemsize == 12 and ROW4_DTYPE.itemsize == 4
 
 EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_load_pack_inputs', 'rlgs_run',
            'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
-           'rlgs_rows_view', 'rlgs_read_rows16', 'rlgs_rows16_view', 'rlgs_read_rows12', 'rlgs_rows12_view', 'rlgs_read_rows16e', 'rlgs_rows16e_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
+           'rlgs_rows_view', 'rlgs_read_rows16', 'rlgs_rows16_view', 'rlgs_read_rows12', 'rlgs_rows12_view', 'rlgs_read_rows16e', 'rlgs_rows16e_view', 'rlgs_read_rows4e', 'rlgs_rows4e_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
            'rlgs_read_durations', 'rlgs_env_obs_dim', 'rlgs_env_reset', 'rlgs_env_step', 'rlgs_env_observe', 'rlgs_env_sync']
 
 _lib = None
@@ -110,6 +111,8 @@ def lib():
     L.rlgs_rows12_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
     L.rlgs_read_rows16e.argtypes = [vp, i32, i64, i64, vp]
     L.rlgs_rows16e_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.rlgs_read_rows4e.argtypes = [vp, i32, i64, i64, vp]
+    L.rlgs_rows4e_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
     L.rlgs_read_job_plane.argtypes = [vp, i32, i32, vp]
     L.rlgs_returns.argtypes = [vp, vp]
     L.rlgs_returns_device_ptr.argtypes = [vp, C.POINTER(vp)]

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
     if (ENV && valid && !act && writer) { env.reward[rep] = 0.f; env.done[rep] = 1; }
     const GrpSm s = grp_carve(smem_raw + (size_t)G.g * grp_smem_bytes(c.N, c.G, slot_cap, LPR), c.N, c.G, slot_cap, LPR);
     float reward_acc = 0.f;
-    constexpr int ROW_BYTES = (ROWS == 2 || ROWS == 4) ? 16 : (ROWS == 3 ? 12 : 64);
+    constexpr int ROW_BYTES = (ROWS == 2 || ROWS == 4) ? 16 : (ROWS == 3 ? 12 : (ROWS == 5 ? 4 : 64));
     unsigned char *row_cur = nullptr;   // next row of this replica inside the current chunk
     int rows_left = 0;                  // rows that still fit the chunk behind row_cur
     if (ROWS && (int64_t)st.d + tick_budget > (int64_t)rs.n_chunks * RLGS_ROW_CHUNK)   // the launch stops when the allocated chunks are full
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
 
         // median loads are issued early; they are consumed when the row is written
         int med_lo_arr = 0, med_hi_arr = 0;
-        if (ROWS && act && st.Q > 0) {
+        if (ROWS && ROWS != 5 && act && st.Q > 0) {   // rlgs_row4e carries no pending times: the host replays the queue
             med_lo_arr = D.stack[st.head + (st.Q - 1) / 2].arrival_tick;
             med_hi_arr = D.stack[st.head + st.Q / 2].arrival_tick;
         }
@@ -675,7 +675,9 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                     rows_left = RLGS_ROW_CHUNK - 1 - ((st.d - 1) & (RLGS_ROW_CHUNK - 1));
                 }
                 const int maxp = st.Q > 0 ? st.d - st.bottom_arr : 0, mlo = st.Q > 0 ? st.d - med_lo_arr : 0, mhi = st.Q > 0 ? st.d - med_hi_arr : 0;
-                if (ROWS == 2) {
+                if (ROWS == 5) {   // rlgs_row4e: idle_nodes:12 | started:1 | queued[18:0]:19
+                    if (writer) *reinterpret_cast<uint32_t *>(row_cur) = (uint32_t)st.idle_nodes | (started ? 0x1000u : 0u) | ((uint32_t)st.Q << 13);
+                } else if (ROWS == 2) {
                     if (writer) *reinterpret_cast<int4 *>(row_cur) = pack_row16(st.idle_nodes, st.F, st.Q, maxp, mlo, mhi);
                 } else if (ROWS == 3 || ROWS == 4) {   // rlgs_row12 / rlgs_row16e: lanes 0..2 (0..3) of the group store one word each
                     const uint32_t idle = (uint32_t)st.idle_nodes;
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
 #undef GBALLOT
 #undef GSHFL
     if (!resident) return;                        // the remaining code is per group (group-local synchronisation only)
-    if (ROWS >= 2 && st.d >= (1 << 24)) { st.status = RLGS_ERR_WIRE; st.done = 1; }   // pending times no longer fit the 24-bit wire fields
+    if (ROWS >= 2 && ROWS <= 4 && st.d >= (1 << 24)) { st.status = RLGS_ERR_WIRE; st.done = 1; }   // pending times no longer fit the 24-bit wire fields
 
     st.events = (int64_t)st.cursor + st.start_seq + st.F;   // arrivals + starts + finishes
     if (!st.done && st.status == RLGS_OK && (J - st.cursor) + st.R == 0) st.done = 1;   // the while condition of schedule.py:185

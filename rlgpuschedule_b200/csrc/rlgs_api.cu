@@ -75,7 +75,7 @@ struct rlgs_sim {
     LegParams lp;
     int R = 0, device = 0;
     int lpr = 32;           // lanes of a warp per replica (fifo tick loop)
-    int wire = 0;           // 0 = rows are kept as rlgs_row, 1 = rlgs_row16, 2 = rlgs_row12, 3 = rlgs_row16e (RLGS_ROWFMT_*)
+    int wire = 0;           // 0 = rows are kept as rlgs_row, 1 = rlgs_row16, 2 = rlgs_row12, 3 = rlgs_row16e, 4 = rlgs_row4e (RLGS_ROWFMT_*)
     std::vector<char> derived;   // per replica: job planes 0..2 in h_jobs were rebuilt from the event rows
     int planes_mask = 0;    // bit k: job plane k is on the host (h_jobs)
     size_t row_bytes = sizeof(rlgs_row);
@@ -84,6 +84,7 @@ struct rlgs_sim {
     int xp_replica = -1;    // replica whose prefix sums are cached below (expansion of wire rows)
     std::vector<int64_t> xp[9];
     std::vector<int32_t> xp_start;   // start ticks of the started jobs, ascending
+    std::vector<int32_t> xp_pend;    // rlgs_row4e: max_pending, median_lo, median_hi of every row of xp_replica (queue replay)
     bool legacy = false;
     bool pack = false;      // horus schedule + horus placement (pack_horus.cuh)
     PackParams pp;
@@ -179,9 +180,10 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     }
     if (opts->enable_network_costs && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "network costs are implemented for the fifo tick loop only");
     if (opts->enable_network_costs && !(opts->bandwidth > 0)) return fail(RLGS_ERR_BAD_ARG, "bandwidth must be > 0");
-    if (opts->rows_format < RLGS_ROWFMT_WIDE || opts->rows_format > RLGS_ROWFMT_EVENT16) return fail(RLGS_ERR_BAD_ARG, "rows_format must be one of RLGS_ROWFMT_*");
+    if (opts->rows_format < RLGS_ROWFMT_WIDE || opts->rows_format > RLGS_ROWFMT_EVENT4) return fail(RLGS_ERR_BAD_ARG, "rows_format must be one of RLGS_ROWFMT_*");
     if (opts->rows_format != RLGS_ROWFMT_WIDE && sched != RLGS_SCHED_FIFO) return fail(RLGS_ERR_UNSUPPORTED, "the wire rows belong to the fifo tick loop");
     if (opts->rows_format != RLGS_ROWFMT_WIDE && N > 4095) return fail(RLGS_ERR_UNSUPPORTED, "a wire row holds at most 4095 nodes");
+    if (opts->rows_format == RLGS_ROWFMT_EVENT4 && opts->enable_network_costs) return fail(RLGS_ERR_UNSUPPORTED, "RLGS_ROWFMT_EVENT4 needs end = start + dur_ticks: no network costs");
     if (opts->fetch_jobs < 0 || opts->fetch_jobs > 2) return fail(RLGS_ERR_BAD_ARG, "fetch_jobs must be 0, 1 or 2");
     if (opts->fetch_jobs == 2 && (sched != RLGS_SCHED_FIFO || opts->enable_network_costs)) return fail(RLGS_ERR_UNSUPPORTED, "fetch_jobs = 2 needs the fifo tick loop without network costs (start = end - dur_ticks)");
     const int lpr_in = opts->lanes_per_replica;
@@ -219,7 +221,7 @@ extern "C" int32_t rlgs_create(const rlgs_cluster_spec *spec, const rlgs_opts *o
     s->slot_cap = (s->slot_cap + 31) & ~31;
     if (s->slot_cap > 65504) { delete s; return fail(RLGS_ERR_BAD_ARG, "slot_cap must be <= 65504"); }
     s->wire = opts->rows_format;
-    s->row_bytes = s->wire == RLGS_ROWFMT_WIRE16 ? sizeof(rlgs_row16) : (s->wire == RLGS_ROWFMT_WIRE12 ? sizeof(rlgs_row12) : (s->wire == RLGS_ROWFMT_EVENT16 ? sizeof(rlgs_row16e) : sizeof(rlgs_row)));
+    s->row_bytes = s->wire == RLGS_ROWFMT_WIRE16 ? sizeof(rlgs_row16) : (s->wire == RLGS_ROWFMT_WIRE12 ? sizeof(rlgs_row12) : (s->wire == RLGS_ROWFMT_EVENT16 ? sizeof(rlgs_row16e) : (s->wire == RLGS_ROWFMT_EVENT4 ? sizeof(rlgs_row4e) : sizeof(rlgs_row))));
     s->derived.assign(s->R, 0);
     // lanes per replica: a warp carries 32 / lpr replicas.  Few replicas -> wide groups (more SMs busy, shortest tick);
     // many replicas -> narrow groups (every warp instruction serves 4 replicas).  148 SMs x >= 8 warps each.
@@ -578,7 +580,7 @@ static cudaError_t launch_grp(rlgs_sim *s, int first, int count, int budget, con
     return cudaGetLastError();
 }
 
-// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16, 3 = rlgs_row12, 4 = rlgs_row16e.  The network-cost and env-with-rows variants exist for one replica per warp only
+// rows: 0 = none, 1 = rlgs_row, 2 = rlgs_row16, 3 = rlgs_row12, 4 = rlgs_row16e, 5 = rlgs_row4e (no network costs).  The network-cost and env-with-rows variants exist for one replica per warp only
 // (rlgs_create pins lanes_per_replica to 32 for them).
 template <int LPR, bool PK>
 static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget, int rows, bool env, const EnvIO &io, const RowStore &rs, cudaStream_t st) {
@@ -589,6 +591,7 @@ static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget,
         if (rows == 1) return launch_grp<32, PK, false, 1, true>(s, first, count, budget, rs, io, st);
         if (rows == 2) return launch_grp<32, PK, false, 2, true>(s, first, count, budget, rs, io, st);
         if (rows == 3) return launch_grp<32, PK, false, 3, true>(s, first, count, budget, rs, io, st);
+        if (rows == 5) return cudaErrorNotSupported;
         return launch_grp<32, PK, false, 4, true>(s, first, count, budget, rs, io, st);
     }
     if (env && rows) return LPR == 32 && !s->wire ? launch_grp<32, PK, true, 1, false>(s, first, count, budget, rs, io, st) : cudaErrorNotSupported;
@@ -597,6 +600,7 @@ static cudaError_t launch_fifo_lp(rlgs_sim *s, int first, int count, int budget,
     if (rows == 1) return launch_grp<LPR, PK, false, 1, false>(s, first, count, budget, rs, io, st);
     if (rows == 2) return launch_grp<LPR, PK, false, 2, false>(s, first, count, budget, rs, io, st);
     if (rows == 3) return launch_grp<LPR, PK, false, 3, false>(s, first, count, budget, rs, io, st);
+    if (rows == 5) return launch_grp<LPR, PK, false, 5, false>(s, first, count, budget, rs, io, st);
     return launch_grp<LPR, PK, false, 4, false>(s, first, count, budget, rs, io, st);
 }
 
@@ -873,15 +877,67 @@ static int32_t copy_rows_raw(rlgs_sim *s, int r, int64_t first, int64_t count, u
 // Job planes 0..2 (start, end, finish_order) of replica r in h_jobs: copied from the device, or rebuilt from the replica's event
 // rows (RLGS_ROWFMT_EVENT16, no network costs): start_tick = the row that names the job, end_tick = start_tick + dur_ticks when
 // the run got that far, finish order = (end tick, start tick), the order release_finished_jobs walks running_jobs (schedule.py:141-162).
+// RLGS_ROWFMT_EVENT4: replays the queue of replica r from its 4-byte rows (see rlgs_row4e in include/rlgs.h) and rebuilds job
+// planes 0..2 in h_jobs; with `stats` also the pending-time triple of every row (xp_pend).  The queue is kept the way the
+// tick loop keeps it: an array filled from the top, the jobs arriving at a tick stored in front of the current front in
+// trace order (jobs_manager.py:228-241, q1), the scheduling attempt popping the front (schedule.py:188-190).
+static int32_t replay_queue(rlgs_sim *s, int r, bool stats) {
+    const std::vector<rlgs_job> &jobs = s->traces[s->rep_trace[r]].host;
+    const int J = (int)jobs.size();
+    const int64_t n = s->h_state[r].d;
+    std::vector<rlgs_row4e> w((size_t)std::max<int64_t>(n, 1));
+    if (n > 0) { int32_t rc = copy_rows_raw(s, r, 0, n, reinterpret_cast<unsigned char *>(w.data())); if (rc) return rc; }
+    const size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
+    const bool tables = (s->planes_mask & 7) != 7;   // tables copied from the device are left alone
+    int32_t *st = s->h_jobs + off, *en = s->h_jobs + plane + off, *fo = s->h_jobs + 2 * plane + off;
+    if (tables) for (int i = 0; i < J; ++i) { st[i] = -1; en[i] = -1; fo[i] = -1; }
+    std::vector<int32_t> queue((size_t)std::max(J, 1));
+    int front = J, Q = 0, cursor = 0;
+    int64_t back_arr = 0;
+    std::vector<std::pair<int64_t, int32_t>> fin;   // (end << 32 | start, job)
+    if (stats) s->xp_pend.assign((size_t)n * 3, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        int k = 0;
+        while (cursor + k < J && jobs[(size_t)(cursor + k)].arrival_tick <= i) ++k;
+        if (k) {
+            if (Q == 0) back_arr = i;
+            front -= k;
+            for (int b = 0; b < k; ++b) queue[(size_t)(front + b)] = cursor + b;
+            cursor += k; Q += k;
+        }
+        const uint32_t x = w[(size_t)i].w;
+        if (x & 0x1000u) {
+            if (Q == 0) return fail(RLGS_ERR_STATE, "row %lld of replica %d starts a job from an empty queue", (long long)i, r);
+            const int j = queue[(size_t)front];
+            ++front; --Q;
+            const int64_t e = i + jobs[(size_t)j].dur_ticks;
+            if (tables) { st[j] = (int32_t)i; if (e <= n) en[j] = (int32_t)e; }
+            if (e <= n) fin.push_back(std::make_pair((e << 32) | i, j));
+        }
+        if ((x >> 13) != ((uint32_t)Q & 0x7ffffu)) return fail(RLGS_ERR_STATE, "row %lld of replica %d: queue length %u on the device, %d in the replay", (long long)i, r, x >> 13, Q);
+        if (stats && Q > 0) {
+            int32_t *o = &s->xp_pend[(size_t)i * 3];
+            o[0] = (int32_t)(i + 1 - back_arr);
+            o[1] = (int32_t)(i + 1 - jobs[(size_t)queue[(size_t)(front + (Q - 1) / 2)]].arrival_tick);
+            o[2] = (int32_t)(i + 1 - jobs[(size_t)queue[(size_t)(front + Q / 2)]].arrival_tick);
+        }
+    }
+    std::sort(fin.begin(), fin.end());
+    if ((int)fin.size() != s->h_state[r].F) return fail(RLGS_ERR_STATE, "replica %d: %zu finished jobs in the event rows, %d on the device", r, fin.size(), s->h_state[r].F);
+    if (tables) { for (size_t k = 0; k < fin.size(); ++k) fo[k] = fin[k].second; s->derived[r] = 1; }
+    return RLGS_OK;
+}
+
 static int32_t ensure_tables(rlgs_sim *s, int r) {
     if ((s->planes_mask & 7) == 7 || s->derived[r]) return RLGS_OK;
-    const bool can_derive = s->wire == RLGS_ROWFMT_EVENT16 && !s->legacy && !s->opts.enable_network_costs && s->opts.rows_mode != RLGS_ROWS_NONE &&
+    const bool can_derive = (s->wire == RLGS_ROWFMT_EVENT16 || s->wire == RLGS_ROWFMT_EVENT4) && !s->legacy && !s->opts.enable_network_costs && s->opts.rows_mode != RLGS_ROWS_NONE &&
                             (int)s->traces[s->rep_trace[r]].host.size() == s->h_desc[r].J;
     if (!can_derive) return fetch_planes(s, 3);
     { int32_t rc_a = alloc_host_jobs(s, false); if (rc_a) return rc_a; }
     const std::vector<rlgs_job> &jobs = s->traces[s->rep_trace[r]].host;
     const int J = (int)jobs.size();
     const int64_t n = s->h_state[r].d;
+    if (s->wire == RLGS_ROWFMT_EVENT4) return replay_queue(s, r, false);
     std::vector<rlgs_row16e> w((size_t)std::max<int64_t>(n, 1));
     if (n > 0) { int32_t rc = copy_rows_raw(s, r, 0, n, reinterpret_cast<unsigned char *>(w.data())); if (rc) return rc; }
     const size_t plane = (size_t)s->R * (size_t)s->Jmax, off = (size_t)r * s->Jmax;
@@ -979,6 +1035,7 @@ static int32_t prepare_expansion(rlgs_sim *s, int r) {
     if (s->xp_replica == r) return RLGS_OK;
     int32_t rc = ensure_tables(s, r);
     if (rc) return rc;
+    if (s->wire == RLGS_ROWFMT_EVENT4) { s->xp_replica = -1; rc = replay_queue(s, r, true); if (rc) return rc; }   // the pending-time triples
     const TraceBuf &tb = s->traces[s->rep_trace[r]];
     const int J = tb.n;
     if ((int)tb.host.size() != J) return fail(RLGS_ERR_STATE, "no host copy of the trace of replica %d", r);
@@ -1027,6 +1084,7 @@ static int32_t read_wire_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t cou
 extern "C" int32_t rlgs_read_rows16(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE16); }
 extern "C" int32_t rlgs_read_rows12(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row12 *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_WIRE12); }
 extern "C" int32_t rlgs_read_rows16e(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row16e *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_EVENT16); }
+extern "C" int32_t rlgs_read_rows4e(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row4e *out) { return read_wire_rows(s, r, first, count, out, RLGS_ROWFMT_EVENT4); }
 
 extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t count, rlgs_row *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
@@ -1065,6 +1123,13 @@ extern "C" int32_t rlgs_read_rows(rlgs_sim *s, int32_t r, int64_t first, int64_t
             o.max_pending = (int32_t)((x[1] >> 20) | ((x[2] & 0xfffu) << 12));
             o.median_lo = (int32_t)((x[2] >> 12) | ((x[3] & 0xfu) << 20));
             o.median_hi = (int32_t)((x[3] >> 4) & 0xffffffu);
+        } else if (s->wire == RLGS_ROWFMT_EVENT4) {
+            const uint32_t x = reinterpret_cast<const rlgs_row4e *>(w.data())[k].w;
+            const int32_t *pt = &s->xp_pend[(size_t)i * 3];
+            o.max_pending = pt[0]; o.median_lo = pt[1]; o.median_hi = pt[2];
+            o.idle_nodes = (int32_t)(x & 0xfffu);
+            o.finished = (int32_t)n_fin;
+            o.queued = (int32_t)(arrived - n_sta);
         } else {
             const uint32_t *x = reinterpret_cast<const uint32_t *>(w.data() + (size_t)k * s->row_bytes);   // rlgs_row12 / rlgs_row16e share w[0..2]
             o.max_pending = (int32_t)(x[0] & 0xffffffu);
@@ -1118,6 +1183,12 @@ extern "C" int32_t rlgs_rows16_view(rlgs_sim *s, int32_t r, int32_t chunk, const
 extern "C" int32_t rlgs_rows16e_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row16e **rows, int64_t *count) {
     if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (s->wire != RLGS_ROWFMT_EVENT16) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
+    return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
+}
+
+extern "C" int32_t rlgs_rows4e_view(rlgs_sim *s, int32_t r, int32_t chunk, const rlgs_row4e **rows, int64_t *count) {
+    if (!s || !rows || !count) return fail(RLGS_ERR_BAD_ARG, "null argument");
+    if (s->wire != RLGS_ROWFMT_EVENT4) return fail(RLGS_ERR_STATE, "the handle keeps its rows in another format (opts.rows_format)");
     return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 

@@ -21,9 +21,10 @@ class Simulator(object):
         pack_seed: None = utilisation draws of the horus score return their mean (the reference's behaviour on
         zero-spread traces); an int seeds the build-defined counter-based draw.  horus+: pack_seed also seeds the k-means draws
         (core/jobs/utils.py:39,60); pack_rng=False keeps the utilisation draws at their mean while the k-means stays seeded.
-        rows_format: 'event16' (default for fifo without network costs: 12-byte row + the tick's start event, from which the job
-        tables are rebuilt on the host when they were not copied) / 'wire12' / 'wire16' keep compact rows on the device and on the
-        wire and expand them in rows(); 'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto.
+        rows_format: 'event4' (default for fifo without network costs: a 4-byte event row per tick — idle nodes + "the queue head
+        started"; the host replays the queue to rebuild the job tables and the pending-time columns when asked) / 'event16' (12-byte
+        row + the job started at the tick) / 'wire12' / 'wire16' keep compact rows on the device and on the wire and expand them in
+        rows(); 'wide' keeps the self-contained 64-byte rows.  lanes_per_replica: 8 / 16 / 32 lanes of a warp per replica, 0 = auto.
         fetch_jobs: True = start / end / finish_order tables copied to the host inside run(); 'end' = end and finish_order only
         (fifo without network costs: a finished job started at end - dur_ticks)."""
         if schedule not in _ffi.SCHED:
@@ -33,7 +34,7 @@ class Simulator(object):
         if rows_format is None:
             rows_format = 'wide'
             if schedule == 'fifo' and cluster.num_nodes <= 4095:
-                rows_format = 'wire12' if enable_network_costs else 'event16'
+                rows_format = 'wire12' if enable_network_costs else 'event4'
         if rows_format not in _ffi.ROWFMT:
             raise ValueError('rows_format must be one of %s' % sorted(_ffi.ROWFMT))
         self.cluster = cluster
@@ -177,21 +178,22 @@ class Simulator(object):
 
     def rows_chunk_view(self, replica, chunk):
         """Zero-copy numpy view of one 4096-row chunk of a replica in the pinned host mirror: ROW_DTYPE for 'wide' handles,
-        ROW16_DTYPE / ROW12_DTYPE (the packed wire rows, see include/rlgs.h) for 'wire16' / 'wire12' handles."""
+        ROW16_DTYPE / ROW12_DTYPE / ROW4_DTYPE (the packed wire rows, see include/rlgs.h) for the other formats."""
         p, n = C.c_void_p(), C.c_int64(0)
         L = _ffi.lib()
         fn, dt = {'wide': (L.rlgs_rows_view, _ffi.ROW_DTYPE), 'wire16': (L.rlgs_rows16_view, _ffi.ROW16_DTYPE),
-                  'wire12': (L.rlgs_rows12_view, _ffi.ROW12_DTYPE), 'event16': (L.rlgs_rows16e_view, _ffi.ROW16_DTYPE)}[self._kw['rows_format']]
+                  'wire12': (L.rlgs_rows12_view, _ffi.ROW12_DTYPE), 'event16': (L.rlgs_rows16e_view, _ffi.ROW16_DTYPE),
+                  'event4': (L.rlgs_rows4e_view, _ffi.ROW4_DTYPE)}[self._kw['rows_format']]
         _ffi.check(fn(self._h, replica, chunk, C.byref(p), C.byref(n)))
         buf = (C.c_char * (n.value * dt.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=dt, count=n.value)
 
     def rows_wire(self, replica=0):
-        """The packed wire rows of a replica ('wire16' / 'wire12' handles), unexpanded."""
+        """The packed wire rows of a replica (every format but 'wide'), unexpanded."""
         n = self.summary(replica)['n_ticks']
         L = _ffi.lib()
         fn, dt = {'wire16': (L.rlgs_read_rows16, _ffi.ROW16_DTYPE), 'wire12': (L.rlgs_read_rows12, _ffi.ROW12_DTYPE),
-                  'event16': (L.rlgs_read_rows16e, _ffi.ROW16_DTYPE)}[self._kw['rows_format']]
+                  'event16': (L.rlgs_read_rows16e, _ffi.ROW16_DTYPE), 'event4': (L.rlgs_read_rows4e, _ffi.ROW4_DTYPE)}[self._kw['rows_format']]
         out = np.zeros(n, dt)
         if n:
             _ffi.check(fn(self._h, replica, 0, n, out.ctypes.data))

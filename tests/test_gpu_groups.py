@@ -14,7 +14,7 @@ from rlgpuschedule_b200 import _ffi, log_manager as lm
 pytestmark = pytest.mark.gpu
 
 LPRS = (8, 16, 32)
-FORMATS = ('event16', 'wire12', 'wire16', 'wide')
+FORMATS = ('event4', 'event16', 'wire12', 'wire16', 'wide')
 
 
 def _csvs(sim, cluster, tr, r):
@@ -81,6 +81,10 @@ def test_wire_rows_expand_to_the_wide_rows(lpr):
             w = sim.rows_wire(3)['w']
             assert np.array_equal(w[:, 0] & 0xfff, rows[fmt]['idle_nodes']) and np.array_equal(w[:, 0] >> 12, rows[fmt]['finished'])
             assert np.array_equal(sim.rows_chunk_view(3, 0)['w'], w[:4096])
+        if fmt == 'event4':
+            w = sim.rows_wire(3)['w']
+            assert w.ndim == 1 and np.array_equal(w & 0xfff, rows[fmt]['idle_nodes']) and np.array_equal(w >> 13, rows[fmt]['queued'] & 0x7ffff)
+            assert np.array_equal(sim.rows_chunk_view(3, 0)['w'], w[:4096])
         if fmt == 'wire12':
             w = sim.rows_wire(3)['w']
             assert w.shape[1] == 3 and np.array_equal(w[:, 0] & 0xffffff, rows[fmt]['max_pending']) and np.array_equal(w[:, 2], rows[fmt]['median_hi'])
@@ -88,9 +92,9 @@ def test_wire_rows_expand_to_the_wide_rows(lpr):
             _ffi.check(_ffi.lib().rlgs_read_rows(sim._h, 3, 100, 50, part.ctypes.data))
             assert np.array_equal(part, rows[fmt][100:150])
         sim.close()
-    assert rows['wide'].dtype == rows['wire16'].dtype == rows['wire12'].dtype == rows['event16'].dtype == _ffi.ROW_DTYPE
+    assert all(rows[fmt].dtype == _ffi.ROW_DTYPE for fmt in FORMATS)
     for f in _ffi.ROW_DTYPE.names:
-        for fmt in ('wire16', 'wire12', 'event16'):
+        for fmt in FORMATS[:-1]:
             assert np.array_equal(rows['wide'][f], rows[fmt][f]), (fmt, f)
     assert rows['wide']['busy_gpus'].max() > 0 and rows['wide']['sum_pending'].max() > 0 and rows['wide']['util_var_sum'].max() > 0
 
@@ -172,31 +176,42 @@ def test_end_only_job_tables_derive_the_start_ticks(fmt):
     sim.close()
 
 
+@pytest.mark.parametrize('fmt', ['event16', 'event4'])
 @pytest.mark.parametrize('lpr', LPRS)
-def test_event_rows_rebuild_the_job_tables(lpr):
-    """RLGS_ROWFMT_EVENT16: every row names the job that started at its tick, so the row stream is the event log.  The tables
+def test_event_rows_rebuild_the_job_tables(lpr, fmt):
+    """RLGS_ROWFMT_EVENT16: every row names the job that started at its tick; RLGS_ROWFMT_EVENT4: every row says whether the
+    queue head started at its tick and the host replays the queue.  Either way the row stream is the event log: the tables
     rebuilt from it on the host (start, end = start + dur_ticks, finish order = (end, start)) must equal the tables the device
-    wrote itself, on traces with many same-tick finishes and jobs that never start, and the wire word must name the right job."""
-    flags = dict(num_switch=1, num_node_p_switch=3, num_gpu_p_node=8)
+    wrote itself, on a trace with many same-tick finishes and jobs that never start, and the expanded rows (EVENT4: pending
+    times out of the replayed queue) must print the oracle's cluster.csv."""
+    flags = dict(num_switch=2, num_node_p_switch=4, num_gpu_p_node=8)
     cluster = rl.cluster_from_flags(flags)
-    df = tracegen.frame_gen(700, 21, 60)
-    df.loc[df.index[::7], 'minutes'] = 6.0                      # many equal durations: several jobs finish at the same tick
-    df.loc[df.index[5], 'used_gpus'] = 64.0; df.loc[df.index[5], 'gpu_per_container'] = 8   # wider than the cluster: never starts
+    df = tracegen.frame_gen(700, 21, 400)
+    df.loc[df.index[::3], 'minutes'] = 6.0                      # many equal durations: several jobs finish at the same tick
+    df.loc[df.index[-5], 'used_gpus'] = 128.0; df.loc[df.index[-5], 'gpu_per_container'] = 8   # wider than the cluster: blocks the queue for good
     tr = rl.prepare_trace(df, cluster)
     o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**flags), cpu_sim.prepare_trace(df))
+    assert (np.diff(o['end'][o['finish_order']]) == 0).sum() > 20 and (o['start'] < 0).sum() > 20   # the trace does what the docstring says
     tables = {}
     for fetch in (False, True):
-        sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=5, rows=True, lanes_per_replica=lpr, rows_format='event16', fetch_jobs=fetch)
+        sim = rl.Simulator(cluster, 'fifo', 'yarn', n_replicas=5, rows=True, lanes_per_replica=lpr, rows_format=fmt, fetch_jobs=fetch)
         sim.load_trace(tr)
         sim.run()
         tables[fetch] = sim.jobs(4)
-        if not fetch:
-            w = sim.rows_wire(4)['w'][:, 3]
-            ticks = np.nonzero(w)[0]
-            assert np.array_equal(o['start'][w[ticks] - 1], ticks) and len(ticks) == (o['start'] >= 0).sum()
-            assert lm.format_cluster_csv(sim.rows(4), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+        w = sim.rows_wire(4)['w']
+        if fmt == 'event16':
+            ticks = np.nonzero(w[:, 3])[0]
+            assert np.array_equal(o['start'][w[ticks, 3] - 1], ticks)
+        else:
+            ticks = np.nonzero(w & 0x1000)[0]
+            assert np.array_equal(np.sort(o['start'][o['start'] >= 0]), ticks)
+        assert len(ticks) == (o['start'] >= 0).sum()
+        assert lm.format_cluster_csv(sim.rows(4), cluster, tr.mem_shift, with_util=False) == cpu_sim.format_cluster_csv(o)
+        part = np.zeros(300, _ffi.ROW_DTYPE)                      # a range that starts mid-run: the cumulative counts catch up
+        _ffi.check(_ffi.lib().rlgs_read_rows(sim._h, 4, 1000, 300, part.ctypes.data))
+        assert np.array_equal(part, sim.rows(4)[1000:1300])
+        assert np.array_equal(sim.jobs(4)['start'], tables[fetch]['start'])   # the expansion left the tables alone
         sim.close()
     for k in ('start', 'end', 'finish_order', 'preempt'):
         assert np.array_equal(tables[False][k], tables[True][k]), k
     assert np.array_equal(tables[False]['finish_order'], o['finish_order']) and np.array_equal(tables[False]['end'], o['end'])
-    assert (np.diff(o['end'][o['finish_order']]) == 0).sum() > 20 and (o['start'] < 0).any()

@@ -175,3 +175,56 @@ def test_plugin_views_and_host_forms_of_the_builtin_entries():
             algorithm.resolve('user', 'horus')
     finally:
         del algorithm.scheduling_algorithms['user']
+
+
+@pytest.mark.parametrize('name', goldutil.case_names('small'))
+def test_start_bits_and_the_trace_determine_the_run(name):
+    """The rule behind RLGS_ROWFMT_EVENT4 (rlgs_row4e, include/rlgs.h), checked against the reference's own files: given only
+    idle_nodes and "a job started at this tick" per tick, a replay of the queue (arrivals pushed to the FRONT in trace order,
+    the attempt pops the front) names every started job, and end = start + dur_ticks, finish order = (end, start) and the
+    pending times at fixed queue positions reproduce job.csv and cluster.csv byte for byte."""
+    g = goldutil.load(name)
+    if g['flags'].get('enable_network_costs'):
+        pytest.skip('network costs change the duration at placement time')
+    ti = goldutil.trace_input(g)
+    cluster = rl.cluster_from_flags(g['flags'])
+    tr = rl.prepare_trace(ti, cluster)
+    o = cpu_sim.run_fifo_yarn(cpu_sim.make_cluster(**g['flags']), cpu_sim.prepare_trace(ti))
+    n, rec = o['n_ticks'], tr.records
+    J = len(rec)
+    bits = np.zeros(n, bool)
+    bits[o['start'][o['start'] >= 0]] = True                      # all that the rows say about starts
+    arr = rec['arrival_tick'].astype(np.int64)
+    ndev = rec['tasks'].astype(np.int64) * rec['gpus_per_task']
+    start, end = np.full(J, -1, np.int64), np.full(J, -1, np.int64)
+    queue, cursor, back_arr = [], 0, 0
+    rows = np.zeros(n, _ffi.ROW_DTYPE)
+    for i in range(n):
+        k = 0
+        while cursor + k < J and arr[cursor + k] <= i:
+            k += 1
+        if k:
+            if not queue:
+                back_arr = i
+            queue[0:0] = list(range(cursor, cursor + k))
+            cursor += k
+        if bits[i]:
+            j = queue.pop(0)
+            start[j] = i
+            if i + rec['dur_ticks'][j] <= n:
+                end[j] = i + rec['dur_ticks'][j]
+        r, d, Q = rows[i], i + 1, len(queue)
+        r['queued'] = Q
+        if Q:
+            r['max_pending'] = d - back_arr
+            r['median_lo'] = d - arr[queue[(Q - 1) // 2]]; r['median_hi'] = d - arr[queue[Q // 2]]
+            r['sum_pending'] = sum(d - arr[q] for q in queue)
+        running = (start >= 0) & ((end < 0) | (end > d))
+        r['running'] = running.sum(); r['finished'] = ((end >= 0) & (end <= d)).sum()
+        r['busy_gpus'] = ndev[running].sum(); r['mem_sum'] = rec['mem_term'][running].sum()
+        r['idle_nodes'] = o['rows']['idle_nodes'][i]
+    fin = sorted((int(end[j]), int(start[j]), j) for j in range(J) if end[j] >= 0)
+    order = np.array([j for _, _, j in fin], np.int32)
+    assert np.array_equal(start, o['start']) and np.array_equal(end, o['end']) and np.array_equal(order, o['finish_order'])
+    assert lm.format_cluster_csv(rows, cluster, tr.mem_shift, with_util=False) == g['cluster']
+    assert lm.format_job_csv(tr, order, start.astype(np.int32), end.astype(np.int32)) == g['job']
