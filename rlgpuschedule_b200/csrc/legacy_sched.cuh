@@ -222,7 +222,10 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
     }
 }
 
-__global__ void __launch_bounds__(32) dlas_gpu_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
+#ifndef RLGS_DLAS_MIN_BLOCKS
+#define RLGS_DLAS_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(32, RLGS_DLAS_MIN_BLOCKS) dlas_gpu_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
                                                       RowStore rs, int64_t *__restrict__ returns) {
     const int lane = lane_id();
     const LegDesc D = descs[blockIdx.x];
@@ -372,7 +375,10 @@ struct SjfSmem { NodeView nv; };
 
 __host__ __device__ inline size_t sjf_smem_bytes(int N) { return (3 * (size_t)N + (size_t)((N + 31) / 32)) * 4; }
 
-__global__ void __launch_bounds__(32) sjf_yarn_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
+#ifndef RLGS_SJF_MIN_BLOCKS
+#define RLGS_SJF_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(32, RLGS_SJF_MIN_BLOCKS) sjf_yarn_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
                                                       ClusterConst c, RowStore rs, int64_t *__restrict__ returns) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = lane_id();
