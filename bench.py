@@ -38,10 +38,10 @@ REF_DIR = os.path.join(ROOT, 'oracle', '_ref', 'reference')
 WORKLOADS = {
     'fifo60k': dict(schedule='fifo', scheme='yarn', n_jobs=60000, seed0=3, n_traces=16, replicas=8880, kw={},
                     text='fifo+yarn, 4x32x8 simulated cluster, 60k-job Philly-style trace (gen(60000, seed, 60000))'),
-    'dlas60k': dict(schedule='dlas-gpu', scheme='count', n_jobs=60000, seed0=3, n_traces=8, replicas=2960,
+    'dlas60k': dict(schedule='dlas-gpu', scheme='count', n_jobs=60000, seed0=3, n_traces=8, replicas=4736,
                     kw=dict(num_queue=4, queue_limit=(30, 60, 150)),
                     text='dlas-gpu (4-queue MLFQ, limits 30/60/150 GPU-ticks), 4x32x8 simulated cluster, 60k-job trace (gen(60000, seed, 60000))'),
-    'sjf10k': dict(schedule='sjf', scheme='yarn', n_jobs=10000, seed0=2, n_traces=8, replicas=2368, kw={},   # 124 registers: 16 warps per SM
+    'sjf10k': dict(schedule='sjf', scheme='yarn', n_jobs=10000, seed0=2, n_traces=8, replicas=4736, kw={},   # 64-register build: 32 warps per SM
                    text='sjf+yarn, 4x32x8 simulated cluster, 10k-job trace (gen(10000, seed, 10000))'),
     'env512x10k': dict(schedule='fifo', scheme='yarn', n_jobs=10000, seed0=1000, n_traces=32, replicas=512, kw={}, env=True,
                        text='RL environment rollouts (random pick inside a 5-job window, counter-based RNG), 4x32x8 simulated cluster, '

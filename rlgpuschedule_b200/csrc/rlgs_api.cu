@@ -618,6 +618,7 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
         launch_fifo(s, first, count, budget, rows ? 1 + s->wire : 0, false, none, rs, st);   // the caller reads cudaGetLastError
     } else {
         LegParams lp = s->lp; lp.event_budget = budget;
+        const bool dense = s->R > 148 * 24;   // more replicas than 24 warps per SM: the 64-register builds of the per-event kernels (legacy_sched.cuh)
         if (s->pack) {
             PackParams pp = s->pp; pp.tick_budget = budget;
 #define RLGS_LAUNCH_PACK(G, Y, PL) pack_horus_kernel<G, Y, PL><<<count, 32, pack_smem_bytes(s->cc.N), st>>>(s->d_pdesc + first, s->d_pstate + first, pp, s->cc, rs, s->d_returns + first)
@@ -626,10 +627,13 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
             else if (pp.gandiva) { if (yarn) RLGS_LAUNCH_PACK(true, true, false); else RLGS_LAUNCH_PACK(true, false, false); }
             else { if (yarn) RLGS_LAUNCH_PACK(false, true, false); else RLGS_LAUNCH_PACK(false, false, false); }
 #undef RLGS_LAUNCH_PACK
-        } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS)
-            dlas_gpu_kernel<<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
-        else
-            sjf_yarn_kernel<<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
+        } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS) {
+            if (dense) dlas_gpu_kernel<32><<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
+            else dlas_gpu_kernel<1><<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
+        } else {
+            if (dense) sjf_yarn_kernel<32><<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
+            else sjf_yarn_kernel<1><<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
+        }
     }
 }
 
@@ -660,7 +664,8 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr);
         if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp (> 227 KB)", smem);
     } else if (!s->pack && s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
-        CU(cudaFuncSetAttribute(sjf_yarn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
+        CU(cudaFuncSetAttribute(sjf_yarn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
+        CU(cudaFuncSetAttribute(sjf_yarn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
     int32_t max_arrival = 0;
     for (int r = 0; r < R; ++r) {

@@ -133,8 +133,11 @@ class Scheduler(object):
         summ = sim.summary(0)
         legacy = self.schedule not in ('fifo', 'horus', 'horus+', 'gandiva')
         if not legacy:
-            self.log_manager.write_cluster_rows(sim.rows(0), cluster, trace.mem_shift,
-                                                util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
+            util_seed = getattr(flags, 'seed', None)
+            if util_seed is None and getattr(flags, 'columnar', False):
+                util_seed = int.from_bytes(os.urandom(4), 'little')   # one draw stream for cluster.csv and cluster.parquet
+            rows0 = sim.rows(0)
+            self.log_manager.write_cluster_rows(rows0, cluster, trace.mem_shift, util_mode=getattr(flags, 'util_mode', 'sample'), seed=util_seed)
             j = sim.jobs(0)
             logging.info('Total Time Taken in seconds: %d' % took)
             extra = {}
@@ -145,8 +148,8 @@ class Scheduler(object):
                              jct=sim.job_plane(0, _ffi.PLANE_PREEMPT))
             self.log_manager.jcts((trace, j['finish_order'], j['start'], j['end'], j['preempt'], sim.durations(0) if net else None, extra))
             if getattr(flags, 'columnar', False):
-                self.log_manager.write_columnar(sim.rows(0), cluster, trace, j, trace.mem_shift, get_duration=extra.get('get_duration'),
-                                                jct=extra.get('jct'), util_mode=getattr(flags, 'util_mode', 'sample'), seed=getattr(flags, 'seed', None))
+                self.log_manager.write_columnar(rows0, cluster, trace, j, trace.mem_shift, get_duration=extra.get('get_duration'),
+                                                jct=extra.get('jct'), util_mode=getattr(flags, 'util_mode', 'sample'), seed=util_seed)
         else:
             from . import _ffi
             j = sim.jobs(0)
