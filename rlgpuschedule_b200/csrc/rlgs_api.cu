@@ -1218,7 +1218,7 @@ extern "C" int32_t rlgs_returns_device_ptr(rlgs_sim *s, void **dev_ptr) {
 
 // ------------------------------------------------------------------------------------------------
 // Vectorised RL environment (replaces the stub model/env.py:1-6 of the reference; semantics are
-// build-defined, see fifo_yarn.cuh EnvIO).  All pointers are DEVICE pointers (torch tensors);
+// build-defined, see fifo_grp.cuh EnvIO).  All pointers are DEVICE pointers (torch tensors);
 // calls are asynchronous on the handle's stream (rlgs_set_stream) until rlgs_env_sync.
 // ------------------------------------------------------------------------------------------------
 extern "C" int32_t rlgs_env_obs_dim(rlgs_sim *s, int32_t window_k, int32_t *dim) {
