@@ -13,8 +13,11 @@ One "step" = every replica of the GPU simulated to completion.  An event = arriv
 queue jump; 3 per finished job under non-preemptive fifo.
 
 Prints ONE JSON line (rank 0).  `value` = events/s with traces resident in HBM (rows written to the device-resident row
-store); `e2e` = the same through the C ABI with host buffers: trace upload, simulation, rows + job tables copied back to the
-host, all inside the timed region.  `--impl reference` times the reference's algorithm on the host cores (oracle/cpu_sim.c, the
+store); `e2e` = the same through the C ABI with host buffers: trace upload, simulation, the result of every replica copied
+back to the host, all inside the timed region.  For fifo the result is the per-tick row stream in `--rows-format`: event4
+(default; 4 bytes per tick = the event log, from which rlgs_read_rows / rlgs_read_jobs rebuild every column and table of a
+replica on demand), event16 (also reported as `e2e_stat_rows`: the rows still carry the kernel-computed pending statistics),
+wire12 / wire16 (+ job tables), wide (the 64-byte rows of round 1).  `--impl reference` times the reference's algorithm on the host cores (oracle/cpu_sim.c, the
 C port validated byte-for-byte against the real Python reference) and, when the unmodified Python reference was staged under
 oracle/_ref/reference by __graft_entry__.build(), reports its own measured events/s beside it (`reference_python`).
 """
@@ -390,8 +393,8 @@ def main():
     (env or sim).close()
 
     # ---------------- end-to-end arm through the C ABI with host buffers
-    e2e = None
-    if not args.no_e2e:
+    def e2e_arm(rows_format):
+        """Every step: records host -> device, simulate, the result of every replica device -> pinned host memory."""
         if is_env:
             env2 = Environment(cluster, [(traces[i], first, count) for i, first, count in blocks], n_replicas=R, window_k=5, device=local_rank, seed=1)
 
@@ -402,12 +405,15 @@ def main():
                 return env2.sim.returns()                  # device -> host: episode returns
             closer = env2
         else:
-            sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=(False if args.rows_format.startswith('event') else 'end') if is_fifo else True, device=local_rank, **sim_kw)
+            kw2 = dict(sim_kw)
+            if is_fifo:
+                kw2['rows_format'] = rows_format
+            sim2 = rl.Simulator(cluster, w['schedule'], w['scheme'], n_replicas=R, rows='host', fetch_jobs=(False if rows_format.startswith('event') else 'end') if is_fifo else True, device=local_rank, **kw2)
             attach(sim2)
 
             def step2():
                 attach(sim2)          # host -> device: the step's input records
-                sim2.run()            # simulate; rows + job tables -> pinned host store, overlapped with compute
+                sim2.run()            # simulate; rows (+ job tables, format permitting) -> pinned host store, overlapped with compute
                 return int(sim2.summary(0)['n_finished'])
             closer = sim2
         for _ in range(max(args.warmup, 3)):
@@ -428,13 +434,24 @@ def main():
             rows0 = sim2.rows(0)
             j0 = sim2.jobs(0)
             assert len(rows0) == summ[0]['n_ticks'] and int(rows0['finished'][-1]) == len(j0['finish_order'])
-            row_bytes = {'event4': 4, 'event16': 16, 'wire12': 12, 'wire16': 16, 'wide': 64}[args.rows_format] if is_fifo else 64
-            n_planes = (0 if args.rows_format.startswith('event') else 2) if is_fifo else 3
+            row_bytes = {'event4': 4, 'event16': 16, 'wire12': 12, 'wire16': 16, 'wide': 64}[rows_format] if is_fifo else 64
+            n_planes = (0 if rows_format.startswith('event') else 2) if is_fifo else 3
             n_chunks = -(-max_ticks // _ffi.ROWS_PER_CHUNK)        # whole chunks travel (chunk-major row store)
             d2h = int(n_chunks * R * _ffi.ROWS_PER_CHUNK * row_bytes + n_planes * 4 * R * jmax + R * 264)   # rows + job tables + replica states
-        e2e = {'value': events_all * args.steps / t2.item(), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+        out = {'value': events_all * args.steps / t2.item(), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'ms_per_step': 1e3 * t2.item() / args.steps}
         closer.close()
+        return out
+
+    e2e = e2e_stat_rows = None
+    if not args.no_e2e:
+        e2e = e2e_arm(args.rows_format)
+        if is_fifo and not is_env and args.rows_format == 'event4':
+            # companion number: the same step with the rows that still carry the kernel-computed pending-time statistics
+            e2e_stat_rows = e2e_arm('event16')
+            e2e_stat_rows['rows_format'] = 'event16'
+            e2e_stat_rows['note'] = ('16 bytes per tick: max / median pending times computed by the kernel + the job started at the tick; the default '
+                                     '(event4) sends the event log alone and the library derives those columns on the host when a replica is read')
 
     if rank == 0:
         peaks = {}
@@ -472,7 +489,11 @@ def main():
             roofline = {'bound': 'hbm', 'achieved': alg_gbps, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': alg_gbps / hbm_peak, 'traffic': traffic,
                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                         'profile': prof.get('source'),
-                        'note': 'achieved = SURVEY 8(d) algorithmic bytes of the per-event sweep (runnable entries streamed 32 at a time) / kernel time'}
+                        'dram_GBps': (traffic / per_launch_s / 1e9) if traffic else None,
+                        'dram_frac': (traffic / per_launch_s / 1e9 / hbm_peak) if traffic else None,
+                        'issue_active_pct_in_profile': prof.get('issue_active_pct'),
+                        'note': 'achieved = SURVEY 8(d) algorithmic bytes of the per-event sweep (runnable entries streamed 32 at a time) / kernel time; '
+                                'the entry lists mostly live in L2, and the ncu capture shows the kernel closer to the issue limit than to the DRAM one'}
         roofline['launch'] = 'one step = %d launches of %s; bytes and time are per step' % (launches // max(args.steps, 1), kernel_name)
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -500,6 +521,8 @@ def main():
         }
         if e2e:
             out['e2e'] = e2e
+        if e2e_stat_rows:
+            out['e2e_stat_rows'] = e2e_stat_rows
         if not args.no_cpu and world == 1:   # the CPU baseline is reported at N=1 only, on every usable host core
             os.sched_setaffinity(0, all_cpus)
             out['cpu_baseline'] = cpu_baseline_sample(w)
