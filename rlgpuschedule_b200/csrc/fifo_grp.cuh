@@ -437,10 +437,17 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
     JobRec ring;
     ring.a = make_int4(RLGS_NEVER, 0, 0, 0); ring.b = make_int4(0, 0, 0, 0);
     if (act && ring_base + G.gl < J) ring = load_rec(D.trace + ring_base + G.gl);
-    int ring_next = RLGS_NEVER;   // arrival tick of the first job behind the ring: tells whether a batch that fills the ring ends there
-    if (act && ring_base + LPR < J) ring_next = D.trace[ring_base + LPR].arrival_tick;
-    JobRec h0;   // the queue front lives in registers; after a pop the next record is fetched while the tick finishes
-    h0.a = h0.b = make_int4(0, 0, 0, 0);
+    // arrival tick of the first job behind the ring: tells whether a batch that fills the ring ends there.  The validity flag
+    // is kept apart so that the (predicated) load is not followed by a select on its result — that was a full load wait.
+    int ring_next = RLGS_NEVER;
+    bool ring_next_ok = act && ring_base + LPR < J;
+    if (ring_next_ok) ring_next = D.trace[ring_base + LPR].arrival_tick;
+    // The queue front lives in registers.  After a pop the next record is fetched into h0n and only becomes h0 at the next
+    // attempt: the load then has the rest of the tick to complete.  (Loading straight into h0 made the compiler copy a loaded
+    // word right behind the load — a full global-load wait at every start, 10 % of all stall samples in the v9 capture.)
+    JobRec h0, h0n;
+    h0.a = h0.b = h0n.a = h0n.b = make_int4(0, 0, 0, 0);
+    bool h0_pending = false;
     if (act && st.Q > 0) h0 = load_rec(D.stack + st.head);
 
     // the launch stops at its tick budget or at the safety limit max_ticks, whichever comes first (one compare per tick)
@@ -461,7 +468,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             const unsigned ab = GBALLOT(arr);
             if (__any_sync(RLGS_FULLMASK, ab != 0u)) {
                 int k = __popc(ab);
-                const bool covered = (st.cursor + k < ring_base + LPR) || ring_next > d;
+                const bool covered = (st.cursor + k < ring_base + LPR) || !ring_next_ok || ring_next > d;
                 const int first = (st.cursor - ring_base) & (LPR - 1);
                 JobRec n0;
                 n0.a.x = GSHFL(ring.a.x, first); n0.a.y = GSHFL(ring.a.y, first); n0.a.z = GSHFL(ring.a.z, first); n0.a.w = GSHFL(ring.a.w, first);
@@ -482,6 +489,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                         for (int b = G.gl; b < k; b += LPR) store_rec(D.stack + (st.head - k) + b, load_rec(D.trace + st.cursor + b));
                     }
                     h0 = n0;   // the first arrived job = trace[cursor], which the ring holds in lane `first`
+                    h0_pending = false;
                     if (st.Q == 0) st.bottom_arr = d;
                     st.head -= k; st.Q += k; st.cursor += k;
                     if (ROWS == 1) st.sum_arr += (int64_t)k * d;
@@ -491,7 +499,8 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                         ring_base = st.cursor - (st.cursor % LPR);
                         const int i3 = ring_base + G.gl;
                         if (i3 < J) ring = load_rec(D.trace + i3); else ring.a = make_int4(RLGS_NEVER, 0, 0, 0);
-                        ring_next = ring_base + LPR < J ? D.trace[ring_base + LPR].arrival_tick : RLGS_NEVER;
+                        ring_next_ok = ring_base + LPR < J;
+                        if (ring_next_ok) ring_next = D.trace[ring_base + LPR].arrival_tick;
                     }
                 }
                 __syncwarp();   // the stack records are visible to the whole group (median loads, env window, next head)
@@ -510,6 +519,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
             attempt = act && st.Q > 0 && pick >= 0 && pick < win;
         }
         if (__any_sync(RLGS_FULLMASK, attempt)) {
+            if (h0_pending) { h0 = h0n; h0_pending = false; }
             JobRec hx = h0;
             if (ENV && attempt && pick > 0) hx = load_rec(D.stack + st.head + pick);
             const int T = hx.tasks(), gpc = hx.gpc(), need_g = hx.gpus();
@@ -534,7 +544,13 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                     const uint32_t kn = s.key[ni];
                     const uint32_t busy = NC::busy(s, ni, kn);
                     const uint32_t ew = s.ever[ni >> 5], bit = 1u << (ni & 31);
-                    const uint32_t taken = lowest_bits(~busy & c.gmask, hit ? T * gpc : 0);
+                    // devices in id order (node.py:209-219): with a lane per device, lane i of the group decides bit i (no loop);
+                    // groups narrower than a node fall back to the bit-clearing loop
+                    const uint32_t fm = ~busy & c.gmask;
+                    const int want = hit ? T * gpc : 0;
+                    uint32_t taken;
+                    if (PK || LPR == 32) taken = GBALLOT(((fm >> G.gl) & 1u) && __popc(fm & ((1u << G.gl) - 1u)) < want);
+                    else taken = lowest_bits(fm, want);
                     __syncwarp();                               // every lane has read the old node state
                     if (hit) {
                         if (!(ew & bit)) { st.idle_nodes--; s.ever[ni >> 5] = ew | bit; }
@@ -597,7 +613,7 @@ __global__ void __launch_bounds__(32, RLGS_GRP_MIN_BLOCKS) fifo_grp_kernel(const
                     st.R += 1; st.Q -= 1; st.head += 1;
                     if (st.R > st.max_r) st.max_r = st.R;
                     if (st.Q > 0) {
-                        h0 = load_rec(D.stack + st.head);   // consumed by the next tick's attempt
+                        h0n = load_rec(D.stack + st.head); h0_pending = true;   // consumed by the next attempt
                         if (ENV) st.bottom_arr = D.stack[st.head + st.Q - 1].arrival_tick;
                     }
                 }

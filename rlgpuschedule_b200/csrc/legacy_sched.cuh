@@ -222,9 +222,10 @@ __device__ __forceinline__ void dlas_chunk(const LegDesc &D, const LegParams &P,
     }
 }
 
-// MB = minimum resident blocks per SM the register allocation leaves room for: 1 = as many registers as the code wants (94: 20
-// warps per SM, the fastest choice up to 148 x 20 replicas), 32 = at most 64 registers, small spills, 32 warps per SM (measured on
-// the 60k-job trace: +17 % events/s at 148 x 32 replicas, -11 % at 148 x 20).  rlgs_api.cu picks by the size of the launch.
+// MB = minimum resident blocks per SM the register allocation leaves room for: 20 (16 for sjf) = the registers the code wants
+// (94 / 124: 20 / 16 warps per SM, the fastest choice up to 148 x 20 replicas), 32 = at most 64 registers, small spills, 32 warps
+// per SM (measured on the 60k-job trace: +17 % events/s at 148 x 32 replicas, -11 % at 148 x 20).  rlgs_api.cu picks by the
+// size of the launch.
 template <int MB>
 __global__ void __launch_bounds__(32, MB) dlas_gpu_kernel(const LegDesc *__restrict__ descs, LegState *__restrict__ states, LegParams P,
                                                       RowStore rs, int64_t *__restrict__ returns) {
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(32, MB) sjf_yarn_kernel(const LegDesc *__restr
                     else if (status == L_RUNNING) e.a.w += d; else e.b.y += d;               // :216-230
                 }
                 JobRec jr; jr.a = make_int4(0, e.a.z, e.b.x, e.b.w); jr.b = make_int4(0, 0, 0, job);
-                PlaceResult pr = yarn_place(nv, c, jr, lane, D.place_scratch, 0, n_free_nodes, idle_unused);   // :246
+                                PlaceResult pr = yarn_place(nv, c, jr, lane, D.place_scratch, 0, n_free_nodes, idle_unused);   // :246
                 if (pr.ok) {
                     if (!e.started()) { e.set_started(); if (lane == 0) D.planes[0][job] = event_time; }    // :251-252
                     if (status == L_PENDING) { e.set_status(L_RUNNING); e.b.z += 1 << 16; n_events += 1; }   // :265-267

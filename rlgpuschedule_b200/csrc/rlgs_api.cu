@@ -629,10 +629,10 @@ static void launch(rlgs_sim *s, int first, int count, int budget, bool rows, cud
 #undef RLGS_LAUNCH_PACK
         } else if (s->opts.schedule == RLGS_SCHED_DLAS_GPU || s->opts.schedule == RLGS_SCHED_DLAS) {
             if (dense) dlas_gpu_kernel<32><<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
-            else dlas_gpu_kernel<1><<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
+            else dlas_gpu_kernel<20><<<count, 32, 0, st>>>(s->d_ldesc + first, s->d_lstate + first, lp, rs, s->d_returns + first);
         } else {
             if (dense) sjf_yarn_kernel<32><<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
-            else sjf_yarn_kernel<1><<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
+            else sjf_yarn_kernel<16><<<count, 32, sjf_smem_bytes(s->cc.N), st>>>(s->d_ldesc + first, s->d_lstate + first, lp, s->cc, rs, s->d_returns + first);
         }
     }
 }
@@ -664,7 +664,7 @@ extern "C" int32_t rlgs_run(rlgs_sim *s) {
         size_t smem = (32 / s->lpr) * grp_smem_bytes(s->cc.N, s->cc.G, s->slot_cap, s->lpr);
         if (smem > 227 * 1024) return fail(RLGS_ERR_CAPACITY, "cluster state needs %zu B of shared memory per warp (> 227 KB)", smem);
     } else if (!s->pack && s->lp.nq == 1 && s->opts.schedule != RLGS_SCHED_DLAS_GPU && s->opts.schedule != RLGS_SCHED_DLAS) {
-        CU(cudaFuncSetAttribute(sjf_yarn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
+        CU(cudaFuncSetAttribute(sjf_yarn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
         CU(cudaFuncSetAttribute(sjf_yarn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sjf_smem_bytes(s->cc.N)));
     }
     int32_t max_arrival = 0;

@@ -81,7 +81,9 @@ __device__ __forceinline__ rlgs_row *row_ptr(const RowStore &rs, int replica_loc
     return rs.chunks[i >> RLGS_ROW_CHUNK_LOG] + ((size_t)(rs.replica + replica_local) << RLGS_ROW_CHUNK_LOG) + (i & (RLGS_ROW_CHUNK - 1));
 }
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// volatile: read the special register once and keep the value — under register pressure the compiler otherwise re-reads
+// SR_TID.X (S2R, tens of cycles) wherever `lane` is used (4.7 % of the instructions of dlas_gpu_kernel in the r02 capture)
+__device__ __forceinline__ int lane_id() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
 
 // mask of the k lowest set bits of `freemask` (devices are taken in device-id order, node.py:209-219)
 __device__ __forceinline__ uint32_t lowest_bits(uint32_t freemask, int k) {
@@ -89,6 +91,11 @@ __device__ __forceinline__ uint32_t lowest_bits(uint32_t freemask, int k) {
     uint32_t rem = freemask;
     for (int i = 0; i < k; ++i) rem &= rem - 1;
     return freemask ^ rem;
+}
+// The same for a full, converged warp whose lanes all hold the same (freemask, k): lane i decides bit i, no loop.
+__device__ __forceinline__ uint32_t lowest_bits_warp(uint32_t freemask, int k, int lane) {
+    const bool keep = ((freemask >> lane) & 1u) && __popc(freemask & ((1u << lane) - 1u)) < k;
+    return __ballot_sync(RLGS_FULL, keep);
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {

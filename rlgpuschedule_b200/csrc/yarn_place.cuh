@@ -71,7 +71,7 @@ __device__ __forceinline__ PlaceResult yarn_place(NodeView nv, const ClusterCons
         if (node < 0) return r;
         int u = nv.units[node];
         uint32_t busy = nv.busy[node];
-        uint32_t taken = lowest_bits(~busy & c.gmask, T * gpc);
+        uint32_t taken = lowest_bits_warp(~busy & c.gmask, T * gpc, lane);   // the warp is converged here, node / busy are uniform
         bool was = node_is_free(u, c);
         u += T;
         n_free_nodes += (int)node_is_free(u, c) - (int)was;

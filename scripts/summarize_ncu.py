@@ -2,7 +2,7 @@
 
     python scripts/summarize_ncu.py gpurun_out/x.ncu-rep profiles/r01_x.md "description" [replica_ticks]
 """
-import collections, csv, io, subprocess, sys
+import collections, csv, io, os, subprocess, sys
 
 rep, out, desc = sys.argv[1], sys.argv[2], sys.argv[3]
 replica_ticks = float(sys.argv[4]) if len(sys.argv) > 4 else None
@@ -20,7 +20,7 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__thread_inst_executed.sum', 'smsp__inst_executed.sum',
         'smsp__warps_eligible.avg.per_cycle_active', 'smsp__issue_inst0.avg.pct_of_peak_sustained_active', 'launch__shared_mem_per_block_dynamic']
-lines = ['# ' + desc, '', 'source report: `%s` (ncu --set full --clock-control none --import-source on)' % rep, '']
+lines = ['# ' + desc, '', 'source report: `%s` (%s)' % (rep, os.environ.get('NCU_HOW', 'ncu --set full --clock-control none --import-source on')), '']
 for vals in rows[2:]:
     d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
     lines.append('## launch: %s' % d.get('Kernel Name', '?'))
