@@ -43,6 +43,8 @@ flags.DEFINE_string('queue_limit', '30,60,150', 'dlas-gpu: MLFQ demotion thresho
 flags.DEFINE_string('util_mode', 'sample', "avg_gpu_utilization column: 'sample' (seedable normal draw) or 'mean'")
 flags.DEFINE_integer('seed', None, 'seed of the utilisation draws: the avg_gpu_utilization column and the horus score (the reference draws unseeded)')
 flags.DEFINE_integer('device', 0, 'CUDA device ordinal')
+flags.DEFINE_string('backend', 'cuda', "execution backend (SURVEY 8b): 'cuda' = librlgs.so on the GPU named by --device.  'python' is accepted for "
+                    "interface compatibility and refused: this build has no CPU path; run the reference itself for that")
 flags.DEFINE_boolean('columnar', False, 'also write cluster.parquet / job.parquet (typed columns, no float formatting)')
 flags.DEFINE_version('0.1')
 
@@ -50,6 +52,9 @@ FLAGS = flags.FLAGS
 
 
 def main(log_manager):
+    if FLAGS.backend != 'cuda':
+        raise SystemExit("--backend %s: only 'cuda' is built here (the product path has no CPU fallback); the Python backend is the "
+                         "reference's own run_sim.py" % FLAGS.backend)
     infrastructure = Infrastructure(FLAGS)
     log_manager.init(infrastructure)
     jq_manager = JobQueueManager(FLAGS, os.path.abspath(FLAGS.trace_file))
@@ -59,6 +64,8 @@ def main(log_manager):
 
 
 if __name__ == '__main__':
+    if FLAGS.backend != 'cuda':
+        main(None)   # refuses before a log directory is created
     logging.basicConfig(format='%(asctime)s p%(process)s {%(module)s:%(lineno)d} %(levelname)s: %(message)s', level=logging.DEBUG)
     execution_id = datetime.datetime.now().strftime('%Y-%m-%d-%H-%M-%S-%f')
     output_dir = os.path.join('log', FLAGS.log_path, execution_id)
