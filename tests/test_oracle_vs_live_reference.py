@@ -85,3 +85,32 @@ def test_pack_oracle_equals_live_reference_on_random_cases():
             assert ref['job_csv'] is not None, (seed, sched, scheme, ref['stderr'][-500:])
             assert job == ref['job_csv'], (seed, sched, scheme)
             assert clu == ref_runner.strip_util_column(ref['cluster_csv']), (seed, sched, scheme)
+
+
+# ---- the legacy event loops: the reference's dead code run unmodified under the shim globals (oracle/ref_legacy_runner.py)
+LEGACY = ['sjf', 'shortest', 'shortest-gpu', 'dlas-gpu', 'dlas']
+
+
+def _run_legacy(arg):
+    import ref_legacy_runner
+    seed, sched = arg
+    df, flags = _case(seed)
+    rng = np.random.default_rng(seed + 11)
+    ql = tuple(int(x) for x in np.cumsum(rng.integers(5, 60, int(rng.integers(1, 4)))))   # 2 .. 4 queues
+    work = tempfile.mkdtemp(prefix='rlgs_liveleg_%d_' % seed)
+    trace = os.path.join(work, 't.csv')
+    synth.write(df, trace)
+    ref = ref_legacy_runner.run_legacy(trace, sched, workdir=work, queue_limit=ql, **flags)
+    tr = cpu_sim.prepare_trace(trace)
+    cluster = cpu_sim.make_cluster(**flags)
+    res, count = cpu_sim.run_legacy(cluster, tr, sched, ql)
+    return seed, sched, ref, cpu_sim.format_legacy_job_csv(tr, res, count), cpu_sim.format_legacy_cluster_csv(res, cluster, count)
+
+
+def test_legacy_oracle_equals_live_reference_on_random_cases():
+    args = [(300 + 5 * i + j, sched) for i, sched in enumerate(LEGACY) for j in range(2)]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for seed, sched, ref, job, clu in ex.map(_run_legacy, args):
+            assert ref['job_csv'] is not None and ref['cluster_csv'] is not None, (seed, sched, ref['stderr'][-500:])
+            assert job == ref['job_csv'], (seed, sched)
+            assert clu == ref['cluster_csv'], (seed, sched)
