@@ -13,7 +13,7 @@ One "step" = every replica of the GPU simulated to completion.  An event = arriv
 queue jump; 3 per finished job under non-preemptive fifo.
 
 Prints ONE JSON line (rank 0).  `value` = events/s with traces resident in HBM (rows written to the device-resident row
-store); `e2e` = the same through the C ABI with host buffers: trace upload, simulation, the result of every replica copied
+store); `e2e` = the same through the C ABI with host buffers: trace upload (records in pinned host memory), simulation, the result of every replica copied
 back to the host, all inside the timed region.  For fifo the result is the per-tick row stream in `--rows-format`: event4
 (default; 4 bytes per tick = the event log, from which rlgs_read_rows / rlgs_read_jobs rebuild every column and table of a
 replica on demand), event16 (also reported as `e2e_stat_rows`: the rows still carry the kernel-computed pending statistics),
@@ -308,6 +308,15 @@ def main():
     is_env = bool(w.get('env'))
     cluster = rl.Cluster(**CLUSTER_FLAGS)
     traces = [rl.prepare_trace(f, cluster) for f in frames(w, rank)]
+    pinned = []   # the step's inputs (32-byte job records) live in pinned host memory: the e2e arm uploads them every step
+    for tr in traces:
+        try:
+            buf = torch.from_numpy(np.ascontiguousarray(tr.records).view(np.uint8).copy()).pin_memory()
+            tr.records = buf.numpy().view(_ffi.JOB_DTYPE)
+            pinned.append(buf)
+        except Exception as e:   # keeps the pageable arrays (slower uploads, same result)
+            sys.stderr.write('bench: could not pin the trace records (%r)\n' % (e,))
+            break
     bounds = [R * i // NT for i in range(NT + 1)]
     blocks = [(i, bounds[i], bounds[i + 1] - bounds[i]) for i in range(NT) if bounds[i + 1] > bounds[i]]
     sim_kw = dict(w['kw'])
