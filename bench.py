@@ -385,9 +385,11 @@ def main():
         events_step, jobs_step, ticks_step = (sum(s[k] for s in allsum) for k in ('events', 'n_finished', 'n_ticks'))
         summ, cnt = allsum, [1] * R
     alg_bytes_step = sum(algorithmic_bytes(w, s, cluster.num_nodes, cluster.num_gpus) * c for s, c in zip(summ, cnt))
+    # job-updates: queued + running jobs summed over the processed ticks (fifo) / runnable jobs swept per event (legacy)
+    updates_step = sum((s['sum_queued'] + (s['sum_running'] if is_fifo else 0)) * c for s, c in zip(summ, cnt))
     lpr_used = None
     t = torch.tensor([dt, kernel_ms / 1e3], dtype=torch.float64, device='cuda')
-    tot = torch.tensor([events_step, jobs_step, ticks_step], dtype=torch.float64, device='cuda')
+    tot = torch.tensor([events_step, jobs_step, ticks_step, updates_step], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -395,7 +397,7 @@ def main():
             g = gathered.cpu().numpy().reshape(world, R)
             assert (g[0] == sim.returns()).all(), 'all-gathered returns do not match the local ones'
     dt_max, kern_s = t.tolist()
-    events_all, jobs_all, ticks_all = tot.tolist()
+    events_all, jobs_all, ticks_all, updates_all = tot.tolist()
     value = events_all * args.steps / dt_max
     jmax = max(len(tr.records) for tr in traces)
     max_ticks = max(s['n_ticks'] for s in summ)
@@ -525,6 +527,7 @@ def main():
                        'l2': 'per-step working set (queue stacks + row store + job tables) >> 126 MB L2; no explicit flush',
                        'parallelism': 'replicas: %d GPU x %d (share-nothing), one all-gather of returns' % (world, R)},
             'jobs_per_sec': jobs_all * args.steps / dt_max, 'ticks_per_sec': ticks_all * args.steps / dt_max,
+            'job_updates_per_sec': updates_all * args.steps / dt_max,
             'gpu_launches': launches, 'kernel_ms_per_step': 1e3 * per_launch_s,
             'roofline': roofline, 'clocks': clocks,
         }
