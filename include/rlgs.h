@@ -281,6 +281,13 @@ int32_t rlgs_rows16_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rl
 int32_t rlgs_rows12_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row12 **rows, int64_t *count); /* RLGS_ROWFMT_WIRE12 */
 int32_t rlgs_rows16e_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row16e **rows, int64_t *count); /* RLGS_ROWFMT_EVENT16 */
 int32_t rlgs_rows4e_view(rlgs_sim *sim, int32_t replica, int32_t chunk, const rlgs_row4e **rows, int64_t *count);   /* RLGS_ROWFMT_EVENT4 */
+/* Host-only companion of RLGS_ROWFMT_EVENT4 (no handle, no CUDA call): expands the event log of ONE replica that the caller kept
+ * itself (rlgs_rows4e_view / rlgs_read_rows4e), by the replay rule documented at rlgs_row4e.  jobs[n_jobs] = the trace the
+ * replica ran, rows[n_rows] = its rows.  Outputs, each may be NULL: start_tick / end_tick [n_jobs] (-1 = never), finish_order
+ * [n_jobs] (first *n_finished entries, rest -1), pending[3 * n_rows] = max_pending, median_lo, median_hi of every row.
+ * RLGS_ERR_STATE when the rows do not replay against the trace (check field, start from an empty queue). */
+int32_t rlgs_replay_rows4e(const rlgs_job *jobs, int32_t n_jobs, const rlgs_row4e *rows, int64_t n_rows, int32_t *start_tick,
+                           int32_t *end_tick, int32_t *finish_order, int32_t *n_finished, int32_t *pending);
 /* Per-job int32 column `plane` (trace order): what LOG.job_complete logs for the preemptive schedules
  * (log.py:316-330). */
 enum { RLGS_PLANE_START = 0, RLGS_PLANE_END = 1, RLGS_PLANE_FINISH_ORDER = 2,

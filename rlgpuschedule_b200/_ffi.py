@@ -69,7 +69,7 @@ assert JOB_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64 and ROW16_DTYPE.ite
 
 EXPORTS = ['rlgs_version', 'rlgs_last_error', 'rlgs_create', 'rlgs_destroy', 'rlgs_load_trace', 'rlgs_load_pack_inputs', 'rlgs_run',
            'rlgs_last_run_ms', 'rlgs_set_stream', 'rlgs_get_summary', 'rlgs_read_jobs', 'rlgs_read_rows',
-           'rlgs_rows_view', 'rlgs_read_rows16', 'rlgs_rows16_view', 'rlgs_read_rows12', 'rlgs_rows12_view', 'rlgs_read_rows16e', 'rlgs_rows16e_view', 'rlgs_read_rows4e', 'rlgs_rows4e_view', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
+           'rlgs_rows_view', 'rlgs_read_rows16', 'rlgs_rows16_view', 'rlgs_read_rows12', 'rlgs_rows12_view', 'rlgs_read_rows16e', 'rlgs_rows16e_view', 'rlgs_read_rows4e', 'rlgs_rows4e_view', 'rlgs_replay_rows4e', 'rlgs_read_job_plane', 'rlgs_returns', 'rlgs_returns_device_ptr',
            'rlgs_read_durations', 'rlgs_env_obs_dim', 'rlgs_env_reset', 'rlgs_env_step', 'rlgs_env_observe', 'rlgs_env_sync']
 
 _lib = None
@@ -113,6 +113,7 @@ def lib():
     L.rlgs_rows16e_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
     L.rlgs_read_rows4e.argtypes = [vp, i32, i64, i64, vp]
     L.rlgs_rows4e_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
+    L.rlgs_replay_rows4e.argtypes = [vp, i32, vp, i64, vp, vp, vp, C.POINTER(i32), vp]
     L.rlgs_read_job_plane.argtypes = [vp, i32, i32, vp]
     L.rlgs_returns.argtypes = [vp, vp]
     L.rlgs_returns_device_ptr.argtypes = [vp, C.POINTER(vp)]

@@ -1203,6 +1203,52 @@ extern "C" int32_t rlgs_rows12_view(rlgs_sim *s, int32_t r, int32_t chunk, const
     return rows_view_any(s, r, chunk, reinterpret_cast<const void **>(rows), count);
 }
 
+// Host-only expansion of one replica's rlgs_row4e stream (include/rlgs.h).  Same rule as replay_queue above, which serves the
+// handle's own reads and is pinned by the GPU tests; this entry point is pinned on the CPU (tests/test_abi.py) against the oracle
+// and the reference's golden files.
+extern "C" int32_t rlgs_replay_rows4e(const rlgs_job *jobs, int32_t J, const rlgs_row4e *rows, int64_t n, int32_t *st, int32_t *en,
+                                      int32_t *fo, int32_t *n_finished, int32_t *pending) {
+    if (J < 0 || n < 0 || (J > 0 && !jobs) || (n > 0 && !rows)) return fail(RLGS_ERR_BAD_ARG, "null / negative argument");
+    for (int i = 0; i < J; ++i) { if (st) st[i] = -1; if (en) en[i] = -1; if (fo) fo[i] = -1; }
+    std::vector<int32_t> queue((size_t)std::max(J, 1));
+    int front = J, Q = 0, cursor = 0;
+    int64_t back_arr = 0;
+    std::vector<std::pair<int64_t, int32_t>> fin;   // (end << 32 | start, job)
+    for (int64_t i = 0; i < n; ++i) {
+        int k = 0;
+        while (cursor + k < J && jobs[cursor + k].arrival_tick <= i) ++k;   // the tick's arrivals go to the front, in trace order (q1)
+        if (k) {
+            if (Q == 0) back_arr = i;
+            front -= k;
+            for (int b = 0; b < k; ++b) queue[(size_t)(front + b)] = cursor + b;
+            cursor += k; Q += k;
+        }
+        const uint32_t x = rows[i].w;
+        if (x & 0x1000u) {                                                  // the attempt started the front (schedule.py:188-190)
+            if (Q == 0) return fail(RLGS_ERR_STATE, "row %lld starts a job from an empty queue", (long long)i);
+            const int j = queue[(size_t)front];
+            ++front; --Q;
+            const int64_t e = i + jobs[j].dur_ticks;
+            if (st) st[j] = (int32_t)i;
+            if (e <= n) { if (en) en[j] = (int32_t)e; fin.push_back(std::make_pair((e << 32) | i, j)); }
+        }
+        if ((x >> 13) != ((uint32_t)Q & 0x7ffffu)) return fail(RLGS_ERR_STATE, "row %lld: queue length %u in the row, %d in the replay", (long long)i, x >> 13, Q);
+        if (pending) {
+            int32_t *o = pending + 3 * i;
+            o[0] = o[1] = o[2] = 0;
+            if (Q > 0) {
+                o[0] = (int32_t)(i + 1 - back_arr);
+                o[1] = (int32_t)(i + 1 - jobs[queue[(size_t)(front + (Q - 1) / 2)]].arrival_tick);
+                o[2] = (int32_t)(i + 1 - jobs[queue[(size_t)(front + Q / 2)]].arrival_tick);
+            }
+        }
+    }
+    std::sort(fin.begin(), fin.end());                                      // release order: end tick, then start tick (schedule.py:141-162)
+    if (fo) for (size_t k = 0; k < fin.size(); ++k) fo[k] = fin[k].second;
+    if (n_finished) *n_finished = (int32_t)fin.size();
+    return RLGS_OK;
+}
+
 extern "C" int32_t rlgs_returns(rlgs_sim *s, int64_t *out) {
     if (!s || !out) return fail(RLGS_ERR_BAD_ARG, "null argument");
     if (!s->ran) return fail(RLGS_ERR_STATE, "no completed run");

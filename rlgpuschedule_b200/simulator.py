@@ -221,3 +221,20 @@ class Simulator(object):
         p = C.c_void_p()
         _ffi.check(_ffi.lib().rlgs_returns_device_ptr(self._h, C.byref(p)))
         return p.value
+
+
+def replay_event_rows(trace, rows):
+    """Host-only expansion of one replica's 4-byte event rows (rows_format='event4', e.g. kept from Simulator.rows_wire() or
+    rows_chunk_view()): returns dict(start, end, finish_order, max_pending, median_lo, median_hi).  No device call
+    (rlgs_replay_rows4e, include/rlgs.h)."""
+    rec = np.ascontiguousarray(trace.records)
+    w = np.ascontiguousarray(rows['w'] if rows.dtype.names else rows, dtype='<u4')
+    J, n = len(rec), len(w)
+    st, en, fo = (np.empty(J, np.int32) for _ in range(3))
+    pend = np.empty(3 * max(n, 1), np.int32)
+    nf = C.c_int32(0)
+    _ffi.check(_ffi.lib().rlgs_replay_rows4e(rec.ctypes.data, J, w.ctypes.data, n, st.ctypes.data, en.ctypes.data, fo.ctypes.data,
+                                              C.byref(nf), pend.ctypes.data))
+    pend = pend[:3 * n].reshape(n, 3)
+    return dict(start=st, end=en, finish_order=fo[:nf.value], max_pending=pend[:, 0], median_lo=pend[:, 1], median_hi=pend[:, 2])
+
